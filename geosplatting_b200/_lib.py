@@ -1,0 +1,82 @@
+"""ctypes binding of libgeosplat_b200.so (the C ABI declared in include/geosplat_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, this raises.  PyTorch is only the
+owner of device memory and streams here; every pointer handed to the library is a `tensor.data_ptr()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgeosplat_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "geosplat_b200.h")
+
+_lib: Optional[C.CDLL] = None
+
+
+class GsbCamera(C.Structure):
+    """Mirror of `struct gsb_camera` (include/geosplat_b200.h)."""
+
+    _fields_ = [
+        ("viewmat", C.c_float * 16),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("near_plane", C.c_float), ("far_plane", C.c_float),
+        ("eps2d", C.c_float), ("radius_clip", C.c_float),
+        ("antialiased", C.c_int32), ("camera_id", C.c_int32),
+    ]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", CSRC_DIR, "-j8"], stdout=out)
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"geosplatting_b200: {LIB_PATH} is missing. Build it with `python -c 'import "
+                "__graft_entry__ as g; g.build()'` (or `make -C geosplatting_b200/csrc`). "
+                "There is no CPU or PyTorch fallback for this path.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.gsb_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().gsb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("geosplatting_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("geosplatting_b200: expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous fp32 view/copy (detached)."""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,112 @@
+/*
+ * geosplat_b200.h -- C ABI of libgeosplat_b200.so: the B200 (sm_100a) splat + PBR-shade hot path of
+ * GeoSplatting, written from scratch.
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`
+ *     or the parameter is a `const gsb_camera*` (host struct, passed by value to the kernels);
+ *   - the caller allocates every buffer (PyTorch `tensor.data_ptr()` in the Python host code) and passes
+ *     the CUDA stream to launch on (`cudaStream_t` as `void*`; NULL = legacy default stream);
+ *   - no hidden streams, host threads, allocations or synchronisation, except where stated;
+ *   - returns 0 on success, a negative `GSB_E*` code on failure; `gsb_last_error()` returns the
+ *     message for the calling thread.  The Python host raises RuntimeError on non-zero.
+ *   - fp32 data, int32 ids, int64 sort keys, row-major, densely packed.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the GeoSplatting tree).
+ */
+#ifndef GEOSPLAT_B200_H
+#define GEOSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_OK 0
+#define GSB_EINVAL (-1)   /* bad argument */
+#define GSB_ECUDA (-2)    /* CUDA runtime error (launch / cub) */
+#define GSB_ENOMEM (-3)   /* caller-provided workspace too small */
+
+#define GSB_TILE 16       /* rfstudio/model/gsplat.py:30 block_width = 16 */
+
+const char *gsb_last_error(void);
+int gsb_version(void);
+
+/* One pinhole camera, as rfstudio/model/gsplat.py:340-348 passes it to gsplat.rasterization:
+ * viewmat = Cameras.view_matrix (rfstudio/graphics/_cameras.py:299-314, world->camera, OpenCV axes),
+ * fx..cy = Cameras.intrinsic_matrix (:289-297). */
+typedef struct gsb_camera {
+    float viewmat[16]; /* row-major 4x4 */
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float near_plane, far_plane; /* 0.01, 1e10 (gsplat.py:346-347) */
+    float eps2d;                 /* 0.3 (gsplat default) */
+    float radius_clip;           /* 0.0 */
+    int32_t antialiased;         /* rasterize_mode == 'antialiased' (geosplat.py:796) */
+    int32_t camera_id;           /* goes into the high bits of the sort key */
+} gsb_camera;
+
+/* ---------------------------------------------------------------------------------------------
+ * Rasterizer: replaces gsplat.rasterization (third-party gsplat~=1.4.0, pyproject.toml:24), called at
+ * rfstudio/model/gsplat.py:334-355 and rfstudio/model/geosplat.py:276.  Stage split follows gsplat's
+ * fully_fused_projection -> isect_tiles -> radix sort -> isect_offset_encode -> rasterize_to_pixels.
+ * ------------------------------------------------------------------------------------------- */
+
+/* EWA projection of N Gaussians (unpacked outputs; radii[i]==0 marks a culled Gaussian).
+ * means[N,3] quats[N,4](wxyz, unnormalised) scales[N,3](linear) -> radii[N] means2d[N,2] depths[N]
+ * conics[N,3] comps[N] (1.0 in classic mode) tiles_per_gauss[N]. */
+int gsb_project_fwd(int32_t N, const float *means, const float *quats, const float *scales,
+                    const gsb_camera *cam, int32_t *radii, float *means2d, float *depths, float *conics,
+                    float *comps, int32_t *tiles_per_gauss, void *stream);
+
+/* VJP of gsb_project_fwd.  v_depths may be NULL; v_comps is ignored in classic mode (may be NULL).
+ * Writes (not accumulates) v_means[N,3] v_quats[N,4] v_scales[N,3]; culled rows get zeros. */
+int gsb_project_bwd(int32_t N, const float *means, const float *quats, const float *scales,
+                    const gsb_camera *cam, const int32_t *radii, const float *v_means2d,
+                    const float *v_depths, const float *v_conics, const float *v_comps, float *v_means,
+                    float *v_quats, float *v_scales, void *stream);
+
+/* Bytes of scratch the scan / sort calls below need for N Gaussians and up to M intersections. */
+int gsb_bin_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host);
+
+/* Inclusive prefix sum of tiles_per_gauss -> cum_tiles[N] (int64).  M = cum_tiles[N-1]. */
+int gsb_isect_scan(int32_t N, const int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* Emits the M (key,val) pairs: key = camera_id << (32+tile_n_bits) | tile << 32 | bits(depth),
+ * val = Gaussian index; Gaussian-major, tiles row-major. */
+int gsb_isect_tiles(int32_t N, const float *means2d, const int32_t *radii, const float *depths,
+                    const int64_t *cum_tiles, const gsb_camera *cam, int64_t *isect_ids,
+                    int32_t *flatten_ids, void *stream);
+
+/* Stable radix sort of the low `key_bits` bits (cub::DeviceRadixSort::SortPairs). */
+int gsb_sort_pairs(int64_t M, int32_t key_bits, const int64_t *keys_in, const int32_t *vals_in,
+                   int64_t *keys_out, int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* offsets[n_cameras * n_tiles]: first sorted position of every (camera, tile). */
+int gsb_isect_offsets(int64_t M, const int64_t *sorted_isect_ids, int32_t n_cameras, int32_t tile_w,
+                      int32_t tile_h, int32_t *offsets, void *stream);
+
+/* Front-to-back alpha compositing of one camera (gsplat rasterize_to_pixels_fwd).  Per-Gaussian inputs
+ * are indexed by flatten_ids.  channels in [1,32].  background[channels] may be NULL.
+ * -> render[H,W,channels] alphas[H,W] last_ids[H,W]. */
+int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
+                      const float *conics, const float *colors, const float *opacities,
+                      const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
+                      float *render, float *alphas, int32_t *last_ids, void *stream);
+
+/* VJP of gsb_composite_fwd (gsplat rasterize_to_pixels_bwd).  ACCUMULATES into v_means2d[N,2]
+ * v_conics[N,3] v_colors[N,channels] v_opacities[N]: the caller zero-fills them. */
+int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
+                      const float *conics, const float *colors, const float *opacities,
+                      const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
+                      const float *alphas, const int32_t *last_ids, const float *v_render,
+                      const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
+                      float *v_opacities, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOSPLAT_B200_H */
