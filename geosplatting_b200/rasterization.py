@@ -129,6 +129,10 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
     check(lib.gsb_isect_scan(C.c_int32(N), ptr(tiles_per_gauss), ptr(cum), ptr(ws), C.c_size_t(ws.numel()), st),
           "gsb_isect_scan")
     M = int(cum[-1].item())
+    if M == 0:
+        offsets.zero_()
+        e64 = torch.empty(0, dtype=torch.int64, device=dev)
+        return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
     keys = torch.empty(M, dtype=torch.int64, device=dev)
     vals = torch.empty(M, dtype=torch.int32, device=dev)
     check(lib.gsb_isect_tiles(C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C.byref(cam),
