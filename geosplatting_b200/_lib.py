@@ -53,6 +53,53 @@ def load() -> C.CDLL:
     return _lib
 
 
+class CallStats:
+    """Per-entry-point launch counters and (optionally) CUDA-event timings on the launching stream.
+
+    `bench.py` turns `timing` on to get the live duration of each kernel group inside the timed region;
+    the counters are always on (they are what `gpu_launches` reports).  KERNELS maps a C-ABI entry point
+    to the number of kernels written in this repository that one call launches (cub's internal kernels
+    for scan / radix sort are not counted as ours).
+    """
+
+    KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0}
+    timing = False
+    counts: dict = {}
+    events: dict = {}
+
+    @classmethod
+    def reset(cls, timing: bool = False) -> None:
+        cls.timing = timing
+        cls.counts = {}
+        cls.events = {}
+
+    @classmethod
+    def launches(cls) -> int:
+        return sum(n * cls.KERNELS.get(k, 1) for k, n in cls.counts.items())
+
+    @classmethod
+    def durations_ms(cls) -> dict:
+        """name -> (calls, total_ms); synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.events.items()}
+
+
+def call(name: str, dev: torch.device, *args) -> None:
+    """Invoke C-ABI entry point `name` on `dev`'s current stream; raise on a non-zero return code."""
+    fn = getattr(load(), name)
+    CallStats.counts[name] = CallStats.counts.get(name, 0) + 1
+    if CallStats.timing:
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream(dev))
+        rc = fn(*args)
+        b.record(torch.cuda.current_stream(dev))
+        CallStats.events.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().gsb_last_error().decode("utf-8", "replace")

@@ -20,7 +20,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import GsbCamera, check, f32c, ptr, stream_ptr
+from ._lib import GsbCamera, call, f32c, ptr, stream_ptr
 
 TILE = 16
 _SUPPORTED_CH = (1, 2, 3, 4, 8, 16)
@@ -63,7 +63,6 @@ class _Project(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means: Tensor, quats: Tensor, scales: Tensor, cam: GsbCamera):
-        lib = _lib.load()
         means_c, quats_c, scales_c = f32c(means), f32c(quats), f32c(scales)
         N = means_c.shape[0]
         dev = means_c.device
@@ -73,9 +72,9 @@ class _Project(torch.autograd.Function):
         conics = torch.empty(N, 3, dtype=torch.float32, device=dev)
         comps = torch.empty(N, dtype=torch.float32, device=dev)
         tpg = torch.empty(N, dtype=torch.int32, device=dev)
-        check(lib.gsb_project_fwd(C.c_int32(N), ptr(means_c), ptr(quats_c), ptr(scales_c), C.byref(cam),
+        call("gsb_project_fwd", dev, C.c_int32(N), ptr(means_c), ptr(quats_c), ptr(scales_c), C.byref(cam),
                                   ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tpg),
-                                  stream_ptr(dev)), "gsb_project_fwd")
+                                  stream_ptr(dev))
         ctx.save_for_backward(means_c, quats_c, scales_c, radii)
         ctx.cam = cam
         ctx.mark_non_differentiable(radii, tpg)
@@ -83,7 +82,6 @@ class _Project(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_means2d, v_depths, v_conics, v_comps, _vr, _vt):
-        lib = _lib.load()
         means, quats, scales, radii = ctx.saved_tensors
         N = means.shape[0]
         dev = means.device
@@ -99,9 +97,9 @@ class _Project(torch.autograd.Function):
         v_means = torch.empty(N, 3, dtype=torch.float32, device=dev)
         v_quats = torch.empty(N, 4, dtype=torch.float32, device=dev)
         v_scales = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        check(lib.gsb_project_bwd(C.c_int32(N), ptr(means), ptr(quats), ptr(scales), C.byref(cam), ptr(radii),
+        call("gsb_project_bwd", dev, C.c_int32(N), ptr(means), ptr(quats), ptr(scales), C.byref(cam), ptr(radii),
                                   ptr(v_means2d), ptr(v_depths_c), ptr(v_conics), ptr(v_comps_c), ptr(v_means),
-                                  ptr(v_quats), ptr(v_scales), stream_ptr(dev)), "gsb_project_bwd")
+                                  ptr(v_quats), ptr(v_scales), stream_ptr(dev))
         return v_means, v_quats, v_scales, None
 
 
@@ -111,7 +109,6 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
 
     One host sync (reads M), exactly like gsplat's `isect_tiles`.
     """
-    lib = _lib.load()
     dev = means2d.device
     N = means2d.shape[0]
     tw = (cam.width + TILE - 1) // TILE
@@ -123,11 +120,10 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
         e64 = torch.empty(0, dtype=torch.int64, device=dev)
         return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
     nbytes = C.c_size_t(0)
-    check(lib.gsb_bin_workspace_bytes(C.c_int32(N), C.c_int64(0), C.byref(nbytes)), "gsb_bin_workspace_bytes")
+    call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
     ws = _workspace(dev, nbytes.value)
     cum = torch.empty(N, dtype=torch.int64, device=dev)
-    check(lib.gsb_isect_scan(C.c_int32(N), ptr(tiles_per_gauss), ptr(cum), ptr(ws), C.c_size_t(ws.numel()), st),
-          "gsb_isect_scan")
+    call("gsb_isect_scan", dev, C.c_int32(N), ptr(tiles_per_gauss), ptr(cum), ptr(ws), C.c_size_t(ws.numel()), st)
     M = int(cum[-1].item())
     if M == 0:
         offsets.zero_()
@@ -135,19 +131,19 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
         return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
     keys = torch.empty(M, dtype=torch.int64, device=dev)
     vals = torch.empty(M, dtype=torch.int32, device=dev)
-    check(lib.gsb_isect_tiles(C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C.byref(cam),
-                              ptr(keys), ptr(vals), st), "gsb_isect_tiles")
+    call("gsb_isect_tiles", dev, C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C.byref(cam),
+                              ptr(keys), ptr(vals), st)
     keys_s = torch.empty_like(keys)
     vals_s = torch.empty_like(vals)
-    check(lib.gsb_bin_workspace_bytes(C.c_int32(N), C.c_int64(M), C.byref(nbytes)), "gsb_bin_workspace_bytes")
+    call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(M), C.byref(nbytes))
     ws = _workspace(dev, nbytes.value)
     n_tiles = tw * th
     tile_bits = int(math.floor(math.log2(n_tiles))) + 1
     cam_bits = 0 if n_cameras <= 1 else int(math.floor(math.log2(n_cameras))) + 1
-    check(lib.gsb_sort_pairs(C.c_int64(M), C.c_int32(32 + tile_bits + cam_bits), ptr(keys), ptr(vals),
-                             ptr(keys_s), ptr(vals_s), ptr(ws), C.c_size_t(ws.numel()), st), "gsb_sort_pairs")
-    check(lib.gsb_isect_offsets(C.c_int64(M), ptr(keys_s), C.c_int32(n_cameras), C.c_int32(tw), C.c_int32(th),
-                                ptr(offsets), st), "gsb_isect_offsets")
+    call("gsb_sort_pairs", dev, C.c_int64(M), C.c_int32(32 + tile_bits + cam_bits), ptr(keys), ptr(vals),
+                             ptr(keys_s), ptr(vals_s), ptr(ws), C.c_size_t(ws.numel()), st)
+    call("gsb_isect_offsets", dev, C.c_int64(M), ptr(keys_s), C.c_int32(n_cameras), C.c_int32(tw), C.c_int32(th),
+                                ptr(offsets), st)
     return keys_s, vals_s, offsets.view(n_cameras, th, tw)
 
 
@@ -156,7 +152,6 @@ class _Composite(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, background, offsets, flatten_ids, width, height):
-        lib = _lib.load()
         means2d_c, conics_c, colors_c, opac_c = f32c(means2d), f32c(conics), f32c(colors), f32c(opacities)
         bg_c = None if background is None else f32c(background)
         dev = means2d_c.device
@@ -165,10 +160,10 @@ class _Composite(torch.autograd.Function):
         render = torch.empty(height, width, CH, dtype=torch.float32, device=dev)
         alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
         last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
-        check(lib.gsb_composite_fwd(C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d_c),
+        call("gsb_composite_fwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d_c),
                                     ptr(conics_c), ptr(colors_c), ptr(opac_c), ptr(bg_c), ptr(offsets),
                                     ptr(flatten_ids), C.c_int64(M), ptr(render), ptr(alphas), ptr(last_ids),
-                                    stream_ptr(dev)), "gsb_composite_fwd")
+                                    stream_ptr(dev))
         ctx.save_for_backward(means2d_c, conics_c, colors_c, opac_c, offsets, flatten_ids, alphas, last_ids)
         ctx.bg = bg_c
         ctx.dims = (width, height, CH, M)
@@ -176,7 +171,6 @@ class _Composite(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_render, v_alphas):
-        lib = _lib.load()
         means2d, conics, colors, opac, offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
         width, height, CH, M = ctx.dims
         dev = means2d.device
@@ -188,11 +182,10 @@ class _Composite(torch.autograd.Function):
         v_conics = torch.zeros(N, 3, dtype=torch.float32, device=dev)
         v_colors = torch.zeros(N, CH, dtype=torch.float32, device=dev)
         v_opac = torch.zeros(N, dtype=torch.float32, device=dev)
-        check(lib.gsb_composite_bwd(C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d), ptr(conics),
+        call("gsb_composite_bwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d), ptr(conics),
                                     ptr(colors), ptr(opac), ptr(ctx.bg), ptr(offsets), ptr(flatten_ids),
                                     C.c_int64(M), ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
-                                    ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), stream_ptr(dev)),
-              "gsb_composite_bwd")
+                                    ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), stream_ptr(dev))
         v_bg = None
         if ctx.bg is not None and ctx.needs_input_grad[4]:
             v_bg = ((1.0 - alphas).unsqueeze(-1) * v_render).sum(dim=(0, 1))
