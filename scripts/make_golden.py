@@ -1,0 +1,216 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_*.npz by running the REFERENCE'S OWN Python code for the hot path
+(/root/reference, read-only, this container only) on seeded inputs.
+
+    python scripts/make_golden.py
+
+The third-party kernels the reference calls (`nvdiffrast.torch.texture`) are supplied by this
+repository's CPU restatement (oracle/texture.py), so the fixtures pin:
+  * the reference's own algebra (MGAdapter.make, compute_vertex_normals, RenderableAttrs.splat shade block,
+    TextureSplitSum.sample mip-level rule, _merge/_split_mipmaps, _CubeMapMip fwd/bwd, tone mapping,
+    Cameras.view_matrix / intrinsic_matrix, rot2quat, safe_normalize) -- bit-for-bit what the reference
+    computes on the CPU in fp32;
+  * NOT nvdiffrast / gsplat themselves (absent here: "parity unpinned").
+Gradients are torch autograd through the same code.  Fixtures are small (< 250 KB each) and committed.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+import ref_shim  # noqa: E402
+from geosplatting_b200 import scenes  # noqa: E402
+from oracle import texture as T  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def dr_texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode="auto", boundary_mode="wrap",
+               max_mip_level=None):
+    """nvdiffrast.torch.texture stand-in for the three modes the hot path uses (oracle/texture.py)."""
+    assert uv_da is None and max_mip_level is None
+    if boundary_mode == "clamp":
+        assert filter_mode == "linear" and tex.shape[0] == 1
+        out = T.texture_2d_linear_clamp(tex[0], uv.reshape(-1, 2))
+        return out.reshape(*uv.shape[:-1], tex.shape[-1])
+    assert boundary_mode == "cube" and tex.shape[:2] == (1, 6)
+    d = uv.reshape(-1, 3)
+    if filter_mode == "linear":
+        out = T.texture_cube_linear(tex[0], d)
+    else:
+        assert filter_mode == "linear-mipmap-linear"
+        out = T.texture_cube_mip([tex[0]] + [m[0] for m in mip], d, mip_level_bias.reshape(-1))
+    return out.reshape(*uv.shape[:-1], tex.shape[-1])
+
+
+def synthetic_fg_lut():
+    """Deterministic smooth stand-in for the split-sum DFG LUT [256,256,2] (the real asset is 512 KB)."""
+    i = np.arange(256, dtype=np.float64)[:, None]
+    j = np.arange(256, dtype=np.float64)[None, :]
+    a = 0.5 + 0.45 * np.sin(0.021 * i + 0.013 * j)
+    b = 0.5 + 0.45 * np.cos(0.017 * i - 0.011 * j)
+    return np.stack([a, b], -1).astype(np.float32)
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")
+
+
+def main():
+    ref_shim.install(dr_texture)
+    import rfstudio.graphics as G
+    from rfstudio.graphics import math as RM
+    from rfstudio.graphics._mesh import _texture as RT
+    from rfstudio.graphics import shaders as RS
+    ns = ref_shim.load_geosplat_head()
+    torch.manual_seed(0)
+
+    # ---- A. MGAdapter.make + compute_vertex_normals(fix=True)  (geosplat.py:390-472, _triangle_mesh.py:588-614)
+    verts, faces = scenes.icosphere(1, radius=0.6)  # 42 vertices, 80 faces
+    g = torch.Generator().manual_seed(3)
+    verts = verts * (1.0 + 0.15 * torch.randn(verts.shape[0], 1, generator=g))
+    verts = verts.clone().requires_grad_(True)
+    mesh = G.TriangleMesh(vertices=verts, indices=faces).compute_vertex_normals(fix=True)
+    splats, offsets = ns["MGAdapter"]().make(mesh)
+    outs = dict(means=splats.means, scales=splats.scales, quats=splats.quats, colors=splats.colors,
+                opacities=splats.opacities)
+    cot = {k: torch.randn(v.shape, generator=g) for k, v in outs.items()}
+    loss = sum((outs[k] * cot[k]).sum() for k in outs)
+    v_verts, = torch.autograd.grad(loss, verts)
+    save("ref_mgadapter.npz", vertices=verts, indices=faces, vertex_normals=mesh.normals, offsets=offsets,
+         v_vertices=v_verts, **outs, **{"cot_" + k: v for k, v in cot.items()})
+
+    # ---- B. RenderableAttrs.splat shade block (geosplat.py:83-121) for the three modes
+    N = 600
+    lut = torch.from_numpy(synthetic_fg_lut())
+    ns["_get_fg_lut"] = lambda resolution, device: lut.view(1, 256, 256, 2)
+    sg = scenes.surface_gaussians(N, seed=5)
+    means = sg["means"].clone().requires_grad_(True)
+    normals = torch.nn.functional.normalize(sg["normals"] + 0.2 * torch.randn(N, 3, generator=g), dim=-1)
+    normals = normals.clone().requires_grad_(True)
+    kd = sg["kd"].clone().requires_grad_(True)
+    ks = sg["ks"].clone()
+    ks[:40, 0] = torch.linspace(0, 1, 40)  # sweep roughness over both mip-level branches
+    ks = ks.requires_grad_(True)
+    base = torch.exp(0.5 * torch.randn(6, 16, 16, 3, generator=g)).requires_grad_(True)
+    mips = [torch.exp(0.7 * torch.randn(6, r, r, 3, generator=g)) for r in (32, 16, 8, 4, 2)]
+    packed = RT._merge_mipmaps(mips)
+    packed[:, 3, 30:, 30:] = 0  # _merge_mipmaps leaves this never-read tail uninitialised (torch.empty_like)
+    packed = packed.clone().requires_grad_(True)
+    envmap = G.TextureSplitSum(base=base, mipmaps=packed, num_mipmaps=torch.tensor([5]),
+                               min_roughness=torch.tensor([0.08]), max_roughness=torch.tensor([0.5]), transform=None)
+    cam = scenes.orbit_cameras(1, 64, 64, seed=2)[0]
+    cams = G.Cameras(c2w=torch.from_numpy(cam.c2w)[None], fx=torch.tensor([cam.fx]), fy=torch.tensor([cam.fy]),
+                     cx=torch.tensor([cam.cx]), cy=torch.tensor([cam.cy]), width=torch.tensor([64]),
+                     height=torch.tensor([64]), near=torch.tensor([0.01]), far=torch.tensor([100.0]))
+
+    class _Gaussians:
+        def __init__(self, m):
+            self.means = m
+            self.colors = None
+
+        def __getitem__(self, mask):
+            return self
+
+        def replace_(self, colors):
+            self.colors = colors
+
+    class _FakeGSplatter:
+        def __init__(self, m):
+            self.gaussians = _Gaussians(m)
+
+        def render_rgba(self, cameras):
+            class _R:
+                def item(_self):
+                    return torch.zeros(4, 4, 4)
+            return _R()
+
+    attrs = ns["RenderableAttrs"](kd=kd, ks=ks, normals=normals, occ=None, kd_jitter=None, ks_jitter=None)
+    shade_out = {}
+    for mode in ("pbr", "diffuse", "specular"):
+        fake = _FakeGSplatter(means)
+        gauss = fake.gaussians
+        attrs.splat(fake, cams, exposure=torch.ones(1), envmap=envmap, min_roughness=0.1, max_metallic=1.0,
+                    mode=mode, tone_type="none")
+        colors = gauss.colors
+        cotc = torch.randn(N, 3, generator=g)
+        grads = torch.autograd.grad((colors * cotc).sum(), [means, normals, kd, ks, base, packed], allow_unused=True)
+        shade_out[f"colors_{mode}"] = colors
+        shade_out[f"cot_{mode}"] = cotc
+        for nm, gr in zip(("means", "normals", "kd", "ks", "base", "packed"), grads):
+            shade_out[f"v_{nm}_{mode}"] = torch.zeros(1) if gr is None else gr
+    # the packed env-map gradient is sparse; store it as float16-free sparse triplets to stay small
+    for mode in ("pbr", "diffuse", "specular"):
+        gp = shade_out.pop(f"v_packed_{mode}")
+        if gp.numel() > 1:
+            idx = torch.nonzero(gp.reshape(-1)).reshape(-1)
+            shade_out[f"v_packed_idx_{mode}"] = idx.to(torch.int32)
+            shade_out[f"v_packed_val_{mode}"] = gp.reshape(-1)[idx]
+    save("ref_shade.npz", means=means, normals=normals, kd=kd, ks=ks, base=base,
+         packed=packed.detach(), num_mipmaps=5,
+         cam_pos=torch.from_numpy(cam.c2w[:, 3].copy()), **shade_out)
+
+    # ---- C. tone mapping (geosplat.py:474-476)
+    rgba = (torch.rand(32, 32, 4, generator=g) * 1.6).requires_grad_(True)
+    exposure = torch.tensor([1.3], requires_grad=True)
+    out = ns["_tone_mapping_naive"](rgba, exposure)
+    cott = torch.randn(32, 32, 4, generator=g)
+    v_rgba, v_exp = torch.autograd.grad((out * cott).sum(), [rgba, exposure])
+    save("ref_tonemap.npz", rgba=rgba, exposure=exposure, out=out, cot=cott, v_rgba=v_rgba, v_exposure=v_exp)
+
+    # ---- D. split-sum plumbing: merge/split, sample(), _CubeMapMip fwd/bwd (_texture.py:199-261,:571-613)
+    small = [torch.rand(6, r, r, 3, generator=g) for r in (16, 8, 4)]
+    merged = RT._merge_mipmaps(small)
+    merged[:, 3, 12:, 12:] = 0
+    split = RT._split_mipmaps(merged, num_mipmaps=3)
+    assert all(torch.equal(a, b) for a, b in zip(small, split))
+    nd = torch.randn(300, 3, generator=g)
+    dd = torch.randn(300, 3, generator=g)
+    rough = torch.rand(300, 1, generator=g)
+    env_small = G.TextureSplitSum(base=base.detach(), mipmaps=torch.nan_to_num(merged), num_mipmaps=torch.tensor([3]),
+                                  min_roughness=torch.tensor([0.08]), max_roughness=torch.tensor([0.5]),
+                                  transform=None)
+    l_diff, l_spec = env_small.sample(normals=nd[None, None], directions=dd[None, None], roughness=rough[None, None])
+    cube = torch.rand(6, 8, 8, 3, generator=g).requires_grad_(True)
+    down = RT._CubeMapMip.apply(cube)
+    cotd = torch.randn(6, 4, 4, 3, generator=g)
+    v_cube, = torch.autograd.grad((down * cotd).sum(), cube)
+    save("ref_splitsum.npz", mip0=small[0], mip1=small[1], mip2=small[2], merged=torch.nan_to_num(merged),
+         normals=nd, directions=dd, roughness=rough, base=base.detach(), l_diff=l_diff.reshape(-1, 3),
+         l_spec=l_spec.reshape(-1, 3), cube=cube, down=down, cot_down=cotd, v_cube=v_cube)
+
+    # ---- E. cameras (_cameras.py:289-314)
+    cl = scenes.orbit_cameras(4, 800, 800, seed=7)
+    cams4 = G.Cameras(c2w=torch.from_numpy(np.stack([c.c2w for c in cl])), fx=torch.tensor([c.fx for c in cl]),
+                      fy=torch.tensor([c.fy for c in cl]), cx=torch.tensor([c.cx for c in cl]),
+                      cy=torch.tensor([c.cy for c in cl]), width=torch.tensor([800] * 4),
+                      height=torch.tensor([800] * 4), near=torch.tensor([0.01] * 4), far=torch.tensor([100.0] * 4))
+    save("ref_cameras.npz", c2w=cams4.c2w, fx=cams4.fx, fy=cams4.fy, cx=cams4.cx, cy=cams4.cy,
+         view_matrix=cams4.view_matrix, intrinsic_matrix=cams4.intrinsic_matrix)
+
+    # ---- F. math helpers (math.py:119-128, :246-278)
+    rots = RM.quat2rot(torch.nn.functional.normalize(torch.randn(200, 4, generator=g), dim=-1))
+    vecs = torch.randn(50, 3, generator=g)
+    vecs[:3] = 0
+    save("ref_math.npz", rots=rots, quats=RM.rot2quat(rots), vecs=vecs, safe_normalized=RM.safe_normalize(vecs))
+
+    # ---- G. the reference's FG LUT asset: hash + a 32x32 subsample (shaders.py:22-26)
+    path = "/root/reference/rfstudio/assets/geometry/pbr/bsdf_256_256.bin"
+    raw = open(path, "rb").read()
+    full = np.frombuffer(raw, dtype=np.float32).reshape(256, 256, 2)
+    save("ref_fg_lut_sub.npz", sha256=hashlib.sha256(raw).hexdigest(), sub=full[::8, ::8].copy(),
+         corners=np.stack([full[0, 0], full[0, 255], full[255, 0], full[255, 255]]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""The oracle restatements (oracle/shade.py, oracle/texture.py) against fixtures produced by the
+REFERENCE'S OWN Python code (scripts/make_golden.py, run in the build container).  No GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from geosplatting_b200 import scenes
+from oracle import shade as S
+from oracle import texture as T
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name), allow_pickle=False).items()}
+
+
+def synthetic_fg_lut():
+    i = np.arange(256, dtype=np.float64)[:, None]
+    j = np.arange(256, dtype=np.float64)[None, :]
+    a = 0.5 + 0.45 * np.sin(0.021 * i + 0.013 * j)
+    b = 0.5 + 0.45 * np.cos(0.017 * i - 0.011 * j)
+    return np.stack([a, b], -1).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["pbr", "diffuse", "specular"])
+def test_shade_matches_reference_code(mode):
+    g = load("ref_shade.npz")
+    t = lambda k: torch.tensor(g[k], requires_grad=True)
+    means, normals, kd, ks, base, packed = t("means"), t("normals"), t("kd"), t("ks"), t("base"), t("packed")
+    mips = T.split_mipmaps(packed, int(g["num_mipmaps"]))
+    colors = S.shade(means, normals, kd, ks, torch.tensor(g["cam_pos"]), torch.from_numpy(synthetic_fg_lut()), base,
+                     mips, min_roughness=0.1, max_metallic=1.0, mode=mode)
+    assert np.abs(colors.detach().numpy() - g[f"colors_{mode}"]).max() < 2e-6
+    grads = torch.autograd.grad((colors * torch.tensor(g[f"cot_{mode}"])).sum(), [means, normals, kd, ks, base, packed],
+                                allow_unused=True)
+    for nm, gr in zip(("means", "normals", "kd", "ks", "base"), grads):
+        ref = g[f"v_{nm}_{mode}"]
+        if ref.size == 1:
+            assert gr is None or float(gr.abs().max()) == 0
+            continue
+        assert np.abs(gr.numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), nm
+    if f"v_packed_idx_{mode}" in g:
+        dense = np.zeros(packed.numel(), np.float32)
+        dense[g[f"v_packed_idx_{mode}"]] = g[f"v_packed_val_{mode}"]
+        assert np.abs(grads[5].numpy().reshape(-1) - dense).max() <= 1e-4 * max(1.0, np.abs(dense).max())
+
+
+def test_tonemap_matches_reference_code():
+    g = load("ref_tonemap.npz")
+    rgba = torch.tensor(g["rgba"], requires_grad=True)
+    ex = torch.tensor(g["exposure"], requires_grad=True)
+    out = S.tone_map_naive(rgba, ex)
+    assert np.abs(out.detach().numpy() - g["out"]).max() < 1e-6
+    v_rgba, v_ex = torch.autograd.grad((out * torch.tensor(g["cot"])).sum(), [rgba, ex])
+    assert np.abs(v_rgba.numpy() - g["v_rgba"]).max() < 1e-5
+    assert abs(float(v_ex) - float(g["v_exposure"])) < 1e-3 * abs(float(g["v_exposure"]))
+
+
+def test_splitsum_plumbing_matches_reference_code():
+    g = load("ref_splitsum.npz")
+    mips = [torch.tensor(g[f"mip{i}"]) for i in range(3)]
+    assert np.array_equal(T.merge_mipmaps(mips).numpy(), g["merged"])
+    back = T.split_mipmaps(torch.tensor(g["merged"]), 3)
+    assert all(torch.equal(a, b) for a, b in zip(mips, back))
+    l_diff, l_spec = S.splitsum_sample(torch.tensor(g["base"]), mips, torch.tensor(g["normals"]),
+                                       torch.tensor(g["directions"]), torch.tensor(g["roughness"])[:, 0])
+    assert np.abs(l_diff.numpy() - g["l_diff"]).max() < 1e-6
+    assert np.abs(l_spec.numpy() - g["l_spec"]).max() < 1e-6
+    cube = torch.tensor(g["cube"])
+    assert np.abs(S.cubemap_mip_fwd(cube).numpy() - g["down"]).max() < 1e-7
+    assert np.abs(S.cubemap_mip_bwd(torch.tensor(g["cot_down"])).numpy() - g["v_cube"]).max() < 1e-6
+
+
+def test_cameras_match_reference_code():
+    g = load("ref_cameras.npz")
+    for i in range(g["c2w"].shape[0]):
+        cam = scenes.PinholeCamera(g["c2w"][i], float(g["fx"][i]), float(g["fy"][i]), float(g["cx"][i]),
+                                   float(g["cy"][i]), 800, 800)
+        assert np.abs(cam.view_matrix - g["view_matrix"][i]).max() < 1e-6
+        assert np.array_equal(cam.intrinsic_matrix, g["intrinsic_matrix"][i])
+
+
+def test_math_helpers_match_reference_code():
+    g = load("ref_math.npz")
+    q = scenes.rotmat_to_quat(torch.tensor(g["rots"])).numpy()
+    assert np.abs(q - g["quats"]).max() < 1e-6
+    assert np.abs(S.safe_normalize(torch.tensor(g["vecs"])).numpy() - g["safe_normalized"]).max() < 1e-7
+
+
+def test_cube_face_convention_inverts_the_reference_map():
+    """oracle/texture.cube_face_uv must invert `_cube_to_dir` (_texture.py:178-197): the direction of
+    texel (s, y, x) must come back as face s with (u, v) at that texel's centre."""
+    R = 8
+    dirs = S.cube_texel_dirs(R).reshape(-1, 3)
+    face, u, v = T.cube_face_uv(dirs)
+    exp_face = torch.arange(6).repeat_interleave(R * R)
+    assert torch.equal(face, exp_face)
+    ys, xs = torch.meshgrid(torch.arange(R), torch.arange(R), indexing="ij")
+    assert torch.allclose(u.reshape(6, R, R), ((xs + 0.5) / R).expand(6, R, R), atol=1e-6)
+    assert torch.allclose(v.reshape(6, R, R), ((ys + 0.5) / R).expand(6, R, R), atol=1e-6)
