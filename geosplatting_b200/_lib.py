@@ -62,7 +62,7 @@ class CallStats:
     for scan / radix sort are not counted as ours).
     """
 
-    KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0}
+    KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0, "gsb_envstack_texels": 0}
     timing = False
     counts: dict = {}
     events: dict = {}

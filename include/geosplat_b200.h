@@ -106,6 +106,69 @@ int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, const flo
                       const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
                       float *v_opacities, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split-sum shade: replaces the per-Gaussian shade block of RenderableAttrs.splat
+ * (rfstudio/model/geosplat.py:83-121), TextureSplitSum.sample (rfstudio/graphics/_mesh/_texture.py:
+ * 571-613, including the per-view _split_mipmaps re-materialisation :247-261) and the three
+ * nvdiffrast.torch.texture calls behind them (geosplat.py:93, _texture.py:596,:604).
+ *
+ * Env-map stack (native layout of this library): RGBA float4 texels; specular levels l = 0..L-1 of
+ * resolution R0>>l as [6,R,R] each, concatenated, followed by the diffuse base [6,Rb,Rb].
+ * ------------------------------------------------------------------------------------------- */
+
+/* Number of float4 texels of a stack (host-side helper, no GPU work). */
+int gsb_envstack_texels(int32_t R0, int32_t L, int32_t Rb, int64_t *texels_host);
+
+/* TextureSplitSum.mipmaps [6,4,R0,R0] (quad-tree pack, _texture.py:228-244) + base [6,Rb,Rb,3] -> stack. */
+int gsb_envstack_pack(int32_t R0, int32_t L, int32_t Rb, const float *packed, const float *base, float *stack,
+                      void *stream);
+
+/* Stack gradient -> gradients in the reference layouts (overwrites the texels it owns; the caller
+ * zero-fills v_packed because the quad-tree leaves one unused tail). */
+int gsb_envstack_unpack_grad(int32_t R0, int32_t L, int32_t Rb, const float *v_stack, float *v_packed,
+                             float *v_base, void *stream);
+
+/* colors[N,3] from means[N,3] normals[N,3] kd[N,3] ks[N,2]; cam_pos_host[3] is a HOST pointer;
+ * fg_lut [lut_res,lut_res,2] (rfstudio/graphics/shaders.py:22-26); mode 0 'pbr', 1 'diffuse', 2 'specular'
+ * (geosplat.py:111-121). */
+int gsb_shade_fwd(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
+                  const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack,
+                  int32_t R0, int32_t L, int32_t Rb, float min_roughness, float max_metallic,
+                  float env_min_roughness, float env_max_roughness, int32_t mode, float *colors, void *stream);
+
+/* VJP of gsb_shade_fwd.  Writes v_means/v_normals/v_kd/v_ks; ACCUMULATES texel gradients into
+ * v_env_stack (same layout as env_stack; lets one buffer collect all views of a step). */
+int gsb_shade_bwd(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
+                  const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack,
+                  int32_t R0, int32_t L, int32_t Rb, float min_roughness, float max_metallic,
+                  float env_min_roughness, float env_max_roughness, int32_t mode, const float *v_colors,
+                  float *v_means, float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone texture sampling: replaces nvdiffrast.torch.texture (third-party, unpinned, README.md:36)
+ * for the three call shapes on the path, so that the reference's own TextureSplitSum.sample
+ * (_texture.py:596-611) and _CubeMapMip.backward (_texture.py:220-225) run on this library.
+ * `level_ptrs_host` is a HOST array of n_levels DEVICE pointers to [6,R0>>l,R0>>l,channels] levels.
+ * ------------------------------------------------------------------------------------------- */
+
+/* filter_mode 'linear' (n_levels == 1, level == NULL) or 'linear-mipmap-linear' with explicit mips and a
+ * per-sample mip_level_bias `level[N]`; boundary_mode 'cube'.  dirs[N,3] -> out[N,channels]. */
+int gsb_texture_cube_fwd(int32_t N, int32_t channels, int32_t n_levels, const float *const *level_ptrs_host,
+                         int32_t R0, const float *dirs, const float *level, float *out, void *stream);
+
+/* VJP: ACCUMULATES texel gradients into v_level_ptrs_host[l] (entries or the array may be NULL), writes
+ * v_dirs[N,3] and v_level[N] (either may be NULL). */
+int gsb_texture_cube_bwd(int32_t N, int32_t channels, int32_t n_levels, const float *const *level_ptrs_host,
+                         int32_t R0, const float *dirs, const float *level, const float *v_out,
+                         float *const *v_level_ptrs_host, float *v_dirs, float *v_level, void *stream);
+
+/* 2D, filter 'linear', boundary 'clamp', 2 channels (the FG LUT): tex[H,W,2], uv[N,2] -> out[N,2]. */
+int gsb_texture2d_fwd(int32_t N, int32_t width, int32_t height, const float *tex, const float *uv, float *out,
+                      void *stream);
+/* VJP w.r.t. uv only (the LUT is a constant asset in the reference). */
+int gsb_texture2d_bwd(int32_t N, int32_t width, int32_t height, const float *tex, const float *uv,
+                      const float *v_out, float *v_uv, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
