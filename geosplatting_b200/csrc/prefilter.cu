@@ -1,0 +1,286 @@
+// Split-sum cube-map prefilter: diffuse irradiance, GGX specular prefilter inside a cached cone AABB,
+// the AABB search itself, and the 2x2 mip chain with the reference's (non-transpose) backward.
+//
+// Replaces the reference's own plugin `rfstudio_render_utils`
+// (rfstudio/graphics/_mesh/_splitsum/c_src/cubemap.cu:110-350, torch_bindings.cpp:112-271) and
+// `_CubeMapMip` (rfstudio/graphics/_mesh/_texture.py:199-226).
+//
+// Differences in HOW (results agree to fp32 summation order):
+//  * both backward passes are written in GATHER form -- the weight k(V,L) = max(L.V,0) * D_ggx(V.H) / 4 and the
+//    cone test L.V >= cos(theta_c) are symmetric in (V,L), so the cone AABB table of texel L bounds exactly the
+//    output texels V that L contributes to; no atomics (the reference issues 3 atomicAdd per tap);
+//  * the texel solid angle is separable (pixel_area(x,y) = a(x) * a(y)); a 1-D table lives in shared memory instead
+//    of four atanf per tap;
+//  * the specular forward can write rgb/wsum straight into this library's env stack (float4 texels, .w = wsum).
+#include "texture_math.cuh"
+
+namespace {
+
+// Unit direction of texel (x, y) on `side`.  The cone membership test L.V >= cos(theta_c) sits on a fp32
+// knife edge at high resolution (neighbouring boundary texels differ by ~1e-6 in L.V), so the arithmetic here
+// keeps the reference's expression forms (cubemap.cu:32-46: divide by N, sqrtf, three IEEE divisions) to make
+// the same texels pass the test.
+__device__ __forceinline__ float3 texel_dir(int x, int y, int side, float N) {
+    float fx = 2.0f * (((float)x + 0.5f) / N) - 1.0f;
+    float fy = 2.0f * (((float)y + 0.5f) / N) - 1.0f;
+    float px, py, pz;
+    gsb_face_point(side, fx, fy, px, py, pz);
+    float l = sqrtf(px * px + py * py + pz * pz);
+    return make_float3(px / l, py / l, pz / l);
+}
+
+// cubemap.cu:17-30 verbatim semantics (including the |x - N/2| indexing), one axis.
+__device__ __forceinline__ float axis_area(int x, int N) {
+    if (N <= 1) return 1.0f;
+    int H = N / 2;
+    int a = abs(x - H);
+    return atanf((float)(a + 1) / (float)H) - atanf((float)a / (float)H);
+}
+
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// ---- diffuse --------------------------------------------------------------------------------------------
+// res[t] = post(t) * sum_u pre(u) * src[u] * clamp(D_t . D_u, 0, 0.999)
+//   forward : pre = area(u)/3.141592, post = 1        backward: pre = 1, post = area(t)/3.141592
+template <bool BWD>
+__global__ void __launch_bounds__(256) diffuse_kernel(int R, const float *__restrict__ src, int src_stride,
+                                                       float *__restrict__ dst, int dst_stride) {
+    extern __shared__ float smem[];
+    float *s_area = smem;              // [R]
+    float4 *s_dir = reinterpret_cast<float4 *>(smem + ((R + 3) & ~3));  // chunk of source texels: dir.xyz, pre
+    float4 *s_val = s_dir + 256;                                        // rgb
+    const int total = 6 * R * R;
+    const float invN = (float)R;  // texel_dir takes N
+    for (int i = threadIdx.x; i < R; i += blockDim.x) s_area[i] = axis_area(i, R);
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = t < total;
+    int ts = live ? t / (R * R) : 0, ty = live ? (t / R) % R : 0, tx = live ? t % R : 0;
+    float3 Dt = texel_dir(tx, ty, ts, invN);
+    float3 acc = make_float3(0.f, 0.f, 0.f);
+    for (int base = 0; base < total; base += 256) {
+        int u = base + threadIdx.x;
+        __syncthreads();
+        if (u < total) {
+            int us = u / (R * R), uy = (u / R) % R, ux = u % R;
+            float3 Du = texel_dir(ux, uy, us, invN);
+            float pre = BWD ? 1.0f : s_area[ux] * s_area[uy] / 3.141592f;
+            s_dir[threadIdx.x] = make_float4(Du.x, Du.y, Du.z, pre);
+            const float *p = src + (size_t)u * src_stride;
+            s_val[threadIdx.x] = make_float4(p[0], p[1], p[2], 0.f);
+        }
+        __syncthreads();
+        int n = min(256, total - base);
+        for (int k = 0; k < n; ++k) {
+            float4 d = s_dir[k];
+            float4 v = s_val[k];
+            float c = fminf(fmaxf(Dt.x * d.x + Dt.y * d.y + Dt.z * d.z, 0.0f), 0.999f);
+            float w = c * d.w;
+            acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w;
+        }
+    }
+    if (!live) return;
+    float post = BWD ? s_area[tx] * s_area[ty] / 3.141592f : 1.0f;
+    float *o = dst + (size_t)t * dst_stride;
+    o[0] = acc.x * post; o[1] = acc.y * post; o[2] = acc.z * post;
+}
+
+// ---- specular bounds (cubemap.cu:181-244): AABB on every face of the texels inside the cone ----------------
+__global__ void __launch_bounds__(128) specular_bounds_kernel(int R, float cutoff, float *__restrict__ bounds) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;  // (texel, face)
+    if (id >= 36 * R * R) return;
+    int s = id % 6, o = id / 6;
+    int pz = o / (R * R), py = (o / R) % R, px = o % R;
+    const float invN = (float)R;  // texel_dir takes N
+    float3 V = texel_dir(px, py, pz, invN);
+    const int TS = 16;
+    int min_x = R - 1, max_x = 0, min_y = R - 1, max_y = 0;
+    int nt = (R + TS - 1) / TS;
+    for (int tx = 0; tx < nt; ++tx)
+        for (int ty = 0; ty < nt; ++ty) {
+            int tsx = tx * TS, tsy = ty * TS;
+            int tex = min((tx + 1) * TS, R), tey = min((ty + 1) * TS, R);
+            float3 L0 = texel_dir(tsx, tsy, s, invN), L1 = texel_dir(tex, tsy, s, invN);
+            float3 L2 = texel_dir(tsx, tey, s, invN), L3 = texel_dir(tex, tey, s, invN);
+            float minx = fminf(fminf(L0.x, L1.x), fminf(L2.x, L3.x)), maxx = fmaxf(fmaxf(L0.x, L1.x), fmaxf(L2.x, L3.x));
+            float miny = fminf(fminf(L0.y, L1.y), fminf(L2.y, L3.y)), maxy = fmaxf(fmaxf(L0.y, L1.y), fmaxf(L2.y, L3.y));
+            float minz = fminf(fminf(L0.z, L1.z), fminf(L2.z, L3.z)), maxz = fmaxf(fmaxf(L0.z, L1.z), fmaxf(L2.z, L3.z));
+            float maxdp = fmaxf(minx * V.x, maxx * V.x) + fmaxf(miny * V.y, maxy * V.y) + fmaxf(minz * V.z, maxz * V.z);
+            if (maxdp >= cutoff) {
+                for (int y = tsy; y < tey; ++y)
+                    for (int x = tsx; x < tex; ++x) {
+                        float3 L = texel_dir(x, y, s, invN);
+                        if (dot3(L, V) >= cutoff) {
+                            min_x = min(min_x, x); max_x = max(max_x, x);
+                            min_y = min(min_y, y); max_y = max(max_y, y);
+                        }
+                    }
+            }
+        }
+    float4 *b = reinterpret_cast<float4 *>(bounds) + (size_t)o * 6 + s;
+    *b = make_float4((float)min_x, (float)max_x, (float)min_y, (float)max_y);
+}
+
+__device__ __forceinline__ float ndf_ggx(float alphaSqr, float cosTheta) {
+    float c = fminf(fmaxf(cosTheta, 0.0f), 1.0f);
+    float d = (c * alphaSqr - c) * c + 1.0f;
+    return alphaSqr / (d * d * 3.14159265358979323846f);
+}
+
+// ---- specular (cubemap.cu:246-350) -----------------------------------------------------------------------
+// forward : out[t] = (sum_u area(u) k(t,u) src[u], sum_u area(u) k(t,u))            [optionally rgb /= wsum]
+// backward: gin[t] = area(t) * sum_u k(t,u) * g[u] (/ wsum[u] when the forward normalised)
+template <bool BWD>
+__global__ void __launch_bounds__(128) specular_kernel(int R, const float *__restrict__ src, int src_stride,
+                                                        const float *__restrict__ wsum_src,
+                                                        const float4 *__restrict__ bounds, float alphaSqr,
+                                                        float cutoff, int normalize, float *__restrict__ dst) {
+    extern __shared__ float s_area[];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) s_area[i] = axis_area(i, R);
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * R * R) return;
+    int ts = t / (R * R), ty = (t / R) % R, tx = t % R;
+    const float invN = (float)R;  // texel_dir takes N
+    float3 V = texel_dir(tx, ty, ts, invN);
+    float3 acc = make_float3(0.f, 0.f, 0.f);
+    float wsum = 0.f;
+    for (int s = 0; s < 6; ++s) {
+        float4 b = __ldg(bounds + (size_t)t * 6 + s);
+        int xmin = (int)b.x, xmax = (int)b.y, ymin = (int)b.z, ymax = (int)b.w;
+        if (xmin > xmax) continue;
+        for (int y = ymin; y <= ymax; ++y) {
+            float ay = s_area[y];
+            for (int x = xmin; x <= xmax; ++x) {
+                float3 L = texel_dir(x, y, s, invN);
+                float d = dot3(L, V);
+                if (!(d >= cutoff)) continue;
+                // GGX D(V.H) with H = normalize(L+V).  The reference evaluates 1 - c^2 (1 - a^2) from c = V.H,
+                // which cancels catastrophically near c = 1; here sin^2 = |V x L|^2 / |L+V|^2 is formed
+                // directly, so the weight is accurate to ~1e-6 instead of ~1e-3.
+                float3 Hh = make_float3(L.x + V.x, L.y + V.y, L.z + V.z);
+                float3 cr = make_float3(V.y * L.z - V.z * L.y, V.z * L.x - V.x * L.z, V.x * L.y - V.y * L.x);
+                float s2 = fminf(dot3(cr, cr) / dot3(Hh, Hh), 1.0f);
+                float dd = s2 + (1.0f - s2) * alphaSqr;
+                float k = fmaxf(d, 0.f) * (alphaSqr / (dd * dd * 3.14159265358979323846f));
+                size_t u = ((size_t)s * R + y) * R + x;
+                const float *p = src + u * src_stride;
+                float w;
+                if (BWD) {
+                    w = k / 4.0f;
+                    if (normalize) w /= __ldg(wsum_src + u * 4 + 3);
+                } else {
+                    w = k * (s_area[x] * ay) / 4.0f;
+                }
+                acc.x += __ldg(p) * w; acc.y += __ldg(p + 1) * w; acc.z += __ldg(p + 2) * w;
+                wsum += w;
+            }
+        }
+    }
+    if (BWD) {
+        float a = s_area[tx] * s_area[ty];
+        float *o = dst + (size_t)t * 3;
+        o[0] = acc.x * a; o[1] = acc.y * a; o[2] = acc.z * a;
+    } else {
+        float4 r = normalize ? make_float4(acc.x / wsum, acc.y / wsum, acc.z / wsum, wsum)
+                             : make_float4(acc.x, acc.y, acc.z, wsum);
+        reinterpret_cast<float4 *>(dst)[t] = r;
+    }
+}
+
+// ---- mip chain (_texture.py:199-226) -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mip_fwd_kernel(int Ro, const float *__restrict__ in, int in_stride,
+                                                       float *__restrict__ out, int out_stride) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * Ro * Ro) return;
+    int s = t / (Ro * Ro), y = (t / Ro) % Ro, x = t % Ro;
+    int Ri = Ro * 2;
+    const float *p00 = in + (((size_t)s * Ri + 2 * y) * Ri + 2 * x) * in_stride;
+    const float *p10 = p00 + in_stride, *p01 = p00 + (size_t)Ri * in_stride, *p11 = p01 + in_stride;
+    float *o = out + (size_t)t * out_stride;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (p00[c] + p10[c] + p01[c] + p11[c]) * 0.25f;
+}
+
+// d(in)[fine texel] = bilinear cube sample of 0.25 * d(out) along the fine texel's direction.
+__global__ void __launch_bounds__(256) mip_bwd_kernel(int Ro, const float *__restrict__ dout, float *__restrict__ din) {
+    int Ri = Ro * 2;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * Ri * Ri) return;
+    int s = t / (Ri * Ri), y = (t / Ri) % Ri, x = t % Ri;
+    // _texture.py:213-219: linspace(-1 + 1/res, 1 - 1/res, res) == texel centres
+    float3 d = texel_dir(x, y, s, (float)Ri);
+    CubeTaps taps = gsb_cube_taps(d.x, d.y, d.z, Ro);
+    float3 v = gsb_cube_sample<3, false>(dout, taps, nullptr, nullptr);
+    float *o = din + (size_t)t * 3;
+    o[0] = 0.25f * v.x; o[1] = 0.25f * v.y; o[2] = 0.25f * v.z;
+}
+
+}  // namespace
+
+#define GSB_API extern "C" __attribute__((visibility("default")))
+
+GSB_API int gsb_diffuse_cubemap_fwd(int32_t R, const float *cubemap, float *out, int32_t out_stride, void *stream) {
+    GSB_CHECK_ARG(R >= 1 && R <= 64 && cubemap && out && (out_stride == 3 || out_stride == 4));
+    int total = 6 * R * R;
+    size_t smem = sizeof(float) * ((R + 3) & ~3) + 2 * 256 * sizeof(float4);
+    diffuse_kernel<false><<<gsb_div_up(total, 256), 256, smem, (cudaStream_t)stream>>>(R, cubemap, 3, out, out_stride);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_diffuse_cubemap_bwd(int32_t R, const float *grad_out, int32_t grad_stride, float *grad_in,
+                                    void *stream) {
+    GSB_CHECK_ARG(R >= 1 && R <= 64 && grad_out && grad_in && (grad_stride == 3 || grad_stride == 4));
+    int total = 6 * R * R;
+    size_t smem = sizeof(float) * ((R + 3) & ~3) + 2 * 256 * sizeof(float4);
+    diffuse_kernel<true><<<gsb_div_up(total, 256), 256, smem, (cudaStream_t)stream>>>(R, grad_out, grad_stride,
+                                                                                      grad_in, 3);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_specular_bounds(int32_t R, float costheta_cutoff, float *bounds, void *stream) {
+    GSB_CHECK_ARG(R >= 1 && R <= 4096 && bounds);
+    long long n = 36LL * R * R;
+    specular_bounds_kernel<<<gsb_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(R, costheta_cutoff, bounds);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_specular_cubemap_fwd(int32_t R, const float *cubemap, const float *bounds, float roughness,
+                                     float costheta_cutoff, int32_t normalize, float *out, void *stream) {
+    GSB_CHECK_ARG(R >= 1 && R <= 4096 && cubemap && bounds && out);
+    float alpha = roughness * roughness;
+    specular_kernel<false><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, (cudaStream_t)stream>>>(
+        R, cubemap, 3, nullptr, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float *grad_out, const float *fwd_out,
+                                     float roughness, float costheta_cutoff, float *grad_in, void *stream) {
+    GSB_CHECK_ARG(R >= 1 && R <= 4096 && bounds && grad_out && grad_in);
+    float alpha = roughness * roughness;
+    specular_kernel<true><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, (cudaStream_t)stream>>>(
+        R, grad_out, 4, fwd_out, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff,
+        fwd_out != nullptr, grad_in);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_cubemap_mip_fwd(int32_t R_out, const float *in, int32_t in_stride, float *out, int32_t out_stride,
+                                void *stream) {
+    GSB_CHECK_ARG(R_out >= 1 && in && out && (in_stride == 3 || in_stride == 4) && (out_stride == 3 || out_stride == 4));
+    mip_fwd_kernel<<<gsb_div_up(6 * R_out * R_out, 256), 256, 0, (cudaStream_t)stream>>>(R_out, in, in_stride, out,
+                                                                                         out_stride);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_cubemap_mip_bwd(int32_t R_out, const float *grad_out, float *grad_in, void *stream) {
+    GSB_CHECK_ARG(R_out >= 1 && grad_out && grad_in);
+    mip_bwd_kernel<<<gsb_div_up(24 * R_out * R_out, 256), 256, 0, (cudaStream_t)stream>>>(R_out, grad_out, grad_in);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}

@@ -1,0 +1,305 @@
+"""Host side of the split-sum prefilter (C ABI: gsb_diffuse_cubemap_*, gsb_specular_*, gsb_cubemap_mip_*).
+
+Mirrors, with the same names and argument meaning:
+    rfstudio_render_utils plugin    _splitsum/c_src/torch_bindings.cpp:112-271  -> class `render_utils`
+    diffuse_cubemap / specular_cubemap   _splitsum/_wrap.py:95-157               -> same names
+    __ndfBounds                      _splitsum/_wrap.py:120-135                  -> ndf_bounds
+    _CubeMapMip                      graphics/_mesh/_texture.py:199-226          -> cubemap_mip
+    TextureCubeMap.as_splitsum       graphics/_mesh/_texture.py:530-557          -> as_splitsum / as_envstack
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from ._lib import call, f32c, ptr, stream_ptr
+from .shade import EnvStack
+
+
+def _check_cubemap(t: Tensor, channels: int, name: str) -> None:
+    # same checks as CHECK_TENSOR in torch_bindings.cpp:27-31
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dim() != 4 or t.shape[0] != 6 or t.shape[1] != t.shape[2] or t.shape[3] != channels:
+        raise RuntimeError(f"{name} must have shape [6,R,R,{channels}], got {tuple(t.shape)}")
+
+
+class render_utils:
+    """Function-for-function stand-in for the pybind module `rfstudio_render_utils`."""
+
+    @staticmethod
+    def diffuse_cubemap_fwd(cubemap: Tensor) -> Tensor:
+        _check_cubemap(cubemap, 3, "cubemap")
+        c = f32c(cubemap)
+        out = torch.empty_like(c)
+        call("gsb_diffuse_cubemap_fwd", c.device, C.c_int32(c.shape[1]), ptr(c), ptr(out), C.c_int32(3),
+             stream_ptr(c.device))
+        return out
+
+    @staticmethod
+    def diffuse_cubemap_bwd(cubemap: Tensor, grad: Tensor) -> Tensor:
+        _check_cubemap(cubemap, 3, "cubemap")
+        _check_cubemap(grad, 3, "grad")
+        g = f32c(grad)
+        out = torch.empty_like(g)
+        call("gsb_diffuse_cubemap_bwd", g.device, C.c_int32(g.shape[1]), ptr(g), C.c_int32(3), ptr(out),
+             stream_ptr(g.device))
+        return out
+
+    @staticmethod
+    def specular_bounds(resolution: int, costheta_cutoff: float, index: int) -> Tensor:
+        dev = torch.device("cuda", index)
+        out = torch.zeros(6, resolution, resolution, 24, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("gsb_specular_bounds", dev, C.c_int32(resolution), C.c_float(costheta_cutoff), ptr(out),
+                 stream_ptr(dev))
+        return out
+
+    @staticmethod
+    def specular_cubemap_fwd(cubemap: Tensor, bounds: Tensor, roughness: float, costheta_cutoff: float) -> Tensor:
+        _check_cubemap(cubemap, 3, "cubemap")
+        _check_cubemap(bounds, 24, "bounds")
+        c, b = f32c(cubemap), f32c(bounds)
+        R = c.shape[1]
+        out = torch.empty(6, R, R, 4, dtype=torch.float32, device=c.device)
+        call("gsb_specular_cubemap_fwd", c.device, C.c_int32(R), ptr(c), ptr(b), C.c_float(roughness),
+             C.c_float(costheta_cutoff), C.c_int32(0), ptr(out), stream_ptr(c.device))
+        return out
+
+    @staticmethod
+    def specular_cubemap_bwd(cubemap: Tensor, bounds: Tensor, grad: Tensor, roughness: float,
+                             costheta_cutoff: float) -> Tensor:
+        _check_cubemap(cubemap, 3, "cubemap")
+        _check_cubemap(bounds, 24, "bounds")
+        _check_cubemap(grad, 4, "grad")
+        b, g = f32c(bounds), f32c(grad)
+        R = g.shape[1]
+        out = torch.empty(6, R, R, 3, dtype=torch.float32, device=g.device)
+        call("gsb_specular_cubemap_bwd", g.device, C.c_int32(R), ptr(b), ptr(g), None, C.c_float(roughness),
+             C.c_float(costheta_cutoff), ptr(out), stream_ptr(g.device))
+        return out
+
+
+# ---- _wrap.py:82-157 ------------------------------------------------------------------------------------
+class _diffuse_cubemap_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cubemap):
+        out = render_utils.diffuse_cubemap_fwd(cubemap)
+        ctx.save_for_backward(cubemap)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cubemap, = ctx.saved_tensors
+        return render_utils.diffuse_cubemap_bwd(cubemap, dout.contiguous())
+
+
+def diffuse_cubemap(cubemap: Tensor) -> Tensor:
+    assert cubemap.is_cuda
+    out = _diffuse_cubemap_func.apply(cubemap)
+    if torch.is_anomaly_enabled():
+        assert torch.all(torch.isfinite(out)), "Output of diffuse_cubemap contains inf or NaN"
+    return out
+
+
+class _specular_cubemap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cubemap, roughness, costheta_cutoff, bounds):
+        out = render_utils.specular_cubemap_fwd(cubemap, bounds, roughness, costheta_cutoff)
+        ctx.save_for_backward(cubemap, bounds)
+        ctx.roughness, ctx.theta_cutoff = roughness, costheta_cutoff
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cubemap, bounds = ctx.saved_tensors
+        grad = render_utils.specular_cubemap_bwd(cubemap, bounds, dout.contiguous(), ctx.roughness, ctx.theta_cutoff)
+        return grad, None, None, None
+
+
+_ndf_bounds_cache: Dict[Tuple[int, float, float, int], Tuple[float, Tensor]] = {}
+
+
+def ndf_cutoff_costheta(roughness: float, cutoff: float) -> float:
+    """_wrap.py:120-132: cos(theta) at which the cumulative GGX NDF (1e6 uniform angles) reaches `cutoff`."""
+    def ndf_ggx(alpha_sqr, costheta):
+        costheta = np.clip(costheta, 0.0, 1.0)
+        d = (costheta * alpha_sqr - costheta) * costheta + 1.0
+        return alpha_sqr / (d * d * np.pi)
+
+    n_samples = 1000000
+    costheta = np.cos(np.linspace(0, np.pi / 2.0, n_samples))
+    D = np.cumsum(ndf_ggx(roughness ** 4, costheta))
+    idx = np.argmax(D >= D[..., -1] * cutoff)
+    return float(costheta[idx])
+
+
+def ndf_bounds(res: int, roughness: float, cutoff: float, index: int) -> Tuple[float, Tensor]:
+    """(cos(theta_cutoff), bounds[6,res,res,24]); cached per (res, roughness, cutoff, device) like _wrap.py:133-154."""
+    key = (res, roughness, cutoff, index)
+    if key not in _ndf_bounds_cache:
+        ct = ndf_cutoff_costheta(roughness, cutoff)
+        _ndf_bounds_cache[key] = (ct, render_utils.specular_bounds(res, ct, index))
+    return _ndf_bounds_cache[key]
+
+
+def specular_cubemap(cubemap: Tensor, roughness: float, cutoff: float = 0.99) -> Tensor:
+    assert cubemap.shape[0] == 6 and cubemap.shape[1] == cubemap.shape[2], \
+        "Bad shape for cubemap tensor: %s" % str(cubemap.shape)
+    assert cubemap.is_cuda
+    ct, bounds = ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device.index or 0)
+    out = _specular_cubemap.apply(cubemap, roughness, ct, bounds)
+    if torch.is_anomaly_enabled():
+        assert torch.all(torch.isfinite(out)), "Output of specular_cubemap contains inf or NaN"
+    return out[..., 0:3] / out[..., 3:]
+
+
+# ---- _texture.py:199-226 --------------------------------------------------------------------------------
+class _CubeMapMip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cubemap):
+        assert cubemap.shape[0] == 6 and cubemap.shape[1] == cubemap.shape[2]
+        c = f32c(cubemap)
+        Ro = c.shape[1] // 2
+        out = torch.empty(6, Ro, Ro, c.shape[3], dtype=torch.float32, device=c.device)
+        assert c.shape[3] == 3
+        call("gsb_cubemap_mip_fwd", c.device, C.c_int32(Ro), ptr(c), C.c_int32(3), ptr(out), C.c_int32(3),
+             stream_ptr(c.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = f32c(dout)
+        Ro = d.shape[1]
+        out = torch.empty(6, 2 * Ro, 2 * Ro, 3, dtype=torch.float32, device=d.device)
+        call("gsb_cubemap_mip_bwd", d.device, C.c_int32(Ro), ptr(d), ptr(out), stream_ptr(d.device))
+        return out
+
+
+def cubemap_mip(cubemap: Tensor) -> Tensor:
+    return _CubeMapMip.apply(cubemap)
+
+
+def _roughness_schedule(n_levels: int, min_roughness: float, max_roughness: float) -> List[float]:
+    # _texture.py:545-548
+    r = [(idx / (n_levels - 2)) * (max_roughness - min_roughness) + min_roughness for idx in range(n_levels - 1)]
+    return r + [1.0]
+
+
+def merge_mipmaps(mipmaps: List[Tensor]) -> Tensor:
+    """_texture.py:228-244 (pure indexing; the never-read tail of channel 3 is zero here, uninitialised there)."""
+    R = mipmaps[0].shape[-2]
+    res = mipmaps[0].new_zeros(6, 4, R, R)
+    res[:, :3] = mipmaps[0].permute(0, 3, 1, 2)
+    o = 0
+    for i in range(1, len(mipmaps)):
+        h = R // 2
+        assert mipmaps[i].shape[1:3] == (h, h)
+        res[:, 3, o:o + h, o:o + h] = mipmaps[i][..., 0]
+        res[:, 3, o:o + h, o + h:o + R] = mipmaps[i][..., 1]
+        res[:, 3, o + h:o + R, o:o + h] = mipmaps[i][..., 2]
+        o += h
+        R = h
+    return res
+
+
+def as_splitsum(cubemap: Tensor, *, cutoff: float = 0.99, min_resolution: int = 16, min_roughness: float = 0.08,
+                max_roughness: float = 0.5):
+    """TextureCubeMap.as_splitsum (_texture.py:530-557) operator by operator, returning the TextureSplitSum
+    fields (base [6,Rm,Rm,3], mipmaps [6,4,R,R], num_mipmaps, min_roughness, max_roughness)."""
+    mips = [cubemap]
+    while mips[-1].shape[1] > min_resolution:
+        mips.append(cubemap_mip(mips[-1]))
+    assert len(mips) > 2, "Min resolution is too large."
+    base = diffuse_cubemap(mips[-1])
+    rough = _roughness_schedule(len(mips), min_roughness, max_roughness)
+    spec = [specular_cubemap(m, roughness=r, cutoff=cutoff) for m, r in zip(mips, rough)]
+    return base, merge_mipmaps(spec), len(mips), min_roughness, max_roughness
+
+
+class _PrefilterStack(torch.autograd.Function):
+    """cubemap [6,R,R,3] -> env stack [T,4] in one autograd node: mip chain, per-level GGX prefilter written
+    normalised straight into the stack (texel.w keeps wsum for the backward), diffuse base."""
+
+    @staticmethod
+    def forward(ctx, cubemap, cutoff, min_resolution, min_roughness, max_roughness):
+        c = f32c(cubemap)
+        dev = c.device
+        st = stream_ptr(dev)
+        R0 = c.shape[1]
+        chain = [c]
+        while chain[-1].shape[1] > min_resolution:
+            Ro = chain[-1].shape[1] // 2
+            nxt = torch.empty(6, Ro, Ro, 3, dtype=torch.float32, device=dev)
+            call("gsb_cubemap_mip_fwd", dev, C.c_int32(Ro), ptr(chain[-1]), C.c_int32(3), ptr(nxt), C.c_int32(3), st)
+            chain.append(nxt)
+        L = len(chain)
+        assert L > 2, "Min resolution is too large."
+        Rb = chain[-1].shape[1]
+        T = EnvStack.texels(R0, L, Rb)
+        stack = torch.empty(T, 4, dtype=torch.float32, device=dev)
+        rough = _roughness_schedule(L, min_roughness, max_roughness)
+        o = 0
+        cts = []
+        for l in range(L):
+            r = R0 >> l
+            ct, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
+            cts.append(ct)
+            call("gsb_specular_cubemap_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(bounds), C.c_float(rough[l]),
+                 C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), st)
+            o += 6 * r * r
+        stack[o:].zero_()
+        call("gsb_diffuse_cubemap_fwd", dev, C.c_int32(Rb), ptr(chain[-1]), C.c_void_p(stack.data_ptr() + o * 16),
+             C.c_int32(4), st)
+        ctx.save_for_backward(stack)
+        ctx.meta = (R0, L, Rb, rough, cts, cutoff)
+        return stack
+
+    @staticmethod
+    def backward(ctx, v_stack):
+        stack, = ctx.saved_tensors
+        R0, L, Rb, rough, cts, cutoff = ctx.meta
+        v = f32c(v_stack)
+        dev = v.device
+        st = stream_ptr(dev)
+        offs, o = [], 0
+        for l in range(L):
+            offs.append(o)
+            o += 6 * (R0 >> l) ** 2
+        # gradient w.r.t. each chain level from its own prefilter
+        g_levels = []
+        for l in range(L):
+            r = R0 >> l
+            _, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
+            g = torch.empty(6, r, r, 3, dtype=torch.float32, device=dev)
+            call("gsb_specular_cubemap_bwd", dev, C.c_int32(r), ptr(bounds), C.c_void_p(v.data_ptr() + offs[l] * 16),
+                 C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), st)
+            g_levels.append(g)
+        gb = torch.empty(6, Rb, Rb, 3, dtype=torch.float32, device=dev)
+        call("gsb_diffuse_cubemap_bwd", dev, C.c_int32(Rb), C.c_void_p(v.data_ptr() + o * 16), C.c_int32(4), ptr(gb), st)
+        g_levels[-1] += gb
+        # back through the mip chain (coarse -> fine)
+        for l in range(L - 1, 0, -1):
+            Ro = R0 >> l
+            up = torch.empty(6, 2 * Ro, 2 * Ro, 3, dtype=torch.float32, device=dev)
+            call("gsb_cubemap_mip_bwd", dev, C.c_int32(Ro), ptr(g_levels[l]), ptr(up), st)
+            g_levels[l - 1] += up
+        return g_levels[0], None, None, None, None
+
+
+def as_envstack(cubemap: Tensor, *, cutoff: float = 0.99, min_resolution: int = 16, min_roughness: float = 0.08,
+                max_roughness: float = 0.5) -> EnvStack:
+    """Same result as as_splitsum, produced directly in the native env-stack layout (no quad-tree pack, no
+    per-view unpack): the fast path GeoSplatter.get_envmap -> RenderableAttrs.splat uses."""
+    if not cubemap.is_cuda:
+        raise RuntimeError("geosplatting_b200.as_envstack needs CUDA tensors; there is no CPU path")
+    data = _PrefilterStack.apply(cubemap, cutoff, min_resolution, min_roughness, max_roughness)
+    R0 = cubemap.shape[1]
+    L = 1
+    while (R0 >> (L - 1)) > min_resolution:
+        L += 1
+    return EnvStack(data, R0, L, R0 >> (L - 1), min_roughness, max_roughness)

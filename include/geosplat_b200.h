@@ -169,6 +169,34 @@ int gsb_texture2d_fwd(int32_t N, int32_t width, int32_t height, const float *tex
 int gsb_texture2d_bwd(int32_t N, int32_t width, int32_t height, const float *tex, const float *uv,
                       const float *v_out, float *v_uv, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split-sum prefilter: replaces the reference's own plugin `rfstudio_render_utils`
+ * (rfstudio/graphics/_mesh/_splitsum/c_src/torch_bindings.cpp:112-271 -> cubemap.cu:110-350) and the mip
+ * chain `_CubeMapMip` (rfstudio/graphics/_mesh/_texture.py:199-226).  cubemap is [6,R,R,3]; `*_stride`
+ * arguments (3 or 4 floats per texel) let a kernel read/write this library's float4 env stack directly.
+ * ------------------------------------------------------------------------------------------- */
+
+/* torch_bindings.cpp:112 diffuse_cubemap_fwd: cosine-weighted irradiance of every texel direction. */
+int gsb_diffuse_cubemap_fwd(int32_t R, const float *cubemap, float *out, int32_t out_stride, void *stream);
+/* torch_bindings.cpp:140 diffuse_cubemap_bwd (gather form, writes grad_in[6,R,R,3]). */
+int gsb_diffuse_cubemap_bwd(int32_t R, const float *grad_out, int32_t grad_stride, float *grad_in, void *stream);
+/* torch_bindings.cpp:168 specular_bounds: bounds[6,R,R,24] = per face (xmin,xmax,ymin,ymax) as floats. */
+int gsb_specular_bounds(int32_t R, float costheta_cutoff, float *bounds, void *stream);
+/* torch_bindings.cpp:193 specular_cubemap_fwd: out[6,R,R,4] = (sum w*rgb, sum w); normalize != 0 stores
+ * (rgb/wsum, wsum) instead, which is what _wrap.py:157 computes next. */
+int gsb_specular_cubemap_fwd(int32_t R, const float *cubemap, const float *bounds, float roughness,
+                             float costheta_cutoff, int32_t normalize, float *out, void *stream);
+/* torch_bindings.cpp:226 specular_cubemap_bwd: grad_out[6,R,R,4] (channels 0..2 read, like the plugin) ->
+ * grad_in[6,R,R,3].  fwd_out != NULL: grad_out is the cotangent of the NORMALISED rgb and fwd_out[...,3]
+ * holds wsum (the forward's own output). */
+int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float *grad_out, const float *fwd_out,
+                             float roughness, float costheta_cutoff, float *grad_in, void *stream);
+/* _CubeMapMip.forward: 2x2 box filter per face, in [6,2R,2R,.] -> out [6,R,R,.]. */
+int gsb_cubemap_mip_fwd(int32_t R_out, const float *in, int32_t in_stride, float *out, int32_t out_stride,
+                        void *stream);
+/* _CubeMapMip.backward: grad_in[6,2R,2R,3] = bilinear cube resample of 0.25*grad_out[6,R,R,3]. */
+int gsb_cubemap_mip_bwd(int32_t R_out, const float *grad_out, float *grad_in, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
