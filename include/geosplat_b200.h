@@ -197,6 +197,36 @@ int gsb_cubemap_mip_fwd(int32_t R_out, const float *in, int32_t in_stride, float
 /* _CubeMapMip.backward: grad_in[6,2R,2R,3] = bilinear cube resample of 0.25*grad_out[6,R,R,3]. */
 int gsb_cubemap_mip_bwd(int32_t R_out, const float *grad_out, float *grad_in, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MGAdaptor mesh -> Gaussian sampling, vertex normals, tone map.
+ * ------------------------------------------------------------------------------------------- */
+
+/* TriangleMesh.compute_vertex_normals_(fix=True) (rfstudio/graphics/_mesh/_triangle_mesh.py:588-614):
+ * vertices[V,3], faces[F,3] int64 -> raw[V,3] (area-weighted sums, kept for the backward), normals[V,3]. */
+int gsb_vertex_normals_fwd(int32_t V, int32_t F, const float *vertices, const int64_t *faces, float *raw,
+                           float *normals, void *stream);
+/* VJP: ACCUMULATES into v_vertices[V,3]; scratch[V,3] is caller-provided workspace. */
+int gsb_vertex_normals_bwd(int32_t V, int32_t F, const float *vertices, const int64_t *faces, const float *raw,
+                           const float *v_normals, float *scratch, float *v_vertices, void *stream);
+
+/* MGAdapter().make(mesh, normal_interpolation = vertex_normals != NULL) (rfstudio/model/geosplat.py:426-472):
+ * -> N = 6F Gaussians ordered [ring0:(e01,e12,e20), ring1:(...)] in blocks of F:
+ * means[N,3] scales[N,3](log) quats[N,4](wxyz) normals[N,3] (Splats.colors) opacities[N](logit 0.99)
+ * offsets[N,3] (= n * sqrt(area), detached). */
+int gsb_mgadapter_fwd(int32_t F, const float *vertices, const float *vertex_normals, const int64_t *faces,
+                      float *means, float *scales, float *quats, float *normals, float *opacities, float *offsets,
+                      void *stream);
+/* VJP: ACCUMULATES into v_vertices[V,3] and v_vertex_normals[V,3] (may be NULL). */
+int gsb_mgadapter_bwd(int32_t F, const float *vertices, const float *vertex_normals, const int64_t *faces,
+                      const float *v_means, const float *v_scales, const float *v_quats, const float *v_normals,
+                      float *v_vertices, float *v_vertex_normals, void *stream);
+
+/* _tone_mapping_naive (rfstudio/model/geosplat.py:474-476): rgba[P,4], exposure[1] (device) -> out[P,4]. */
+int gsb_tonemap_fwd(int64_t P, const float *rgba, const float *exposure, float *out, void *stream);
+/* VJP: writes v_rgba[P,4], ACCUMULATES into v_exposure[1]. */
+int gsb_tonemap_bwd(int64_t P, const float *rgba, const float *exposure, const float *v_out, float *v_rgba,
+                    float *v_exposure, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

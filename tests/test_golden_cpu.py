@@ -101,3 +101,20 @@ def test_cube_face_convention_inverts_the_reference_map():
     ys, xs = torch.meshgrid(torch.arange(R), torch.arange(R), indexing="ij")
     assert torch.allclose(u.reshape(6, R, R), ((xs + 0.5) / R).expand(6, R, R), atol=1e-6)
     assert torch.allclose(v.reshape(6, R, R), ((ys + 0.5) / R).expand(6, R, R), atol=1e-6)
+
+
+def test_mgadapter_oracle_matches_reference_code():
+    from oracle import mgadapter as MG
+    g = load("ref_mgadapter.npz")
+    verts = torch.tensor(g["vertices"], requires_grad=True)
+    faces = torch.tensor(g["indices"])
+    vn = MG.vertex_normals(verts, faces)
+    assert np.abs(vn.detach().numpy() - g["vertex_normals"]).max() < 1e-6
+    means, scales, quats, colors, opac, offsets = MG.make(verts, faces, vn)
+    for name, t in (("means", means), ("scales", scales), ("quats", quats), ("colors", colors), ("opacities", opac),
+                    ("offsets", offsets)):
+        assert np.abs(t.detach().numpy() - g[name]).max() < 2e-6, name
+    loss = sum((t * torch.tensor(g["cot_" + k])).sum() for k, t in
+               (("means", means), ("scales", scales), ("quats", quats), ("colors", colors), ("opacities", opac)))
+    gv, = torch.autograd.grad(loss, verts)
+    assert np.abs(gv.numpy() - g["v_vertices"]).max() <= 1e-4 * np.abs(g["v_vertices"]).max()
