@@ -1,0 +1,84 @@
+"""View sharding over ranks (one process per GPU) and the single per-step gradient all-reduce.
+
+The reference is single-GPU and renders the views of a batch in a Python loop (rfstudio/model/geosplat.py:869-879,
+loss = mean over views at rfstudio/trainer/geosplat_trainer.py:171-180).  A view's forward/backward touches only
+the replicated Gaussian set and its own camera, so the path shards over views with NO data-path collective;
+the only exchange is one sum all-reduce of the per-Gaussian (and env-map / exposure) gradients per step, on
+one packed fp32 buffer (72 B per Gaussian) -- NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, TypeVar
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+T = TypeVar("T")
+
+
+def shard_views(items: Sequence[T], rank: int, world_size: int) -> List[T]:
+    """Rank r renders views r, r+R, r+2R, ... of the global batch."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    return list(items[rank::world_size])
+
+
+def view_counts(n_views: int, world_size: int) -> List[int]:
+    return [len(range(r, n_views, world_size)) for r in range(world_size)]
+
+
+class GradientBucket:
+    """One flat fp32 buffer holding every gradient that must be summed across ranks.
+
+    pack() copies the tensors in (one fused foreach copy), all_reduce() issues ONE collective, unpack() hands
+    back views.  The buffer is allocated once and reused every step."""
+
+    def __init__(self, shapes: Sequence[torch.Size], device, dtype=torch.float32):
+        self.shapes = [torch.Size(s) for s in shapes]
+        self.sizes = [int(torch.Size(s).numel()) for s in self.shapes]
+        self.flat = torch.zeros(sum(self.sizes), dtype=dtype, device=device)
+        self.views: List[Tensor] = []
+        o = 0
+        for s, n in zip(self.shapes, self.sizes):
+            self.views.append(self.flat[o:o + n].view(s))
+            o += n
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def pack(self, tensors: Sequence[Optional[Tensor]]) -> None:
+        assert len(tensors) == len(self.views)
+        src, dst = [], []
+        for t, v in zip(tensors, self.views):
+            if t is None:
+                v.zero_()
+            else:
+                assert t.shape == v.shape, (t.shape, v.shape)
+                src.append(t.detach())
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+
+    def all_reduce(self, group=None, average_over: Optional[int] = None) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average_over:
+            self.flat.mul_(1.0 / average_over)
+
+    def unpack(self) -> List[Tensor]:
+        return self.views
+
+
+def allreduce_gradients(tensors: Sequence[Optional[Tensor]], bucket: Optional[GradientBucket] = None, group=None,
+                        average_over: Optional[int] = None) -> List[Tensor]:
+    """Sum `tensors` across ranks with a single collective; returns views into the bucket."""
+    if bucket is None:
+        if any(t is None for t in tensors):
+            raise ValueError("allreduce_gradients: pass a GradientBucket when some gradients are None")
+        ref = tensors[0]
+        bucket = GradientBucket([t.shape for t in tensors], ref.device, ref.dtype)
+    bucket.pack(tensors)
+    bucket.all_reduce(group, average_over)
+    return bucket.unpack()

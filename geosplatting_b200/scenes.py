@@ -168,3 +168,28 @@ def icosphere(subdivisions: int, radius: float = 0.6) -> Tuple[torch.Tensor, tor
             np.stack([f[:, 0], m01, m20], 1), np.stack([f[:, 1], m12, m01], 1),
             np.stack([f[:, 2], m20, m12], 1), np.stack([m01, m12, m20], 1)], 0)
     return torch.from_numpy((v * radius).astype(np.float32)), torch.from_numpy(f)
+
+
+def cube_sphere(n: int, radius: float = 0.6, bump: float = 0.06) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Closed triangle mesh of a bumpy sphere from a subdivided cube: 12*n*n faces, so the MGAdaptor emits
+    72*n*n Gaussians (n=83 -> 496k, n=118 -> 1.00M, n=167 -> 2.01M, n=264 -> 5.02M: the BASELINE configs).
+    Vertices are shared across cube edges (welded), winding is outward."""
+    lin = np.linspace(-1.0, 1.0, n + 1)
+    a, b = np.meshgrid(lin, lin, indexing="ij")
+    one = np.ones_like(a)
+    # (point on face, such that cross(d/da, d/db) points outward)
+    faces_pts = [np.stack([one, a, b], -1), np.stack([-one, b, a], -1), np.stack([b, one, a], -1),
+                 np.stack([a, -one, b], -1), np.stack([a, b, one], -1), np.stack([b, a, -one], -1)]
+    pts = np.concatenate([p.reshape(-1, 3) for p in faces_pts], 0)
+    key = np.round((pts + 1.0) * n / 2.0).astype(np.int64)          # integer lattice coords in [0, n]
+    flat = (key[:, 0] * (n + 1) + key[:, 1]) * (n + 1) + key[:, 2]
+    uniq, first, inv = np.unique(flat, return_index=True, return_inverse=True)
+    verts = pts[first]
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    quads = np.stack([idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, 1:]], -1).reshape(-1, 4)
+    tris = np.concatenate([quads[:, [0, 1, 2]], quads[:, [0, 2, 3]]], 0)
+    all_tris = np.concatenate([tris + f * (n + 1) * (n + 1) for f in range(6)], 0)
+    all_tris = inv.reshape(-1)[all_tris]
+    d = verts / np.linalg.norm(verts, axis=1, keepdims=True)
+    r = radius * (1.0 + bump * np.sin(5.0 * d[:, 0:1]) * np.cos(4.0 * d[:, 1:2]) + 0.6 * bump * np.sin(9.0 * d[:, 2:3]))
+    return torch.from_numpy((d * r).astype(np.float32)), torch.from_numpy(all_tris.astype(np.int64))

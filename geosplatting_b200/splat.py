@@ -1,0 +1,136 @@
+"""The reference-facing operators of the hot path, over the C-ABI kernels.
+
+Mirrors (same names, argument meaning, side effects and errors):
+    Splats                      rfstudio/graphics/_splats.py:17-32       (fields only; densify/cull are out of scope)
+    GSplatter.render_rgba       rfstudio/model/gsplat.py:284-358
+    RenderableAttrs.splat       rfstudio/model/geosplat.py:53-132
+    GeoSplatter.render_report   rfstudio/model/geosplat.py:856-879 (the per-view loop) -> render_views()
+Cameras are `scenes.PinholeCamera` (same conventions as rfstudio/graphics/_cameras.py: OpenGL c2w,
+`view_matrix` / `intrinsic_matrix` properties), passed one per view as the reference does (`cameras.shape == (1,)`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from .mgadapter import tone_mapping_naive
+from .rasterization import rasterization
+from .scenes import PinholeCamera
+from .shade import EnvStack, shade
+
+
+@dataclass
+class Splats:
+    means: Tensor       # [N,3]
+    scales: Tensor      # [N,3] log-scales
+    quats: Tensor       # [N,4] wxyz, un-normalised
+    colors: Tensor      # [N,3]
+    opacities: Tensor   # [N,1] logits
+
+    @property
+    def shape(self) -> Tuple[int]:
+        return (self.means.shape[0],)
+
+    def replace_(self, **kw) -> "Splats":
+        for k, v in kw.items():
+            setattr(self, k, v)
+        return self
+
+    def __getitem__(self, mask) -> "Splats":
+        if mask is Ellipsis:
+            return replace(self)
+        return Splats(self.means[mask], self.scales[mask], self.quats[mask], self.colors[mask], self.opacities[mask])
+
+
+def _single_camera(cameras: Union[PinholeCamera, Sequence[PinholeCamera]]) -> PinholeCamera:
+    if isinstance(cameras, PinholeCamera):
+        return cameras
+    assert len(cameras) == 1  # gsplat.py:293 / geosplat.py:66
+    return cameras[0]
+
+
+@dataclass
+class GSplatter:
+    """rfstudio/model/gsplat.py:20-58; only what GeoSplatter uses: sh_degree=0 (colours raw), block_width=16,
+    rasterize_mode in {'classic','antialiased'}."""
+
+    gaussians: Optional[Splats] = None
+    sh_degree: int = 0
+    block_width: int = 16
+    background_color: str = "random"
+    rasterize_mode: str = "classic"
+
+    def render_rgba(self, inputs) -> Tensor:
+        """-> [H,W,4] (linear RGB + alpha), differentiable w.r.t. the Gaussians (gsplat.py:284-358)."""
+        camera = _single_camera(inputs)
+        if self.rasterize_mode not in ("antialiased", "classic"):
+            raise ValueError(f"Unknown rasterize_mode: {self.rasterize_mode}")
+        if self.sh_degree != 0:
+            raise NotImplementedError("geosplatting_b200.GSplatter: sh_degree must be 0 (GeoSplatter, geosplat.py:794)")
+        g = self.gaussians
+        render, alpha, _ = rasterization(
+            means=g.means, quats=g.quats, scales=g.scales.exp(), opacities=torch.sigmoid(g.opacities).squeeze(-1),
+            colors=g.colors, viewmats=torch.from_numpy(camera.view_matrix)[None],
+            Ks=torch.from_numpy(camera.intrinsic_matrix)[None], width=camera.width, height=camera.height,
+            tile_size=self.block_width, packed=True, near_plane=0.01, far_plane=1e10, render_mode="RGB",
+            sh_degree=None, sparse_grad=False, absgrad=False, rasterize_mode=self.rasterize_mode)
+        return torch.cat((render[..., :3], alpha), dim=-1).squeeze(0)
+
+
+@dataclass
+class RenderableAttrs:
+    """rfstudio/model/geosplat.py:43-51 (occ / *_jitter belong to stages outside this path)."""
+
+    kd: Tensor        # [N,3]
+    ks: Tensor        # [N,2]
+    normals: Tensor   # [N,3]
+
+    def splat(self, gsplat: GSplatter, cameras, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
+              min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
+              culling: bool = False) -> Tensor:
+        """geosplat.py:53-132.  `envmap` is this library's EnvStack (splitsum.as_envstack(cubemap) or
+        EnvStack.from_splitsum(TextureSplitSum fields)); `fg_lut` is `_get_fg_lut(256, device)`."""
+        camera = _single_camera(cameras)
+        cam_pos = camera.c2w[:, 3]
+        if culling:
+            with torch.no_grad():
+                d = torch.as_tensor(cam_pos, device=self.normals.device) - gsplat.gaussians.means
+                wo = torch.nn.functional.normalize(d, dim=-1)
+                mask = (self.normals * wo).sum(-1) > 0.0
+            if not mask.any():
+                raise ValueError("No valid splat found.")
+        else:
+            mask = ...
+        origin = gsplat.gaussians
+        gsplat.gaussians = origin[mask]
+        try:
+            normals, kd, ks = (self.normals, self.kd, self.ks) if mask is Ellipsis else \
+                (self.normals[mask], self.kd[mask], self.ks[mask])
+            colors = shade(gsplat.gaussians.means, normals, kd, ks, [float(x) for x in cam_pos], envmap, fg_lut,
+                           min_roughness=min_roughness, max_metallic=max_metallic, mode=mode)
+            gsplat.gaussians.replace_(colors=colors)
+            rgba = gsplat.render_rgba(camera)
+            if tone_type == "none":
+                out = torch.cat((rgba[..., :3] * exposure, rgba[..., 3:]), dim=-1)
+            elif tone_type == "naive":
+                out = tone_mapping_naive(rgba, exposure)
+            elif tone_type == "aces":
+                rgb = rgba[..., :3] * exposure
+                out = torch.cat(((rgb * (2.51 * rgb + 0.03)) / (rgb * (2.43 * rgb + 0.59) + 0.14), rgba[..., 3:]), dim=-1)
+            else:
+                raise ValueError(tone_type)
+        finally:
+            gsplat.gaussians = origin   # geosplat.py:131 restores the caller's Gaussians
+        return out
+
+
+def render_views(attrs: RenderableAttrs, gsplat: GSplatter, cameras: Sequence[PinholeCamera], *, exposures: Tensor,
+                 envmap: EnvStack, fg_lut: Tensor, min_roughness: float = 0.1, max_metallic: float = 1.0,
+                 mode: str = "pbr") -> List[Tensor]:
+    """The per-view loop of GeoSplatter.render_report (geosplat.py:869-879)."""
+    return [attrs.splat(gsplat, [cam], exposure=exposures[i:i + 1], envmap=envmap, fg_lut=fg_lut,
+                        min_roughness=min_roughness, max_metallic=max_metallic, mode=mode)
+            for i, cam in enumerate(cameras)]
