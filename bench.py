@@ -1,14 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- training views/sec (fwd+bwd) of the splat + shade hot path on N B200s of one node.
+"""bench.py -- training views/sec (fwd+bwd) of the splat + PBR-shade hot path on N B200s of one node.
 
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the CPU oracle on the box's host cores
 
-A "step" is one training view: shade -> project -> bin/sort -> composite forward, then the backward of
-all of them for a fixed random image cotangent.  Views are sharded over ranks (one process per GPU,
-no data-path collective inside a view; the per-step gradient all-reduce is measured by
-`--allreduce`), so `scaling` is "weak": every rank renders its own views of the same Gaussian set.
-Prints ONE JSON line (contract in the task statement; keys documented in DESIGN.md section 7).
+A "step" is one training view of BASELINE.json's metric configuration (1M Gaussians, 800x800): split-sum
+shade -> EWA projection -> tile bin / radix sort -> alpha composite -> tone map, then the backward of all of
+them for a fixed random image cotangent (gradients to means / log-scales / quats / opacities / kd / ks /
+normals / env-map texels / exposure).  The Gaussians come from the MGAdaptor kernel on a 167k-face mesh.
+Views are sharded over ranks (one process per GPU, no data-path collective inside a view; every
+`--allreduce-every` views the packed per-Gaussian gradients are summed with ONE NCCL all-reduce, inside the
+timed region), so `scaling` is "weak".  Prints ONE JSON line; keys are documented in DESIGN.md section 7.
 """
 from __future__ import annotations
 
@@ -26,6 +28,7 @@ if ROOT not in sys.path:
 
 METRIC = "training views/sec (fwd+bwd) @1M Gaussians 800x800"
 UNIT = "views/s"
+PARAM_NAMES = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
 
 
 def parse_args():
@@ -34,22 +37,27 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--mesh-n", type=int, default=118, help="cube-sphere subdivision: 72*n*n Gaussians (118 -> 1.0M)")
     ap.add_argument("--res", type=int, default=800)
-    ap.add_argument("--views", type=int, default=8, help="distinct cameras cycled through per rank")
+    ap.add_argument("--light-res", type=int, default=512, help="env cube-map resolution (GeoSplatter.light_resolution)")
+    ap.add_argument("--views", type=int, default=8, help="distinct cameras cycled through per rank (batch size 8)")
+    ap.add_argument("--allreduce-every", type=int, default=8, help="views per gradient all-reduce when N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--allreduce", action="store_true", help="all-reduce the per-Gaussian gradients every --views steps")
+    ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")
     return ap.parse_args()
 
 
+def n_gaussians(a):
+    return 72 * a.mesh_n * a.mesh_n
+
+
 def workload_name(a):
-    return (f"surface-disc Gaussians N={a.gaussians}, {a.res}x{a.res}, antialiased, fwd+bwd per view, "
-            f"{a.views} orbit cameras/rank (dataparser intrinsics)")
+    return (f"MGAdaptor Gaussians of a {12 * a.mesh_n ** 2}-face bumpy sphere (N={n_gaussians(a)}), {a.res}x{a.res}, "
+            f"split-sum PBR shade (env cube {a.light_res}^2, 6 mips) + antialiased raster + tone map, fwd+bwd per view, "
+            f"{a.views} orbit cameras/rank with the dataparser intrinsics")
 
 
-# ------------------------------------------------------------------------------------------------
-# clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -57,17 +65,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index = index
-        self.proc = None
-        self.path = None
+        self.index, self.proc, self.path = index, None, None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
@@ -79,13 +86,14 @@ class ClockSampler:
             self.proc.terminate()
             self.proc.wait(timeout=5)
             rows = [r.strip().split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = sorted(float(r[1]) for r in rows if len(r) >= 9)
+            rows = [r for r in rows if len(r) >= 9]
+            sm = sorted(float(r[1]) for r in rows)
             if sm:
                 out["sm_mhz"] = sm[len(sm) // 2]
-                out["sm_max_mhz"] = max(float(r[2]) for r in rows if len(r) >= 9)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for k, nm in enumerate(names):
-                    if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows if len(r) >= 9):
+                out["sm_max_mhz"] = max(float(r[2]) for r in rows)
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                    if any(r[5 + k].strip() == "Active" for r in rows):
                         out["reasons"].append(nm)
                 out["samples"] = len(sm)
         except Exception as e:  # pragma: no cover
@@ -98,124 +106,151 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------------
-# algorithmic bytes (SURVEY.md section 8d / DESIGN.md section 4)
-# ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(N, Nv, M, P, T, key_bits):
+    """Per-launch algorithmic bytes."""
     p = (key_bits + 7) // 8
-    per_kernel = {
-        "gsb_project_fwd": 44 * N + 40 * Nv,
-        "gsb_isect_tiles": 16 * Nv + 12 * M,
-        "gsb_sort_pairs": 24 * p * M,
-        "gsb_isect_offsets": 8 * M + 4 * T,
-        "gsb_composite_fwd": 40 * M + 20 * P,
-        "gsb_composite_bwd": 76 * M + 24 * P,
-        "gsb_project_bwd": 120 * Nv + 44 * N,
-        "gsb_shade_fwd": 56 * N,
-        "gsb_shade_bwd": 112 * N,
+    return {
+        "gsb_shade_fwd": 56 * N, "gsb_shade_bwd": 68 * N + 44 * N,
+        "gsb_project_fwd": 44 * N + 40 * Nv, "gsb_project_bwd": 120 * Nv + 44 * N,
+        "gsb_isect_tiles": 16 * Nv + 12 * M, "gsb_sort_pairs": 24 * p * M, "gsb_isect_offsets": 8 * M + 4 * T,
+        "gsb_composite_fwd": 40 * M + 20 * P, "gsb_composite_bwd": 76 * M + 24 * P,
+        "gsb_tonemap_fwd": 32 * P, "gsb_tonemap_bwd": 48 * P,
     }
-    return per_kernel
 
 
 # ------------------------------------------------------------------------------------------------
-# this repository's arm
-# ------------------------------------------------------------------------------------------------
+def build_scene_host(a):
+    """CPU tensors of the scene: mesh, per-Gaussian material attributes, env cube map, cameras."""
+    import torch
+
+    from geosplatting_b200 import scenes
+    verts, faces = scenes.cube_sphere(a.mesh_n)
+    N = 6 * faces.shape[0]
+    g = torch.Generator().manual_seed(0)
+    kd = torch.rand(N, 3, generator=g) * 0.8 + 0.1
+    ks = torch.rand(N, 2, generator=g)
+    cubemap = torch.exp(torch.randn(6, a.light_res, a.light_res, 3, generator=g)).clamp_min(1e-2)
+    return dict(verts=verts, faces=faces, kd=kd, ks=ks, cubemap=cubemap)
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
 
-    from geosplatting_b200 import _lib, scenes
-    from geosplatting_b200.rasterization import rasterization
+    from geosplatting_b200 import _lib, scenes, splitsum
+    from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
+    from geosplatting_b200.parallel import GradientBucket, shard_views
+    from geosplatting_b200.shade import EnvStack, synthetic_fg_lut
+    from geosplatting_b200.splat import GSplatter, RenderableAttrs, Splats
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    g = scenes.surface_gaussians(a.gaussians, seed=0)
+    sc = build_scene_host(a)
     W = H = a.res
-    cams = scenes.orbit_cameras(a.views * world, W, H, seed=1)[rank::world]
-    host = {k: g[k].contiguous().pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    cams = shard_views(scenes.orbit_cameras(a.views * world, W, H, seed=1), rank, world)
+    lut = synthetic_fg_lut(dev)
+    with torch.no_grad():
+        vd, fd = sc["verts"].to(dev), sc["faces"].to(dev)
+        sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+        env0 = splitsum.as_envstack(sc["cubemap"].to(dev))
+    host = {"means": sp.means, "scales": sp.scales, "quats": sp.quats, "opacities": sp.opacities,
+            "kd": sc["kd"], "ks": sc["ks"], "normals": sp.colors}
+    host = {k: v.detach().cpu().contiguous().pin_memory() for k, v in host.items()}
+    N = host["means"].shape[0]
+    params = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+    env_data = env0.data.detach().clone().requires_grad_(True)
+    env = EnvStack(env_data, env0.R0, env0.L, env0.Rb, env0.min_roughness, env0.max_roughness)
+    exposure = torch.ones(1, device=dev, requires_grad=True)
     gen = torch.Generator().manual_seed(1234 + rank)
     v_img_host = torch.randn(H, W, 4, generator=gen).pin_memory()
-    params = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
     v_img = v_img_host.to(dev)
-    vms = [torch.from_numpy(c.view_matrix)[None] for c in cams]  # host tensors: no D2H sync to read them
-    Ks = [torch.from_numpy(c.intrinsic_matrix)[None] for c in cams]
-    names = ("means", "quats", "scales", "opacities", "colors")
     stats = {}
 
-    def step(i, p):
-        c = i % len(cams)
-        render, alpha, info = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"],
-                                            vms[c], Ks[c], W, H, packed=True, rasterize_mode="antialiased")
-        rgba = torch.cat((render[0], alpha[0]), dim=-1)
-        grads = torch.autograd.grad(rgba, [p[k] for k in names], grad_outputs=v_img)
-        stats["info"] = info
-        return rgba, grads
+    def render(p, env_, ex, cam):
+        gs = GSplatter(gaussians=Splats(p["means"], p["scales"], p["quats"], p["normals"], p["opacities"]),
+                       rasterize_mode="antialiased")
+        attrs = RenderableAttrs(kd=p["kd"], ks=p["ks"], normals=p["normals"])
+        return attrs.splat(gs, [cam], exposure=ex, envmap=env_, fg_lut=lut, min_roughness=0.1, max_metallic=1.0)
+
+    grad_inputs = [params[k] for k in PARAM_NAMES] + [env_data, exposure]
+    bucket = GradientBucket([t.shape for t in grad_inputs], dev) if world > 1 else None
+    accum = [None]
+
+    def step(i):
+        img = render(params, env, exposure, cams[i % len(cams)])
+        grads = torch.autograd.grad(img, grad_inputs, grad_outputs=v_img)
+        if world > 1:
+            accum[0] = grads if accum[0] is None else [x + y for x, y in zip(accum[0], grads)]
+            if (i + 1) % a.allreduce_every == 0:
+                bucket.pack(accum[0])
+                bucket.all_reduce(average_over=a.allreduce_every * world)
+                accum[0] = None
+        return img, grads
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # inputs (76 MB) + lists (~100 MB) exceed nothing like L2=126 MB on their own, so flush L2 between
-    # iterations by writing a 256 MB buffer (outside the per-kernel event pairs, inside the step loop).
+    # Working set per step (Gaussian state 76 MB + lists ~60 MB + env stack 34 MB) is comparable to the 126 MB L2,
+    # so flush L2 between iterations by writing a 256 MB buffer (outside every per-kernel event pair).
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
     for i in range(a.warmup):
-        step(i, params)
+        step(i)
+    accum[0] = None
     barrier()
 
-    # ---- timed region: EXACTLY K steps, device-timed, per-kernel events on ---------------------------
+    # ---- timed region: EXACTLY K steps, device-timed, per-kernel events on -----------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     _lib.CallStats.reset(timing=True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
+    wall0 = time.perf_counter()
     for i in range(a.steps):
         flush.zero_()
         ev[i][0].record()
-        step(i, params)
+        step(i)
         ev[i][1].record()
     barrier()
-    step_ms = [s.elapsed_time(e) for s, e in ev]
-    total_ms = sum(step_ms)
+    wall = time.perf_counter() - wall0
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
     durations = _lib.CallStats.durations_ms()
     launches = _lib.CallStats.launches()
     clocks = sampler.stop() if rank == 0 else None
     _lib.CallStats.reset(timing=False)
-
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = a.steps * world / (total_ms_max / 1e3)
 
-    # ---- end-to-end through the public API with HOST buffers ----------------------------------------
+    # ---- end to end through the public API with HOST buffers ------------------------------------------------
     e2e = None
     if not a.no_e2e:
         out_host = torch.empty(H, W, 4).pin_memory()
-        grad_host = {k: torch.empty_like(host[k]).pin_memory() for k in names}
+        grad_host = {k: torch.empty_like(host[k]).pin_memory() for k in PARAM_NAMES}
+        ex_host = torch.empty(1).pin_memory()
         n_e2e = max(3, min(a.steps, 10))
 
         def e2e_step(i):
-            p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+            p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in PARAM_NAMES}
             vimg = v_img_host.to(dev, non_blocking=True)
-            c = i % len(cams)
-            render, alpha, _ = rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"],
-                                             vms[c], Ks[c], W, H, packed=True, rasterize_mode="antialiased")
-            rgba = torch.cat((render[0], alpha[0]), dim=-1)
-            grads = torch.autograd.grad(rgba, [p[k] for k in names], grad_outputs=vimg)
-            out_host.copy_(rgba.detach(), non_blocking=True)
-            for k, gk in zip(names, grads):
+            img = render(p, env, exposure, cams[i % len(cams)])
+            grads = torch.autograd.grad(img, [p[k] for k in PARAM_NAMES] + [exposure], grad_outputs=vimg)
+            out_host.copy_(img.detach(), non_blocking=True)
+            for k, gk in zip(PARAM_NAMES, grads):
                 grad_host[k].copy_(gk, non_blocking=True)
+            ex_host.copy_(grads[-1], non_blocking=True)
 
         for i in range(2):
             e2e_step(i)
@@ -229,25 +264,58 @@ def run_b200(a):
         te = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = sum(host[k].numel() * 4 for k in names) + v_img_host.numel() * 4
-        d2h = out_host.numel() * 4 + sum(grad_host[k].numel() * 4 for k in names)
-        e2e = {"value": n_e2e * world / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": n_e2e}
+        h2d = sum(host[k].numel() * 4 for k in PARAM_NAMES) + v_img_host.numel() * 4
+        d2h = out_host.numel() * 4 + sum(grad_host[k].numel() * 4 for k in PARAM_NAMES) + 4
+        e2e = {"value": round(n_e2e * world / (float(te.item()) / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e,
+               "what": "pinned host Gaussian state + image cotangent -> device, splat fwd+bwd, image + all per-Gaussian gradients -> host"}
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
-    info = stats["info"]
-    M = int(info["flatten_gaussian_ids"].shape[0])
-    Nv = int(info["gaussian_ids"].shape[0])
+    # ---- optional: one full train step (a1-a12, B = 8 views) ------------------------------------------------
+    full = None
+    if a.full_step:
+        vd = sc["verts"].to(dev).requires_grad_(True)
+        cube = sc["cubemap"].to(dev).requires_grad_(True)
+        kd = params["kd"]
+        ks = params["ks"]
+
+        def full_step():
+            vn = compute_vertex_normals(vd, fd)
+            spl, _ = MGAdapter().make(vd, fd, vn)
+            e_ = splitsum.as_envstack(cube)
+            p = {"means": spl.means, "scales": spl.scales, "quats": spl.quats, "opacities": spl.opacities, "kd": kd,
+                 "ks": ks, "normals": spl.colors}
+            loss = 0.0
+            for c in cams[:8]:
+                loss = loss + (render(p, e_, exposure, c) * v_img).sum()
+            torch.autograd.grad(loss, [vd, cube, kd, ks, exposure])
+
+        for _ in range(2):
+            full_step()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_full = 3
+        s.record()
+        for _ in range(n_full):
+            full_step()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e) / n_full
+        full = {"ms_per_step": round(ms, 3), "views_per_step": min(8, len(cams)),
+                "views_per_s": round(min(8, len(cams)) / (ms / 1e3), 2),
+                "what": "vertex normals + MGAdaptor + prefilter (fwd+bwd) + 8 views fwd+bwd, one rank"}
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
+    M, Nv = stats_last_view(params, cams[0], W, H)
     tw, th = (W + 15) // 16, (H + 15) // 16
     key_bits = 32 + (tw * th).bit_length()
-    alg = algorithmic_bytes(a.gaussians, Nv, M, W * H, tw * th, key_bits)
+    alg = algorithmic_bytes(N, Nv, M, W * H, tw * th, key_bits)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     per_kernel = {}
     for k, (calls, ms) in durations.items():
         if calls == 0 or ms <= 0:
@@ -258,13 +326,17 @@ def run_b200(a):
             gbs = alg[k] / (avg_ms * 1e-3) / 1e9
             per_kernel[k].update({"alg_bytes": alg[k], "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
     dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["share"])
-    evals = 256.0 * M
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_kind,
+                "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_kind,
                 "alg_bytes_per_launch": alg[dom], "avg_ms": per_kernel[dom]["avg_ms"],
-                "note": "composite kernels are FP32/MUFU-issue bound, not HBM bound (DESIGN.md section 4); "
-                        "pixel x Gaussian evaluation upper bound per launch = 256*M",
-                "pix_gauss_evals_upper": evals}
+                "note": "the composite kernels are FP32/MUFU issue bound, not HBM bound (DESIGN.md section 4): "
+                        "a tile's 16x16 pixels each evaluate every listed Gaussian",
+                "pix_gauss_evals_upper_per_launch": 256.0 * M}
 
     out = None
     if rank == 0:
@@ -272,46 +344,89 @@ def run_b200(a):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(total_ms_max / a.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "gaussians": a.gaussians, "visible": Nv, "intersections": M,
-                       "resolution": [W, H], "views_per_rank": len(cams), "l2": "flushed between steps (256 MB write)",
-                       "parallelism": f"views sharded over {world} rank(s)"},
+            "config": {"workload": workload_name(a), "gaussians": N, "visible": Nv, "intersections": M,
+                       "resolution": [W, H], "views_per_rank": len(cams),
+                       "l2": "flushed between steps (256 MB write)",
+                       "parallelism": f"views sharded over {world} rank(s)" +
+                                      (f", 1 NCCL all-reduce of {bucket.nbytes} B per {a.allreduce_every} views" if bucket else "")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
-            "impl": "b200",
+            "wall_s_timed_region": round(wall, 3), "impl": "b200",
         }
+        if full:
+            out["full_step"] = full
     return out, rank, world
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU oracle arm (also used for cpu_baseline)
+def stats_last_view(params, cam, W, H):
+    """(M, Nv) of one view, read back outside the timed region."""
+    import torch
+
+    from geosplatting_b200.rasterization import rasterization
+    with torch.no_grad():
+        _, _, info = rasterization(params["means"], params["quats"], params["scales"].exp(),
+                                   torch.sigmoid(params["opacities"]).squeeze(-1), params["normals"],
+                                   torch.from_numpy(cam.view_matrix)[None], torch.from_numpy(cam.intrinsic_matrix)[None],
+                                   W, H, rasterize_mode="antialiased")
+        return int(info["flatten_gaussian_ids"].shape[0]), int(info["gaussian_ids"].shape[0])
+
+
 # ------------------------------------------------------------------------------------------------
 def run_oracle(a, steps, warmup, budget_s=150.0):
-    """fwd+bwd of one view per step with the CPU oracle on all host threads."""
+    """fwd+bwd of one view per step with the CPU oracle (torch shade restatement + C rasterizer, all host threads).
+    The Gaussians come from the torch MGAdaptor restatement, the env map from torch mip + C prefilter, both OUTSIDE
+    the timed region (they are per-step work, the metric is per view)."""
     import numpy as np
+    import torch
 
     from geosplatting_b200 import scenes
+    from geosplatting_b200.shade import synthetic_fg_lut
+    from oracle import mgadapter as OMG
     from oracle import raster as R
+    from oracle import shade as OS
 
-    g = scenes.surface_gaussians(a.gaussians, seed=0)
-    gn = {k: g[k].numpy() for k in ("means", "quats", "scales", "opacities", "colors")}
+    cores = R.num_threads()
+    torch.set_num_threads(cores)
+    sc = build_scene_host(a)
     W = H = a.res
     cams = scenes.orbit_cameras(a.views, W, H, seed=1)
+    with torch.no_grad():
+        vn = OMG.vertex_normals(sc["verts"], sc["faces"])
+        means, ls, quats, normals, opac, _ = OMG.make(sc["verts"], sc["faces"], vn)
+    # env levels: the timed unit (a view) only samples them; use the mip chain of the cube map as the stack
+    mips = [sc["cubemap"]]
+    while mips[-1].shape[1] > 16:
+        mips.append(OS.cubemap_mip_fwd(mips[-1]))
+    base = mips[-1]
+    lut = synthetic_fg_lut("cpu")
     rng = np.random.default_rng(1234)
-    vr = rng.normal(size=(H, W, 3)).astype(np.float32)
-    va = rng.normal(size=(H, W, 1)).astype(np.float32)
-    cores = R.num_threads()
+    cot = torch.from_numpy(rng.normal(size=(H, W, 4)).astype(np.float32))
+    scales = ls.exp().numpy()
+    op = torch.sigmoid(opac)[:, 0].numpy()
 
     def step(i):
         c = cams[i % len(cams)]
+        m = means.clone().requires_grad_(True)
+        n_ = normals.clone().requires_grad_(True)
+        kd = sc["kd"].clone().requires_grad_(True)
+        ks = sc["ks"].clone().requires_grad_(True)
+        col = OS.shade(m, n_, kd, ks, torch.from_numpy(c.position.copy()), lut, base, mips, min_roughness=0.1,
+                       max_metallic=1.0, mode="pbr")
         ocam = R.Camera(c.view_matrix, c.fx, c.fy, c.cx, c.cy, c.width, c.height)
-        render, alpha, info = R.rasterization(gn["means"], gn["quats"], gn["scales"], gn["opacities"], gn["colors"],
-                                              ocam, rasterize_mode="antialiased")
-        R.rasterization_bwd(gn["means"], gn["quats"], gn["scales"], gn["opacities"], gn["colors"], ocam, info, alpha,
-                            vr, va, rasterize_mode="antialiased")
+        coln = col.detach().numpy()
+        render, alpha, info = R.rasterization(means.numpy(), quats.numpy(), scales, op, coln, ocam,
+                                              rasterize_mode="antialiased")
+        rgba = torch.from_numpy(np.concatenate([render, alpha], -1)).requires_grad_(True)
+        ex = torch.ones(1, requires_grad=True)
+        img = OS.tone_map_naive(rgba, ex)
+        v_rgba, _ = torch.autograd.grad((img * cot).sum(), [rgba, ex])
+        g = R.rasterization_bwd(means.numpy(), quats.numpy(), scales, op, coln, ocam, info, alpha,
+                                v_rgba[..., :3].contiguous().numpy(), v_rgba[..., 3:].contiguous().numpy(),
+                                rasterize_mode="antialiased")
+        torch.autograd.grad(col, [m, n_, kd, ks], grad_outputs=torch.from_numpy(g[4]))
 
     t0 = time.perf_counter()
     step(0)
     t_first = time.perf_counter() - t0
-    # bound the run: never more than budget_s of CPU work in total
     max_steps = max(1, int(budget_s / max(t_first, 1e-3)))
     warm = min(warmup, max(0, max_steps // 4))
     timed = max(1, min(steps, max_steps - warm))
@@ -322,23 +437,22 @@ def run_oracle(a, steps, warmup, budget_s=150.0):
         step(i)
     dt = time.perf_counter() - t0
     return {"value": timed / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{timed} full view(s) fwd+bwd of the same workload (C oracle, OpenMP {cores} threads; "
-                      f"raster only until the shade oracle lands)", "ms_per_step": dt / timed * 1e3,
-            "steps_timed": timed}
+            "sample": f"{timed} full view(s) fwd+bwd of the same workload: torch restatement of the shade "
+                      f"(autograd backward) + C restatement of the rasterizer (OpenMP), {cores} host threads",
+            "ms_per_step": dt / timed * 1e3, "steps_timed": timed}
 
 
 def main():
     a = parse_args()
     if a.impl == "reference":
-        rank = int(os.environ.get("RANK", "0"))
-        if rank != 0:
+        if int(os.environ.get("RANK", "0")) != 0:
             return
         cb = run_oracle(a, a.steps, a.warmup)
         out = {"metric": METRIC, "value": round(cb["value"], 5), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": round(cb["ms_per_step"], 2), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": workload_name(a), "gaussians": a.gaussians, "resolution": [a.res, a.res]},
-               "impl": "reference", "cpu_baseline": cb,
+               "config": {"workload": workload_name(a), "gaussians": n_gaussians(a), "resolution": [a.res, a.res]},
+               "impl": "reference", "cpu_baseline": {k: (round(v, 5) if isinstance(v, float) else v) for k, v in cb.items()},
                "e2e": {"value": round(cb["value"], 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
         print(json.dumps(out))
