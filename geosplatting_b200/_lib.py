@@ -62,7 +62,9 @@ class CallStats:
     for scan / radix sort are not counted as ours).
     """
 
-    KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0, "gsb_envstack_texels": 0}
+    KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0, "gsb_envstack_texels": 0,
+               "gsb_composite_workspace_bytes": 0, "gsb_composite_fwd": 3, "gsb_vertex_normals_fwd": 2,
+               "gsb_vertex_normals_bwd": 2}
     timing = False
     counts: dict = {}
     events: dict = {}

@@ -1,10 +1,17 @@
-// Alpha compositing forward / backward: one 256-thread CTA per 16x16 tile.  The tile's depth-sorted list is
-// staged through shared memory in batches of 256 records; each of the 8 warps owns an 8x4 pixel sub-rectangle
-// and first CULLS the batch against it (conservative axis-aligned extent of the alpha >= 1/255 ellipse, one
-// ballot per 32 records), then walks only its hits front-to-back (forward) or back-to-front from its pixels'
-// last contributors (backward).  GeoSplatting's Gaussians are a few pixels wide, so a warp typically keeps
-// ~1/3 of a tile's list; culling never changes results because a culled pair is exactly one the reference
-// kernel would `continue` on (alpha < 1/255 at every pixel centre of the sub-rectangle).
+// Alpha compositing forward / backward.
+//
+// Work decomposition (B200): the unit of work is one WARP owning an 8x4 pixel sub-rectangle of a 16x16 tile
+// (8 units per tile, ~20k units for 800x800).  Three kernels:
+//   pack_records    : per Gaussian, one 48-byte record {x, y, hx, hy | conic a,b,c, opacity | r, g, b, -} where
+//                     (hx, hy) is the axis-aligned half extent of the region in which alpha >= 1/255;
+//   build_sublists  : per (tile, sub-rectangle), the tile's depth-sorted list filtered to the records whose
+//                     extent overlaps the sub-rectangle (order preserved, ballot + popc compaction);
+//   composite fwd/bwd: each warp walks ITS sub-list only, 32 records at a time staged in a private shared-memory
+//                     slab with register prefetch of the next 32 -- no block-level barrier anywhere, per-warp
+//                     early termination, and the hardware block scheduler balances ~20k small units.
+// GeoSplatting's Gaussians are a few pixels wide, so a sub-list holds ~1/3 of its tile's list.  Filtering never
+// changes results: a filtered pair is exactly one the reference kernel would `continue` on (alpha < 1/255 at
+// every pixel centre of the sub-rectangle), and `last_ids` still indexes the 16x16 tile list.
 // Backward: per-lane partial gradients are summed with a transposing butterfly (14 shuffles for 9 values instead
 // of 45) and written with one atomic per value per (Gaussian, warp).
 //
@@ -16,9 +23,15 @@
 
 namespace {
 
-constexpr int BLOCK = GSB_TILE * GSB_TILE;  // 256 threads
-constexpr int WARPS = BLOCK / 32;
-constexpr int SUB_W = 8, SUB_H = 4;         // pixel footprint of one warp
+constexpr int SUB_W = 8, SUB_H = 4;                       // pixel footprint of one warp
+constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 8 sub-rectangles per tile
+constexpr int WPB = 2;                                    // warps (units) per CTA in the composite kernels
+
+struct Rec {
+    float4 k;  // x, y, hx, hy
+    float4 q;  // conic a, b, c, opacity
+    float4 c;  // r, g, b, unused
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -26,16 +39,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// Pixel owned by a thread: warp w -> sub-rectangle (w&1, w>>1), lane l -> (l&7, l>>3) inside it.
-__device__ __forceinline__ void thread_pixel(int tr, int &lx, int &ly) {
-    int w = tr >> 5, l = tr & 31;
-    lx = (w & 1) * SUB_W + (l & 7);
-    ly = (w >> 1) * SUB_H + (l >> 3);
-}
-
 // Half extents of {d : 0.5 d^T C d <= tau}, tau = ln(255 * opac): the only region where alpha >= 1/255.
-// Returns a negative extent when the Gaussian can contribute nowhere.  Inflated so that rounding in the
-// per-pixel evaluation can never contradict a cull.
+// Negative when the Gaussian can contribute nowhere.  Inflated so that rounding in the per-pixel evaluation can
+// never contradict a cull.
 __device__ __forceinline__ float2 alpha_extent(float ca, float cb, float cc, float opac) {
     float t = 255.0f * opac;
     if (!(t > 1.0f)) return make_float2(-1e30f, -1e30f);
@@ -47,34 +53,106 @@ __device__ __forceinline__ float2 alpha_extent(float ca, float cb, float cc, flo
 }
 
 template <int CH>
-__global__ void __launch_bounds__(BLOCK)
-composite_fwd_kernel(int W, int H, int tile_w, const float2 *__restrict__ means2d, const float *__restrict__ conics,
-                     const float *__restrict__ colors, const float *__restrict__ opacities,
-                     const float *__restrict__ background, const int32_t *__restrict__ offsets,
-                     const int32_t *__restrict__ flatten_ids, int n_tiles, int M, float *__restrict__ render,
-                     float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
-    __shared__ float4 s_k[BLOCK];     // x, y, hx, hy
-    __shared__ float4 s_q[BLOCK];     // qa, qb, qc (log2e-scaled conic), opac
-    __shared__ float s_rgb[BLOCK * CH];
+__global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *__restrict__ means2d,
+                                                            const float *__restrict__ conics,
+                                                            const float *__restrict__ colors,
+                                                            const float *__restrict__ opacities, Rec *__restrict__ rec) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    float2 xy = means2d[g];
+    float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
+    float op = opacities[g];
+    float2 ext = alpha_extent(ca, cb, cc, op);
+    Rec r;
+    r.k = make_float4(xy.x, xy.y, ext.x, ext.y);
+    r.q = make_float4(ca, cb, cc, op);
+    float c3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < (CH < 3 ? CH : 3); ++k) c3[k] = colors[(size_t)g * CH + k];
+    r.c = make_float4(c3[0], c3[1], c3[2], 0.f);
+    rec[g] = r;
+}
 
-    const int tile_id = blockIdx.y * tile_w + blockIdx.x;
-    const int tr = threadIdx.x;
-    const int lane = tr & 31, warp = tr >> 5;
-    int lx, ly;
-    thread_pixel(tr, lx, ly);
-    const int i = blockIdx.y * GSB_TILE + ly;
-    const int j = blockIdx.x * GSB_TILE + lx;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < H && j < W);
-    bool done = !inside;
-    // centre of the warp's sub-rectangle in pixel-centre coordinates
-    const float rcx = (float)(blockIdx.x * GSB_TILE + (warp & 1) * SUB_W) + 0.5f * SUB_W;
-    const float rcy = (float)(blockIdx.y * GSB_TILE + (warp >> 1) * SUB_H) + 0.5f * SUB_H;
+// One CTA per tile, warp w filters the tile list for sub-rectangle w.  Sub-list w of tile t lives at
+// entries[SUBS * start_t + w * len_t ...] (worst-case capacity, no prefix sum needed).
+__global__ void __launch_bounds__(32 * SUBS) build_sublists_kernel(int tile_w, int n_tiles, int M,
+                                                                     const int32_t *__restrict__ offsets,
+                                                                     const int32_t *__restrict__ flatten_ids,
+                                                                     const Rec *__restrict__ rec,
+                                                                     int2 *__restrict__ entries,
+                                                                     int32_t *__restrict__ counts) {
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int start = offsets[tile];
+    const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
+    const int len = end - start;
+    const int tx = tile % tile_w, ty = tile / tile_w;
+    const float rcx = (float)(tx * GSB_TILE + (w & 1) * SUB_W) + 0.5f * SUB_W;
+    const float rcy = (float)(ty * GSB_TILE + (w >> 1) * SUB_H) + 0.5f * SUB_H;
     const float rhx = 0.5f * (SUB_W - 1), rhy = 0.5f * (SUB_H - 1);
+    int2 *out = entries + (size_t)SUBS * start + (size_t)w * len;
+    int n = 0;
+    constexpr int U = 4;  // 4 x 32 list entries per iteration: two dependent load latencies per 128 entries
+    for (int base = start; base < end; base += 32 * U) {
+        int gid[U];
+        float4 k[U];
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+            const int pos = base + s * 32 + lane;
+            gid[s] = (pos < end) ? flatten_ids[pos] : -1;
+        }
+#pragma unroll
+        for (int s = 0; s < U; ++s)
+            k[s] = (gid[s] >= 0) ? __ldg(&rec[gid[s]].k) : make_float4(0.f, 0.f, -1e30f, -1e30f);
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+            const bool hit = (fabsf(k[s].x - rcx) <= k[s].z + rhx) && (fabsf(k[s].y - rcy) <= k[s].w + rhy);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) out[n + __popc(m & ((1u << lane) - 1u))] = make_int2(base + s * 32 + lane, gid[s]);
+            n += __popc(m);
+        }
+    }
+    if (lane == 0) counts[tile * SUBS + w] = n;
+}
 
-    const int range_start = offsets[tile_id];
-    const int range_end = (tile_id == n_tiles - 1) ? M : offsets[tile_id + 1];
-    const int num_batches = (range_end - range_start + BLOCK - 1) / BLOCK;
+struct Unit {
+    int tile, w, i, j;
+    bool inside;
+    float px, py;
+};
+
+__device__ __forceinline__ Unit make_unit(int unit, int lane, int tile_w, int W, int H) {
+    Unit u;
+    u.tile = unit / SUBS;
+    u.w = unit % SUBS;
+    const int tx = u.tile % tile_w, ty = u.tile / tile_w;
+    u.j = tx * GSB_TILE + (u.w & 1) * SUB_W + (lane & 7);
+    u.i = ty * GSB_TILE + (u.w >> 1) * SUB_H + (lane >> 3);
+    u.inside = (u.i < H && u.j < W);
+    u.px = (float)u.j + 0.5f;
+    u.py = (float)u.i + 0.5f;
+    return u;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(32 * WPB)
+composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
+                     const float *__restrict__ colors, const float *__restrict__ background,
+                     const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
+                     const int32_t *__restrict__ counts, float *__restrict__ render, float *__restrict__ alphas,
+                     int32_t *__restrict__ last_ids) {
+    __shared__ Rec s_rec[WPB][32];
+    __shared__ int2 s_ent[WPB][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int unit = blockIdx.x * WPB + wib;
+    if (unit >= n_units) return;
+    const Unit u = make_unit(unit, lane, tile_w, W, H);
+    bool done = !u.inside;
+
+    const int start = offsets[u.tile];
+    const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
+    const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
+    const int n = counts[unit];
 
     float T = 1.0f;
     float acc[CH];
@@ -82,55 +160,48 @@ composite_fwd_kernel(int W, int H, int tile_w, const float2 *__restrict__ means2
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
     int cur_idx = 0;
 
-    for (int b = 0; b < num_batches; ++b) {
-        if (__syncthreads_count(done) >= BLOCK) break;
-        const int batch_start = range_start + BLOCK * b;
-        const int idx = batch_start + tr;
-        if (idx < range_end) {
-            const int g = flatten_ids[idx];
-            const float2 xy = means2d[g];
-            const float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
-            const float op = opacities[g];
-            const float2 ext = alpha_extent(ca, cb, cc, op);
-            s_k[tr] = make_float4(xy.x, xy.y, ext.x, ext.y);
-            s_q[tr] = make_float4(0.5f * LOG2E * ca, LOG2E * cb, 0.5f * LOG2E * cc, op);
-#pragma unroll
-            for (int k = 0; k < CH; ++k) s_rgb[tr * CH + k] = colors[(size_t)g * CH + k];
-        } else {
-            s_k[tr] = make_float4(0.f, 0.f, -1e30f, -1e30f);
-        }
-        __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;  // this warp is finished; it still helps staging
-#pragma unroll 1
-        for (int c = 0; c < BLOCK / 32; ++c) {
-            const float4 kc = s_k[c * 32 + lane];
-            const bool hit = (fabsf(kc.x - rcx) <= kc.z + rhx) && (fabsf(kc.y - rcy) <= kc.w + rhy);
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int t = c * 32 + __ffs(m) - 1;
-                m &= m - 1;
-                if (done) continue;
-                const float4 kk = s_k[t];
-                const float4 q = s_q[t];
-                const float dx = kk.x - px, dy = kk.y - py;
-                const float sigma = q.x * dx * dx + q.z * dy * dy + q.y * dx * dy;
-                const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-sigma));
-                if (sigma < 0.f || alpha < GSB_ALPHA_MIN) continue;
-                const float next_T = T * (1.0f - alpha);
-                if (next_T <= GSB_T_STOP) {
-                    done = true;
-                    continue;
-                }
-                const float vis = alpha * T;
-#pragma unroll
-                for (int k = 0; k < CH; ++k) acc[k] += s_rgb[t * CH + k] * vis;
-                cur_idx = batch_start + t;
-                T = next_T;
+    // prefetch chunk 0
+    int2 e = make_int2(0, 0);
+    Rec r;
+    if (lane < n) { e = list[lane]; r = rec[e.y]; }
+    for (int base = 0; base < n; base += 32) {
+        __syncwarp();
+        s_ent[wib][lane] = e;
+        s_rec[wib][lane] = r;
+        __syncwarp();
+        const int nb = base + 32;
+        if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }   // next chunk in flight during the loop
+        const int cnt = min(32, n - base);
+        for (int t = 0; t < cnt; ++t) {
+            if (done) continue;
+            const float4 kk = s_rec[wib][t].k;
+            const float4 q = s_rec[wib][t].q;
+            const float dx = kk.x - u.px, dy = kk.y - u.py;
+            const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
+            const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-LOG2E * sigma));
+            if (sigma < 0.f || alpha < GSB_ALPHA_MIN) continue;
+            const float next_T = T * (1.0f - alpha);
+            if (next_T <= GSB_T_STOP) {
+                done = true;
+                continue;
             }
+            const float vis = alpha * T;
+            const float4 c = s_rec[wib][t].c;
+            acc[0] += c.x * vis;
+            if (CH > 1) acc[1] += c.y * vis;
+            if (CH > 2) acc[2] += c.z * vis;
+            if (CH > 3) {
+                const int g = s_ent[wib][t].y;
+#pragma unroll
+                for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+            }
+            cur_idx = s_ent[wib][t].x;
+            T = next_T;
         }
+        if (__all_sync(0xffffffffu, done)) break;
     }
-    if (inside) {
-        const size_t pix = (size_t)i * W + j;
+    if (u.inside) {
+        const size_t pix = (size_t)u.i * W + u.j;
         alphas[pix] = 1.0f - T;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
@@ -141,7 +212,7 @@ composite_fwd_kernel(int W, int H, int tile_w, const float2 *__restrict__ means2
 
 // Sum 8 per-lane values over the warp with a transposing butterfly: after the call, lanes 4s..4s+3 all hold the
 // warp total of value s (s = 0..7).  4+2+1+1+1 = 9 shuffles.
-__device__ __forceinline__ float warp_reduce8(float v[8], int lane) {
+__device__ __forceinline__ float warp_reduce8(const float v[8], int lane) {
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
     float a[4];
 #pragma unroll
@@ -162,7 +233,7 @@ __device__ __forceinline__ float warp_reduce8(float v[8], int lane) {
     float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     r += __shfl_xor_sync(0xffffffffu, r, 2);
     r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;  // lane holds value index ((b4?4:0) + (b3?2:0) + (b2?1:0))
+    return r;  // value index = lane >> 2
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -172,40 +243,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int CH>
-__global__ void __launch_bounds__(BLOCK)
-composite_bwd_kernel(int W, int H, int tile_w, const float2 *__restrict__ means2d, const float *__restrict__ conics,
-                     const float *__restrict__ colors, const float *__restrict__ opacities,
-                     const float *__restrict__ background, const int32_t *__restrict__ offsets,
-                     const int32_t *__restrict__ flatten_ids, int n_tiles, int M,
-                     const float *__restrict__ alphas, const int32_t *__restrict__ last_ids,
-                     const float *__restrict__ v_render, const float *__restrict__ v_alphas,
-                     float *__restrict__ v_means2d, float *__restrict__ v_conics, float *__restrict__ v_colors,
-                     float *__restrict__ v_opacities) {
-    __shared__ int32_t s_id[BLOCK];
-    __shared__ float4 s_k[BLOCK];   // x, y, hx, hy
-    __shared__ float4 s_q[BLOCK];   // ca, cb, cc, opac
-    __shared__ float s_rgb[BLOCK * CH];
-    __shared__ int s_max[WARPS];
+__global__ void __launch_bounds__(32 * WPB)
+composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
+                     const float *__restrict__ colors, const float *__restrict__ background,
+                     const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
+                     const int32_t *__restrict__ counts, const float *__restrict__ alphas,
+                     const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
+                     const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
+                     float *__restrict__ v_colors, float *__restrict__ v_opacities) {
+    __shared__ Rec s_rec[WPB][32];
+    __shared__ int2 s_ent[WPB][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int unit = blockIdx.x * WPB + wib;
+    if (unit >= n_units) return;
+    const Unit u = make_unit(unit, lane, tile_w, W, H);
+    const size_t pix = u.inside ? (size_t)u.i * W + u.j : 0;
 
-    const int tile_id = blockIdx.y * tile_w + blockIdx.x;
-    const int tr = threadIdx.x;
-    const int lane = tr & 31, warp = tr >> 5;
-    int lx, ly;
-    thread_pixel(tr, lx, ly);
-    const int i = blockIdx.y * GSB_TILE + ly;
-    const int j = blockIdx.x * GSB_TILE + lx;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < H && j < W);
-    const size_t pix = inside ? (size_t)i * W + j : 0;
-    const float rcx = (float)(blockIdx.x * GSB_TILE + (warp & 1) * SUB_W) + 0.5f * SUB_W;
-    const float rcy = (float)(blockIdx.y * GSB_TILE + (warp >> 1) * SUB_H) + 0.5f * SUB_H;
-    const float rhx = 0.5f * (SUB_W - 1), rhy = 0.5f * (SUB_H - 1);
+    const int start = offsets[u.tile];
+    const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
+    const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
+    int n = counts[unit];
 
-    const int range_start = offsets[tile_id];
-    const int range_end = (tile_id == n_tiles - 1) ? M : offsets[tile_id + 1];
-    const int num_batches = (range_end - range_start + BLOCK - 1) / BLOCK;
-
-    const float T_final = inside ? 1.0f - alphas[pix] : 1.0f;
+    const float T_final = u.inside ? 1.0f - alphas[pix] : 1.0f;
     float T = T_final;
     float buffer[CH];
     float v_out[CH];
@@ -213,147 +272,162 @@ composite_bwd_kernel(int W, int H, int tile_w, const float2 *__restrict__ means2
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
         buffer[k] = 0.f;
-        v_out[k] = inside ? v_render[pix * CH + k] : 0.f;
+        v_out[k] = u.inside ? v_render[pix * CH + k] : 0.f;
         if (background) bg_dot += background[k] * v_out[k];
     }
-    const float v_a_out = inside ? v_alphas[pix] : 0.f;
-    const int bin_final = inside ? last_ids[pix] : -1;
-
+    const float v_a_out = u.inside ? v_alphas[pix] : 0.f;
+    const int bin_final = u.inside ? last_ids[pix] : -1;
     int wmax = bin_final;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int block_max = s_max[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) block_max = max(block_max, s_max[w]);
-    const int warp_bin_final = wmax;
 
-    for (int b = 0; b < num_batches; ++b) {
-        // batches walk the list from its END: entry t of batch b is list position batch_end - t
-        const int batch_end = range_end - 1 - BLOCK * b;
-        const int batch_size = min(BLOCK, batch_end + 1 - range_start);
-        if (batch_end - batch_size + 1 > block_max) continue;  // nothing in this batch contributed anywhere
-        __syncthreads();
-        const int idx = batch_end - tr;
-        if (idx >= range_start) {
-            const int g = flatten_ids[idx];
-            s_id[tr] = g;
-            const float2 xy = means2d[g];
-            const float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
-            const float op = opacities[g];
-            const float2 ext = alpha_extent(ca, cb, cc, op);
-            s_k[tr] = make_float4(xy.x, xy.y, ext.x, ext.y);
-            s_q[tr] = make_float4(ca, cb, cc, op);
-#pragma unroll
-            for (int k = 0; k < CH; ++k) s_rgb[tr * CH + k] = colors[(size_t)g * CH + k];
-        } else {
-            s_k[tr] = make_float4(0.f, 0.f, -1e30f, -1e30f);
+    // Entries are sorted by tile-list position: drop the tail that lies behind every pixel's last contributor
+    // (binary search for the first position > wmax).
+    {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (list[mid].x <= wmax) lo = mid + 1; else hi = mid;
         }
-        __syncthreads();
-        if (batch_end - batch_size + 1 > warp_bin_final) continue;  // warp-uniform
-#pragma unroll 1
-        for (int c = 0; c < BLOCK / 32; ++c) {
-            if (batch_end - (c * 32 + 31) > warp_bin_final) continue;  // whole chunk is behind this warp's pixels
-            const float4 kc = s_k[c * 32 + lane];
-            const bool hit = (fabsf(kc.x - rcx) <= kc.z + rhx) && (fabsf(kc.y - rcy) <= kc.w + rhy) &&
-                             (batch_end - (c * 32 + lane) <= warp_bin_final);
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int t = c * 32 + __ffs(m) - 1;   // ascending t == descending list position
-                m &= m - 1;
-                const float4 kk = s_k[t];
-                const float4 q = s_q[t];
-                const float dx = kk.x - px, dy = kk.y - py;
-                bool valid = (batch_end - t <= bin_final);
-                float alpha = 0.f, vis = 0.f;
-                const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
-                vis = ex2_approx(-LOG2E * sigma);
-                alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
-                if (sigma < 0.f || alpha < GSB_ALPHA_MIN) valid = false;
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                float v[8];
-                float v_op = 0.f;
+        n = lo;
+    }
+    if (n == 0) return;
+
+    // walk back to front: chunk c covers sub-list indices [hi_c - 32, hi_c), lane l holds index hi_c - 1 - l
+    int2 e = make_int2(0, 0);
+    Rec r;
+    if (n - 1 - lane >= 0) { e = list[n - 1 - lane]; r = rec[e.y]; }
+    for (int top = n; top > 0; top -= 32) {
+        __syncwarp();
+        s_ent[wib][lane] = e;
+        s_rec[wib][lane] = r;
+        __syncwarp();
+        const int nt = top - 32;
+        if (nt - 1 - lane >= 0) { e = list[nt - 1 - lane]; r = rec[e.y]; }
+        const int cnt = min(32, top);
+        for (int t = 0; t < cnt; ++t) {
+            const float4 kk = s_rec[wib][t].k;
+            const float4 q = s_rec[wib][t].q;
+            const int2 en = s_ent[wib][t];
+            const float dx = kk.x - u.px, dy = kk.y - u.py;
+            const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
+            const float vis = ex2_approx(-LOG2E * sigma);
+            const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
+            const bool valid = (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = 0.f;
-                float v_rgb_extra[CH > 3 ? CH - 3 : 1];
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            float v_op = 0.f;
+            float v_extra[CH > 3 ? CH - 3 : 1];
 #pragma unroll
-                for (int k = 0; k < (CH > 3 ? CH - 3 : 1); ++k) v_rgb_extra[k] = 0.f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - alpha);
-                    T *= ra;
-                    const float fac = alpha * T;
-                    float v_alpha = 0.f;
+            for (int k = 0; k < (CH > 3 ? CH - 3 : 1); ++k) v_extra[k] = 0.f;
+            if (valid) {
+                const float ra = 1.0f / (1.0f - alpha);
+                T *= ra;
+                const float fac = alpha * T;
+                const float4 c = s_rec[wib][t].c;
+                float v_alpha = 0.f;
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        const float cch = s_rgb[t * CH + k];
-                        const float g_ = fac * v_out[k];
-                        if (k < 3) v[k] = g_; else v_rgb_extra[k - 3] = g_;
-                        v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
-                        buffer[k] += cch * fac;
-                    }
-                    v_alpha += T_final * ra * v_a_out;
-                    if (background) v_alpha += -T_final * ra * bg_dot;
-                    if (q.w * vis <= GSB_ALPHA_CLAMP) {
-                        const float v_sigma = -q.w * vis * v_alpha;
-                        v[3] = 0.5f * v_sigma * dx * dx;
-                        v[4] = v_sigma * dx * dy;
-                        v[5] = 0.5f * v_sigma * dy * dy;
-                        v[6] = v_sigma * (q.x * dx + q.y * dy);
-                        v[7] = v_sigma * (q.y * dx + q.z * dy);
-                        v_op = vis * v_alpha;
-                    }
+                for (int k = 0; k < CH; ++k) {
+                    float cch;
+                    if (k == 0) cch = c.x; else if (k == 1) cch = c.y; else if (k == 2) cch = c.z;
+                    else cch = __ldg(colors + (size_t)en.y * CH + k);
+                    const float g_ = fac * v_out[k];
+                    if (k < 3) v[k] = g_; else v_extra[k > 3 ? k - 3 : 0] = g_;
+                    v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
+                    buffer[k] += cch * fac;
                 }
-                const float r = warp_reduce8(v, lane);
-                v_op = warp_sum(v_op);
-                const int g = s_id[t];
-                if ((lane & 3) == 0) {
-                    const int s = lane >> 2;   // value index held by this lane group
-                    float *dst;
-                    if (s < 3) dst = (s < min(CH, 3)) ? v_colors + (size_t)g * CH + s : nullptr;
-                    else if (s < 6) dst = v_conics + 3 * (size_t)g + (s - 3);
-                    else dst = v_means2d + 2 * (size_t)g + (s - 6);
-                    if (dst) atomicAdd(dst, r);
-                } else if (lane == 1) {
-                    atomicAdd(v_opacities + g, v_op);
+                v_alpha += T_final * ra * v_a_out;
+                if (background) v_alpha += -T_final * ra * bg_dot;
+                if (q.w * vis <= GSB_ALPHA_CLAMP) {
+                    const float v_sigma = -q.w * vis * v_alpha;
+                    v[3] = 0.5f * v_sigma * dx * dx;
+                    v[4] = v_sigma * dx * dy;
+                    v[5] = 0.5f * v_sigma * dy * dy;
+                    v[6] = v_sigma * (q.x * dx + q.y * dy);
+                    v[7] = v_sigma * (q.y * dx + q.z * dy);
+                    v_op = vis * v_alpha;
                 }
-                if (CH > 3) {
+            }
+            const float red = warp_reduce8(v, lane);
+            v_op = warp_sum(v_op);
+            const int g = en.y;
+            if ((lane & 3) == 0) {
+                const int s = lane >> 2;
+                float *dst;
+                if (s < 3) dst = (s < (CH < 3 ? CH : 3)) ? v_colors + (size_t)g * CH + s : nullptr;
+                else if (s < 6) dst = v_conics + 3 * (size_t)g + (s - 3);
+                else dst = v_means2d + 2 * (size_t)g + (s - 6);
+                if (dst) atomicAdd(dst, red);
+            } else if (lane == 1) {
+                atomicAdd(v_opacities + g, v_op);
+            }
+            if (CH > 3) {
 #pragma unroll
-                    for (int k = 3; k < CH; ++k) {
-                        float e = warp_sum(v_rgb_extra[k - 3]);
-                        if (lane == 2) atomicAdd(v_colors + (size_t)g * CH + k, e);
-                    }
+                for (int k = 3; k < CH; ++k) {
+                    float ex = warp_sum(v_extra[k - 3]);
+                    if (lane == 2) atomicAdd(v_colors + (size_t)g * CH + k, ex);
                 }
             }
         }
     }
 }
 
+struct Workspace {
+    Rec *rec;
+    int32_t *counts;
+    int2 *entries;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t workspace_bytes(int64_t N, int64_t M, int n_tiles) {
+    return align256(sizeof(Rec) * (size_t)N) + align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
+           align256(sizeof(int2) * (size_t)SUBS * (size_t)M) + 256;
+}
+
+Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    Workspace w;
+    w.rec = reinterpret_cast<Rec *>(p);
+    p += align256(sizeof(Rec) * (size_t)N);
+    w.counts = reinterpret_cast<int32_t *>(p);
+    p += align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
+    w.entries = reinterpret_cast<int2 *>(p);
+    (void)M;
+    return w;
+}
+
 template <int CH>
-int launch_fwd(int W, int H, const float *means2d, const float *conics, const float *colors,
+int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conics, const float *colors,
                const float *opacities, const float *background, const int32_t *offsets,
-               const int32_t *flatten_ids, int64_t M, float *render, float *alphas, int32_t *last_ids,
+               const int32_t *flatten_ids, int64_t M, float *render, float *alphas, int32_t *last_ids, void *ws,
                cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
-    dim3 grid(tw, th), block(BLOCK);
-    composite_fwd_kernel<CH><<<grid, block, 0, st>>>(W, H, tw, reinterpret_cast<const float2 *>(means2d), conics,
-                                                     colors, opacities, background, offsets, flatten_ids, tw * th,
-                                                     (int)M, render, alphas, last_ids);
+    int n_tiles = tw * th, n_units = n_tiles * SUBS;
+    Workspace w = carve(ws, N, M, n_tiles);
+    if (N > 0)
+        pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
+                                                                    conics, colors, opacities, w.rec);
+    build_sublists_kernel<<<n_tiles, 32 * SUBS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec, w.entries,
+                                                         w.counts);
+    composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, render, alphas,
+        last_ids);
     return 0;
 }
 
 template <int CH>
-int launch_bwd(int W, int H, const float *means2d, const float *conics, const float *colors,
-               const float *opacities, const float *background, const int32_t *offsets,
-               const int32_t *flatten_ids, int64_t M, const float *alphas, const int32_t *last_ids,
-               const float *v_render, const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
-               float *v_opacities, cudaStream_t st) {
+int launch_bwd(int W, int H, int64_t N, const float *colors, const float *background, const int32_t *offsets,
+               int64_t M, const float *alphas, const int32_t *last_ids, const float *v_render, const float *v_alphas,
+               float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, void *ws, cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
-    dim3 grid(tw, th), block(BLOCK);
-    composite_bwd_kernel<CH><<<grid, block, 0, st>>>(
-        W, H, tw, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, background, offsets,
-        flatten_ids, tw * th, (int)M, alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors,
-        v_opacities);
+    int n_tiles = tw * th, n_units = n_tiles * SUBS;
+    Workspace w = carve(ws, N, M, n_tiles);
+    composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, alphas, last_ids,
+        v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
 }
 
@@ -372,35 +446,47 @@ int launch_bwd(int W, int H, const float *means2d, const float *conics, const fl
             return GSB_EINVAL;                 \
     }
 
-extern "C" __attribute__((visibility("default"))) int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
-                                 const float *conics, const float *colors, const float *opacities,
-                                 const float *background, const int32_t *offsets, const int32_t *flatten_ids,
-                                 int64_t M, float *render, float *alphas, int32_t *last_ids, void *stream) {
-    GSB_CHECK_ARG(width > 0 && height > 0 && M >= 0 && M < 2147483647LL);
-    GSB_CHECK_ARG(offsets && render && alphas && last_ids);
+#define GSB_API extern "C" __attribute__((visibility("default")))
+
+GSB_API int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, int32_t height, size_t *bytes_host) {
+    GSB_CHECK_ARG(N >= 0 && M >= 0 && width > 0 && height > 0 && bytes_host != nullptr);
+    int tw = (width + GSB_TILE - 1) / GSB_TILE, th = (height + GSB_TILE - 1) / GSB_TILE;
+    *bytes_host = workspace_bytes(N, M, tw * th);
+    return GSB_OK;
+}
+
+GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
+                              const float *conics, const float *colors, const float *opacities,
+                              const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
+                              float *render, float *alphas, int32_t *last_ids, void *workspace,
+                              size_t workspace_bytes_, void *stream) {
+    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 268435455LL);
+    GSB_CHECK_ARG(offsets && render && alphas && last_ids && workspace);
     GSB_CHECK_ARG(M == 0 || (means2d && conics && colors && opacities && flatten_ids));
-    GSB_DISPATCH_CH(channels, (launch_fwd<C_>(width, height, means2d, conics, colors, opacities, background,
-                                               offsets, flatten_ids, M, render, alphas, last_ids,
+    int tw = (width + GSB_TILE - 1) / GSB_TILE, th = (height + GSB_TILE - 1) / GSB_TILE;
+    if (workspace_bytes(N, M, tw * th) > workspace_bytes_) {
+        gsb_set_error("gsb_composite_fwd: workspace too small (%zu < %zu)", workspace_bytes_, workspace_bytes(N, M, tw * th));
+        return GSB_ENOMEM;
+    }
+    GSB_DISPATCH_CH(channels, (launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities, background,
+                                               offsets, flatten_ids, M, render, alphas, last_ids, workspace,
                                                (cudaStream_t)stream)));
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
-                                 const float *conics, const float *colors, const float *opacities,
-                                 const float *background, const int32_t *offsets, const int32_t *flatten_ids,
-                                 int64_t M, const float *alphas, const int32_t *last_ids, const float *v_render,
-                                 const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
-                                 float *v_opacities, void *stream) {
-    GSB_CHECK_ARG(width > 0 && height > 0 && M >= 0 && M < 2147483647LL);
-    GSB_CHECK_ARG(offsets && alphas && last_ids && v_render && v_alphas);
+GSB_API int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
+                              const float *background, const int32_t *offsets, int64_t M, const float *alphas,
+                              const int32_t *last_ids, const float *v_render, const float *v_alphas,
+                              float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                              const void *workspace, void *stream) {
+    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 268435455LL);
+    GSB_CHECK_ARG(offsets && alphas && last_ids && v_render && v_alphas && workspace);
     if (M == 0) return GSB_OK;
-    GSB_CHECK_ARG(means2d && conics && colors && opacities && flatten_ids);
-    GSB_CHECK_ARG(v_means2d && v_conics && v_colors && v_opacities);
-    GSB_DISPATCH_CH(channels, (launch_bwd<C_>(width, height, means2d, conics, colors, opacities, background,
-                                               offsets, flatten_ids, M, alphas, last_ids, v_render, v_alphas,
-                                               v_means2d, v_conics, v_colors, v_opacities,
-                                               (cudaStream_t)stream)));
+    GSB_CHECK_ARG(colors && v_means2d && v_conics && v_colors && v_opacities);
+    GSB_DISPATCH_CH(channels, (launch_bwd<C_>(width, height, N, colors, background, offsets, M, alphas, last_ids,
+                                               v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities,
+                                               const_cast<void *>(workspace), (cudaStream_t)stream)));
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -155,37 +155,38 @@ class _Composite(torch.autograd.Function):
         means2d_c, conics_c, colors_c, opac_c = f32c(means2d), f32c(conics), f32c(colors), f32c(opacities)
         bg_c = None if background is None else f32c(background)
         dev = means2d_c.device
-        CH = colors_c.shape[1]
+        N, CH = colors_c.shape
         M = flatten_ids.shape[0]
         render = torch.empty(height, width, CH, dtype=torch.float32, device=dev)
         alphas = torch.empty(height, width, dtype=torch.float32, device=dev)
         last_ids = torch.empty(height, width, dtype=torch.int32, device=dev)
-        call("gsb_composite_fwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d_c),
-                                    ptr(conics_c), ptr(colors_c), ptr(opac_c), ptr(bg_c), ptr(offsets),
-                                    ptr(flatten_ids), C.c_int64(M), ptr(render), ptr(alphas), ptr(last_ids),
-                                    stream_ptr(dev))
-        ctx.save_for_backward(means2d_c, conics_c, colors_c, opac_c, offsets, flatten_ids, alphas, last_ids)
+        nbytes = C.c_size_t(0)
+        call("gsb_composite_workspace_bytes", dev, C.c_int64(N), C.c_int64(M), C.c_int32(width), C.c_int32(height),
+             C.byref(nbytes))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)   # kept alive for the backward
+        call("gsb_composite_fwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), C.c_int64(N),
+             ptr(means2d_c), ptr(conics_c), ptr(colors_c), ptr(opac_c), ptr(bg_c), ptr(offsets), ptr(flatten_ids),
+             C.c_int64(M), ptr(render), ptr(alphas), ptr(last_ids), ptr(ws), C.c_size_t(ws.numel()), stream_ptr(dev))
+        ctx.save_for_backward(colors_c, offsets, alphas, last_ids, ws)
         ctx.bg = bg_c
-        ctx.dims = (width, height, CH, M)
+        ctx.dims = (width, height, CH, M, N)
         return render, alphas
 
     @staticmethod
     def backward(ctx, v_render, v_alphas):
-        means2d, conics, colors, opac, offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
-        width, height, CH, M = ctx.dims
-        dev = means2d.device
-        N = means2d.shape[0]
-        v_render = torch.zeros_like(alphas).unsqueeze(-1).expand(height, width, CH).contiguous() \
-            if v_render is None else f32c(v_render)
+        colors, offsets, alphas, last_ids, ws = ctx.saved_tensors
+        width, height, CH, M, N = ctx.dims
+        dev = colors.device
+        v_render = torch.zeros(height, width, CH, dtype=torch.float32, device=dev) if v_render is None \
+            else f32c(v_render)
         v_alphas = torch.zeros_like(alphas) if v_alphas is None else f32c(v_alphas)
         v_means2d = torch.zeros(N, 2, dtype=torch.float32, device=dev)
         v_conics = torch.zeros(N, 3, dtype=torch.float32, device=dev)
         v_colors = torch.zeros(N, CH, dtype=torch.float32, device=dev)
         v_opac = torch.zeros(N, dtype=torch.float32, device=dev)
-        call("gsb_composite_bwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), ptr(means2d), ptr(conics),
-                                    ptr(colors), ptr(opac), ptr(ctx.bg), ptr(offsets), ptr(flatten_ids),
-                                    C.c_int64(M), ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
-                                    ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), stream_ptr(dev))
+        call("gsb_composite_bwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), C.c_int64(N), ptr(colors),
+             ptr(ctx.bg), ptr(offsets), C.c_int64(M), ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
+             ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opac), ptr(ws), stream_ptr(dev))
         v_bg = None
         if ctx.bg is not None and ctx.needs_input_grad[4]:
             v_bg = ((1.0 - alphas).unsqueeze(-1) * v_render).sum(dim=(0, 1))

@@ -89,22 +89,24 @@ int gsb_sort_pairs(int64_t M, int32_t key_bits, const int64_t *keys_in, const in
 int gsb_isect_offsets(int64_t M, const int64_t *sorted_isect_ids, int32_t n_cameras, int32_t tile_w,
                       int32_t tile_h, int32_t *offsets, void *stream);
 
-/* Front-to-back alpha compositing of one camera (gsplat rasterize_to_pixels_fwd).  Per-Gaussian inputs
- * are indexed by flatten_ids.  channels in [1,32].  background[channels] may be NULL.
- * -> render[H,W,channels] alphas[H,W] last_ids[H,W]. */
-int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
-                      const float *conics, const float *colors, const float *opacities,
-                      const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
-                      float *render, float *alphas, int32_t *last_ids, void *stream);
+/* Bytes of scratch gsb_composite_fwd needs (per-Gaussian records + per-(tile, 8x4 sub-rectangle) lists). */
+int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, int32_t height, size_t *bytes_host);
 
-/* VJP of gsb_composite_fwd (gsplat rasterize_to_pixels_bwd).  ACCUMULATES into v_means2d[N,2]
- * v_conics[N,3] v_colors[N,channels] v_opacities[N]: the caller zero-fills them. */
-int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, const float *means2d,
-                      const float *conics, const float *colors, const float *opacities,
-                      const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
-                      const float *alphas, const int32_t *last_ids, const float *v_render,
-                      const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors,
-                      float *v_opacities, void *stream);
+/* Front-to-back alpha compositing of one camera (gsplat rasterize_to_pixels_fwd).  Per-Gaussian inputs [N,.]
+ * are indexed by flatten_ids.  channels in {1,2,3,4,8,16}.  background[channels] may be NULL.
+ * -> render[H,W,channels] alphas[H,W] last_ids[H,W] (position of the last contributor in the tile list).
+ * `workspace` is filled here and must be handed UNCHANGED to gsb_composite_bwd of the same view. */
+int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
+                      const float *conics, const float *colors, const float *opacities, const float *background,
+                      const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render, float *alphas,
+                      int32_t *last_ids, void *workspace, size_t workspace_bytes, void *stream);
+
+/* VJP of gsb_composite_fwd (gsplat rasterize_to_pixels_bwd).  ACCUMULATES into v_means2d[N,2] v_conics[N,3]
+ * v_colors[N,channels] v_opacities[N]: the caller zero-fills them. */
+int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
+                      const float *background, const int32_t *offsets, int64_t M, const float *alphas,
+                      const int32_t *last_ids, const float *v_render, const float *v_alphas, float *v_means2d,
+                      float *v_conics, float *v_colors, float *v_opacities, const void *workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Split-sum shade: replaces the per-Gaussian shade block of RenderableAttrs.splat
