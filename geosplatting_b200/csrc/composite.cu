@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(32 * SUBS) build_sublists_kernel(int tile_w, i
                                                                      const int32_t *__restrict__ flatten_ids,
                                                                      const Rec *__restrict__ rec,
                                                                      int2 *__restrict__ entries,
-                                                                     int32_t *__restrict__ counts) {
+                                                                     int32_t *__restrict__ counts,
+                                                                     int32_t *__restrict__ unit_ids) {
     const int tile = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int start = offsets[tile];
@@ -112,7 +113,62 @@ __global__ void __launch_bounds__(32 * SUBS) build_sublists_kernel(int tile_w, i
             n += __popc(m);
         }
     }
-    if (lane == 0) counts[tile * SUBS + w] = n;
+    if (lane == 0) {
+        counts[tile * SUBS + w] = n;
+        unit_ids[tile * SUBS + w] = tile * SUBS + w;
+    }
+}
+
+// Longest-processing-time-first order of the TILES (their 8 units stay adjacent in launch order so that they
+// share the tile's records in L1/L2): single-CTA counting sort on the mean per-unit work (4096 buckets of width 4,
+// heaviest first; order inside a bucket is irrelevant).  `n_units` here is the number of tiles.
+__device__ __forceinline__ int tile_work(const int32_t *__restrict__ counts, int tile) {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SUBS; ++k) s += counts[tile * SUBS + k];
+    return s >> 3;  // mean sub-list length of the tile's 8 units
+}
+
+__global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int32_t *__restrict__ counts,
+                                                          int32_t *__restrict__ order) {
+    constexpr int NB = 4096;
+    __shared__ int hist[NB];
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NB; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_units; i += 1024) atomicAdd(&hist[NB - 1 - min(tile_work(counts, i) >> 2, NB - 1)], 1);
+    __syncthreads();
+    // exclusive scan of hist: each thread owns 4 consecutive buckets
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = hist[tid * 4 + k]; sum += v[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int w = warp_tot[tid], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= o) wi += t;
+        }
+        warp_tot[tid] = wi - w;
+    }
+    __syncthreads();
+    int base = warp_tot[tid >> 5] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hist[tid * 4 + k] = base; base += v[k]; }
+    __syncthreads();
+    for (int i = tid; i < n_units; i += 1024) {
+        int pos = atomicAdd(&hist[NB - 1 - min(tile_work(counts, i) >> 2, NB - 1)], 1);
+        order[pos] = i;
+    }
 }
 
 struct Unit {
@@ -139,13 +195,15 @@ __global__ void __launch_bounds__(32 * WPB)
 composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
-                     const int32_t *__restrict__ counts, float *__restrict__ render, float *__restrict__ alphas,
+                     const int32_t *__restrict__ counts, const int32_t *__restrict__ order,
+                     int32_t *__restrict__ work, float *__restrict__ render, float *__restrict__ alphas,
                      int32_t *__restrict__ last_ids) {
     __shared__ Rec s_rec[WPB][32];
     __shared__ int2 s_ent[WPB][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int unit = blockIdx.x * WPB + wib;
-    if (unit >= n_units) return;
+    const int slot = blockIdx.x * WPB + wib;
+    if (slot >= n_units) return;
+    const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);   // heaviest tiles are scheduled first (LPT)
     const Unit u = make_unit(unit, lane, tile_w, W, H);
     bool done = !u.inside;
 
@@ -163,6 +221,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     // prefetch chunk 0
     int2 e = make_int2(0, 0);
     Rec r;
+    int processed = n;
     if (lane < n) { e = list[lane]; r = rec[e.y]; }
     for (int base = 0; base < n; base += 32) {
         __syncwarp();
@@ -172,34 +231,49 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         const int nb = base + 32;
         if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }   // next chunk in flight during the loop
         const int cnt = min(32, n - base);
-        for (int t = 0; t < cnt; ++t) {
-            if (done) continue;
-            const float4 kk = s_rec[wib][t].k;
-            const float4 q = s_rec[wib][t].q;
-            const float dx = kk.x - u.px, dy = kk.y - u.py;
-            const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
-            const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-LOG2E * sigma));
-            if (sigma < 0.f || alpha < GSB_ALPHA_MIN) continue;
-            const float next_T = T * (1.0f - alpha);
-            if (next_T <= GSB_T_STOP) {
-                done = true;
-                continue;
-            }
-            const float vis = alpha * T;
-            const float4 c = s_rec[wib][t].c;
-            acc[0] += c.x * vis;
-            if (CH > 1) acc[1] += c.y * vis;
-            if (CH > 2) acc[2] += c.z * vis;
-            if (CH > 3) {
-                const int g = s_ent[wib][t].y;
+        // 4 entries per iteration: the four alpha evaluations are independent (ILP hides the LDS / MUFU latency of a
+        // lone warp); only the transmittance update is sequential.
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += 4) {
+            float a4[4];
 #pragma unroll
-                for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int t = min(t0 + jj, 31);
+                const float4 kk = s_rec[wib][t].k;
+                const float4 q = s_rec[wib][t].q;
+                const float dx = kk.x - u.px, dy = kk.y - u.py;
+                const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
+                const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-LOG2E * sigma));
+                a4[jj] = (sigma < 0.f || alpha < GSB_ALPHA_MIN || t0 + jj >= cnt) ? 0.f : alpha;
             }
-            cur_idx = s_ent[wib][t].x;
-            T = next_T;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float alpha = a4[jj];
+                if (done || alpha == 0.f) continue;
+                const int t = t0 + jj;
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= GSB_T_STOP) {
+                    done = true;
+                    continue;
+                }
+                const float vis = alpha * T;
+                const float4 c = s_rec[wib][t].c;
+                acc[0] += c.x * vis;
+                if (CH > 1) acc[1] += c.y * vis;
+                if (CH > 2) acc[2] += c.z * vis;
+                if (CH > 3) {
+                    const int g = s_ent[wib][t].y;
+#pragma unroll
+                    for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+                }
+                cur_idx = s_ent[wib][t].x;
+                T = next_T;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
-        if (__all_sync(0xffffffffu, done)) break;
+        if (__all_sync(0xffffffffu, done)) { processed = min(n, base + 32); break; }
     }
+    if (lane == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
     if (u.inside) {
         const size_t pix = (size_t)u.i * W + u.j;
         alphas[pix] = 1.0f - T;
@@ -247,15 +321,17 @@ __global__ void __launch_bounds__(32 * WPB)
 composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
-                     const int32_t *__restrict__ counts, const float *__restrict__ alphas,
+                     const int32_t *__restrict__ counts, const int32_t *__restrict__ order,
+                     const float *__restrict__ alphas,
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                      float *__restrict__ v_colors, float *__restrict__ v_opacities) {
     __shared__ Rec s_rec[WPB][32];
     __shared__ int2 s_ent[WPB][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int unit = blockIdx.x * WPB + wib;
-    if (unit >= n_units) return;
+    const int slot = blockIdx.x * WPB + wib;
+    if (slot >= n_units) return;
+    const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);
     const Unit u = make_unit(unit, lane, tile_w, W, H);
     const size_t pix = u.inside ? (size_t)u.i * W + u.j : 0;
 
@@ -305,69 +381,86 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         const int nt = top - 32;
         if (nt - 1 - lane >= 0) { e = list[nt - 1 - lane]; r = rec[e.y]; }
         const int cnt = min(32, top);
-        for (int t = 0; t < cnt; ++t) {
-            const float4 kk = s_rec[wib][t].k;
-            const float4 q = s_rec[wib][t].q;
-            const int2 en = s_ent[wib][t];
-            const float dx = kk.x - u.px, dy = kk.y - u.py;
-            const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
-            const float vis = ex2_approx(-LOG2E * sigma);
-            const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
-            const bool valid = (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            float v[8];
+        // two entries per iteration: their evaluations and warp reductions are independent, which gives a lone warp
+        // the ILP to cover shuffle / MUFU latency; only the (T, buffer) recurrence is sequential.
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += 2) {
+            float v[2][8], v_op[2];
+            int gid[2];
+            bool any[2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = 0.f;
-            float v_op = 0.f;
-            float v_extra[CH > 3 ? CH - 3 : 1];
+            for (int jj = 0; jj < 2; ++jj) {
+                const int t = min(t0 + jj, 31);
+                const float4 kk = s_rec[wib][t].k;
+                const float4 q = s_rec[wib][t].q;
+                const int2 en = s_ent[wib][t];
+                gid[jj] = en.y;
+                const float dx = kk.x - u.px, dy = kk.y - u.py;
+                const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
+                const float vis = ex2_approx(-LOG2E * sigma);
+                const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
+                const bool valid = (t0 + jj < cnt) && (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
+                any[jj] = __any_sync(0xffffffffu, valid);
 #pragma unroll
-            for (int k = 0; k < (CH > 3 ? CH - 3 : 1); ++k) v_extra[k] = 0.f;
-            if (valid) {
-                const float ra = 1.0f / (1.0f - alpha);
-                T *= ra;
-                const float fac = alpha * T;
-                const float4 c = s_rec[wib][t].c;
-                float v_alpha = 0.f;
+                for (int k = 0; k < 8; ++k) v[jj][k] = 0.f;
+                v_op[jj] = 0.f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - alpha);
+                    T *= ra;
+                    const float fac = alpha * T;
+                    const float4 c = s_rec[wib][t].c;
+                    float v_alpha = 0.f;
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    float cch;
-                    if (k == 0) cch = c.x; else if (k == 1) cch = c.y; else if (k == 2) cch = c.z;
-                    else cch = __ldg(colors + (size_t)en.y * CH + k);
-                    const float g_ = fac * v_out[k];
-                    if (k < 3) v[k] = g_; else v_extra[k > 3 ? k - 3 : 0] = g_;
-                    v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
-                    buffer[k] += cch * fac;
-                }
-                v_alpha += T_final * ra * v_a_out;
-                if (background) v_alpha += -T_final * ra * bg_dot;
-                if (q.w * vis <= GSB_ALPHA_CLAMP) {
-                    const float v_sigma = -q.w * vis * v_alpha;
-                    v[3] = 0.5f * v_sigma * dx * dx;
-                    v[4] = v_sigma * dx * dy;
-                    v[5] = 0.5f * v_sigma * dy * dy;
-                    v[6] = v_sigma * (q.x * dx + q.y * dy);
-                    v[7] = v_sigma * (q.y * dx + q.z * dy);
-                    v_op = vis * v_alpha;
+                    for (int k = 0; k < 3; ++k) {
+                        if (k >= CH) break;
+                        const float cch = (k == 0) ? c.x : (k == 1) ? c.y : c.z;
+                        v[jj][k] = fac * v_out[k];
+                        v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
+                        buffer[k] += cch * fac;
+                    }
+                    if (CH > 3) {
+#pragma unroll
+                        for (int k = 3; k < CH; ++k) {
+                            const float cch = __ldg(colors + (size_t)en.y * CH + k);
+                            // rare wide-channel path (D=14 G-buffer, ED): straight atomics, no butterfly
+                            atomicAdd(v_colors + (size_t)en.y * CH + k, fac * v_out[k]);
+                            v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
+                            buffer[k] += cch * fac;
+                        }
+                    }
+                    v_alpha += T_final * ra * v_a_out;
+                    if (background) v_alpha += -T_final * ra * bg_dot;
+                    if (q.w * vis <= GSB_ALPHA_CLAMP) {
+                        const float v_sigma = -q.w * vis * v_alpha;
+                        v[jj][3] = 0.5f * v_sigma * dx * dx;
+                        v[jj][4] = v_sigma * dx * dy;
+                        v[jj][5] = 0.5f * v_sigma * dy * dy;
+                        v[jj][6] = v_sigma * (q.x * dx + q.y * dy);
+                        v[jj][7] = v_sigma * (q.y * dx + q.z * dy);
+                        v_op[jj] = vis * v_alpha;
+                    }
                 }
             }
-            const float red = warp_reduce8(v, lane);
-            v_op = warp_sum(v_op);
-            const int g = en.y;
-            if ((lane & 3) == 0) {
-                const int s = lane >> 2;
-                float *dst;
-                if (s < 3) dst = (s < (CH < 3 ? CH : 3)) ? v_colors + (size_t)g * CH + s : nullptr;
-                else if (s < 6) dst = v_conics + 3 * (size_t)g + (s - 3);
-                else dst = v_means2d + 2 * (size_t)g + (s - 6);
-                if (dst) atomicAdd(dst, red);
-            } else if (lane == 1) {
-                atomicAdd(v_opacities + g, v_op);
-            }
-            if (CH > 3) {
+            if (!(any[0] || any[1])) continue;
+            float red[2];
 #pragma unroll
-                for (int k = 3; k < CH; ++k) {
-                    float ex = warp_sum(v_extra[k - 3]);
-                    if (lane == 2) atomicAdd(v_colors + (size_t)g * CH + k, ex);
+            for (int jj = 0; jj < 2; ++jj) {
+                red[jj] = warp_reduce8(v[jj], lane);
+                v_op[jj] = warp_sum(v_op[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                if (!any[jj]) continue;
+                const int g = gid[jj];
+                if ((lane & 3) == 0) {
+                    const int sidx = lane >> 2;
+                    float *dst;
+                    if (sidx < 3) dst = (sidx < (CH < 3 ? CH : 3)) ? v_colors + (size_t)g * CH + sidx : nullptr;
+                    else if (sidx < 6) dst = v_conics + 3 * (size_t)g + (sidx - 3);
+                    else dst = v_means2d + 2 * (size_t)g + (sidx - 6);
+                    if (dst) atomicAdd(dst, red[jj]);
+                } else if (lane == 1) {
+                    atomicAdd(v_opacities + g, v_op[jj]);
                 }
             }
         }
@@ -376,15 +469,20 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 
 struct Workspace {
     Rec *rec;
-    int32_t *counts;
+    int32_t *counts, *unit_ids, *sorted_counts, *order;
+    void *cub_temp;
+    size_t cub_bytes;
     int2 *entries;
 };
+
+constexpr size_t CUB_TEMP_BYTES = 1 << 20;
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t workspace_bytes(int64_t N, int64_t M, int n_tiles) {
-    return align256(sizeof(Rec) * (size_t)N) + align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
-           align256(sizeof(int2) * (size_t)SUBS * (size_t)M) + 256;
+    return align256(sizeof(Rec) * (size_t)N) + 4 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
+           align256(CUB_TEMP_BYTES + 64 * (size_t)n_tiles * SUBS) + align256(sizeof(int2) * (size_t)SUBS * (size_t)M) +
+           256;
 }
 
 Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
@@ -392,8 +490,14 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
     Workspace w;
     w.rec = reinterpret_cast<Rec *>(p);
     p += align256(sizeof(Rec) * (size_t)N);
-    w.counts = reinterpret_cast<int32_t *>(p);
-    p += align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
+    const size_t ub = align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
+    w.counts = reinterpret_cast<int32_t *>(p); p += ub;
+    w.unit_ids = reinterpret_cast<int32_t *>(p); p += ub;
+    w.sorted_counts = reinterpret_cast<int32_t *>(p); p += ub;
+    w.order = reinterpret_cast<int32_t *>(p); p += ub;
+    w.cub_temp = p;
+    w.cub_bytes = align256(CUB_TEMP_BYTES + 64 * (size_t)n_tiles * SUBS);
+    p += w.cub_bytes;
     w.entries = reinterpret_cast<int2 *>(p);
     (void)M;
     return w;
@@ -411,10 +515,11 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
                                                                     conics, colors, opacities, w.rec);
     build_sublists_kernel<<<n_tiles, 32 * SUBS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec, w.entries,
-                                                         w.counts);
+                                                         w.counts, w.unit_ids);
+    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, render, alphas,
-        last_ids);
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order,
+        w.sorted_counts, render, alphas, last_ids);
     return 0;
 }
 
@@ -425,9 +530,10 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
+    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.sorted_counts, w.order);   // order by the forward's measured work
     composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, alphas, last_ids,
-        v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order, alphas,
+        last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
 }
 
@@ -468,9 +574,14 @@ GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, i
         gsb_set_error("gsb_composite_fwd: workspace too small (%zu < %zu)", workspace_bytes_, workspace_bytes(N, M, tw * th));
         return GSB_ENOMEM;
     }
-    GSB_DISPATCH_CH(channels, (launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities, background,
-                                               offsets, flatten_ids, M, render, alphas, last_ids, workspace,
-                                               (cudaStream_t)stream)));
+    int rc = 0;
+    GSB_DISPATCH_CH(channels, (rc = launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities, background,
+                                                    offsets, flatten_ids, M, render, alphas, last_ids, workspace,
+                                                    (cudaStream_t)stream)));
+    if (rc != 0) {
+        gsb_set_error("gsb_composite_fwd: internal sort scratch too small");
+        return GSB_ENOMEM;
+    }
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -151,7 +151,8 @@ __device__ __forceinline__ float3 gsb_cube_sample(const float *__restrict__ tex,
     return make_float3(top.x + (bot.x - top.x) * fv, top.y + (bot.y - top.y) * fv, top.z + (bot.z - top.z) * fv);
 }
 
-// Scatter v (cotangent of the sampled colour, already scaled) into the texel gradients.
+// Scatter v (cotangent of the sampled colour, already scaled) into the texel gradients.  For the float4 env stack
+// one vector reduction (red.global.add.v4.f32, sm_90+) per tap replaces three scalar ones.
 template <int STRIDE>
 __device__ __forceinline__ void gsb_cube_scatter(float *__restrict__ v_tex, const CubeTaps &t, float3 v) {
     float w[4];
@@ -159,10 +160,14 @@ __device__ __forceinline__ void gsb_cube_scatter(float *__restrict__ v_tex, cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (t.idx[k] < 0 || w[k] == 0.f) continue;
-        float *p = v_tex + (size_t)t.idx[k] * STRIDE;
-        atomicAdd(p, w[k] * v.x);
-        atomicAdd(p + 1, w[k] * v.y);
-        atomicAdd(p + 2, w[k] * v.z);
+        if (STRIDE == 4) {
+            atomicAdd(reinterpret_cast<float4 *>(v_tex) + t.idx[k], make_float4(w[k] * v.x, w[k] * v.y, w[k] * v.z, 0.f));
+        } else {
+            float *p = v_tex + (size_t)t.idx[k] * STRIDE;
+            atomicAdd(p, w[k] * v.x);
+            atomicAdd(p + 1, w[k] * v.y);
+            atomicAdd(p + 2, w[k] * v.z);
+        }
     }
 }
 
