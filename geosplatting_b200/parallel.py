@@ -50,6 +50,7 @@ class GradientBucket:
 
     def pack(self, tensors: Sequence[Optional[Tensor]]) -> None:
         assert len(tensors) == len(self.views)
+        self.wait()
         src, dst = [], []
         for t, v in zip(tensors, self.views):
             if t is None:
@@ -61,13 +62,25 @@ class GradientBucket:
         if src:
             torch._foreach_copy_(dst, src)
 
-    def all_reduce(self, group=None, average_over: Optional[int] = None) -> None:
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+    def all_reduce(self, group=None, average_over: Optional[int] = None, async_op: bool = False) -> None:
+        """ONE sum all-reduce of the whole bucket.  With async_op=True the collective runs on NCCL's stream and
+        overlaps the next views' kernels; call wait() before the bucket is read or packed again."""
         if average_over:
-            self.flat.mul_(1.0 / average_over)
+            self.flat.mul_(1.0 / average_over)   # pre-scale: sum of (g / n) == mean
+        self._work = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if async_op:
+                self._work = work
+
+    def wait(self) -> None:
+        work = getattr(self, "_work", None)
+        if work is not None:
+            work.wait()
+            self._work = None
 
     def unpack(self) -> List[Tensor]:
+        self.wait()
         return self.views
 
 
