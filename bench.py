@@ -312,15 +312,19 @@ def run_b200(a):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_full = 3
+        _lib.CallStats.reset(timing=True)
         s.record()
         for _ in range(n_full):
             full_step()
         e.record()
         barrier()
+        fk = {k: round(ms_ / n_full, 3) for k, (c_, ms_) in _lib.CallStats.durations_ms().items() if ms_ / n_full > 0.05}
+        _lib.CallStats.reset(timing=False)
         ms = s.elapsed_time(e) / n_full
         full = {"ms_per_step": round(ms, 3), "views_per_step": min(8, len(cams)),
                 "views_per_s": round(min(8, len(cams)) / (ms / 1e3), 2),
-                "what": "vertex normals + MGAdaptor + prefilter (fwd+bwd) + 8 views fwd+bwd, one rank"}
+                "what": "vertex normals + MGAdaptor + prefilter (fwd+bwd) + 8 views fwd+bwd, one rank",
+                "kernel_ms_per_step": fk}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     M, Nv = stats_last_view(params, cams[0], W, H)

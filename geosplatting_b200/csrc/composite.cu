@@ -75,15 +75,18 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
 
 // One CTA per tile, warp w filters the tile list for sub-rectangle w.  Sub-list w of tile t lives at
 // entries[SUBS * start_t + w * len_t ...] (worst-case capacity, no prefix sum needed).
-__global__ void __launch_bounds__(32 * SUBS) build_sublists_kernel(int tile_w, int n_tiles, int M,
+__global__ void __launch_bounds__(64) build_sublists_kernel(int tile_w, int n_tiles, int M,
                                                                      const int32_t *__restrict__ offsets,
                                                                      const int32_t *__restrict__ flatten_ids,
                                                                      const Rec *__restrict__ rec,
                                                                      int2 *__restrict__ entries,
                                                                      int32_t *__restrict__ counts,
                                                                      int32_t *__restrict__ unit_ids) {
-    const int tile = blockIdx.x;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // CTA = 2 warps = 2 of the 8 sub-rectangles of a tile; 4 consecutive CTAs share the tile's list in L1/L2
+    const int unit = blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (unit >= n_tiles * SUBS) return;
+    const int tile = unit / SUBS, w = unit % SUBS;
+    const int lane = threadIdx.x & 31;
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int len = end - start;
@@ -514,8 +517,8 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
     if (N > 0)
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
                                                                     conics, colors, opacities, w.rec);
-    build_sublists_kernel<<<n_tiles, 32 * SUBS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec, w.entries,
-                                                         w.counts, w.unit_ids);
+    build_sublists_kernel<<<gsb_div_up(n_units, 2), 64, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec,
+                                                                 w.entries, w.counts, w.unit_ids);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
         W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order,

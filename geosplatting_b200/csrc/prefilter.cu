@@ -188,6 +188,100 @@ __global__ void __launch_bounds__(128) specular_kernel(int R, const float *__res
     }
 }
 
+// ---- specular, warp-cooperative fast path (R % 8 == 0) ----------------------------------------------------
+// Same sums as specular_kernel, reorganised for issue efficiency (that kernel spends ~150 instructions per tap
+// on IEEE divisions and square roots):
+//   * per-texel unit directions + solid angle are tabulated once per call (dirs[u] = L.xyz, area) with the
+//     reference-form arithmetic of texel_dir, so the cone membership is unchanged;
+//   * the source is pre-multiplied per texel (forward: rgb * area with .w = area, so the same loop also yields
+//     wsum; backward: grad / wsum), so forward and backward share ONE gather loop
+//         acc[t] += k(t,u) * pre[u],   k = max(L.V,0) * D_ggx / 4
+//   * a warp owns an 8x4 patch of output texels and walks the UNION of its lanes' cone AABBs, so every tap is a
+//     broadcast 2 x LDG.128 and there is no loop divergence; |L+V|^2 = 2 + 2 L.V for unit vectors.
+__global__ void __launch_bounds__(256) dir_table_kernel(int R, float4 *__restrict__ dirs) {
+    __shared__ float s_area_tab[1024];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) s_area_tab[i] = axis_area(i, R);
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * R * R) return;
+    int s = t / (R * R), y = (t / R) % R, x = t % R;
+    float3 d = texel_dir(x, y, s, (float)R);
+    dirs[t] = make_float4(d.x, d.y, d.z, s_area_tab[x] * s_area_tab[y]);
+}
+
+// mode 0: forward  pre = (rgb * area, area)      mode 1: backward pre = (g, 0)      mode 2: backward pre = (g / wsum, 0)
+__global__ void __launch_bounds__(256) prep_source_kernel(int R, const float *__restrict__ src, int src_stride,
+                                                           const float *__restrict__ wsum_src,
+                                                           const float4 *__restrict__ dirs, int mode,
+                                                           float4 *__restrict__ pre) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * R * R) return;
+    const float *p = src + (size_t)t * src_stride;
+    float3 v = make_float3(p[0], p[1], p[2]);
+    if (mode == 0) {
+        float a = dirs[t].w;
+        pre[t] = make_float4(v.x * a, v.y * a, v.z * a, a);
+    } else {
+        float iw = (mode == 2) ? 1.0f / wsum_src[(size_t)t * 4 + 3] : 1.0f;
+        pre[t] = make_float4(v.x * iw, v.y * iw, v.z * iw, 0.f);
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float4 *__restrict__ dirs,
+                                                               const float4 *__restrict__ pre,
+                                                               const float4 *__restrict__ bounds, float alphaSqr,
+                                                               float cutoff, int normalize, float *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);           // 8x4 patches, (R/8) x (R/4) per face
+    const int ppf = (R / 8) * (R / 4);
+    if (patch >= 6 * ppf) return;
+    const int ts = patch / ppf, pr = patch % ppf;
+    const int tx = (pr % (R / 8)) * 8 + (lane & 7), ty = (pr / (R / 8)) * 4 + (lane >> 3);
+    const int t = (ts * R + ty) * R + tx;
+    const float4 Vd = __ldg(dirs + t);
+    const float3 V = make_float3(Vd.x, Vd.y, Vd.z);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inv4pi = 0.25f / 3.14159265358979323846f;
+    for (int s = 0; s < 6; ++s) {
+        const float4 b = __ldg(bounds + (size_t)t * 6 + s);
+        int xmin = (int)b.x, xmax = (int)b.y, ymin = (int)b.z, ymax = (int)b.w;
+        if (xmin > xmax) { xmin = ymin = 1 << 30; xmax = ymax = -1; }   // this lane's cone misses face s
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        if (xmax < xmin) continue;   // warp-uniform
+        for (int y = ymin; y <= ymax; ++y) {
+            const float4 *drow = dirs + ((size_t)s * R + y) * R;
+            const float4 *prow = pre + ((size_t)s * R + y) * R;
+#pragma unroll 4
+            for (int x = xmin; x <= xmax; ++x) {
+                const float4 Ld = __ldg(drow + x);
+                const float3 L = make_float3(Ld.x, Ld.y, Ld.z);
+                const float d = dot3(L, V);
+                if (!(d >= cutoff)) continue;
+                const float4 P = __ldg(prow + x);
+                const float3 cr = make_float3(V.y * L.z - V.z * L.y, V.z * L.x - V.x * L.z, V.x * L.y - V.y * L.x);
+                const float s2 = fminf(__fdividef(dot3(cr, cr), 2.0f + 2.0f * d), 1.0f);
+                const float dd = s2 + (1.0f - s2) * alphaSqr;
+                const float k = d * __fdividef(alphaSqr * inv4pi, dd * dd);
+                acc.x += P.x * k; acc.y += P.y * k; acc.z += P.z * k; acc.w += P.w * k;
+            }
+        }
+    }
+    if (BWD) {
+        float *o = dst + (size_t)t * 3;
+        o[0] = acc.x * Vd.w; o[1] = acc.y * Vd.w; o[2] = acc.z * Vd.w;
+    } else {
+        float4 r = normalize ? make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w) : acc;
+        reinterpret_cast<float4 *>(dst)[t] = r;
+    }
+}
+
 // ---- mip chain (_texture.py:199-226) -------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mip_fwd_kernel(int Ro, const float *__restrict__ in, int in_stride,
                                                        float *__restrict__ out, int out_stride) {
@@ -248,23 +342,56 @@ GSB_API int gsb_specular_bounds(int32_t R, float costheta_cutoff, float *bounds,
     return GSB_OK;
 }
 
+GSB_API int gsb_specular_workspace_bytes(int32_t R, size_t *bytes_host) {
+    GSB_CHECK_ARG(R >= 1 && R <= 4096 && bytes_host != nullptr);
+    *bytes_host = 2 * sizeof(float4) * 6 * (size_t)R * R + 512;
+    return GSB_OK;
+}
+
+static float4 *ws_align(void *ws) {
+    return reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+}
+
 GSB_API int gsb_specular_cubemap_fwd(int32_t R, const float *cubemap, const float *bounds, float roughness,
-                                     float costheta_cutoff, int32_t normalize, float *out, void *stream) {
+                                     float costheta_cutoff, int32_t normalize, float *out, void *workspace,
+                                     void *stream) {
     GSB_CHECK_ARG(R >= 1 && R <= 4096 && cubemap && bounds && out);
     float alpha = roughness * roughness;
-    specular_kernel<false><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, (cudaStream_t)stream>>>(
-        R, cubemap, 3, nullptr, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (workspace != nullptr && R % 8 == 0 && R <= 1024) {
+        float4 *dirs = ws_align(workspace), *pre = dirs + 6 * (size_t)R * R;
+        int total = 6 * R * R;
+        dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
+        prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, cubemap, 3, nullptr, dirs, 0, pre);
+        specular_gather_kernel<false><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+            R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out);
+    } else {
+        specular_kernel<false><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, st>>>(
+            R, cubemap, 3, nullptr, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize,
+            out);
+    }
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 
 GSB_API int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float *grad_out, const float *fwd_out,
-                                     float roughness, float costheta_cutoff, float *grad_in, void *stream) {
+                                     float roughness, float costheta_cutoff, float *grad_in, void *workspace,
+                                     void *stream) {
     GSB_CHECK_ARG(R >= 1 && R <= 4096 && bounds && grad_out && grad_in);
     float alpha = roughness * roughness;
-    specular_kernel<true><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, (cudaStream_t)stream>>>(
-        R, grad_out, 4, fwd_out, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff,
-        fwd_out != nullptr, grad_in);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (workspace != nullptr && R % 8 == 0 && R <= 1024) {
+        float4 *dirs = ws_align(workspace), *pre = dirs + 6 * (size_t)R * R;
+        int total = 6 * R * R;
+        dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
+        prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, grad_out, 4, fwd_out, dirs, fwd_out ? 2 : 1, pre);
+        specular_gather_kernel<true><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+            R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, 0, grad_in);
+    } else {
+        specular_kernel<true><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, st>>>(
+            R, grad_out, 4, fwd_out, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff,
+            fwd_out != nullptr, grad_in);
+    }
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -20,6 +20,12 @@ from ._lib import call, f32c, ptr, stream_ptr
 from .shade import EnvStack
 
 
+def _spec_workspace(R: int, dev) -> Tensor:
+    n = C.c_size_t(0)
+    call("gsb_specular_workspace_bytes", dev, C.c_int32(R), C.byref(n))
+    return torch.empty(n.value, dtype=torch.uint8, device=dev)
+
+
 def _check_cubemap(t: Tensor, channels: int, name: str) -> None:
     # same checks as CHECK_TENSOR in torch_bindings.cpp:27-31
     if not t.is_cuda:
@@ -67,7 +73,8 @@ class render_utils:
         R = c.shape[1]
         out = torch.empty(6, R, R, 4, dtype=torch.float32, device=c.device)
         call("gsb_specular_cubemap_fwd", c.device, C.c_int32(R), ptr(c), ptr(b), C.c_float(roughness),
-             C.c_float(costheta_cutoff), C.c_int32(0), ptr(out), stream_ptr(c.device))
+             C.c_float(costheta_cutoff), C.c_int32(0), ptr(out), ptr(_spec_workspace(R, c.device)),
+             stream_ptr(c.device))
         return out
 
     @staticmethod
@@ -80,7 +87,7 @@ class render_utils:
         R = g.shape[1]
         out = torch.empty(6, R, R, 3, dtype=torch.float32, device=g.device)
         call("gsb_specular_cubemap_bwd", g.device, C.c_int32(R), ptr(b), ptr(g), None, C.c_float(roughness),
-             C.c_float(costheta_cutoff), ptr(out), stream_ptr(g.device))
+             C.c_float(costheta_cutoff), ptr(out), ptr(_spec_workspace(R, g.device)), stream_ptr(g.device))
         return out
 
 
@@ -243,6 +250,7 @@ class _PrefilterStack(torch.autograd.Function):
         T = EnvStack.texels(R0, L, Rb)
         stack = torch.empty(T, 4, dtype=torch.float32, device=dev)
         rough = _roughness_schedule(L, min_roughness, max_roughness)
+        ws = _spec_workspace(R0, dev)   # sized for the finest level, reused by every level (stream-ordered)
         o = 0
         cts = []
         for l in range(L):
@@ -250,7 +258,7 @@ class _PrefilterStack(torch.autograd.Function):
             ct, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
             cts.append(ct)
             call("gsb_specular_cubemap_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(bounds), C.c_float(rough[l]),
-                 C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), st)
+                 C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), ptr(ws), st)
             o += 6 * r * r
         stack[o:].zero_()
         call("gsb_diffuse_cubemap_fwd", dev, C.c_int32(Rb), ptr(chain[-1]), C.c_void_p(stack.data_ptr() + o * 16),
@@ -271,13 +279,14 @@ class _PrefilterStack(torch.autograd.Function):
             offs.append(o)
             o += 6 * (R0 >> l) ** 2
         # gradient w.r.t. each chain level from its own prefilter
+        ws = _spec_workspace(R0, dev)
         g_levels = []
         for l in range(L):
             r = R0 >> l
             _, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
             g = torch.empty(6, r, r, 3, dtype=torch.float32, device=dev)
             call("gsb_specular_cubemap_bwd", dev, C.c_int32(r), ptr(bounds), C.c_void_p(v.data_ptr() + offs[l] * 16),
-                 C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), st)
+                 C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), ptr(ws), st)
             g_levels.append(g)
         gb = torch.empty(6, Rb, Rb, 3, dtype=torch.float32, device=dev)
         call("gsb_diffuse_cubemap_bwd", dev, C.c_int32(Rb), C.c_void_p(v.data_ptr() + o * 16), C.c_int32(4), ptr(gb), st)

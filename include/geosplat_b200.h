@@ -187,12 +187,15 @@ int gsb_specular_bounds(int32_t R, float costheta_cutoff, float *bounds, void *s
 /* torch_bindings.cpp:193 specular_cubemap_fwd: out[6,R,R,4] = (sum w*rgb, sum w); normalize != 0 stores
  * (rgb/wsum, wsum) instead, which is what _wrap.py:157 computes next. */
 int gsb_specular_cubemap_fwd(int32_t R, const float *cubemap, const float *bounds, float roughness,
-                             float costheta_cutoff, int32_t normalize, float *out, void *stream);
+                             float costheta_cutoff, int32_t normalize, float *out, void *workspace, void *stream);
+/* Scratch for the two calls around this comment (direction table + pre-multiplied source); a NULL workspace
+ * selects the slower table-free kernel. */
+int gsb_specular_workspace_bytes(int32_t R, size_t *bytes_host);
 /* torch_bindings.cpp:226 specular_cubemap_bwd: grad_out[6,R,R,4] (channels 0..2 read, like the plugin) ->
  * grad_in[6,R,R,3].  fwd_out != NULL: grad_out is the cotangent of the NORMALISED rgb and fwd_out[...,3]
  * holds wsum (the forward's own output). */
 int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float *grad_out, const float *fwd_out,
-                             float roughness, float costheta_cutoff, float *grad_in, void *stream);
+                             float roughness, float costheta_cutoff, float *grad_in, void *workspace, void *stream);
 /* _CubeMapMip.forward: 2x2 box filter per face, in [6,2R,2R,.] -> out [6,R,R,.]. */
 int gsb_cubemap_mip_fwd(int32_t R_out, const float *in, int32_t in_stride, float *out, int32_t out_stride,
                         void *stream);
