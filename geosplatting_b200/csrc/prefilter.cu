@@ -227,11 +227,15 @@ __global__ void __launch_bounds__(256) prep_source_kernel(int R, const float *__
     }
 }
 
-template <bool BWD>
+// SPLIT == false: one launch dimension, a warp sums all six faces and writes the result.
+// SPLIT == true : gridDim.y = 6, a warp sums ONE face and adds into a zeroed float4 accumulator (small levels have
+//                 too few 8x4 patches to fill 148 SMs); specular_finalize_kernel then writes the result.
+template <bool BWD, bool SPLIT>
 __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float4 *__restrict__ dirs,
                                                                const float4 *__restrict__ pre,
                                                                const float4 *__restrict__ bounds, float alphaSqr,
-                                                               float cutoff, int normalize, float *__restrict__ dst) {
+                                                               float cutoff, int normalize, float *__restrict__ dst,
+                                                               float4 *__restrict__ accum) {
     const int lane = threadIdx.x & 31;
     const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);           // 8x4 patches, (R/8) x (R/4) per face
     const int ppf = (R / 8) * (R / 4);
@@ -242,8 +246,10 @@ __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float
     const float4 Vd = __ldg(dirs + t);
     const float3 V = make_float3(Vd.x, Vd.y, Vd.z);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float inv4pi = 0.25f / 3.14159265358979323846f;
-    for (int s = 0; s < 6; ++s) {
+    const float kscale = alphaSqr * (0.25f / 3.14159265358979323846f);
+    const float e_scale = 0.25f * (1.0f - alphaSqr);
+    const int s_begin = SPLIT ? blockIdx.y : 0, s_end = SPLIT ? blockIdx.y + 1 : 6;
+    for (int s = s_begin; s < s_end; ++s) {
         const float4 b = __ldg(bounds + (size_t)t * 6 + s);
         int xmin = (int)b.x, xmax = (int)b.y, ymin = (int)b.z, ymax = (int)b.w;
         if (xmin > xmax) { xmin = ymin = 1 << 30; xmax = ymax = -1; }   // this lane's cone misses face s
@@ -258,24 +264,48 @@ __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float
         for (int y = ymin; y <= ymax; ++y) {
             const float4 *drow = dirs + ((size_t)s * R + y) * R;
             const float4 *prow = pre + ((size_t)s * R + y) * R;
+            // branch-free body, 4 taps in flight: the loads are warp-broadcast L1 hits and the four weight
+            // evaluations are independent, which is what a latency-bound lone warp needs
 #pragma unroll 4
             for (int x = xmin; x <= xmax; ++x) {
                 const float4 Ld = __ldg(drow + x);
+                const float4 P = __ldg(prow + x);
                 const float3 L = make_float3(Ld.x, Ld.y, Ld.z);
                 const float d = dot3(L, V);
-                if (!(d >= cutoff)) continue;
-                const float4 P = __ldg(prow + x);
-                const float3 cr = make_float3(V.y * L.z - V.z * L.y, V.z * L.x - V.x * L.z, V.x * L.y - V.y * L.x);
-                const float s2 = fminf(__fdividef(dot3(cr, cr), 2.0f + 2.0f * d), 1.0f);
-                const float dd = s2 + (1.0f - s2) * alphaSqr;
-                const float k = d * __fdividef(alphaSqr * inv4pi, dd * dd);
+                // H bisects the unit vectors L and V, so 1 - (V.H)^2 = sin^2(theta/2) = |V - L|^2 / 4: exact
+                // differences of nearby unit vectors, no cancellation, no division.
+                const float ex = V.x - L.x, ey = V.y - L.y, ez = V.z - L.z;
+                const float e = ex * ex + ey * ey + ez * ez;
+                const float dd = fmaf(e, e_scale, alphaSqr);     // s2 + (1 - s2) * alphaSqr with s2 = e / 4
+                const float k = (d >= cutoff) ? d * __fdividef(kscale, dd * dd) : 0.f;
                 acc.x += P.x * k; acc.y += P.y * k; acc.z += P.z * k; acc.w += P.w * k;
             }
         }
     }
+    if (SPLIT) {
+        atomicAdd(accum + t, acc);
+        return;
+    }
     if (BWD) {
         float *o = dst + (size_t)t * 3;
         o[0] = acc.x * Vd.w; o[1] = acc.y * Vd.w; o[2] = acc.z * Vd.w;
+    } else {
+        float4 r = normalize ? make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w) : acc;
+        reinterpret_cast<float4 *>(dst)[t] = r;
+    }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) specular_finalize_kernel(int R, const float4 *__restrict__ accum,
+                                                                 const float4 *__restrict__ dirs, int normalize,
+                                                                 float *__restrict__ dst) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * R * R) return;
+    const float4 acc = accum[t];
+    if (BWD) {
+        const float a = dirs[t].w;
+        float *o = dst + (size_t)t * 3;
+        o[0] = acc.x * a; o[1] = acc.y * a; o[2] = acc.z * a;
     } else {
         float4 r = normalize ? make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w) : acc;
         reinterpret_cast<float4 *>(dst)[t] = r;
@@ -344,7 +374,7 @@ GSB_API int gsb_specular_bounds(int32_t R, float costheta_cutoff, float *bounds,
 
 GSB_API int gsb_specular_workspace_bytes(int32_t R, size_t *bytes_host) {
     GSB_CHECK_ARG(R >= 1 && R <= 4096 && bytes_host != nullptr);
-    *bytes_host = 2 * sizeof(float4) * 6 * (size_t)R * R + 512;
+    *bytes_host = 3 * sizeof(float4) * 6 * (size_t)R * R + 512;
     return GSB_OK;
 }
 
@@ -363,8 +393,18 @@ GSB_API int gsb_specular_cubemap_fwd(int32_t R, const float *cubemap, const floa
         int total = 6 * R * R;
         dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
         prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, cubemap, 3, nullptr, dirs, 0, pre);
-        specular_gather_kernel<false><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
-            R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out);
+        if (R <= 64) {
+            float4 *accum = pre + 6 * (size_t)R * R;
+            GSB_CHECK_CUDA(cudaMemsetAsync(accum, 0, sizeof(float4) * total, st));
+            specular_gather_kernel<false, true><<<dim3(gsb_div_up(total / 32, 4), 6), 128, 0, st>>>(
+                R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out,
+                accum);
+            specular_finalize_kernel<false><<<gsb_div_up(total, 256), 256, 0, st>>>(R, accum, dirs, normalize, out);
+        } else {
+            specular_gather_kernel<false, false><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+                R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize, out,
+                nullptr);
+        }
     } else {
         specular_kernel<false><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, st>>>(
             R, cubemap, 3, nullptr, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, normalize,
@@ -385,8 +425,17 @@ GSB_API int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float
         int total = 6 * R * R;
         dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
         prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, grad_out, 4, fwd_out, dirs, fwd_out ? 2 : 1, pre);
-        specular_gather_kernel<true><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
-            R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, 0, grad_in);
+        if (R <= 64) {
+            float4 *accum = pre + 6 * (size_t)R * R;
+            GSB_CHECK_CUDA(cudaMemsetAsync(accum, 0, sizeof(float4) * total, st));
+            specular_gather_kernel<true, true><<<dim3(gsb_div_up(total / 32, 4), 6), 128, 0, st>>>(
+                R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, 0, grad_in, accum);
+            specular_finalize_kernel<true><<<gsb_div_up(total, 256), 256, 0, st>>>(R, accum, dirs, 0, grad_in);
+        } else {
+            specular_gather_kernel<true, false><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+                R, dirs, pre, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, 0, grad_in,
+                nullptr);
+        }
     } else {
         specular_kernel<true><<<gsb_div_up(6 * R * R, 128), 128, sizeof(float) * R, st>>>(
             R, grad_out, 4, fwd_out, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff,
