@@ -12,8 +12,8 @@
 // GeoSplatting's Gaussians are a few pixels wide, so a sub-list holds ~1/3 of its tile's list.  Filtering never
 // changes results: a filtered pair is exactly one the reference kernel would `continue` on (alpha < 1/255 at
 // every pixel centre of the sub-rectangle), and `last_ids` still indexes the 16x16 tile list.
-// Backward: per-lane partial gradients are summed with a transposing butterfly (14 shuffles for 9 values instead
-// of 45) and written with one atomic per value per (Gaussian, warp).
+// Backward: same units and sub-lists; pixel-parallel recurrence and Gaussian-parallel gradient accumulation are
+// separated by a transpose through shared memory (see composite_bwd_kernel), one atomic per value per (Gaussian, warp).
 //
 // Replaces gsplat 1.4.0 rasterize_to_pixels_fwd/bwd (third-party), reached from
 // rfstudio/model/gsplat.py:334-355.  Bound: FP32 / MUFU issue, not HBM.
@@ -287,40 +287,28 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     }
 }
 
-// Sum 8 per-lane values over the warp with a transposing butterfly: after the call, lanes 4s..4s+3 all hold the
-// warp total of value s (s = 0..7).  4+2+1+1+1 = 9 shuffles.
-__device__ __forceinline__ float warp_reduce8(const float v[8], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    float a[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float send = b4 ? v[k] : v[k + 4];
-        float keep = b4 ? v[k + 4] : v[k];
-        a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    float c[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        float send = b3 ? a[k] : a[k + 2];
-        float keep = b3 ? a[k + 2] : a[k];
-        c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    float send = b2 ? c[0] : c[1];
-    float keep = b2 ? c[1] : c[0];
-    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;  // value index = lane >> 2
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+// Backward.  The per-Gaussian gradient is a sum over pixels, the transmittance recurrence runs over Gaussians: the
+// kernel does each along the axis where it is register-local and TRANSPOSES through shared memory in between, so no
+// warp shuffle and no cross-lane reduction is left.  Per chunk of 32 sub-list entries (walked back to front):
+//   phase A (lane = pixel)   : evaluate the 32 entries, run the T / suffix-colour recurrence, and store per (entry,
+//                              pixel) the three scalars the gradient needs -- vis = exp(-sigma) (0 if the pair does not
+//                              contribute), T before the Gaussian, E = (suffix . v_out - T_final (v_alpha - bg . v_out))
+//                              / (1 - alpha) -- into 32 x 33 slabs (row = entry, conflict-free both ways);
+//   phase B (lane = Gaussian): read its row, accumulate the 9 gradient values over the 32 pixels in registers, one
+//                              atomic per value per (Gaussian, warp) -- only for Gaussians that touched a pixel.
+// v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
+// (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
+constexpr int BSTRIDE = 33;
+constexpr int WPB_B = 2;   // warps per CTA in the backward (15 KB of shared memory per warp)
 
 template <int CH>
-__global__ void __launch_bounds__(32 * WPB)
+__global__ void __launch_bounds__(32 * WPB_B)
 composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
@@ -329,10 +317,16 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                      float *__restrict__ v_colors, float *__restrict__ v_opacities) {
-    __shared__ Rec s_rec[WPB][32];
-    __shared__ int2 s_ent[WPB][32];
+    constexpr int C3 = CH < 3 ? CH : 3;                 // channels carried in the packed record
+    constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
+    __shared__ float s_vis[WPB_B][32 * BSTRIDE];
+    __shared__ float s_T[WPB_B][32 * BSTRIDE];
+    __shared__ float s_E[WPB_B][32 * BSTRIDE];
+    __shared__ Rec s_rec[WPB_B][32];
+    __shared__ int2 s_ent[WPB_B][32];
+    __shared__ float4 s_vo[WPB_B][32][NV4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int slot = blockIdx.x * WPB + wib;
+    const int slot = blockIdx.x * WPB_B + wib;
     if (slot >= n_units) return;
     const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);
     const Unit u = make_unit(unit, lane, tile_w, W, H);
@@ -344,18 +338,23 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     int n = counts[unit];
 
     const float T_final = u.inside ? 1.0f - alphas[pix] : 1.0f;
-    float T = T_final;
-    float buffer[CH];
     float v_out[CH];
     float bg_dot = 0.f;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
-        buffer[k] = 0.f;
         v_out[k] = u.inside ? v_render[pix * CH + k] : 0.f;
         if (background) bg_dot += background[k] * v_out[k];
     }
-    const float v_a_out = u.inside ? v_alphas[pix] : 0.f;
+    const float c0 = T_final * ((u.inside ? v_alphas[pix] : 0.f) - bg_dot);
     const int bin_final = u.inside ? last_ids[pix] : -1;
+    {
+        float vo4[NV4 * 4];
+#pragma unroll
+        for (int k = 0; k < NV4 * 4; ++k) vo4[k] = (k < CH) ? v_out[k] : 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k)
+            s_vo[wib][lane][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
+    }
     int wmax = bin_final;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -372,9 +371,15 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     }
     if (n == 0) return;
 
-    // walk back to front: chunk c covers sub-list indices [hi_c - 32, hi_c), lane l holds index hi_c - 1 - l
+    float *const my_vis = s_vis[wib], *const my_T = s_T[wib], *const my_E = s_E[wib];
+    const float bx = (float)(u.j - (lane & 7)) + 0.5f, by = (float)(u.i - (lane >> 3)) + 0.5f;  // pixel (0,0) of the unit
+    float T = T_final;
+    float B = 0.f;    // suffix colour behind the current Gaussian, dotted with v_out
+
+    // walk back to front: chunk c covers sub-list indices [top - 32, top), slab row t holds index top - 1 - t
     int2 e = make_int2(0, 0);
     Rec r;
+    r.k = r.q = r.c = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n - 1 - lane >= 0) { e = list[n - 1 - lane]; r = rec[e.y]; }
     for (int top = n; top > 0; top -= 32) {
         __syncwarp();
@@ -384,87 +389,110 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         const int nt = top - 32;
         if (nt - 1 - lane >= 0) { e = list[nt - 1 - lane]; r = rec[e.y]; }
         const int cnt = min(32, top);
-        // two entries per iteration: their evaluations and warp reductions are independent, which gives a lone warp
-        // the ILP to cover shuffle / MUFU latency; only the (T, buffer) recurrence is sequential.
+
+        // ---- phase A: lane = pixel -------------------------------------------------------------------------
+        unsigned touched = 0u;   // bit t: entry t contributes to at least one pixel of the unit
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += 2) {
-            float v[2][8], v_op[2];
-            int gid[2];
-            bool any[2];
+        for (int t0 = 0; t0 < cnt; t0 += 4) {
+            float vis4[4], al4[4];
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
+            for (int jj = 0; jj < 4; ++jj) {
                 const int t = min(t0 + jj, 31);
                 const float4 kk = s_rec[wib][t].k;
                 const float4 q = s_rec[wib][t].q;
-                const int2 en = s_ent[wib][t];
-                gid[jj] = en.y;
+                const int pos = s_ent[wib][t].x;
                 const float dx = kk.x - u.px, dy = kk.y - u.py;
                 const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
                 const float vis = ex2_approx(-LOG2E * sigma);
                 const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
-                const bool valid = (t0 + jj < cnt) && (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
-                any[jj] = __any_sync(0xffffffffu, valid);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[jj][k] = 0.f;
-                v_op[jj] = 0.f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - alpha);
-                    T *= ra;
-                    const float fac = alpha * T;
-                    const float4 c = s_rec[wib][t].c;
-                    float v_alpha = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        if (k >= CH) break;
-                        const float cch = (k == 0) ? c.x : (k == 1) ? c.y : c.z;
-                        v[jj][k] = fac * v_out[k];
-                        v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
-                        buffer[k] += cch * fac;
-                    }
-                    if (CH > 3) {
-#pragma unroll
-                        for (int k = 3; k < CH; ++k) {
-                            const float cch = __ldg(colors + (size_t)en.y * CH + k);
-                            // rare wide-channel path (D=14 G-buffer, ED): straight atomics, no butterfly
-                            atomicAdd(v_colors + (size_t)en.y * CH + k, fac * v_out[k]);
-                            v_alpha += (cch * T - buffer[k] * ra) * v_out[k];
-                            buffer[k] += cch * fac;
-                        }
-                    }
-                    v_alpha += T_final * ra * v_a_out;
-                    if (background) v_alpha += -T_final * ra * bg_dot;
-                    if (q.w * vis <= GSB_ALPHA_CLAMP) {
-                        const float v_sigma = -q.w * vis * v_alpha;
-                        v[jj][3] = 0.5f * v_sigma * dx * dx;
-                        v[jj][4] = v_sigma * dx * dy;
-                        v[jj][5] = 0.5f * v_sigma * dy * dy;
-                        v[jj][6] = v_sigma * (q.x * dx + q.y * dy);
-                        v[jj][7] = v_sigma * (q.y * dx + q.z * dy);
-                        v_op[jj] = vis * v_alpha;
-                    }
-                }
-            }
-            if (!(any[0] || any[1])) continue;
-            float red[2];
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                red[jj] = warp_reduce8(v[jj], lane);
-                v_op[jj] = warp_sum(v_op[jj]);
+                const bool valid = (t0 + jj < cnt) && (pos <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
+                vis4[jj] = valid ? vis : 0.f;
+                al4[jj] = valid ? alpha : 0.f;
+                if (__any_sync(0xffffffffu, valid)) touched |= 1u << t;
             }
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                if (!any[jj]) continue;
-                const int g = gid[jj];
-                if ((lane & 3) == 0) {
-                    const int sidx = lane >> 2;
-                    float *dst;
-                    if (sidx < 3) dst = (sidx < (CH < 3 ? CH : 3)) ? v_colors + (size_t)g * CH + sidx : nullptr;
-                    else if (sidx < 6) dst = v_conics + 3 * (size_t)g + (sidx - 3);
-                    else dst = v_means2d + 2 * (size_t)g + (sidx - 6);
-                    if (dst) atomicAdd(dst, red[jj]);
-                } else if (lane == 1) {
-                    atomicAdd(v_opacities + g, v_op[jj]);
+            for (int jj = 0; jj < 4; ++jj) {
+                const int t = min(t0 + jj, 31);
+                // alpha == 0 (pair does not contribute) makes every update below the identity: no branch
+                const float ra = rcp_approx(1.0f - al4[jj]);
+                T *= ra;
+                const float4 c = s_rec[wib][t].c;
+                float w = c.x * v_out[0];
+                if (C3 > 1) w += c.y * v_out[1];
+                if (C3 > 2) w += c.z * v_out[2];
+                if (CH > 3) {
+                    const int g = s_ent[wib][t].y;
+#pragma unroll
+                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)g * CH + k) * v_out[k];
                 }
+                my_vis[t * BSTRIDE + lane] = vis4[jj];
+                my_T[t * BSTRIDE + lane] = T;
+                my_E[t * BSTRIDE + lane] = ra * (B - c0);
+                B += w * (al4[jj] * T);
+            }
+        }
+        __syncwarp();
+        if (touched == 0u) continue;
+
+        // ---- phase B: lane = Gaussian (slab row `lane`) ------------------------------------------------------
+        {
+            const float4 kk = s_rec[wib][lane].k;
+            const float4 q = s_rec[wib][lane].q;
+            const float4 c = s_rec[wib][lane].c;
+            const int g = s_ent[wib][lane].y;
+            float col[CH];
+            col[0] = c.x;
+            if (CH > 1) col[1] = c.y;
+            if (CH > 2) col[2] = c.z;
+            const bool mine = (touched >> lane) & 1u;
+            if (CH > 3) {
+#pragma unroll
+                for (int k = 3; k < CH; ++k) col[k] = mine ? __ldg(colors + (size_t)g * CH + k) : 0.f;
+            }
+            float g_col[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) g_col[k] = 0.f;
+            float sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, g_op = 0.f;
+            const float *row_vis = my_vis + lane * BSTRIDE, *row_T = my_T + lane * BSTRIDE,
+                        *row_E = my_E + lane * BSTRIDE;
+#pragma unroll 8
+            for (int p = 0; p < 32; ++p) {
+                const float vis = row_vis[p], Tp = row_T[p], Ep = row_E[p];
+                float vo[NV4 * 4];
+#pragma unroll
+                for (int k = 0; k < NV4; ++k) {
+                    const float4 v4 = s_vo[wib][p][k];
+                    vo[4 * k] = v4.x; vo[4 * k + 1] = v4.y; vo[4 * k + 2] = v4.z; vo[4 * k + 3] = v4.w;
+                }
+                const float ov = q.w * vis;
+                const float fac = fminf(GSB_ALPHA_CLAMP, ov) * Tp;
+                float w = 0.f;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    w += col[k] * vo[k];
+                    g_col[k] += fac * vo[k];
+                }
+                float v_alpha = Tp * w - Ep;
+                v_alpha = (ov <= GSB_ALPHA_CLAMP) ? v_alpha : 0.f;   // clamped alpha passes no gradient to sigma / opacity
+                g_op += vis * v_alpha;
+                const float v_sigma = -ov * v_alpha;
+                const float dx = kk.x - (bx + (float)(p & 7)), dy = kk.y - (by + (float)(p >> 3));   // exact pixel centre
+                const float t1 = v_sigma * dx, t2 = v_sigma * dy;
+                sxx += t1 * dx;
+                sxy += t1 * dy;
+                syy += t2 * dy;
+                sx += t1;
+                sy += t2;
+            }
+            if (mine) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) atomicAdd(v_colors + (size_t)g * CH + k, g_col[k]);
+                atomicAdd(v_conics + 3 * (size_t)g, 0.5f * sxx);
+                atomicAdd(v_conics + 3 * (size_t)g + 1, sxy);
+                atomicAdd(v_conics + 3 * (size_t)g + 2, 0.5f * syy);
+                atomicAdd(v_means2d + 2 * (size_t)g, q.x * sx + q.y * sy);
+                atomicAdd(v_means2d + 2 * (size_t)g + 1, q.y * sx + q.z * sy);
+                atomicAdd(v_opacities + g, g_op);
             }
         }
     }
@@ -534,7 +562,7 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.sorted_counts, w.order);   // order by the forward's measured work
-    composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
+    composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB_B), 32 * WPB_B, 0, st>>>(
         W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order, alphas,
         last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
