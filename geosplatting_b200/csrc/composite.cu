@@ -26,6 +26,7 @@ namespace {
 constexpr int SUB_W = 8, SUB_H = 4;                       // pixel footprint of one warp
 constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 8 sub-rectangles per tile
 constexpr int WPB = 2;                                    // warps (units) per CTA in the composite kernels
+constexpr int FG = 8;                                     // entries evaluated together in the forward
 
 struct Rec {
     float4 k;  // x, y, hx, hy
@@ -219,7 +220,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     float acc[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-    int cur_idx = 0;
+    int last_k = -1;   // sub-list index of the pixel's last contributor
 
     // prefetch chunk 0
     int2 e = make_int2(0, 0);
@@ -234,28 +235,57 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         const int nb = base + 32;
         if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }   // next chunk in flight during the loop
         const int cnt = min(32, n - base);
-        // 4 entries per iteration: the four alpha evaluations are independent (ILP hides the LDS / MUFU latency of a
-        // lone warp); only the transmittance update is sequential.
+        // Groups of FG entries.  The FG alpha evaluations are independent (ILP for a warp that runs alone: the longest
+        // sub-list of a view is this kernel's critical path); the transmittance chain is one multiply per entry.
+        // alpha == 0 stands for "does not contribute" and makes every update the identity, so the common case has no
+        // branch.  Only a group in which some pixel reaches the T <= 1e-4 stop replays the exact per-entry logic.
+        bool all_done = false;
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += 4) {
-            float a4[4];
+        for (int t0 = 0; t0 < cnt; t0 += FG) {
+            float a[FG];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
+            for (int jj = 0; jj < FG; ++jj) {
                 const int t = min(t0 + jj, 31);
                 const float4 kk = s_rec[wib][t].k;
                 const float4 q = s_rec[wib][t].q;
                 const float dx = kk.x - u.px, dy = kk.y - u.py;
                 const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
                 const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-LOG2E * sigma));
-                a4[jj] = (sigma < 0.f || alpha < GSB_ALPHA_MIN || t0 + jj >= cnt) ? 0.f : alpha;
+                a[jj] = (done || sigma < 0.f || alpha < GSB_ALPHA_MIN || t0 + jj >= cnt) ? 0.f : alpha;
+            }
+            float Tend = T;
+#pragma unroll
+            for (int jj = 0; jj < FG; ++jj) Tend *= 1.0f - a[jj];
+            // T only decreases, so a pixel trips the stop inside this group iff the group's end value is below it
+            if (!__any_sync(0xffffffffu, Tend <= GSB_T_STOP)) {
+#pragma unroll
+                for (int jj = 0; jj < FG; ++jj) {
+                    const float alpha = a[jj];
+                    const int t = min(t0 + jj, 31);
+                    const float vis = alpha * T;
+                    T *= 1.0f - alpha;
+                    if (alpha > 0.f) {   // predicated: a non-contributing Gaussian's colour is never read into the sum
+                        const float4 c = s_rec[wib][t].c;
+                        acc[0] += c.x * vis;
+                        if (CH > 1) acc[1] += c.y * vis;
+                        if (CH > 2) acc[2] += c.z * vis;
+                        if (CH > 3) {
+                            const int g = s_ent[wib][t].y;
+#pragma unroll
+                            for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+                        }
+                        last_k = base + t;
+                    }
+                }
+                continue;
             }
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float alpha = a4[jj];
+            for (int jj = 0; jj < FG; ++jj) {
+                const float alpha = a[jj];
                 if (done || alpha == 0.f) continue;
                 const int t = t0 + jj;
                 const float next_T = T * (1.0f - alpha);
-                if (next_T <= GSB_T_STOP) {
+                if (next_T <= GSB_T_STOP) {   // this entry is excluded
                     done = true;
                     continue;
                 }
@@ -269,13 +299,15 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 #pragma unroll
                     for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
                 }
-                cur_idx = s_ent[wib][t].x;
+                last_k = base + t;
                 T = next_T;
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
-        if (__all_sync(0xffffffffu, done)) { processed = min(n, base + 32); break; }
+        if (all_done) { processed = min(n, base + 32); break; }
     }
+    int cur_idx = 0;
+    if (last_k >= 0) cur_idx = list[last_k].x;
     if (lane == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
     if (u.inside) {
         const size_t pix = (size_t)u.i * W + u.j;
