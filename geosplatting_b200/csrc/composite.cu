@@ -74,53 +74,84 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
     rec[g] = r;
 }
 
-// One CTA per tile, warp w filters the tile list for sub-rectangle w.  Sub-list w of tile t lives at
-// entries[SUBS * start_t + w * len_t ...] (worst-case capacity, no prefix sum needed).
-__global__ void __launch_bounds__(64) build_sublists_kernel(int tile_w, int n_tiles, int M,
-                                                                     const int32_t *__restrict__ offsets,
-                                                                     const int32_t *__restrict__ flatten_ids,
-                                                                     const Rec *__restrict__ rec,
-                                                                     int2 *__restrict__ entries,
-                                                                     int32_t *__restrict__ counts,
-                                                                     int32_t *__restrict__ unit_ids) {
-    // CTA = 2 warps = 2 of the 8 sub-rectangles of a tile; 4 consecutive CTAs share the tile's list in L1/L2
-    const int unit = blockIdx.x * 2 + (threadIdx.x >> 5);
-    if (unit >= n_tiles * SUBS) return;
-    const int tile = unit / SUBS, w = unit % SUBS;
-    const int lane = threadIdx.x & 31;
+// One CTA (8 warps) per tile walks the tile's depth-sorted list ONCE, 256 entries per step, and appends every entry
+// to the sub-lists of the sub-rectangles its extent overlaps, order preserved (per sub-rectangle: ballot + popc
+// inside a warp, an 8 x 8 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
+// (list entry -> record is a dependent gather).  Sub-list w of tile t lives at entries[SUBS * start_t + w * len_t ...]
+// (worst-case capacity, no global prefix sum needed).
+constexpr int BUILD_THREADS = 256;
+
+__global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_w, int n_tiles, int M,
+                                                                        const int32_t *__restrict__ offsets,
+                                                                        const int32_t *__restrict__ flatten_ids,
+                                                                        const Rec *__restrict__ rec,
+                                                                        int2 *__restrict__ entries,
+                                                                        int32_t *__restrict__ counts) {
+    static_assert(SUBS == 8 && BUILD_THREADS == 256, "build_sublists: 8 warps x 8 sub-rectangles");
+    __shared__ int s_cnt[2][8][SUBS];   // [parity][warp][sub-rectangle] hits of this step
+    __shared__ int s_pre[2][8][SUBS];   // exclusive prefix over warps
+    __shared__ int s_base[2][SUBS];     // sub-list length before this step
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int len = end - start;
+    if (len <= 0) {
+        if (tid < SUBS) counts[tile * SUBS + tid] = 0;
+        return;
+    }
     const int tx = tile % tile_w, ty = tile / tile_w;
-    const float rcx = (float)(tx * GSB_TILE + (w & 1) * SUB_W) + 0.5f * SUB_W;
-    const float rcy = (float)(ty * GSB_TILE + (w >> 1) * SUB_H) + 0.5f * SUB_H;
+    const float x0 = (float)(tx * GSB_TILE) + 0.5f * SUB_W, y0 = (float)(ty * GSB_TILE) + 0.5f * SUB_H;
     const float rhx = 0.5f * (SUB_W - 1), rhy = 0.5f * (SUB_H - 1);
-    int2 *out = entries + (size_t)SUBS * start + (size_t)w * len;
-    int n = 0;
-    constexpr int U = 4;  // 4 x 32 list entries per iteration: two dependent load latencies per 128 entries
-    for (int base = start; base < end; base += 32 * U) {
-        int gid[U];
-        float4 k[U];
+    int2 *const out = entries + (size_t)SUBS * start;
+    if (tid < SUBS) s_base[0][tid] = 0;
+
+    const float4 miss = make_float4(0.f, 0.f, -1e30f, -1e30f);
+    // pipeline: gid of step i+2 and record of step i+1 are in flight while step i is processed
+    int gid0 = (start + tid < end) ? flatten_ids[start + tid] : -1;
+    int gid1 = (start + BUILD_THREADS + tid < end) ? flatten_ids[start + BUILD_THREADS + tid] : -1;
+    float4 k0 = (gid0 >= 0) ? __ldg(&rec[gid0].k) : miss;
+    int par = 0;
+    for (int base = start; base < end; base += BUILD_THREADS, par ^= 1) {
+        const int p2 = base + 2 * BUILD_THREADS + tid;
+        const int gid2 = (p2 < end) ? flatten_ids[p2] : -1;
+        const float4 k1 = (gid1 >= 0) ? __ldg(&rec[gid1].k) : miss;
+
+        unsigned hits = 0u;          // bit w: this entry overlaps sub-rectangle w
+        int my_pre[SUBS];            // hits of lower lanes of my warp
 #pragma unroll
-        for (int s = 0; s < U; ++s) {
-            const int pos = base + s * 32 + lane;
-            gid[s] = (pos < end) ? flatten_ids[pos] : -1;
-        }
-#pragma unroll
-        for (int s = 0; s < U; ++s)
-            k[s] = (gid[s] >= 0) ? __ldg(&rec[gid[s]].k) : make_float4(0.f, 0.f, -1e30f, -1e30f);
-#pragma unroll
-        for (int s = 0; s < U; ++s) {
-            const bool hit = (fabsf(k[s].x - rcx) <= k[s].z + rhx) && (fabsf(k[s].y - rcy) <= k[s].w + rhy);
+        for (int w = 0; w < SUBS; ++w) {
+            const float rcx = x0 + (float)((w & 1) * SUB_W), rcy = y0 + (float)((w >> 1) * SUB_H);
+            const bool hit = (fabsf(k0.x - rcx) <= k0.z + rhx) && (fabsf(k0.y - rcy) <= k0.w + rhy);
             const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) out[n + __popc(m & ((1u << lane) - 1u))] = make_int2(base + s * 32 + lane, gid[s]);
-            n += __popc(m);
+            my_pre[w] = __popc(m & ((1u << lane) - 1u));
+            if (hit) hits |= 1u << w;
+            if (lane == w) s_cnt[par][warp][w] = __popc(m);
         }
+        __syncthreads();
+        if (tid < 8 * SUBS) {
+            const int wp = tid >> 3, w = tid & 7;
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const int c = s_cnt[par][v][w];
+                pre += (v < wp) ? c : 0;
+                tot += c;
+            }
+            s_pre[par][wp][w] = pre;
+            if (wp == 0) s_base[par ^ 1][w] = s_base[par][w] + tot;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < SUBS; ++w) {
+            if (hits & (1u << w))
+                out[(size_t)w * len + s_base[par][w] + s_pre[par][warp][w] + my_pre[w]] = make_int2(base + tid, gid0);
+        }
+        gid0 = gid1; gid1 = gid2; k0 = k1;
     }
-    if (lane == 0) {
-        counts[tile * SUBS + w] = n;
-        unit_ids[tile * SUBS + w] = tile * SUBS + w;
-    }
+    // `par` now names the buffer the last step wrote its totals to
+    __syncthreads();
+    if (tid < SUBS) counts[tile * SUBS + tid] = s_base[par][tid];
 }
 
 // Longest-processing-time-first order of the TILES (their 8 units stay adjacent in launch order so that they
@@ -337,6 +368,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
 // (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
 constexpr int BSTRIDE = 33;
+constexpr int BG = 8;      // entries evaluated together in phase A
 constexpr int WPB_B = 2;   // warps per CTA in the backward (15 KB of shared memory per warp)
 
 template <int CH>
@@ -425,42 +457,43 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         // ---- phase A: lane = pixel -------------------------------------------------------------------------
         unsigned touched = 0u;   // bit t: entry t contributes to at least one pixel of the unit
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += 4) {
-            float vis4[4], al4[4];
+        for (int t0 = 0; t0 < cnt; t0 += BG) {
+            // independent per entry: alpha, 1 / (1 - alpha), colour . v_out  (ILP for a warp that runs alone)
+            float visg[BG], alg[BG], rag[BG], wg[BG];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
+            for (int jj = 0; jj < BG; ++jj) {
                 const int t = min(t0 + jj, 31);
                 const float4 kk = s_rec[wib][t].k;
                 const float4 q = s_rec[wib][t].q;
-                const int pos = s_ent[wib][t].x;
+                const float4 c = s_rec[wib][t].c;
+                const int2 en = s_ent[wib][t];
                 const float dx = kk.x - u.px, dy = kk.y - u.py;
                 const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
                 const float vis = ex2_approx(-LOG2E * sigma);
                 const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
-                const bool valid = (t0 + jj < cnt) && (pos <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
-                vis4[jj] = valid ? vis : 0.f;
-                al4[jj] = valid ? alpha : 0.f;
-                if (__any_sync(0xffffffffu, valid)) touched |= 1u << t;
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int t = min(t0 + jj, 31);
-                // alpha == 0 (pair does not contribute) makes every update below the identity: no branch
-                const float ra = rcp_approx(1.0f - al4[jj]);
-                T *= ra;
-                const float4 c = s_rec[wib][t].c;
+                const bool valid = (t0 + jj < cnt) && (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
+                visg[jj] = valid ? vis : 0.f;
+                alg[jj] = valid ? alpha : 0.f;
+                rag[jj] = rcp_approx(1.0f - alg[jj]);
                 float w = c.x * v_out[0];
                 if (C3 > 1) w += c.y * v_out[1];
                 if (C3 > 2) w += c.z * v_out[2];
                 if (CH > 3) {
-                    const int g = s_ent[wib][t].y;
 #pragma unroll
-                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)g * CH + k) * v_out[k];
+                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)en.y * CH + k) * v_out[k];
                 }
-                my_vis[t * BSTRIDE + lane] = vis4[jj];
+                wg[jj] = w;
+                if (__any_sync(0xffffffffu, valid)) touched |= 1u << t;
+            }
+            // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch
+#pragma unroll
+            for (int jj = 0; jj < BG; ++jj) {
+                const int t = min(t0 + jj, 31);
+                T *= rag[jj];
+                my_vis[t * BSTRIDE + lane] = visg[jj];
                 my_T[t * BSTRIDE + lane] = T;
-                my_E[t * BSTRIDE + lane] = ra * (B - c0);
-                B += w * (al4[jj] * T);
+                my_E[t * BSTRIDE + lane] = rag[jj] * (B - c0);
+                B += wg[jj] * (alg[jj] * T);
             }
         }
         __syncwarp();
@@ -577,8 +610,8 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
     if (N > 0)
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
                                                                     conics, colors, opacities, w.rec);
-    build_sublists_kernel<<<gsb_div_up(n_units, 2), 64, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec,
-                                                                 w.entries, w.counts, w.unit_ids);
+    build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec,
+                                                             w.entries, w.counts);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
         W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order,
