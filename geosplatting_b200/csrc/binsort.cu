@@ -40,6 +40,23 @@ extern "C" __attribute__((visibility("default"))) int gsb_isect_scan(int32_t N, 
     return GSB_OK;
 }
 
+__global__ void isect_total_kernel(int N, const int64_t *__restrict__ cum_tiles, volatile int64_t *total_out) {
+    *total_out = cum_tiles[N - 1];
+    __threadfence_system();
+}
+
+extern "C" __attribute__((visibility("default"))) int gsb_isect_total(int32_t N, const int64_t *cum_tiles, int64_t *total_out, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && total_out != nullptr);
+    if (N == 0) {
+        GSB_CHECK_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), (cudaStream_t)stream));
+        return GSB_OK;
+    }
+    GSB_CHECK_ARG(cum_tiles != nullptr);
+    isect_total_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(N, cum_tiles, total_out);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int gsb_sort_pairs(int64_t M, int32_t key_bits, const int64_t *keys_in, const int32_t *vals_in,
                               int64_t *keys_out, int32_t *vals_out, void *workspace, size_t workspace_bytes,
                               void *stream) {

@@ -103,38 +103,68 @@ class _Project(torch.autograd.Function):
         return v_means, v_quats, v_scales, None
 
 
-def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, cam: GsbCamera,
-             n_cameras: int = 1):
-    """-> (isect_ids[M] i64 sorted, flatten_ids[M] i32 (Gaussian index), isect_offsets[th,tw] i32).
+_total_slots: Dict[int, list] = {}
 
-    One host sync (reads M), exactly like gsplat's `isect_tiles`.
-    """
+
+def _total_slot(device: torch.device) -> Tensor:
+    """A pinned host int64 the device writes M into (ring of 8 per device: a slot is read before it is reused)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ring = _total_slots.setdefault(key, [[torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(8)], 0])
+    ring[1] = (ring[1] + 1) % len(ring[0])
+    return ring[0][ring[1]]
+
+
+class BinCount:
+    """First half of the binning: the prefix sum of tiles-per-Gaussian is queued and M = cum[-1] is on its way
+    to a pinned host slot.  `total()` waits for it -- call it as late as possible so that other work queued in
+    between (the shade) covers the wait."""
+
+    def __init__(self, tiles_per_gauss: Tensor):
+        dev = tiles_per_gauss.device
+        self.N = N = tiles_per_gauss.shape[0]
+        self.cum = None
+        self._M = 0 if N == 0 else None
+        if N == 0:
+            return
+        nbytes = C.c_size_t(0)
+        call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
+        ws = _workspace(dev, nbytes.value)
+        st = stream_ptr(dev)
+        self.cum = torch.empty(N, dtype=torch.int64, device=dev)
+        call("gsb_isect_scan", dev, C.c_int32(N), ptr(tiles_per_gauss), ptr(self.cum), ptr(ws), C.c_size_t(ws.numel()), st)
+        self._slot = _total_slot(dev)
+        call("gsb_isect_total", dev, C.c_int32(N), ptr(self.cum), C.c_void_p(self._slot.data_ptr()), st)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(dev))
+
+    def total(self) -> int:
+        if self._M is None:
+            self._event.synchronize()     # no device->host copy: the kernel stored M straight into pinned memory
+            self._M = int(self._slot[0])
+        return self._M
+
+
+def bin_finish(count: BinCount, means2d: Tensor, radii: Tensor, depths: Tensor, cam: GsbCamera, n_cameras: int = 1):
+    """Second half: key emission, radix sort, per-tile offsets.
+    -> (isect_ids[M] i64 sorted, flatten_ids[M] i32 (Gaussian index), isect_offsets[n_cameras,th,tw] i32)."""
     dev = means2d.device
     N = means2d.shape[0]
     tw = (cam.width + TILE - 1) // TILE
     th = (cam.height + TILE - 1) // TILE
     st = stream_ptr(dev)
     offsets = torch.empty(n_cameras * th * tw, dtype=torch.int32, device=dev)
-    if N == 0:
-        offsets.zero_()
-        e64 = torch.empty(0, dtype=torch.int64, device=dev)
-        return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
-    nbytes = C.c_size_t(0)
-    call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
-    ws = _workspace(dev, nbytes.value)
-    cum = torch.empty(N, dtype=torch.int64, device=dev)
-    call("gsb_isect_scan", dev, C.c_int32(N), ptr(tiles_per_gauss), ptr(cum), ptr(ws), C.c_size_t(ws.numel()), st)
-    M = int(cum[-1].item())
+    M = count.total()
     if M == 0:
         offsets.zero_()
         e64 = torch.empty(0, dtype=torch.int64, device=dev)
         return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
     keys = torch.empty(M, dtype=torch.int64, device=dev)
     vals = torch.empty(M, dtype=torch.int32, device=dev)
-    call("gsb_isect_tiles", dev, C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C.byref(cam),
+    call("gsb_isect_tiles", dev, C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(count.cum), C.byref(cam),
                               ptr(keys), ptr(vals), st)
     keys_s = torch.empty_like(keys)
     vals_s = torch.empty_like(vals)
+    nbytes = C.c_size_t(0)
     call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(M), C.byref(nbytes))
     ws = _workspace(dev, nbytes.value)
     n_tiles = tw * th
@@ -145,6 +175,14 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
     call("gsb_isect_offsets", dev, C.c_int64(M), ptr(keys_s), C.c_int32(n_cameras), C.c_int32(tw), C.c_int32(th),
                                 ptr(offsets), st)
     return keys_s, vals_s, offsets.view(n_cameras, th, tw)
+
+
+def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, cam: GsbCamera,
+             n_cameras: int = 1):
+    """-> (isect_ids[M] i64 sorted, flatten_ids[M] i32 (Gaussian index), isect_offsets[th,tw] i32).
+
+    One host wait (for M), like gsplat's `isect_tiles`."""
+    return bin_finish(BinCount(tiles_per_gauss), means2d, radii, depths, cam, n_cameras)
 
 
 class _Composite(torch.autograd.Function):
@@ -227,70 +265,59 @@ def _pad_channels(colors: Tensor) -> Tuple[Tensor, int]:
     raise ValueError(f"rasterization: at most {_SUPPORTED_CH[-1]} colour channels are supported, got {D}")
 
 
-def rasterization(
-    means: Tensor,
-    quats: Tensor,
-    scales: Tensor,
-    opacities: Tensor,
-    colors: Tensor,
-    viewmats: Tensor,
-    Ks: Tensor,
-    width: int,
-    height: int,
-    near_plane: float = 0.01,
-    far_plane: float = 1e10,
-    radius_clip: float = 0.0,
-    eps2d: float = 0.3,
-    sh_degree: Optional[int] = None,
-    packed: bool = True,
-    tile_size: int = 16,
-    backgrounds: Optional[Tensor] = None,
-    render_mode: str = "RGB",
-    sparse_grad: bool = False,
-    absgrad: bool = False,
-    rasterize_mode: str = "classic",
-    channel_chunk: int = 32,
-    distributed: bool = False,
-    camera_model: str = "pinhole",
-) -> Tuple[Tensor, Tensor, dict]:
-    """Same contract as gsplat 1.4.0 ``rasterization`` for the argument set the reference uses.
-
-    means[N,3] quats[N,4](wxyz) scales[N,3] opacities[N] colors[N,D] viewmats[C,4,4] Ks[C,3,3]
-    -> render[C,H,W,D(+1)], alpha[C,H,W,1], info.  Differentiable w.r.t. means, quats, scales,
-    opacities, colors (and backgrounds).
-    """
+def _check_geometry(means, quats, scales, viewmats, Ks):
     if means.dim() != 2 or means.shape[1] != 3:
         raise AssertionError(f"means must be [N,3], got {tuple(means.shape)}")
     N = means.shape[0]
     assert quats.shape == (N, 4), quats.shape
     assert scales.shape == (N, 3), scales.shape
-    assert opacities.shape == (N,), opacities.shape
     assert viewmats.dim() == 3 and viewmats.shape[1:] == (4, 4), viewmats.shape
-    Cn = viewmats.shape[0]
-    assert Ks.shape == (Cn, 3, 3), Ks.shape
-    assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED"), render_mode
-    assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
-    if tile_size != TILE:
-        raise NotImplementedError("geosplatting_b200: tile_size is fixed at 16 (rfstudio/model/gsplat.py:30)")
-    if sh_degree is not None:
-        raise NotImplementedError("geosplatting_b200: sh_degree must be None (GeoSplatter uses sh_degree=0 -> "
-                                  "colors are passed raw, rfstudio/model/gsplat.py:305-307)")
-    if camera_model != "pinhole" or distributed or sparse_grad or absgrad:
-        raise NotImplementedError("geosplatting_b200: only pinhole / dense-grad / single-process rasterization")
+    assert Ks.shape == (viewmats.shape[0], 3, 3), Ks.shape
     if not means.is_cuda:
         raise RuntimeError("geosplatting_b200.rasterization needs CUDA tensors; there is no CPU path")
-    assert colors.dim() == 2 and colors.shape[0] == N, colors.shape
-    if backgrounds is not None:
-        assert backgrounds.shape[0] == Cn, backgrounds.shape
 
+
+class Projected:
+    """State between `rasterization_begin` and `rasterization_end`: per camera the projection outputs and the
+    pending intersection count."""
+
+    def __init__(self, width, height, aa, N):
+        self.width, self.height, self.aa, self.N = width, height, aa, N
+        self.cams = []      # (cam, means2d, depths, conics, comps, radii, tpg, BinCount)
+
+
+def rasterization_begin(means: Tensor, quats: Tensor, scales: Tensor, viewmats: Tensor, Ks: Tensor, width: int,
+                        height: int, *, near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0,
+                        eps2d: float = 0.3, rasterize_mode: str = "classic") -> Projected:
+    """First half of `rasterization`: everything that depends on geometry only (projection, tile counts, the
+    prefix sum, M on its way to the host).  Work queued between begin and end -- RenderableAttrs.splat puts the
+    shade there -- runs while the host would otherwise wait for M."""
+    _check_geometry(means, quats, scales, viewmats, Ks)
+    assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
     aa = rasterize_mode == "antialiased"
     vm_host = viewmats.detach().to("cpu", torch.float32)
     k_host = Ks.detach().to("cpu", torch.float32)
-    renders, alphas_out, per_cam = [], [], []
-    for c in range(Cn):
+    st = Projected(width, height, aa, means.shape[0])
+    for c in range(viewmats.shape[0]):
         cam = make_camera(vm_host[c], k_host[c], width, height, near_plane=near_plane, far_plane=far_plane,
                           eps2d=eps2d, radius_clip=radius_clip, antialiased=aa, camera_id=0)
         means2d, depths, conics, comps, radii, tpg = _Project.apply(means, quats, scales, cam)
+        st.cams.append((cam, means2d, depths, conics, comps, radii, tpg, BinCount(tpg)))
+    return st
+
+
+def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backgrounds: Optional[Tensor] = None,
+                      render_mode: str = "RGB", tile_size: int = TILE) -> Tuple[Tensor, Tensor, dict]:
+    """Second half of `rasterization`: binning, sort and compositing with the per-Gaussian colours."""
+    N, width, height, aa = st.N, st.width, st.height, st.aa
+    Cn = len(st.cams)
+    assert opacities.shape == (N,), opacities.shape
+    assert colors.dim() == 2 and colors.shape[0] == N, colors.shape
+    assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED"), render_mode
+    if backgrounds is not None:
+        assert backgrounds.shape[0] == Cn, backgrounds.shape
+    renders, alphas_out, per_cam = [], [], []
+    for c, (cam, means2d, depths, conics, comps, radii, tpg, count) in enumerate(st.cams):
         opac = opacities * comps if aa else opacities
         if render_mode in ("RGB+D", "RGB+ED"):
             feats = torch.cat((colors, depths[:, None]), dim=-1)
@@ -306,7 +333,7 @@ def rasterization(
         feats_p, D = _pad_channels(feats)
         if bg is not None and feats_p.shape[1] != bg.shape[0]:
             bg = torch.cat((bg, bg.new_zeros(feats_p.shape[1] - bg.shape[0])))
-        isect_ids, flatten_ids, offsets = bin_sort(means2d.detach(), radii, depths.detach(), tpg, cam)
+        isect_ids, flatten_ids, offsets = bin_finish(count, means2d.detach(), radii, depths.detach(), cam)
         render, alpha = _Composite.apply(means2d, conics, feats_p, opac, bg, offsets.view(-1), flatten_ids,
                                          width, height)
         render = render[..., :D]
@@ -316,9 +343,8 @@ def rasterization(
         alphas_out.append(alpha[..., None])
         per_cam.append((means2d, depths, conics, comps, radii, tpg, opac, isect_ids, flatten_ids, offsets))
 
-    render = torch.stack(renders, 0)
-    alpha = torch.stack(alphas_out, 0)
-
+    render = renders[0][None] if Cn == 1 else torch.stack(renders, 0)
+    alpha = alphas_out[0][None] if Cn == 1 else torch.stack(alphas_out, 0)
     # ---- info (packed=True layout), lazily materialised -------------------------------------------
     def _packed():
         cams, gids = [], []
@@ -372,3 +398,51 @@ def rasterization(
         radii_unpacked=lambda: torch.stack([pc[4] for pc in per_cam]),
     )
     return render, alpha, _LazyInfo(eager, lazy)
+
+
+def rasterization(
+    means: Tensor,
+    quats: Tensor,
+    scales: Tensor,
+    opacities: Tensor,
+    colors: Tensor,
+    viewmats: Tensor,
+    Ks: Tensor,
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+) -> Tuple[Tensor, Tensor, dict]:
+    """Same contract as gsplat 1.4.0 ``rasterization`` for the argument set the reference uses.
+
+    means[N,3] quats[N,4](wxyz) scales[N,3] opacities[N] colors[N,D] viewmats[C,4,4] Ks[C,3,3]
+    -> render[C,H,W,D(+1)], alpha[C,H,W,1], info.  Differentiable w.r.t. means, quats, scales,
+    opacities, colors (and backgrounds).
+    """
+    _check_geometry(means, quats, scales, viewmats, Ks)
+    assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED"), render_mode
+    assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
+    if tile_size != TILE:
+        raise NotImplementedError("geosplatting_b200: tile_size is fixed at 16 (rfstudio/model/gsplat.py:30)")
+    if sh_degree is not None:
+        raise NotImplementedError("geosplatting_b200: sh_degree must be None (GeoSplatter uses sh_degree=0 -> "
+                                  "colors are passed raw, rfstudio/model/gsplat.py:305-307)")
+    if camera_model != "pinhole" or distributed or sparse_grad or absgrad:
+        raise NotImplementedError("geosplatting_b200: only pinhole / dense-grad / single-process rasterization")
+    st = rasterization_begin(means, quats, scales, viewmats, Ks, width, height, near_plane=near_plane,
+                             far_plane=far_plane, radius_clip=radius_clip, eps2d=eps2d, rasterize_mode=rasterize_mode)
+    return rasterization_end(st, opacities, colors, backgrounds=backgrounds, render_mode=render_mode,
+                             tile_size=tile_size)

@@ -17,7 +17,7 @@ import torch
 from torch import Tensor
 
 from .mgadapter import tone_mapping_naive
-from .rasterization import rasterization
+from .rasterization import Projected, rasterization_begin, rasterization_end
 from .scenes import PinholeCamera
 from .shade import EnvStack, shade
 
@@ -63,21 +63,30 @@ class GSplatter:
     background_color: str = "random"
     rasterize_mode: str = "classic"
 
-    def render_rgba(self, inputs) -> Tensor:
-        """-> [H,W,4] (linear RGB + alpha), differentiable w.r.t. the Gaussians (gsplat.py:284-358)."""
+    def begin_render(self, inputs) -> Projected:
+        """Geometry half of `render_rgba`: activations, projection and the intersection count (the colours are not
+        needed yet, so RenderableAttrs.splat shades while the host waits for the count)."""
         camera = _single_camera(inputs)
         if self.rasterize_mode not in ("antialiased", "classic"):
             raise ValueError(f"Unknown rasterize_mode: {self.rasterize_mode}")
         if self.sh_degree != 0:
             raise NotImplementedError("geosplatting_b200.GSplatter: sh_degree must be 0 (GeoSplatter, geosplat.py:794)")
         g = self.gaussians
-        render, alpha, _ = rasterization(
-            means=g.means, quats=g.quats, scales=g.scales.exp(), opacities=torch.sigmoid(g.opacities).squeeze(-1),
-            colors=g.colors, viewmats=torch.from_numpy(camera.view_matrix)[None],
+        return rasterization_begin(
+            means=g.means, quats=g.quats, scales=g.scales.exp(), viewmats=torch.from_numpy(camera.view_matrix)[None],
             Ks=torch.from_numpy(camera.intrinsic_matrix)[None], width=camera.width, height=camera.height,
-            tile_size=self.block_width, packed=True, near_plane=0.01, far_plane=1e10, render_mode="RGB",
-            sh_degree=None, sparse_grad=False, absgrad=False, rasterize_mode=self.rasterize_mode)
+            near_plane=0.01, far_plane=1e10, rasterize_mode=self.rasterize_mode)
+
+    def finish_render(self, st: Projected) -> Tensor:
+        g = self.gaussians
+        render, alpha, _ = rasterization_end(st, torch.sigmoid(g.opacities).squeeze(-1), g.colors,
+                                             render_mode="RGB", tile_size=self.block_width)
         return torch.cat((render[..., :3], alpha), dim=-1).squeeze(0)
+
+    def render_rgba(self, inputs) -> Tensor:
+        """-> [H,W,4] (linear RGB + alpha), differentiable w.r.t. the Gaussians (gsplat.py:284-358: `rasterization`
+        with packed=True, tile 16, near 0.01, far 1e10, render_mode 'RGB', sh_degree None, dense gradients)."""
+        return self.finish_render(self.begin_render(inputs))
 
 
 @dataclass
@@ -109,10 +118,11 @@ class RenderableAttrs:
         try:
             normals, kd, ks = (self.normals, self.kd, self.ks) if mask is Ellipsis else \
                 (self.normals[mask], self.kd[mask], self.ks[mask])
+            st = gsplat.begin_render(camera)          # projection + intersection count are queued first ...
             colors = shade(gsplat.gaussians.means, normals, kd, ks, [float(x) for x in cam_pos], envmap, fg_lut,
                            min_roughness=min_roughness, max_metallic=max_metallic, mode=mode)
             gsplat.gaussians.replace_(colors=colors)
-            rgba = gsplat.render_rgba(camera)
+            rgba = gsplat.finish_render(st)           # ... so the shade covers the host's wait for the count
             if tone_type == "none":
                 out = torch.cat((rgba[..., :3] * exposure, rgba[..., 3:]), dim=-1)
             elif tone_type == "naive":

@@ -75,6 +75,12 @@ int gsb_bin_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host);
 int gsb_isect_scan(int32_t N, const int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* Publishes M = cum_tiles[N-1] to *total_out with a plain store from the device.  total_out may be device memory
+ * or PINNED HOST memory (cudaHostAlloc / torch pin_memory; device-addressable under unified addressing): the host
+ * then learns M by waiting on an event of `stream` instead of queueing a copy behind whatever the copy engines are
+ * doing (gsplat's isect_tiles reads M with a blocking device->host copy). */
+int gsb_isect_total(int32_t N, const int64_t *cum_tiles, int64_t *total_out, void *stream);
+
 /* Emits the M (key,val) pairs: key = camera_id << (32+tile_n_bits) | tile << 32 | bits(depth),
  * val = Gaussian index; Gaussian-major, tiles row-major. */
 int gsb_isect_tiles(int32_t N, const float *means2d, const int32_t *radii, const float *depths,
