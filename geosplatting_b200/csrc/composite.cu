@@ -57,12 +57,15 @@ template <int CH>
 __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *__restrict__ means2d,
                                                             const float *__restrict__ conics,
                                                             const float *__restrict__ colors,
-                                                            const float *__restrict__ opacities, Rec *__restrict__ rec) {
+                                                            const float *__restrict__ opacities, int opacity_is_logit,
+                                                            const float *__restrict__ comps, Rec *__restrict__ rec) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     float2 xy = means2d[g];
     float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
     float op = opacities[g];
+    if (opacity_is_logit) op = 1.0f / (1.0f + expf(-op));   // torch.sigmoid (rfstudio/model/gsplat.py:338)
+    if (comps) op *= comps[g];                               // antialiasing compensation (gsplat: opacities * compensations)
     float2 ext = alpha_extent(ca, cb, cc, op);
     Rec r;
     r.k = make_float4(xy.x, xy.y, ext.x, ext.y);
@@ -601,15 +604,16 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
 
 template <int CH>
 int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conics, const float *colors,
-               const float *opacities, const float *background, const int32_t *offsets,
-               const int32_t *flatten_ids, int64_t M, float *render, float *alphas, int32_t *last_ids, void *ws,
-               cudaStream_t st) {
+               const float *opacities, int opacity_is_logit, const float *comps, const float *background,
+               const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render, float *alphas,
+               int32_t *last_ids, void *ws, cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
     if (N > 0)
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
-                                                                    conics, colors, opacities, w.rec);
+                                                                    conics, colors, opacities, opacity_is_logit,
+                                                                    comps, w.rec);
     build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec,
                                                              w.entries, w.counts);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
@@ -659,9 +663,10 @@ GSB_API int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, i
 
 GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
                               const float *conics, const float *colors, const float *opacities,
-                              const float *background, const int32_t *offsets, const int32_t *flatten_ids, int64_t M,
-                              float *render, float *alphas, int32_t *last_ids, void *workspace,
-                              size_t workspace_bytes_, void *stream) {
+                              int32_t opacity_is_logit, const float *comps, const float *background,
+                              const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render,
+                              float *alphas, int32_t *last_ids, void *workspace, size_t workspace_bytes_,
+                              void *stream) {
     GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 268435455LL);
     GSB_CHECK_ARG(offsets && render && alphas && last_ids && workspace);
     GSB_CHECK_ARG(M == 0 || (means2d && conics && colors && opacities && flatten_ids));
@@ -671,9 +676,9 @@ GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, i
         return GSB_ENOMEM;
     }
     int rc = 0;
-    GSB_DISPATCH_CH(channels, (rc = launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities, background,
-                                                    offsets, flatten_ids, M, render, alphas, last_ids, workspace,
-                                                    (cudaStream_t)stream)));
+    GSB_DISPATCH_CH(channels, (rc = launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities,
+                                                    opacity_is_logit, comps, background, offsets, flatten_ids, M,
+                                                    render, alphas, last_ids, workspace, (cudaStream_t)stream)));
     if (rc != 0) {
         gsb_set_error("gsb_composite_fwd: internal sort scratch too small");
         return GSB_ENOMEM;

@@ -396,6 +396,55 @@ __global__ void __launch_bounds__(256) tonemap_bwd_kernel(long long P, const flo
     }
 }
 
+// Planar variants: read the rasterizer's own outputs (render[P,3], alphas[P]) and write the RGBA image, so no
+// concatenated copy of the image is ever made (the reference builds it with torch.cat, gsplat.py:358).
+__global__ void __launch_bounds__(256) tonemap_planar_fwd_kernel(long long P, const float *__restrict__ render,
+                                                                  const float *__restrict__ alphas,
+                                                                  const float *__restrict__ exposure, int naive,
+                                                                  float4 *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float e = __ldg(exposure);
+    float r = render[3 * i] * e, g = render[3 * i + 1] * e, b = render[3 * i + 2] * e, d;
+    if (naive) {
+        r = 1.0f - softplus100(1.0f - r, d);
+        g = 1.0f - softplus100(1.0f - g, d);
+        b = 1.0f - softplus100(1.0f - b, d);
+    }
+    out[i] = make_float4(r, g, b, alphas[i]);
+}
+
+__global__ void __launch_bounds__(256) tonemap_planar_bwd_kernel(long long P, const float *__restrict__ render,
+                                                                  const float *__restrict__ exposure, int naive,
+                                                                  const float4 *__restrict__ v_out,
+                                                                  float *__restrict__ v_render, float *__restrict__ v_alphas,
+                                                                  float *__restrict__ v_exposure) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float ve = 0.f;
+    if (i < P) {
+        float e = __ldg(exposure);
+        float4 v = v_out[i];
+        float x = render[3 * i], y = render[3 * i + 1], z = render[3 * i + 2];
+        float dx = 1.f, dy = 1.f, dz = 1.f;
+        if (naive) { softplus100(1.0f - x * e, dx); softplus100(1.0f - y * e, dy); softplus100(1.0f - z * e, dz); }
+        v_render[3 * i] = v.x * dx * e;
+        v_render[3 * i + 1] = v.y * dy * e;
+        v_render[3 * i + 2] = v.z * dz * e;
+        v_alphas[i] = v.w;
+        ve = v.x * dx * x + v.y * dy * y + v.z * dz * z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ve += __shfl_xor_sync(0xffffffffu, ve, o);
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ve;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        atomicAdd(v_exposure, t);
+    }
+}
+
 }  // namespace
 
 #define GSB_API extern "C" __attribute__((visibility("default")))
@@ -471,6 +520,29 @@ GSB_API int gsb_tonemap_bwd(int64_t P, const float *rgba, const float *exposure,
     tonemap_bwd_kernel<<<gsb_div_up(P, 256), 256, 0, (cudaStream_t)stream>>>(
         P, reinterpret_cast<const float4 *>(rgba), exposure, reinterpret_cast<const float4 *>(v_out),
         reinterpret_cast<float4 *>(v_rgba), v_exposure);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_tonemap_planar_fwd(int64_t P, const float *render, const float *alphas, const float *exposure,
+                                   int32_t naive, float *out, void *stream) {
+    GSB_CHECK_ARG(P >= 0);
+    if (P == 0) return GSB_OK;
+    GSB_CHECK_ARG(render && alphas && exposure && out);
+    tonemap_planar_fwd_kernel<<<gsb_div_up(P, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, render, alphas, exposure, naive, reinterpret_cast<float4 *>(out));
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_tonemap_planar_bwd(int64_t P, const float *render, const float *exposure, int32_t naive,
+                                   const float *v_out, float *v_render, float *v_alphas, float *v_exposure,
+                                   void *stream) {
+    GSB_CHECK_ARG(P >= 0);
+    if (P == 0) return GSB_OK;
+    GSB_CHECK_ARG(render && exposure && v_out && v_render && v_alphas && v_exposure);
+    tonemap_planar_bwd_kernel<<<gsb_div_up(P, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, render, exposure, naive, reinterpret_cast<const float4 *>(v_out), v_render, v_alphas, v_exposure);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

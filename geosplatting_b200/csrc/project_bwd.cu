@@ -9,10 +9,13 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     int N, const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
     CamK cam, const int32_t *__restrict__ radii, const float2 *__restrict__ v_means2d,
     const float *__restrict__ v_depths, const float *__restrict__ v_conics, const float *__restrict__ v_comps,
-    float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales) {
+    float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
+    const float *__restrict__ opacity_logits, const float *__restrict__ v_opacities_eff,
+    float *__restrict__ v_opacity_logits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float vm3[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    float v_logit = 0.f;
     ProjOut o;
     float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
     float4 q4 = reinterpret_cast<const float4 *>(quats)[i];
@@ -27,10 +30,18 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
         float t10 = b * va + c * vb, t11 = b * vb + c * vc;
         float g00 = -(t00 * a + t01 * b), g01 = -(t00 * b + t01 * c);
         float g10 = -(t10 * a + t11 * b), g11 = -(t10 * b + t11 * c);
+        // fused opacity activation (opacity_eff = sigmoid(logit) * comp): chain rule back to the logit and to comp
+        float v_comp_opac = 0.f;
+        if (opacity_logits) {
+            const float sig = 1.0f / (1.0f + expf(-opacity_logits[i]));
+            const float ve = v_opacities_eff[i];
+            v_comp_opac = ve * sig;
+            v_logit = ve * (cam.antialiased ? o.comp : 1.0f) * sig * (1.0f - sig);
+        }
         if (cam.antialiased) {
             float comp = o.comp;
             float det_conic = a * c - b * b;
-            float v_sq = v_comps[i] * 0.5f / (comp + GSB_COMP_EPS);
+            float v_sq = ((v_comps ? v_comps[i] : 0.f) + v_comp_opac) * 0.5f / (comp + GSB_COMP_EPS);
             float om = 1.0f - comp * comp;
             g00 += v_sq * (om * a - cam.eps2d * det_conic);
             g01 += v_sq * (om * b);
@@ -124,20 +135,24 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     v_means[3 * i] = vm3[0]; v_means[3 * i + 1] = vm3[1]; v_means[3 * i + 2] = vm3[2];
     reinterpret_cast<float4 *>(v_quats)[i] = make_float4(vq[0], vq[1], vq[2], vq[3]);
     v_scales[3 * i] = vs[0]; v_scales[3 * i + 1] = vs[1]; v_scales[3 * i + 2] = vs[2];
+    if (v_opacity_logits) v_opacity_logits[i] = v_logit;
 }
 
 extern "C" __attribute__((visibility("default"))) int gsb_project_bwd(int32_t N, const float *means, const float *quats, const float *scales,
                                const gsb_camera *cam, const int32_t *radii, const float *v_means2d,
                                const float *v_depths, const float *v_conics, const float *v_comps,
-                               float *v_means, float *v_quats, float *v_scales, void *stream) {
+                               float *v_means, float *v_quats, float *v_scales, const float *opacity_logits,
+                               const float *v_opacities_eff, float *v_opacity_logits, void *stream) {
     GSB_CHECK_ARG(N >= 0 && cam != nullptr);
     if (N == 0) return GSB_OK;
     GSB_CHECK_ARG(means && quats && scales && radii && v_means2d && v_conics && v_means && v_quats && v_scales);
-    GSB_CHECK_ARG(!cam->antialiased || v_comps != nullptr);
+    GSB_CHECK_ARG((opacity_logits == nullptr) == (v_opacities_eff == nullptr) &&
+                  (opacity_logits == nullptr) == (v_opacity_logits == nullptr));
+    GSB_CHECK_ARG(!cam->antialiased || v_comps != nullptr || opacity_logits != nullptr);
     CamK k = gsb_make_cam(cam);
     project_bwd_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
         N, means, quats, scales, k, radii, reinterpret_cast<const float2 *>(v_means2d), v_depths, v_conics,
-        v_comps, v_means, v_quats, v_scales);
+        v_comps, v_means, v_quats, v_scales, opacity_logits, v_opacities_eff, v_opacity_logits);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

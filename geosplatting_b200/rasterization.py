@@ -99,7 +99,7 @@ class _Project(torch.autograd.Function):
         v_scales = torch.empty(N, 3, dtype=torch.float32, device=dev)
         call("gsb_project_bwd", dev, C.c_int32(N), ptr(means), ptr(quats), ptr(scales), C.byref(cam), ptr(radii),
                                   ptr(v_means2d), ptr(v_depths_c), ptr(v_conics), ptr(v_comps_c), ptr(v_means),
-                                  ptr(v_quats), ptr(v_scales), stream_ptr(dev))
+                                  ptr(v_quats), ptr(v_scales), None, None, None, stream_ptr(dev))
         return v_means, v_quats, v_scales, None
 
 
@@ -203,7 +203,8 @@ class _Composite(torch.autograd.Function):
              C.byref(nbytes))
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)   # kept alive for the backward
         call("gsb_composite_fwd", dev, C.c_int32(width), C.c_int32(height), C.c_int32(CH), C.c_int64(N),
-             ptr(means2d_c), ptr(conics_c), ptr(colors_c), ptr(opac_c), ptr(bg_c), ptr(offsets), ptr(flatten_ids),
+             ptr(means2d_c), ptr(conics_c), ptr(colors_c), ptr(opac_c), C.c_int32(0), None, ptr(bg_c), ptr(offsets),
+             ptr(flatten_ids),
              C.c_int64(M), ptr(render), ptr(alphas), ptr(last_ids), ptr(ws), C.c_size_t(ws.numel()), stream_ptr(dev))
         ctx.save_for_backward(colors_c, offsets, alphas, last_ids, ws)
         ctx.bg = bg_c

@@ -16,6 +16,7 @@ from typing import List, Optional, Sequence, Tuple, Union
 import torch
 from torch import Tensor
 
+from .fused import splat_view
 from .mgadapter import tone_mapping_naive
 from .rasterization import Projected, rasterization_begin, rasterization_end
 from .scenes import PinholeCamera
@@ -99,10 +100,22 @@ class RenderableAttrs:
 
     def splat(self, gsplat: GSplatter, cameras, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
               min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-              culling: bool = False) -> Tensor:
+              culling: bool = False, fused: bool = True) -> Tensor:
         """geosplat.py:53-132.  `envmap` is this library's EnvStack (splitsum.as_envstack(cubemap) or
-        EnvStack.from_splitsum(TextureSplitSum fields)); `fg_lut` is `_get_fg_lut(256, device)`."""
+        EnvStack.from_splitsum(TextureSplitSum fields)); `fg_lut` is `_get_fg_lut(256, device)`.
+
+        With culling=False and tone_type 'naive' / 'none' (what GeoSplatter.render_report uses) the whole view is
+        one autograd node over the C-ABI kernels (fused.splat_view); `fused=False`, culling or 'aces' take the
+        stage-by-stage operators below -- same kernels, same results, more host work."""
         camera = _single_camera(cameras)
+        if fused and not culling and tone_type in ("naive", "none") and exposure.numel() == 1:
+            if gsplat.sh_degree != 0:
+                raise NotImplementedError("geosplatting_b200.GSplatter: sh_degree must be 0 (GeoSplatter, geosplat.py:794)")
+            g = gsplat.gaussians
+            return splat_view(g.means, g.scales, g.quats, g.opacities, self.kd, self.ks, self.normals, camera,
+                              exposure=exposure, envmap=envmap, fg_lut=fg_lut, min_roughness=min_roughness,
+                              max_metallic=max_metallic, mode=mode, tone_type=tone_type,
+                              rasterize_mode=gsplat.rasterize_mode)
         cam_pos = camera.c2w[:, 3]
         if culling:
             with torch.no_grad():

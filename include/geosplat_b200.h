@@ -62,11 +62,16 @@ int gsb_project_fwd(int32_t N, const float *means, const float *quats, const flo
                     float *comps, int32_t *tiles_per_gauss, void *stream);
 
 /* VJP of gsb_project_fwd.  v_depths may be NULL; v_comps is ignored in classic mode (may be NULL).
- * Writes (not accumulates) v_means[N,3] v_quats[N,4] v_scales[N,3]; culled rows get zeros. */
+ * Writes (not accumulates) v_means[N,3] v_quats[N,4] v_scales[N,3]; culled rows get zeros.
+ * Fused opacity activation (all three NULL to disable): when gsb_composite_fwd was given opacity logits and comps,
+ * pass the logits and gsb_composite_bwd's v_opacities here; the kernel adds d(opacity)/d(comp) to v_comps and writes
+ * v_opacity_logits[N] (the backward of torch.sigmoid(opacities) * compensations, rfstudio/model/gsplat.py:338 +
+ * gsplat rendering.py). */
 int gsb_project_bwd(int32_t N, const float *means, const float *quats, const float *scales,
                     const gsb_camera *cam, const int32_t *radii, const float *v_means2d,
                     const float *v_depths, const float *v_conics, const float *v_comps, float *v_means,
-                    float *v_quats, float *v_scales, void *stream);
+                    float *v_quats, float *v_scales, const float *opacity_logits, const float *v_opacities_eff,
+                    float *v_opacity_logits, void *stream);
 
 /* Bytes of scratch the scan / sort calls below need for N Gaussians and up to M intersections. */
 int gsb_bin_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host);
@@ -100,15 +105,20 @@ int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, int32_t h
 
 /* Front-to-back alpha compositing of one camera (gsplat rasterize_to_pixels_fwd).  Per-Gaussian inputs [N,.]
  * are indexed by flatten_ids.  channels in {1,2,3,4,8,16}.  background[channels] may be NULL.
+ * The opacity a Gaussian composites with is (opacity_is_logit ? sigmoid(opacities[g]) : opacities[g]) *
+ * (comps ? comps[g] : 1): pass activated, compensated opacities with (0, NULL) -- gsplat's contract -- or the raw
+ * logits and gsb_project_fwd's comps to fuse rfstudio/model/gsplat.py:338 and gsplat's `opacities * compensations`.
  * -> render[H,W,channels] alphas[H,W] last_ids[H,W] (position of the last contributor in the tile list).
  * `workspace` is filled here and must be handed UNCHANGED to gsb_composite_bwd of the same view. */
 int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
-                      const float *conics, const float *colors, const float *opacities, const float *background,
-                      const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render, float *alphas,
-                      int32_t *last_ids, void *workspace, size_t workspace_bytes, void *stream);
+                      const float *conics, const float *colors, const float *opacities, int32_t opacity_is_logit,
+                      const float *comps, const float *background, const int32_t *offsets,
+                      const int32_t *flatten_ids, int64_t M, float *render, float *alphas, int32_t *last_ids,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* VJP of gsb_composite_fwd (gsplat rasterize_to_pixels_bwd).  ACCUMULATES into v_means2d[N,2] v_conics[N,3]
- * v_colors[N,channels] v_opacities[N]: the caller zero-fills them. */
+ * v_colors[N,channels] v_opacities[N]: the caller zero-fills them.  v_opacities is the gradient w.r.t. the opacity
+ * the Gaussian composited with (after any fused activation; gsb_project_bwd finishes that chain). */
 int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
                       const float *background, const int32_t *offsets, int64_t M, const float *alphas,
                       const int32_t *last_ids, const float *v_render, const float *v_alphas, float *v_means2d,
@@ -237,6 +247,15 @@ int gsb_tonemap_fwd(int64_t P, const float *rgba, const float *exposure, float *
 /* VJP: writes v_rgba[P,4], ACCUMULATES into v_exposure[1]. */
 int gsb_tonemap_bwd(int64_t P, const float *rgba, const float *exposure, const float *v_out, float *v_rgba,
                     float *v_exposure, void *stream);
+
+
+/* The same two, fed by the rasterizer's own outputs render[P,3] / alphas[P] instead of a concatenated image
+ * (torch.cat at rfstudio/model/gsplat.py:358).  naive != 0: _tone_mapping_naive; naive == 0: tone_type 'none'
+ * (rgb * exposure, geosplat.py:124).  out / v_out are [P,4]; v_exposure[1] is ACCUMULATED. */
+int gsb_tonemap_planar_fwd(int64_t P, const float *render, const float *alphas, const float *exposure,
+                           int32_t naive, float *out, void *stream);
+int gsb_tonemap_planar_bwd(int64_t P, const float *render, const float *exposure, int32_t naive,
+                           const float *v_out, float *v_render, float *v_alphas, float *v_exposure, void *stream);
 
 #ifdef __cplusplus
 }

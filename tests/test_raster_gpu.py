@@ -148,3 +148,48 @@ def test_idempotent_and_deterministic_forward():
     r2, a2, i2, _ = _run_gpu(g, cam, "antialiased")
     assert np.array_equal(r1, r2) and np.array_equal(a1, a2)
     assert torch.equal(i1["flatten_ids"], i2["flatten_ids"])
+
+
+@pytest.mark.parametrize("D", [1, 4, 14])
+def test_wide_channel_backward(D):
+    """D-channel feature splat (the D=14 G-buffer of rfstudio/model/geosplat.py:276-295 is padded to 16 channels):
+    forward and every gradient against the C oracle's composite."""
+    g = scenes.random_gaussians(3_000, seed=13, scale_lo=0.02, scale_hi=0.12)
+    cam = scenes.look_at_camera((0.9, 0.6, 2.1), 112, 80)
+    rng = np.random.default_rng(5)
+    feats = rng.uniform(-1, 1, size=(3_000, D)).astype(np.float32)
+    gn = to_np(g)
+    ocam = oracle_camera(cam)
+    _, o_alpha3, o_info = R.rasterization(gn["means"], gn["quats"], gn["scales"], gn["opacities"], gn["colors"], ocam,
+                                          rasterize_mode="classic")
+    o_render, o_alpha, o_last = R.composite_fwd(o_info["means2d"], o_info["conics"], feats[o_info["gaussian_ids"]],
+                                                o_info["opacities"], o_info["isect_offsets"][0], o_info["flatten_ids"],
+                                                cam.width, cam.height)
+    vr = rng.normal(size=(cam.height, cam.width, D)).astype(np.float32)
+    va = rng.normal(size=(cam.height, cam.width)).astype(np.float32)
+    frag = o_info["fragile"]
+    vr[frag] = 0
+    va[frag] = 0
+    o_g = R.composite_bwd(o_info["means2d"], o_info["conics"], feats[o_info["gaussian_ids"]], o_info["opacities"],
+                          o_info["isect_offsets"][0], o_info["flatten_ids"], cam.width, cam.height, o_alpha, o_last,
+                          vr, va)
+    t = {k: v.to(DEV) for k, v in g.items()}
+    f = torch.from_numpy(feats).to(DEV).requires_grad_(True)
+    op = t["opacities"].clone().requires_grad_(True)
+    vm = torch.from_numpy(cam.view_matrix)[None].to(DEV)
+    K = torch.from_numpy(cam.intrinsic_matrix)[None].to(DEV)
+    render, alpha, info = rasterization(t["means"], t["quats"], t["scales"], op, f, vm, K, cam.width, cam.height,
+                                        rasterize_mode="classic")
+    ok = ~frag
+    assert render.shape == (1, cam.height, cam.width, D)
+    assert np.abs(render[0].detach().cpu().numpy() - o_render)[ok].max() <= 1e-4
+    loss = (render[0] * torch.from_numpy(vr).to(DEV)).sum() + (alpha[0, ..., 0] * torch.from_numpy(va).to(DEV)).sum()
+    v_f, v_op = torch.autograd.grad(loss, [f, op])
+    gids = o_info["gaussian_ids"]
+    o_v_colors, o_v_opac = o_g[2], o_g[3]
+    full_c = np.zeros((3_000, D), np.float32)
+    full_c[gids] = o_v_colors
+    full_o = np.zeros(3_000, np.float32)
+    full_o[gids] = o_v_opac
+    assert rel_l2(v_f.cpu().numpy(), full_c) <= 2e-4
+    assert rel_l2(v_op.cpu().numpy(), full_o) <= 2e-4
