@@ -228,4 +228,11 @@ struct EnvStack {
     }
     __host__ __device__ __forceinline__ long long base_offset() const { return level_offset(L); }
     __host__ __device__ __forceinline__ long long total_texels() const { return level_offset(L) + 6LL * Rb * Rb; }
+    // First texel of the "hot" tail: the coarse levels (resolution <= 32, at most 6144 texels each) and the base.
+    // Every Gaussian with a high roughness lands its texel gradients there, hundreds to thousands per texel.
+    __host__ __device__ __forceinline__ long long hot_begin() const {
+        int l = 0;
+        while (l < L && (R0 >> l) > 32) ++l;
+        return level_offset(l);
+    }
 };

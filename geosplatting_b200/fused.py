@@ -19,7 +19,7 @@ from torch import Tensor
 from ._lib import call, f32c, ptr, stream_ptr
 from .rasterization import BinCount, bin_finish, make_camera
 from .scenes import PinholeCamera
-from .shade import MODES, EnvStack
+from .shade import MODES, EnvStack, shade_workspace
 
 
 class ViewMeta(NamedTuple):
@@ -136,11 +136,12 @@ class _SplatView(torch.autograd.Function):
         v_kd = torch.empty(N, 3, dtype=torch.float32, device=dev)
         v_ks = torch.empty(N, 2, dtype=torch.float32, device=dev)
         v_env = torch.zeros_like(env)
+        sws = shade_workspace(dev, meta.R0, meta.L, meta.Rb)
         call("gsb_shade_bwd", dev, C.c_int32(N), ptr(means), ptr(normals), ptr(kd), ptr(ks), cam_pos, ptr(lut),
              C.c_int32(lut.shape[0]), ptr(env), C.c_int32(meta.R0), C.c_int32(meta.L), C.c_int32(meta.Rb),
              C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
              C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(v_colors), ptr(v_means_s), ptr(v_normals),
-             ptr(v_kd), ptr(v_ks), ptr(v_env), st)
+             ptr(v_kd), ptr(v_ks), ptr(v_env), ptr(sws), C.c_size_t(sws.numel()), st)
         v_means.add_(v_means_s)                                          # via the projection and via the view vector
         return (v_means, v_scales, v_quats, v_logits.view(logits_shape), v_kd, v_ks, v_normals, v_env,
                 v_exp.reshape(exposure_shape), None, None, None)

@@ -154,13 +154,19 @@ int gsb_shade_fwd(int32_t N, const float *means, const float *normals, const flo
                   int32_t R0, int32_t L, int32_t Rb, float min_roughness, float max_metallic,
                   float env_min_roughness, float env_max_roughness, int32_t mode, float *colors, void *stream);
 
+/* Bytes of scratch gsb_shade_bwd can use: private copies of the coarse env levels' gradients (their few thousand
+ * texels take the gradients of every rough Gaussian; same-address reductions serialise in L2). */
+int gsb_shade_workspace_bytes(int32_t R0, int32_t L, int32_t Rb, size_t *bytes_host);
+
 /* VJP of gsb_shade_fwd.  Writes v_means/v_normals/v_kd/v_ks; ACCUMULATES texel gradients into
- * v_env_stack (same layout as env_stack; lets one buffer collect all views of a step). */
+ * v_env_stack (same layout as env_stack; lets one buffer collect all views of a step).  `workspace` (16-byte
+ * aligned, gsb_shade_workspace_bytes) may be NULL: every texel gradient then goes straight to v_env_stack. */
 int gsb_shade_bwd(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
                   const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack,
                   int32_t R0, int32_t L, int32_t Rb, float min_roughness, float max_metallic,
                   float env_min_roughness, float env_max_roughness, int32_t mode, const float *v_colors,
-                  float *v_means, float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, void *stream);
+                  float *v_means, float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, void *workspace,
+                  size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone texture sampling: replaces nvdiffrast.torch.texture (third-party, unpinned, README.md:36)
