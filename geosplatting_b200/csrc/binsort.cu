@@ -2,6 +2,7 @@
 // offsets.  Integer/byte work, HBM-bound; the sort is cub::DeviceRadixSort restricted to the live key
 // bits (32 depth bits + tile bits + camera bits), as gsplat 1.4.0 isect_tiles/isect_offset_encode do.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include "gsb_common.cuh"
@@ -107,6 +108,142 @@ extern "C" __attribute__((visibility("default"))) int gsb_isect_offsets(int64_t 
     GSB_CHECK_ARG(sorted_isect_ids != nullptr);
     isect_offsets_kernel<<<gsb_div_up(M, 256), 256, 0, (cudaStream_t)stream>>>(
         M, sorted_isect_ids, total, n_tiles, gsb_tile_bits(n_tiles), offsets);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+// ---- two-stage binning ----------------------------------------------------------------------------------------
+// The single sort above moves M 12-byte pairs through ceil((32 + tile bits) / 8) = 6 radix passes.  Sorting the N
+// Gaussians by depth first (4 passes over N 8-byte pairs) and then the M (tile id, Gaussian) pairs by tile id alone
+// (2 passes over M 8-byte pairs, stable) produces the identical order with about a third of the traffic, and never
+// materialises the 64-bit keys.
+
+struct OrderedTiles {
+    const int32_t *tiles_per_gauss;
+    const int32_t *order;
+    __host__ __device__ __forceinline__ int64_t operator()(const int32_t &i) const {
+        return (int64_t)tiles_per_gauss[order[i]];
+    }
+};
+
+__global__ void __launch_bounds__(256) iota_kernel(int N, int32_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = i;
+}
+
+static size_t depth_sort_temp_bytes(int32_t N) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int)N, 0, 32);
+    return b;
+}
+
+static size_t ordered_scan_temp_bytes(int32_t N) {
+    size_t b = 0;
+    thrust::transform_iterator<OrderedTiles, thrust::counting_iterator<int32_t>, int64_t> in(
+        thrust::counting_iterator<int32_t>(0), OrderedTiles{nullptr, nullptr});
+    cub::DeviceScan::InclusiveSum((void *)nullptr, b, in, (int64_t *)nullptr, (int)N);
+    return b;
+}
+
+static size_t tile_sort_temp_bytes(int64_t M) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, M, 0, 32);
+    return b;
+}
+
+extern "C" __attribute__((visibility("default"))) int gsb_bin2_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host) {
+    GSB_CHECK_ARG(N >= 0 && M >= 0 && bytes_host != nullptr);
+    // count step: sorted depth keys [N] u32 + iota [N] + cub temp;  sort step: tile keys [M] + sorted tile keys [M] +
+    // unsorted Gaussian ids [M] + cub temp.  The two steps never overlap in time: take the larger.
+    size_t a = 2 * align256(sizeof(uint32_t) * (size_t)N) +
+               align256(depth_sort_temp_bytes(N) > ordered_scan_temp_bytes(N) ? depth_sort_temp_bytes(N)
+                                                                                : ordered_scan_temp_bytes(N));
+    size_t b = 3 * align256(sizeof(uint32_t) * (size_t)M) + align256(tile_sort_temp_bytes(M));
+    *bytes_host = (a > b ? a : b) + 256;
+    return GSB_OK;
+}
+
+// Depth order of the Gaussians (stable: ties keep ascending index), the prefix sum of tiles-per-Gaussian in that
+// order, and M published to *total_out (device or pinned host memory, see gsb_isect_total).
+extern "C" __attribute__((visibility("default"))) int gsb_bin2_count(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order,
+                              int64_t *cum_ordered, int64_t *total_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    GSB_CHECK_ARG(N >= 0 && total_out != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        GSB_CHECK_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+        return GSB_OK;
+    }
+    GSB_CHECK_ARG(depths && tiles_per_gauss && order && cum_ordered && workspace);
+    size_t need = 0;
+    GSB_CHECK_ARG(gsb_bin2_workspace_bytes(N, 0, &need) == GSB_OK);
+    if (need > workspace_bytes) {
+        gsb_set_error("gsb_bin2_count: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GSB_ENOMEM;
+    }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)N);
+    int32_t *iota = reinterpret_cast<int32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)N);
+    void *temp = p;
+    iota_kernel<<<gsb_div_up(N, 256), 256, 0, st>>>(N, iota);
+    // depths of visible Gaussians are positive floats (>= near plane): their bit patterns order like the values;
+    // culled Gaussians carry depth 0 and emit nothing.
+    size_t tb = depth_sort_temp_bytes(N);
+    GSB_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, reinterpret_cast<const uint32_t *>(depths), keys_sorted,
+                                                   iota, order, (int)N, 0, 32, st));
+    thrust::transform_iterator<OrderedTiles, thrust::counting_iterator<int32_t>, int64_t> in(
+        thrust::counting_iterator<int32_t>(0), OrderedTiles{tiles_per_gauss, order});
+    tb = ordered_scan_temp_bytes(N);
+    GSB_CHECK_CUDA(cub::DeviceScan::InclusiveSum(temp, tb, in, cum_ordered, (int)N, st));
+    isect_total_kernel<<<1, 1, 0, st>>>(N, cum_ordered, total_out);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+__global__ void __launch_bounds__(256) tile_offsets_kernel(int64_t M, const uint32_t *__restrict__ tile_keys, int n_tiles,
+                                                            int32_t *__restrict__ offsets) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int cur = (int)tile_keys[i];
+    int prev = (i == 0) ? -1 : (int)tile_keys[i - 1];
+    for (int id = prev + 1; id <= cur; ++id) offsets[id] = (int32_t)i;
+    if (i == M - 1)
+        for (int id = cur + 1; id < n_tiles; ++id) offsets[id] = (int32_t)M;
+}
+
+// Emission in depth order, stable sort by tile id, per-tile offsets.  -> flatten_ids[M], offsets[tile_w * tile_h]:
+// bit-identical to gsb_isect_tiles + gsb_sort_pairs + gsb_isect_offsets.
+extern "C" __attribute__((visibility("default"))) int gsb_bin2_sort(int32_t N, int64_t M, const float *means2d, const int32_t *radii, const int32_t *order,
+                             const int64_t *cum_ordered, const gsb_camera *cam, int32_t *flatten_ids,
+                             int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && M >= 0 && cam != nullptr && offsets != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tile_w = (cam->width + GSB_TILE - 1) / GSB_TILE, tile_h = (cam->height + GSB_TILE - 1) / GSB_TILE;
+    const int n_tiles = tile_w * tile_h;
+    if (M == 0 || N == 0) {
+        GSB_CHECK_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)n_tiles, st));
+        return GSB_OK;
+    }
+    GSB_CHECK_ARG(means2d && radii && order && cum_ordered && flatten_ids && workspace);
+    size_t need = 0;
+    GSB_CHECK_ARG(gsb_bin2_workspace_bytes(0, M, &need) == GSB_OK);
+    if (need > workspace_bytes) {
+        gsb_set_error("gsb_bin2_sort: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GSB_ENOMEM;
+    }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)M);
+    uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)M);
+    int32_t *gids = reinterpret_cast<int32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)M);
+    void *temp = p;
+    int rc = gsb_isect_tiles_ordered(N, means2d, radii, order, cum_ordered, cam, keys, gids, stream);
+    if (rc != GSB_OK) return rc;
+    size_t tb = tile_sort_temp_bytes(M);
+    GSB_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_sorted, gids, flatten_ids, M, 0,
+                                                   gsb_tile_bits(n_tiles), st));
+    tile_offsets_kernel<<<gsb_div_up(M, 256), 256, 0, st>>>(M, keys_sorted, n_tiles, offsets);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -70,6 +70,46 @@ __global__ void __launch_bounds__(256) isect_tiles_kernel(int N, const float2 *_
         }
 }
 
+// Two-stage binning, emission step: thread i handles the i-th Gaussian IN DEPTH ORDER and writes the ids of the tiles
+// it touches (row-major) and its own index.  A stable sort of these pairs by tile id alone then yields exactly the
+// order of a stable sort on (tile | depth) of Gaussian-major pairs: depth ties keep ascending Gaussian index in
+// both (gsb_isect_tiles + gsb_sort_pairs is that single-sort path).
+__global__ void __launch_bounds__(256) isect_tiles_ordered_kernel(int N, const float2 *__restrict__ means2d,
+                                                                   const int32_t *__restrict__ radii,
+                                                                   const int32_t *__restrict__ order,
+                                                                   const int64_t *__restrict__ cum_ordered, CamK cam,
+                                                                   uint32_t *__restrict__ tile_keys,
+                                                                   int32_t *__restrict__ gauss_ids) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int g = order[i];
+    int r = radii[g];
+    if (r <= 0) return;
+    float2 m = means2d[g];
+    int x0, x1, y0, y1;
+    gsb_tile_range(m.x, m.y, r, cam.tile_w, cam.tile_h, x0, x1, y0, y1);
+    int64_t pos = (i == 0) ? 0 : cum_ordered[i - 1];
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            tile_keys[pos] = (uint32_t)(y * cam.tile_w + x);
+            gauss_ids[pos] = g;
+            ++pos;
+        }
+}
+
+extern "C" __attribute__((visibility("default"))) int gsb_isect_tiles_ordered(int32_t N, const float *means2d, const int32_t *radii,
+                                       const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam,
+                                       uint32_t *tile_keys, int32_t *gauss_ids, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && cam != nullptr);
+    if (N == 0) return GSB_OK;
+    GSB_CHECK_ARG(means2d && radii && order && cum_ordered && tile_keys && gauss_ids);
+    CamK k = gsb_make_cam(cam);
+    isect_tiles_ordered_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+        N, reinterpret_cast<const float2 *>(means2d), radii, order, cum_ordered, k, tile_keys, gauss_ids);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int gsb_project_fwd(int32_t N, const float *means, const float *quats, const float *scales,
                                const gsb_camera *cam, int32_t *radii, float *means2d, float *depths,
                                float *conics, float *comps, int32_t *tiles_per_gauss, void *stream) {

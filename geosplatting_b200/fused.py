@@ -68,7 +68,7 @@ class _SplatView(torch.autograd.Function):
         radii, tpg = ibuf[:N], ibuf[N:]
         call("gsb_project_fwd", dev, C.c_int32(N), ptr(means_c), ptr(quats_c), ptr(scales), C.byref(cam), ptr(radii),
              ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tpg), st)
-        count = BinCount(tpg)                                  # M is on its way to the host ...
+        count = BinCount(tpg, depths)                          # M is on its way to the host ...
 
         colors = torch.empty(N, 3, dtype=torch.float32, device=dev)
         call("gsb_shade_fwd", dev, C.c_int32(N), ptr(means_c), ptr(normals_c), ptr(kd_c), ptr(ks_c), cam_pos, ptr(lut),
@@ -76,7 +76,7 @@ class _SplatView(torch.autograd.Function):
              C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
              C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(colors), st)
 
-        _, flatten_ids, offsets = bin_finish(count, means2d, radii, depths, cam)   # ... and is awaited only here
+        flatten_ids, offsets = bin_finish(count, means2d, radii, cam)       # ... and is awaited only here
         M = flatten_ids.shape[0]
         render = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
         alphas = torch.empty(H, W, dtype=torch.float32, device=dev)

@@ -7,7 +7,7 @@ include/geosplat_b200.h.  There is no CPU path: CPU tensors raise.
 
 Stage split (each an autograd Function over one C-ABI call pair):
     _Project   : gsb_project_fwd / gsb_project_bwd          (EWA projection, packed=True semantics)
-    bin_sort   : gsb_isect_scan + gsb_isect_tiles + gsb_sort_pairs + gsb_isect_offsets   (no grad)
+    binning    : gsb_bin2_count + gsb_bin2_sort (depth order of the Gaussians, then a stable sort by tile; no grad)
     _Composite : gsb_composite_fwd / gsb_composite_bwd      (alpha compositing)
 """
 from __future__ import annotations
@@ -115,25 +115,25 @@ def _total_slot(device: torch.device) -> Tensor:
 
 
 class BinCount:
-    """First half of the binning: the prefix sum of tiles-per-Gaussian is queued and M = cum[-1] is on its way
-    to a pinned host slot.  `total()` waits for it -- call it as late as possible so that other work queued in
-    between (the shade) covers the wait."""
+    """First half of the binning (two-stage scheme, gsb_bin2_*): the depth order of the Gaussians and the prefix sum
+    of tiles-per-Gaussian in that order are queued, and M is on its way to a pinned host slot.  `total()` waits for
+    it -- call it as late as possible so that other work queued in between (the shade) covers the wait."""
 
-    def __init__(self, tiles_per_gauss: Tensor):
+    def __init__(self, tiles_per_gauss: Tensor, depths: Tensor):
         dev = tiles_per_gauss.device
         self.N = N = tiles_per_gauss.shape[0]
-        self.cum = None
+        self.order = self.cum = None
         self._M = 0 if N == 0 else None
         if N == 0:
             return
         nbytes = C.c_size_t(0)
-        call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
+        call("gsb_bin2_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
         ws = _workspace(dev, nbytes.value)
-        st = stream_ptr(dev)
+        self.order = torch.empty(N, dtype=torch.int32, device=dev)
         self.cum = torch.empty(N, dtype=torch.int64, device=dev)
-        call("gsb_isect_scan", dev, C.c_int32(N), ptr(tiles_per_gauss), ptr(self.cum), ptr(ws), C.c_size_t(ws.numel()), st)
         self._slot = _total_slot(dev)
-        call("gsb_isect_total", dev, C.c_int32(N), ptr(self.cum), C.c_void_p(self._slot.data_ptr()), st)
+        call("gsb_bin2_count", dev, C.c_int32(N), ptr(depths), ptr(tiles_per_gauss), ptr(self.order), ptr(self.cum),
+             C.c_void_p(self._slot.data_ptr()), ptr(ws), C.c_size_t(ws.numel()), stream_ptr(dev))
         self._event = torch.cuda.Event()
         self._event.record(torch.cuda.current_stream(dev))
 
@@ -144,27 +144,70 @@ class BinCount:
         return self._M
 
 
-def bin_finish(count: BinCount, means2d: Tensor, radii: Tensor, depths: Tensor, cam: GsbCamera, n_cameras: int = 1):
-    """Second half: key emission, radix sort, per-tile offsets.
-    -> (isect_ids[M] i64 sorted, flatten_ids[M] i32 (Gaussian index), isect_offsets[n_cameras,th,tw] i32)."""
+def bin_finish(count: BinCount, means2d: Tensor, radii: Tensor, cam: GsbCamera):
+    """Second half: (tile, Gaussian) pairs emitted in depth order, stable sort by tile, per-tile offsets.
+    -> (flatten_ids[M] i32 (Gaussian index), isect_offsets[1,th,tw] i32); bit-identical to `bin_sort`."""
+    dev = means2d.device
+    N = means2d.shape[0]
+    tw = (cam.width + TILE - 1) // TILE
+    th = (cam.height + TILE - 1) // TILE
+    offsets = torch.empty(th * tw, dtype=torch.int32, device=dev)
+    M = count.total()
+    flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
+    if M == 0:
+        offsets.zero_()
+        return flatten_ids, offsets.view(1, th, tw)
+    nbytes = C.c_size_t(0)
+    call("gsb_bin2_workspace_bytes", dev, C.c_int32(0), C.c_int64(M), C.byref(nbytes))
+    ws = _workspace(dev, nbytes.value)
+    call("gsb_bin2_sort", dev, C.c_int32(N), C.c_int64(M), ptr(means2d), ptr(radii), ptr(count.order), ptr(count.cum),
+         C.byref(cam), ptr(flatten_ids), ptr(offsets), ptr(ws), C.c_size_t(ws.numel()), stream_ptr(dev))
+    return flatten_ids, offsets.view(1, th, tw)
+
+
+def isect_ids_from_lists(flatten_ids: Tensor, offsets: Tensor, depths: Tensor) -> Tensor:
+    """The sorted 64-bit keys gsplat exposes as info['isect_ids'] (tile << 32 | bits(depth)), rebuilt from the sorted
+    lists; the two-stage binning never materialises them."""
+    M = flatten_ids.shape[0]
+    flat = offsets.reshape(-1).long()
+    counts = torch.diff(torch.cat((flat, flat.new_tensor([M]))))
+    tile = torch.repeat_interleave(torch.arange(flat.shape[0], device=flat.device), counts)
+    dbits = depths.detach().contiguous().view(torch.int32)[flatten_ids.long()].long() & 0xFFFFFFFF
+    return (tile << 32) | dbits
+
+
+def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, cam: GsbCamera,
+             n_cameras: int = 1):
+    """gsplat's own stage split (isect_tiles -> one radix sort on the 64-bit (camera | tile | depth) keys ->
+    isect_offset_encode): -> (isect_ids[M] i64 sorted, flatten_ids[M] i32, isect_offsets[n_cameras,th,tw] i32).
+    `rasterization` uses the two-stage scheme above; this path is kept as the stage-faithful reference for it."""
     dev = means2d.device
     N = means2d.shape[0]
     tw = (cam.width + TILE - 1) // TILE
     th = (cam.height + TILE - 1) // TILE
     st = stream_ptr(dev)
     offsets = torch.empty(n_cameras * th * tw, dtype=torch.int32, device=dev)
-    M = count.total()
+    M = 0
+    if N > 0:
+        nbytes = C.c_size_t(0)
+        call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(0), C.byref(nbytes))
+        ws = _workspace(dev, nbytes.value)
+        cum = torch.empty(N, dtype=torch.int64, device=dev)
+        call("gsb_isect_scan", dev, C.c_int32(N), ptr(tiles_per_gauss), ptr(cum), ptr(ws), C.c_size_t(ws.numel()), st)
+        slot = _total_slot(dev)
+        call("gsb_isect_total", dev, C.c_int32(N), ptr(cum), C.c_void_p(slot.data_ptr()), st)
+        torch.cuda.current_stream(dev).synchronize()
+        M = int(slot[0])
     if M == 0:
         offsets.zero_()
         e64 = torch.empty(0, dtype=torch.int64, device=dev)
         return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets.view(n_cameras, th, tw)
     keys = torch.empty(M, dtype=torch.int64, device=dev)
     vals = torch.empty(M, dtype=torch.int32, device=dev)
-    call("gsb_isect_tiles", dev, C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(count.cum), C.byref(cam),
+    call("gsb_isect_tiles", dev, C.c_int32(N), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C.byref(cam),
                               ptr(keys), ptr(vals), st)
     keys_s = torch.empty_like(keys)
     vals_s = torch.empty_like(vals)
-    nbytes = C.c_size_t(0)
     call("gsb_bin_workspace_bytes", dev, C.c_int32(N), C.c_int64(M), C.byref(nbytes))
     ws = _workspace(dev, nbytes.value)
     n_tiles = tw * th
@@ -175,14 +218,6 @@ def bin_finish(count: BinCount, means2d: Tensor, radii: Tensor, depths: Tensor, 
     call("gsb_isect_offsets", dev, C.c_int64(M), ptr(keys_s), C.c_int32(n_cameras), C.c_int32(tw), C.c_int32(th),
                                 ptr(offsets), st)
     return keys_s, vals_s, offsets.view(n_cameras, th, tw)
-
-
-def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, cam: GsbCamera,
-             n_cameras: int = 1):
-    """-> (isect_ids[M] i64 sorted, flatten_ids[M] i32 (Gaussian index), isect_offsets[th,tw] i32).
-
-    One host wait (for M), like gsplat's `isect_tiles`."""
-    return bin_finish(BinCount(tiles_per_gauss), means2d, radii, depths, cam, n_cameras)
 
 
 class _Composite(torch.autograd.Function):
@@ -303,7 +338,7 @@ def rasterization_begin(means: Tensor, quats: Tensor, scales: Tensor, viewmats: 
         cam = make_camera(vm_host[c], k_host[c], width, height, near_plane=near_plane, far_plane=far_plane,
                           eps2d=eps2d, radius_clip=radius_clip, antialiased=aa, camera_id=0)
         means2d, depths, conics, comps, radii, tpg = _Project.apply(means, quats, scales, cam)
-        st.cams.append((cam, means2d, depths, conics, comps, radii, tpg, BinCount(tpg)))
+        st.cams.append((cam, means2d, depths, conics, comps, radii, tpg, BinCount(tpg, depths.detach())))
     return st
 
 
@@ -334,7 +369,7 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
         feats_p, D = _pad_channels(feats)
         if bg is not None and feats_p.shape[1] != bg.shape[0]:
             bg = torch.cat((bg, bg.new_zeros(feats_p.shape[1] - bg.shape[0])))
-        isect_ids, flatten_ids, offsets = bin_finish(count, means2d.detach(), radii, depths.detach(), cam)
+        flatten_ids, offsets = bin_finish(count, means2d.detach(), radii, cam)
         render, alpha = _Composite.apply(means2d, conics, feats_p, opac, bg, offsets.view(-1), flatten_ids,
                                          width, height)
         render = render[..., :D]
@@ -342,7 +377,7 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
             render = torch.cat((render[..., :-1], render[..., -1:] / alpha[..., None].clamp(min=1e-10)), dim=-1)
         renders.append(render)
         alphas_out.append(alpha[..., None])
-        per_cam.append((means2d, depths, conics, comps, radii, tpg, opac, isect_ids, flatten_ids, offsets))
+        per_cam.append((means2d, depths, conics, comps, radii, tpg, opac, None, flatten_ids, offsets))
 
     render = renders[0][None] if Cn == 1 else torch.stack(renders, 0)
     alpha = alphas_out[0][None] if Cn == 1 else torch.stack(alphas_out, 0)
@@ -376,7 +411,8 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
     def isect_ids_all():
         tw, th = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
         tile_bits = int(math.floor(math.log2(tw * th))) + 1
-        return torch.cat([pc[7] | (c << (32 + tile_bits)) for c, pc in enumerate(per_cam)])
+        return torch.cat([isect_ids_from_lists(pc[8], pc[9], pc[1]) | (c << (32 + tile_bits))
+                          for c, pc in enumerate(per_cam)])
 
     def offsets_all():
         out, base = [], 0

@@ -100,6 +100,24 @@ int gsb_sort_pairs(int64_t M, int32_t key_bits, const int64_t *keys_in, const in
 int gsb_isect_offsets(int64_t M, const int64_t *sorted_isect_ids, int32_t n_cameras, int32_t tile_w,
                       int32_t tile_h, int32_t *offsets, void *stream);
 
+/* ---- Two-stage binning: the same flatten_ids / offsets as the three calls above, without the 64-bit keys ----------
+ * gsb_bin2_count : stable depth order of the N Gaussians (order[N]), prefix sum of tiles-per-Gaussian in that order
+ *                  (cum_ordered[N]), and M stored to *total_out (device or pinned host memory, see gsb_isect_total);
+ * gsb_bin2_sort  : (tile id, Gaussian) pairs emitted in depth order, stable radix sort on the tile id alone,
+ *                  per-tile offsets -> flatten_ids[M], offsets[tile_w*tile_h].
+ * A stable sort by tile of depth-ordered pairs equals a stable sort by (tile | depth) of Gaussian-major pairs, ties
+ * included; 4 radix passes over N pairs + 2 over M instead of 6 over M.  One camera per call. */
+int gsb_bin2_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host);
+int gsb_bin2_count(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order,
+                   int64_t *cum_ordered, int64_t *total_out, void *workspace, size_t workspace_bytes, void *stream);
+int gsb_bin2_sort(int32_t N, int64_t M, const float *means2d, const int32_t *radii, const int32_t *order,
+                  const int64_t *cum_ordered, const gsb_camera *cam, int32_t *flatten_ids, int32_t *offsets,
+                  void *workspace, size_t workspace_bytes, void *stream);
+/* The emission step of gsb_bin2_sort on its own (tile_keys[M] u32, gauss_ids[M]). */
+int gsb_isect_tiles_ordered(int32_t N, const float *means2d, const int32_t *radii, const int32_t *order,
+                            const int64_t *cum_ordered, const gsb_camera *cam, uint32_t *tile_keys,
+                            int32_t *gauss_ids, void *stream);
+
 /* Bytes of scratch gsb_composite_fwd needs (per-Gaussian records + per-(tile, 8x4 sub-rectangle) lists). */
 int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, int32_t height, size_t *bytes_host);
 

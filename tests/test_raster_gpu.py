@@ -193,3 +193,29 @@ def test_wide_channel_backward(D):
     full_o[gids] = o_v_opac
     assert rel_l2(v_f.cpu().numpy(), full_c) <= 2e-4
     assert rel_l2(v_op.cpu().numpy(), full_o) <= 2e-4
+
+
+def test_two_stage_binning_equals_single_sort():
+    """gsb_bin2_* (depth order of the Gaussians, then a stable sort by tile) against gsplat's own stage split (one radix
+    sort on the 64-bit tile|depth keys): identical lists, offsets and reconstructed keys -- with exact depth ties
+    (duplicated Gaussians), culled Gaussians and an empty scene."""
+    import sys
+    Rz = sys.modules["geosplatting_b200.rasterization"]
+    g = scenes.random_gaussians(6_000, seed=17, scale_lo=0.01, scale_hi=0.2)
+    g = {k: torch.cat((v, v[:1500])) for k, v in g.items()}          # 1500 exact duplicates -> depth ties
+    for cam in (scenes.look_at_camera((0.3, 0.2, 0.4), 200, 136, target=(0.0, 0.0, -1.0)),   # inside the cloud: culls
+                scenes.orbit_cameras(1, 256, 256, seed=3)[0]):
+        t = {k: v.to(DEV) for k, v in g.items()}
+        gcam = Rz.make_camera(cam.view_matrix, cam.intrinsic_matrix, cam.width, cam.height, antialiased=True)
+        means2d, depths, conics, comps, radii, tpg = Rz._Project.apply(t["means"], t["quats"], t["scales"], gcam)
+        keys_s, vals_s, offs_s = Rz.bin_sort(means2d, radii, depths, tpg, gcam)
+        count = Rz.BinCount(tpg, depths)
+        flat, offs = Rz.bin_finish(count, means2d, radii, gcam)
+        assert count.total() == vals_s.shape[0] > 7_500
+        assert torch.equal(flat, vals_s)
+        assert torch.equal(offs.reshape(-1), offs_s.reshape(-1))
+        assert torch.equal(Rz.isect_ids_from_lists(flat, offs, depths), keys_s)
+    empty = torch.zeros(0, dtype=torch.int32, device=DEV)
+    count = Rz.BinCount(empty, torch.zeros(0, device=DEV))
+    flat, offs = Rz.bin_finish(count, torch.zeros(0, 2, device=DEV), empty, gcam)
+    assert flat.numel() == 0 and int(offs.abs().max()) == 0
