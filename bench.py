@@ -40,8 +40,8 @@ def parse_args():
     ap.add_argument("--mesh-n", type=int, default=118, help="cube-sphere subdivision: 72*n*n Gaussians (118 -> 1.0M)")
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--light-res", type=int, default=512, help="env cube-map resolution (GeoSplatter.light_resolution)")
-    ap.add_argument("--views", type=int, default=8, help="distinct cameras cycled through per rank (batch size 8)")
-    ap.add_argument("--allreduce-every", type=int, default=8, help="views per gradient all-reduce when N > 1")
+    ap.add_argument("--views", type=int, default=8, help="batch: distinct cameras per rank, forwarded then back-propagated together (the trainer's batch of 8); one gradient all-reduce per batch when N > 1")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a batch are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")
@@ -109,7 +109,11 @@ class ClockSampler:
 def algorithmic_bytes(N, Nv, M, P, T, key_bits):
     """Per-launch algorithmic bytes."""
     p = (key_bits + 7) // 8
+    tp = ((T.bit_length()) + 7) // 8          # radix passes over the tile id alone (two-stage binning)
     return {
+        # two-stage binning: 4 passes over N (key,index) pairs + ordered scan | emission + tp passes over M pairs + offsets
+        "gsb_bin2_count": 16 * 4 * N + 16 * N, "gsb_bin2_sort": 12 * N + 12 * Nv + 8 * M + 16 * tp * M + 4 * M + 4 * T,
+        "gsb_tonemap_planar_fwd": 32 * P, "gsb_tonemap_planar_bwd": 44 * P,
         "gsb_shade_fwd": 56 * N, "gsb_shade_bwd": 68 * N + 44 * N,
         "gsb_project_fwd": 44 * N + 40 * Nv, "gsb_project_bwd": 120 * Nv + 44 * N,
         "gsb_isect_tiles": 16 * Nv + 12 * M, "gsb_sort_pairs": 24 * p * M, "gsb_isect_offsets": 8 * M + 4 * T,
@@ -174,6 +178,8 @@ def run_b200(a):
     v_img = v_img_host.to(dev)
     stats = {}
 
+    from geosplatting_b200.fused import splat_views
+
     def render(p, env_, ex, cam):
         gs = GSplatter(gaussians=Splats(p["means"], p["scales"], p["quats"], p["normals"], p["opacities"]),
                        rasterize_mode="antialiased")
@@ -182,75 +188,116 @@ def run_b200(a):
 
     grad_inputs = [params[k] for k in PARAM_NAMES] + [env_data, exposure]
     bucket = GradientBucket([t.shape for t in grad_inputs], dev) if world > 1 else None
-    accum = [None]
+    B = max(1, a.views)                     # the reference's batch: 8 views per step of the trainer
 
-    def step(i):
-        img = render(params, env, exposure, cams[i % len(cams)])
-        grads = torch.autograd.grad(img, grad_inputs, grad_outputs=v_img)
+    def run_views(i0, n):
+        """n consecutive views (steps) the way GeoSplatter.render_report + the trainer run a batch: all forwards,
+        then one backward over the sum (geosplat.py:869-879, geosplat_trainer.py:171-180) -- here with the views
+        spread over two CUDA streams (fused.splat_views) so that neighbouring views overlap on the device."""
+        cs = [cams[(i0 + j) % len(cams)] for j in range(n)]
+        imgs = splat_views(params["means"], params["scales"], params["quats"], params["opacities"], params["kd"],
+                           params["ks"], params["normals"], cs, exposures=exposure, envmap=env, fg_lut=lut,
+                           min_roughness=0.1, max_metallic=1.0, n_streams=a.streams)
+        grads = torch.autograd.grad(imgs, grad_inputs, grad_outputs=[v_img] * n)
         if world > 1:
-            if accum[0] is None:
-                accum[0] = [g.clone() for g in grads]
-            else:
-                torch._foreach_add_(accum[0], list(grads))
-            if (i + 1) % a.allreduce_every == 0:
-                bucket.pack(accum[0])      # waits for the previous collective, then one fused copy
-                bucket.all_reduce(average_over=a.allreduce_every * world, async_op=True)   # overlaps the next views
-                accum[0] = None
-        return img, grads
+            bucket.pack(list(grads))           # waits for the previous collective, then one fused copy
+            bucket.all_reduce(average_over=n * world, async_op=True)   # overlaps the next batch
+        return imgs, grads
+
+    batch_marks = []
+
+    def run_steps(k, marks=None):
+        i = 0
+        while i < k:
+            n = min(B, k - i)
+            flush.zero_()                      # L2 flush between batches (a view's own working set is ~4x L2)
+            if marks is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+                h0 = time.perf_counter()
+            run_views(i, n)
+            if marks is not None:
+                e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                marks.append((n, e0, e1, time.perf_counter() - h0))
+            i += n
+
+    def step(i):                               # one view at a time on the current stream (instrumented pass)
+        img = render(params, env, exposure, cams[i % len(cams)])
+        return img, torch.autograd.grad(img, grad_inputs, grad_outputs=v_img)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Working set per step (Gaussian state 76 MB + lists ~60 MB + env stack 34 MB) is comparable to the 126 MB L2,
-    # so flush L2 between iterations by writing a 256 MB buffer (outside every per-kernel event pair).
+    # One view touches ~400 MB (Gaussian state 76 MB, projection 48 MB, records 48 MB, lists ~60 MB, gradients
+    # 72 MB, env stack 34 MB x2) against a 126 MB L2, and two views are in flight at a time, so no view finds its
+    # inputs cached; on top of that a 256 MB write flushes L2 between batches.
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for i in range(a.warmup):
-        step(i)
-    accum[0] = None
+    n_warm = max(a.warmup, 2 * B)           # at least two full batches: the allocator must have seen a batch's peak
+    run_steps(n_warm)
+    if bucket is not None:
+        bucket.wait()
     barrier()
 
-    # ---- timed region: EXACTLY K steps, device-timed, per-kernel events on -----------------------------------
+    # ---- timed region: EXACTLY K steps (views), device-timed ----------------------------------------------------
+    DOMINANT = {"gsb_composite_fwd", "gsb_composite_bwd"}
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
-    _lib.CallStats.reset(timing=True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    if os.environ.get("BENCH_NO_LIVE"):
+        DOMINANT = set()
+    run_steps(B)                               # the sampler's start-up left the GPU idle for 0.3 s: clocks back up
+    if bucket is not None:
+        bucket.wait()
+    _lib.CallStats.reset(timing=DOMINANT)      # live events around the dominant kernels only (host cost matters)
     barrier()
     wall0 = time.perf_counter()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     t_begin.record()
-    for i in range(a.steps):
-        flush.zero_()
-        ev[i][0].record()
-        step(i)
-        ev[i][1].record()
+    run_steps(a.steps, batch_marks)
     if bucket is not None:
-        bucket.wait()                      # the last collective completes inside the timed region
+        bucket.wait()                          # the last collective completes inside the timed region
     t_end.record()
     barrier()
     wall = time.perf_counter() - wall0
-    total_ms = sum(s.elapsed_time(e) for s, e in ev)
-    if world > 1:
-        # with an asynchronous collective in flight the per-step events no longer add up to the region: use the
-        # region's own events minus the L2-flush writes (measured once, outside)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(a.steps):
-            flush.zero_()
-        f1.record()
-        torch.cuda.synchronize()
-        total_ms = max(total_ms, t_begin.elapsed_time(t_end) - f0.elapsed_time(f1))
-    durations = _lib.CallStats.durations_ms()
+    batches = {"views": [m[0] for m in batch_marks], "device_ms": [round(m[1].elapsed_time(m[2]), 3) for m in batch_marks],
+               "host_enqueue_ms": [round(m[3] * 1e3, 3) for m in batch_marks],
+               "cuda_mallocs_in_region": torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0}
+    live = _lib.CallStats.durations_ms()
     launches = _lib.CallStats.launches()
     clocks = sampler.stop() if rank == 0 else None
-    _lib.CallStats.reset(timing=False)
+    # the L2-flush writes are not part of a step: measure them once, outside, and take them off the region
+    n_flush = (a.steps + B - 1) // B
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_flush):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    total_ms = t_begin.elapsed_time(t_end) - f0.elapsed_time(f1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = a.steps * world / (total_ms_max / 1e3)
+
+    # ---- instrumented pass: the same K views one at a time on one stream, every entry point timed -------------
+    # (kernels of overlapping views share the SMs, so their isolated durations have to be measured sequentially)
+    for i in range(2):
+        step(i)
+    _lib.CallStats.reset(timing=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    torch.cuda.synchronize()
+    for i in range(a.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    seq_ms = sum(s_.elapsed_time(e_) for s_, e_ in ev)
+    durations = _lib.CallStats.durations_ms()
+    _lib.CallStats.reset(timing=False)
 
     # ---- end to end through the public API with HOST buffers ------------------------------------------------
     e2e = None
@@ -381,7 +428,7 @@ def run_b200(a):
         if calls == 0 or ms <= 0:
             continue
         avg_ms = ms / calls
-        per_kernel[k] = {"calls": calls, "avg_ms": round(avg_ms, 4), "share": round(ms / total_ms, 4)}
+        per_kernel[k] = {"calls": calls, "avg_ms": round(avg_ms, 4), "share": round(ms / seq_ms, 4)}
         if k in alg:
             gbs = alg[k] / (avg_ms * 1e-3) / 1e9
             per_kernel[k].update({"alg_bytes": alg[k], "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
@@ -394,7 +441,10 @@ def run_b200(a):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_kind,
                 "alg_bytes_per_launch": alg[dom], "avg_ms": per_kernel[dom]["avg_ms"],
-                "note": "the composite kernels are FP32/MUFU issue bound, not HBM bound (DESIGN.md section 4): "
+                "avg_ms_in_timed_region": (round(live[dom][1] / live[dom][0], 4) if dom in live and live[dom][0] else None),
+                "note": "avg_ms: the kernel alone (instrumented sequential pass of the same K views); "
+                        "avg_ms_in_timed_region: live events in the timed region, where the kernels of two views share "
+                        "the SMs.  The composite kernels are FP32/MUFU issue bound, not HBM bound (DESIGN.md section 4): "
                         "a tile's 16x16 pixels each evaluate every listed Gaussian",
                 "pix_gauss_evals_upper_per_launch": 256.0 * M}
 
@@ -402,13 +452,15 @@ def run_b200(a):
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": round(total_ms_max / a.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": a.warmup, "warmup_views_run": n_warm, "ms_per_step": round(total_ms_max / a.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "gaussians": N, "visible": Nv, "intersections": M,
                        "resolution": [W, H], "views_per_rank": len(cams),
-                       "l2": "flushed between steps (256 MB write)",
+                       "batch": f"{B} views forwarded, then back-propagated together, spread over {a.streams} CUDA streams",
+                       "l2": "per-view working set ~400 MB (inputs 110 MB) vs 126 MB L2; 256 MB flush write between batches",
                        "parallelism": f"views sharded over {world} rank(s)" +
-                                      (f", 1 NCCL all-reduce of {bucket.nbytes} B per {a.allreduce_every} views" if bucket else "")},
+                                      (f", 1 NCCL all-reduce of {bucket.nbytes} B per {B} views" if bucket else "")},
+            "sequential_ms_per_view": round(seq_ms / a.steps, 4), "batches": batches,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
             "wall_s_timed_region": round(wall, 3), "impl": "b200",
         }

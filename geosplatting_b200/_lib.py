@@ -66,12 +66,12 @@ class CallStats:
                "gsb_composite_workspace_bytes": 0, "gsb_specular_workspace_bytes": 0, "gsb_specular_cubemap_fwd": 3,
                "gsb_specular_cubemap_bwd": 3, "gsb_composite_fwd": 4, "gsb_composite_bwd": 2, "gsb_shade_bwd": 2,
                "gsb_shade_workspace_bytes": 0, "gsb_vertex_normals_fwd": 2, "gsb_vertex_normals_bwd": 2}
-    timing = False
+    timing = False        # False, True (every entry point) or a set of entry-point names
     counts: dict = {}
     events: dict = {}
 
     @classmethod
-    def reset(cls, timing: bool = False) -> None:
+    def reset(cls, timing=False) -> None:
         cls.timing = timing
         cls.counts = {}
         cls.events = {}
@@ -91,7 +91,7 @@ def call(name: str, dev: torch.device, *args) -> None:
     """Invoke C-ABI entry point `name` on `dev`'s current stream; raise on a non-zero return code."""
     fn = getattr(load(), name)
     CallStats.counts[name] = CallStats.counts.get(name, 0) + 1
-    if CallStats.timing:
+    if CallStats.timing is True or (CallStats.timing and name in CallStats.timing):
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record(torch.cuda.current_stream(dev))

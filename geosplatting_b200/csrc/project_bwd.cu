@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     const float *__restrict__ v_depths, const float *__restrict__ v_conics, const float *__restrict__ v_comps,
     float *__restrict__ v_means, float *__restrict__ v_quats, float *__restrict__ v_scales,
     const float *__restrict__ opacity_logits, const float *__restrict__ v_opacities_eff,
-    float *__restrict__ v_opacity_logits) {
+    float *__restrict__ v_opacity_logits, int accumulate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float vm3[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
@@ -132,6 +132,13 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
         vq[2] = (vqn2 - d * qy) * inv;
         vq[3] = (vqn3 - d * qz) * inv;
     }
+    if (accumulate) {   // several views of a batch collect in one buffer (same stream: plain read-modify-write)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { vm3[k] += v_means[3 * i + k]; vs[k] += v_scales[3 * i + k]; }
+        float4 q0 = reinterpret_cast<const float4 *>(v_quats)[i];
+        vq[0] += q0.x; vq[1] += q0.y; vq[2] += q0.z; vq[3] += q0.w;
+        if (v_opacity_logits) v_logit += v_opacity_logits[i];
+    }
     v_means[3 * i] = vm3[0]; v_means[3 * i + 1] = vm3[1]; v_means[3 * i + 2] = vm3[2];
     reinterpret_cast<float4 *>(v_quats)[i] = make_float4(vq[0], vq[1], vq[2], vq[3]);
     v_scales[3 * i] = vs[0]; v_scales[3 * i + 1] = vs[1]; v_scales[3 * i + 2] = vs[2];
@@ -142,7 +149,8 @@ extern "C" __attribute__((visibility("default"))) int gsb_project_bwd(int32_t N,
                                const gsb_camera *cam, const int32_t *radii, const float *v_means2d,
                                const float *v_depths, const float *v_conics, const float *v_comps,
                                float *v_means, float *v_quats, float *v_scales, const float *opacity_logits,
-                               const float *v_opacities_eff, float *v_opacity_logits, void *stream) {
+                               const float *v_opacities_eff, float *v_opacity_logits, int32_t accumulate,
+                               void *stream) {
     GSB_CHECK_ARG(N >= 0 && cam != nullptr);
     if (N == 0) return GSB_OK;
     GSB_CHECK_ARG(means && quats && scales && radii && v_means2d && v_conics && v_means && v_quats && v_scales);
@@ -152,7 +160,7 @@ extern "C" __attribute__((visibility("default"))) int gsb_project_bwd(int32_t N,
     CamK k = gsb_make_cam(cam);
     project_bwd_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
         N, means, quats, scales, k, radii, reinterpret_cast<const float2 *>(v_means2d), v_depths, v_conics,
-        v_comps, v_means, v_quats, v_scales, opacity_logits, v_opacities_eff, v_opacity_logits);
+        v_comps, v_means, v_quats, v_scales, opacity_logits, v_opacities_eff, v_opacity_logits, accumulate);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(int N, const float *__re
                                                          float *__restrict__ v_means, float *__restrict__ v_normals,
                                                          float *__restrict__ v_kd, float *__restrict__ v_ks,
                                                          float *__restrict__ v_env_stack, float *__restrict__ replicas,
-                                                         long long hot_begin, long long hot_texels) {
+                                                         long long hot_begin, long long hot_texels, int accumulate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     EnvGrad v_env{v_env_stack, replicas ? replicas + 4 * hot_texels * (blockIdx.x % SHADE_REPLICAS) : nullptr, hot_begin};
@@ -234,6 +234,16 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(int N, const float *__re
     float vm[3], vn[3], vkd[3], vks[2];
     ShadeFwd o;
     shade_one<true>(m, n, k3, k2, p, lut, env, o, vc, vm, vn, vkd, vks, v_env);
+    if (accumulate) {   // several views of a batch (and the projection's v_means) collect in one buffer
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vm[k] += v_means[3 * i + k];
+            vn[k] += v_normals[3 * i + k];
+            vkd[k] += v_kd[3 * i + k];
+        }
+        float2 k0 = reinterpret_cast<const float2 *>(v_ks)[i];
+        vks[0] += k0.x; vks[1] += k0.y;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         v_means[3 * i + k] = vm[k];
@@ -361,7 +371,7 @@ extern "C" __attribute__((visibility("default"))) int gsb_shade_bwd(
     const float *fg_lut, int32_t lut_res, const float *env_stack, int32_t R0, int32_t L, int32_t Rb,
     float min_roughness, float max_metallic, float env_min_roughness, float env_max_roughness, int32_t mode,
     const float *v_colors, float *v_means, float *v_normals, float *v_kd, float *v_ks, float *v_env_stack,
-    void *workspace, size_t workspace_bytes, void *stream) {
+    void *workspace, size_t workspace_bytes, int32_t accumulate, void *stream) {
     GSB_CHECK_ARG(N >= 0 && cam_pos_host && mode >= 0 && mode <= 2 && lut_res > 1 && L >= 2 && R0 > 0 && Rb > 0);
     if (N == 0) return GSB_OK;
     GSB_CHECK_ARG(means && normals && kd && ks && fg_lut && env_stack && v_colors);
@@ -384,7 +394,7 @@ extern "C" __attribute__((visibility("default"))) int gsb_shade_bwd(
     EnvStack e{env_stack, R0, L, Rb};
     shade_bwd_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
         N, means, normals, kd, ks, p, reinterpret_cast<const float2 *>(fg_lut), e, v_colors, v_means, v_normals,
-        v_kd, v_ks, v_env_stack, replicas, hot_begin, hot_texels);
+        v_kd, v_ks, v_env_stack, replicas, hot_begin, hot_texels, accumulate);
     GSB_CHECK_LAUNCH();
     if (replicas) {
         shade_replica_sum_kernel<<<gsb_div_up(hot_texels, 256), 256, 0, (cudaStream_t)stream>>>(

@@ -1,17 +1,26 @@
-"""One autograd node per view for the whole hot path of RenderableAttrs.splat (rfstudio/model/geosplat.py:53-132
-with culling=False): activations -> projection -> intersection count -> split-sum shade -> binning/sort ->
-compositing -> tone map, and the reverse chain in one backward.
+"""One autograd node for a whole batch of views of RenderableAttrs.splat (rfstudio/model/geosplat.py:53-132 with
+culling=False; the per-view loop of GeoSplatter.render_report, geosplat.py:869-879): activations -> projection ->
+intersection count -> split-sum shade -> binning/sort -> compositing -> tone map per view, and the reverse chain of
+every view in one backward.
 
 Same C-ABI kernels as the stage-by-stage operators (rasterization.py, shade.py, mgadapter.py) and the same results;
-what it removes is host work and glue kernels: one autograd node instead of ~15, no torch.cat / stack / slice copies
-of the image (gsb_tonemap_planar_*), sigmoid(opacity) * compensation folded into the record packing and its chain rule
-into gsb_project_bwd, one zero-fill for the four per-Gaussian gradient accumulators, cached camera structs.  At
-~1.3 ms of device time per view the host would otherwise be the bottleneck (scripts/host_overhead.py).
+what it removes is host work, glue kernels and idle SMs:
+  * one autograd node instead of ~15 per view; no torch.cat / stack / slice copies of the image
+    (gsb_tonemap_planar_*); sigmoid(opacity) * compensation folded into the record packing and its chain rule into
+    gsb_project_bwd; cached camera structs; exp(log-scales) once per batch;
+  * the views of a batch are spread round-robin over CUDA streams.  Every view is PREPARED (projection, count, shade)
+    before the first one waits for its intersection count, and binning / compositing -- forward and backward -- of
+    neighbouring views overlap on the device: the composite kernels end in a long, poorly occupied tail (one warp per
+    sub-list) that a second view fills;
+  * the backward kernels of the views on one stream ADD into that stream's gradient buffer (accumulate flag of
+    gsb_project_bwd / gsb_shade_bwd), so a batch costs one zero-fill and one add per stream instead of one add per
+    view and tensor in the autograd engine.
+At ~1.2 ms of device time per view the host would otherwise be the bottleneck (scripts/host_overhead.py).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import NamedTuple
+from typing import List, NamedTuple, Sequence
 
 import torch
 from torch import Tensor
@@ -48,120 +57,235 @@ def _camera_struct(camera: PinholeCamera, antialiased: bool):
     return hit
 
 
-class _SplatView(torch.autograd.Function):
+_side_streams: dict = {}
+
+
+def _streams(dev: torch.device, n: int) -> List[torch.cuda.Stream]:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _side_streams.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
+
+
+class _Shared:
+    """Per-batch inputs in kernel form (contiguous fp32, activated scales)."""
+    __slots__ = ("means", "quats", "scales", "logits", "kd", "ks", "normals", "env", "lut", "meta", "N", "dev")
+
+
+class _View:
+    """State of one view between prepare, finish and backward."""
+    __slots__ = ("cam", "cam_pos", "exposure", "means2d", "depths", "conics", "comps", "radii", "count", "colors",
+                 "offsets", "M", "render", "alphas", "last_ids", "ws", "stream")
+
+
+def _prepare(sh: _Shared, camera: PinholeCamera, exposure: Tensor) -> _View:
+    """Everything of a view that does not need M on the host: projection, intersection count in flight, shade."""
+    v = _View()
+    dev, N, meta = sh.dev, sh.N, sh.meta
+    v.cam, v.cam_pos = _camera_struct(camera, meta.antialiased)
+    v.exposure = f32c(exposure).reshape(1)
+    st = stream_ptr(dev)
+    fbuf = torch.empty(7 * N, dtype=torch.float32, device=dev)
+    v.means2d, v.depths = fbuf[:2 * N].view(N, 2), fbuf[2 * N:3 * N]
+    v.conics, v.comps = fbuf[3 * N:6 * N].view(N, 3), fbuf[6 * N:]
+    ibuf = torch.empty(2 * N, dtype=torch.int32, device=dev)
+    v.radii, tpg = ibuf[:N], ibuf[N:]
+    call("gsb_project_fwd", dev, C.c_int32(N), ptr(sh.means), ptr(sh.quats), ptr(sh.scales), C.byref(v.cam),
+         ptr(v.radii), ptr(v.means2d), ptr(v.depths), ptr(v.conics), ptr(v.comps), ptr(tpg), st)
+    v.count = BinCount(tpg, v.depths)                         # M is on its way to the host ...
+    v.colors = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    call("gsb_shade_fwd", dev, C.c_int32(N), ptr(sh.means), ptr(sh.normals), ptr(sh.kd), ptr(sh.ks), v.cam_pos,
+         ptr(sh.lut), C.c_int32(sh.lut.shape[0]), ptr(sh.env), C.c_int32(meta.R0), C.c_int32(meta.L), C.c_int32(meta.Rb),
+         C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
+         C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(v.colors), st)
+    return v
+
+
+def _finish(sh: _Shared, v: _View) -> Tensor:
+    """Binning, compositing, tone map of a prepared view (the host waits for M here)."""
+    dev, N, meta = sh.dev, sh.N, sh.meta
+    W, H = v.cam.width, v.cam.height
+    st = stream_ptr(dev)
+    flatten_ids, v.offsets = bin_finish(v.count, v.means2d, v.radii, v.cam)   # ... and is awaited only here
+    v.M = M = flatten_ids.shape[0]
+    v.count = None
+    v.render = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    v.alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
+    v.last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+    nbytes = C.c_size_t(0)
+    call("gsb_composite_workspace_bytes", dev, C.c_int64(N), C.c_int64(M), C.c_int32(W), C.c_int32(H), C.byref(nbytes))
+    v.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)          # kept alive for the backward
+    call("gsb_composite_fwd", dev, C.c_int32(W), C.c_int32(H), C.c_int32(3), C.c_int64(N), ptr(v.means2d),
+         ptr(v.conics), ptr(v.colors), ptr(sh.logits), C.c_int32(1), ptr(v.comps) if meta.antialiased else None, None,
+         ptr(v.offsets), ptr(flatten_ids), C.c_int64(M), ptr(v.render), ptr(v.alphas), ptr(v.last_ids), ptr(v.ws),
+         C.c_size_t(v.ws.numel()), st)
+    out = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
+    call("gsb_tonemap_planar_fwd", dev, C.c_int64(H * W), ptr(v.render), ptr(v.alphas), ptr(v.exposure),
+         C.c_int32(meta.naive_tonemap), ptr(out), st)
+    v.means2d = v.depths = v.conics = v.comps = None          # only radii / colors / lists are needed again
+    return out
+
+
+class _Grads:
+    """One stream's gradient buffer: [env 4T | quats 4N | ks 2N | means 3N | scales 3N | logits N | normals 3N | kd 3N]
+    (the float4 / float2 consumers first, so that every view is 16-byte aligned)."""
+
+    def __init__(self, N: int, T: int, dev):
+        self.flat = torch.zeros(4 * T + 19 * N, dtype=torch.float32, device=dev)
+        o = 0
+
+        def take(n):
+            nonlocal o
+            t = self.flat[o:o + n]
+            o += n
+            return t
+
+        self.env, self.quats, self.ks = take(4 * T), take(4 * N), take(2 * N)
+        self.means, self.scales, self.logits = take(3 * N), take(3 * N), take(N)
+        self.normals, self.kd = take(3 * N), take(3 * N)
+
+
+def _view_backward(sh: _Shared, v: _View, v_out: Tensor, g: _Grads, v_exp: Tensor) -> None:
+    dev, N, meta = sh.dev, sh.N, sh.meta
+    W, H = v.cam.width, v.cam.height
+    st = stream_ptr(dev)
+    v_out = f32c(v_out)
+    v_render = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    v_alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
+    call("gsb_tonemap_planar_bwd", dev, C.c_int64(H * W), ptr(v.render), ptr(v.exposure), C.c_int32(meta.naive_tonemap),
+         ptr(v_out), ptr(v_render), ptr(v_alphas), ptr(v_exp), st)
+    acc = torch.zeros(9 * N, dtype=torch.float32, device=dev)           # this view's four atomic accumulators
+    v_means2d, v_conics = acc[:2 * N], acc[2 * N:5 * N]
+    v_colors, v_opac = acc[5 * N:8 * N], acc[8 * N:]
+    call("gsb_composite_bwd", dev, C.c_int32(W), C.c_int32(H), C.c_int32(3), C.c_int64(N), ptr(v.colors), None,
+         ptr(v.offsets), C.c_int64(v.M), ptr(v.alphas), ptr(v.last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
+         ptr(v_conics), ptr(v_colors), ptr(v_opac), ptr(v.ws), st)
+    call("gsb_project_bwd", dev, C.c_int32(N), ptr(sh.means), ptr(sh.quats), ptr(sh.scales), C.byref(v.cam),
+         ptr(v.radii), ptr(v_means2d), None, ptr(v_conics), None, ptr(g.means), ptr(g.quats), ptr(g.scales),
+         ptr(sh.logits), ptr(v_opac), ptr(g.logits), C.c_int32(1), st)
+    sws = shade_workspace(dev, meta.R0, meta.L, meta.Rb)
+    call("gsb_shade_bwd", dev, C.c_int32(N), ptr(sh.means), ptr(sh.normals), ptr(sh.kd), ptr(sh.ks), v.cam_pos,
+         ptr(sh.lut), C.c_int32(sh.lut.shape[0]), ptr(sh.env), C.c_int32(meta.R0), C.c_int32(meta.L), C.c_int32(meta.Rb),
+         C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
+         C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(v_colors), ptr(g.means), ptr(g.normals),
+         ptr(g.kd), ptr(g.ks), ptr(g.env), ptr(sws), C.c_size_t(sws.numel()), C.c_int32(1), st)
+
+
+class _SplatBatch(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means, log_scales, quats, logits, kd, ks, normals, env_data, exposure, camera, lut, meta):
-        means_c, quats_c, kd_c, ks_c, normals_c = f32c(means), f32c(quats), f32c(kd), f32c(ks), f32c(normals)
-        env_c, exp_c = f32c(env_data), f32c(exposure).reshape(1)
-        dev = means_c.device
-        N = means_c.shape[0]
-        logit_c = f32c(logits).reshape(N)
-        scales = f32c(log_scales).exp()                       # rfstudio/model/gsplat.py:337
-        cam, cam_pos = _camera_struct(camera, meta.antialiased)
-        W, H = cam.width, cam.height
-        st = stream_ptr(dev)
-
-        fbuf = torch.empty(7 * N, dtype=torch.float32, device=dev)
-        means2d, depths = fbuf[:2 * N].view(N, 2), fbuf[2 * N:3 * N]
-        conics, comps = fbuf[3 * N:6 * N].view(N, 3), fbuf[6 * N:]
-        ibuf = torch.empty(2 * N, dtype=torch.int32, device=dev)
-        radii, tpg = ibuf[:N], ibuf[N:]
-        call("gsb_project_fwd", dev, C.c_int32(N), ptr(means_c), ptr(quats_c), ptr(scales), C.byref(cam), ptr(radii),
-             ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tpg), st)
-        count = BinCount(tpg, depths)                          # M is on its way to the host ...
-
-        colors = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        call("gsb_shade_fwd", dev, C.c_int32(N), ptr(means_c), ptr(normals_c), ptr(kd_c), ptr(ks_c), cam_pos, ptr(lut),
-             C.c_int32(lut.shape[0]), ptr(env_c), C.c_int32(meta.R0), C.c_int32(meta.L), C.c_int32(meta.Rb),
-             C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
-             C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(colors), st)
-
-        flatten_ids, offsets = bin_finish(count, means2d, radii, cam)       # ... and is awaited only here
-        M = flatten_ids.shape[0]
-        render = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
-        alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
-        last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
-        nbytes = C.c_size_t(0)
-        call("gsb_composite_workspace_bytes", dev, C.c_int64(N), C.c_int64(M), C.c_int32(W), C.c_int32(H),
-             C.byref(nbytes))
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)    # kept alive for the backward
-        call("gsb_composite_fwd", dev, C.c_int32(W), C.c_int32(H), C.c_int32(3), C.c_int64(N), ptr(means2d),
-             ptr(conics), ptr(colors), ptr(logit_c), C.c_int32(1), ptr(comps) if meta.antialiased else None, None,
-             ptr(offsets), ptr(flatten_ids), C.c_int64(M), ptr(render), ptr(alphas), ptr(last_ids), ptr(ws),
-             C.c_size_t(ws.numel()), st)
-        out = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
-        call("gsb_tonemap_planar_fwd", dev, C.c_int64(H * W), ptr(render), ptr(alphas), ptr(exp_c),
-             C.c_int32(meta.naive_tonemap), ptr(out), st)
-
-        ctx.save_for_backward(means_c, quats_c, scales, logit_c, kd_c, ks_c, normals_c, env_c, exp_c, lut, radii,
-                              colors, offsets, render, alphas, last_ids, ws)
-        ctx.misc = (cam, cam_pos, meta, M, tuple(logits.shape), tuple(exposure.shape))
-        return out
+    def forward(ctx, means, log_scales, quats, logits, kd, ks, normals, env_data, lut, meta, cameras, n_streams,
+                *exposures):
+        sh = _Shared()
+        sh.means, sh.quats, sh.kd, sh.ks, sh.normals = f32c(means), f32c(quats), f32c(kd), f32c(ks), f32c(normals)
+        sh.env, sh.lut, sh.meta = f32c(env_data), lut, meta
+        sh.dev = dev = sh.means.device
+        sh.N = N = sh.means.shape[0]
+        sh.logits = f32c(logits).reshape(N)
+        sh.scales = f32c(log_scales).exp()                    # rfstudio/model/gsplat.py:337, once per batch
+        main = torch.cuda.current_stream(dev)
+        side = _streams(dev, n_streams) if n_streams > 1 and len(cameras) > 1 else []
+        for s in side:
+            s.wait_stream(main)
+        where = [side[i % len(side)] if side else main for i in range(len(cameras))]
+        views = []
+        for cam, ex, s in zip(cameras, exposures, where):
+            with torch.cuda.stream(s):
+                v = _prepare(sh, cam, ex)
+                v.stream = s
+                views.append(v)
+        outs = []
+        for v in views:
+            with torch.cuda.stream(v.stream):
+                outs.append(_finish(sh, v))
+        for s in side:
+            main.wait_stream(s)
+        if side:
+            for o in outs:
+                o.record_stream(main)
+        ctx.sh, ctx.views, ctx.side = sh, views, side
+        ctx.shapes = (tuple(logits.shape), [tuple(e.shape) for e in exposures], env_data.shape[0])
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, v_out):
-        (means, quats, scales, logit, kd, ks, normals, env, exp_c, lut, radii, colors, offsets, render, alphas,
-         last_ids, ws) = ctx.saved_tensors
-        cam, cam_pos, meta, M, logits_shape, exposure_shape = ctx.misc
-        dev = means.device
-        N = means.shape[0]
-        W, H = cam.width, cam.height
-        st = stream_ptr(dev)
-        v_out = f32c(v_out)
-
-        v_render = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
-        v_alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
-        v_exp = torch.zeros(1, dtype=torch.float32, device=dev)
-        call("gsb_tonemap_planar_bwd", dev, C.c_int64(H * W), ptr(render), ptr(exp_c), C.c_int32(meta.naive_tonemap),
-             ptr(v_out), ptr(v_render), ptr(v_alphas), ptr(v_exp), st)
-
-        acc = torch.zeros(9 * N, dtype=torch.float32, device=dev)       # the four atomic accumulators, one fill
-        v_means2d, v_conics = acc[:2 * N], acc[2 * N:5 * N]
-        v_colors, v_opac = acc[5 * N:8 * N], acc[8 * N:]
-        call("gsb_composite_bwd", dev, C.c_int32(W), C.c_int32(H), C.c_int32(3), C.c_int64(N), ptr(colors), None,
-             ptr(offsets), C.c_int64(M), ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
-             ptr(v_conics), ptr(v_colors), ptr(v_opac), ptr(ws), st)
-
-        v_means = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        v_quats = torch.empty(N, 4, dtype=torch.float32, device=dev)
-        v_scales = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        v_logits = torch.empty(N, dtype=torch.float32, device=dev)
-        call("gsb_project_bwd", dev, C.c_int32(N), ptr(means), ptr(quats), ptr(scales), C.byref(cam), ptr(radii),
-             ptr(v_means2d), None, ptr(v_conics), None, ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(logit),
-             ptr(v_opac), ptr(v_logits), st)
-        v_scales.mul_(scales)                                            # d exp(s) / d s
-
-        v_means_s = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        v_normals = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        v_kd = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        v_ks = torch.empty(N, 2, dtype=torch.float32, device=dev)
-        v_env = torch.zeros_like(env)
-        sws = shade_workspace(dev, meta.R0, meta.L, meta.Rb)
-        call("gsb_shade_bwd", dev, C.c_int32(N), ptr(means), ptr(normals), ptr(kd), ptr(ks), cam_pos, ptr(lut),
-             C.c_int32(lut.shape[0]), ptr(env), C.c_int32(meta.R0), C.c_int32(meta.L), C.c_int32(meta.Rb),
-             C.c_float(meta.min_roughness), C.c_float(meta.max_metallic), C.c_float(meta.env_min_roughness),
-             C.c_float(meta.env_max_roughness), C.c_int32(meta.mode), ptr(v_colors), ptr(v_means_s), ptr(v_normals),
-             ptr(v_kd), ptr(v_ks), ptr(v_env), ptr(sws), C.c_size_t(sws.numel()), st)
-        v_means.add_(v_means_s)                                          # via the projection and via the view vector
-        return (v_means, v_scales, v_quats, v_logits.view(logits_shape), v_kd, v_ks, v_normals, v_env,
-                v_exp.reshape(exposure_shape), None, None, None)
+    def backward(ctx, *v_outs):
+        sh, views, side = ctx.sh, ctx.views, ctx.side
+        logits_shape, exposure_shapes, T = ctx.shapes
+        dev, N = sh.dev, sh.N
+        main = torch.cuda.current_stream(dev)
+        for s in side:
+            s.wait_stream(main)
+        bufs = {}
+        v_exps = []
+        for v, v_out in zip(views, v_outs):
+            if v_out is None:
+                v_exps.append(None)
+                continue
+            with torch.cuda.stream(v.stream):
+                g = bufs.get(v.stream)
+                if g is None:
+                    g = bufs[v.stream] = _Grads(N, T, dev)     # zero-filled once; every view on this stream adds
+                v_exp = torch.zeros(1, dtype=torch.float32, device=dev)
+                _view_backward(sh, v, v_out, g, v_exp)
+                v_exps.append(v_exp)
+        for s in side:
+            main.wait_stream(s)
+        if not bufs:
+            return (None,) * (12 + len(views))
+        gs = list(bufs.values())
+        total = gs[0]
+        for g in gs:
+            g.flat.record_stream(main)
+        for g in gs[1:]:
+            total.flat.add_(g.flat)                            # one add per extra stream for the whole batch
+        total.scales.mul_(sh.scales.reshape(-1))               # d exp(s) / d s
+        for e in v_exps:
+            if e is not None:
+                e.record_stream(main)
+        return (total.means.view(N, 3), total.scales.view(N, 3), total.quats.view(N, 4), total.logits.view(logits_shape),
+                total.kd.view(N, 3), total.ks.view(N, 2), total.normals.view(N, 3), total.env.view(T, 4), None, None,
+                None, None, *[None if e is None else e.reshape(shp) for e, shp in zip(v_exps, exposure_shapes)])
 
 
-def splat_view(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
-               normals: Tensor, camera: PinholeCamera, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
-               min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-               rasterize_mode: str = "antialiased") -> Tensor:
-    """[H,W,4] tone-mapped RGBA of one view; differentiable w.r.t. every tensor argument and `envmap.data`."""
+def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic, mode, tone_type, rasterize_mode):
     if mode not in MODES:
         raise ValueError(mode)
     if tone_type not in ("naive", "none"):
         raise ValueError(tone_type)
     if rasterize_mode not in ("antialiased", "classic"):
         raise ValueError(f"Unknown rasterize_mode: {rasterize_mode}")
-    if not means.is_cuda:
-        raise RuntimeError("geosplatting_b200.splat_view needs CUDA tensors; there is no CPU path")
     lut = f32c(fg_lut).reshape(fg_lut.shape[-3], fg_lut.shape[-2], 2)
     meta = ViewMeta(envmap.R0, envmap.L, envmap.Rb, envmap.min_roughness, envmap.max_roughness, float(min_roughness),
                     float(max_metallic), MODES[mode], rasterize_mode == "antialiased", int(tone_type == "naive"))
-    return _SplatView.apply(means, log_scales, quats, opacity_logits, kd, ks, normals, envmap.data, exposure, camera,
-                            lut, meta)
+    return meta, lut
+
+
+def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
+                normals: Tensor, cameras: Sequence[PinholeCamera], *, exposures, envmap: EnvStack, fg_lut: Tensor,
+                min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
+                rasterize_mode: str = "antialiased", n_streams: int = 3) -> List[Tensor]:
+    """The per-view loop of GeoSplatter.render_report for a batch of cameras: list of [H,W,4] tone-mapped RGBA images,
+    ready on the caller's stream, differentiable w.r.t. every tensor argument and `envmap.data`.
+
+    `exposures`: one tensor shared by all views or a sequence of one per view.  `n_streams` <= 1 keeps everything on
+    the caller's stream."""
+    if not means.is_cuda:
+        raise RuntimeError("geosplatting_b200.splat_views needs CUDA tensors; there is no CPU path")
+    meta, lut = _meta_and_lut(envmap, fg_lut, min_roughness, max_metallic, mode, tone_type, rasterize_mode)
+    cameras = list(cameras)
+    ex = [exposures] * len(cameras) if isinstance(exposures, Tensor) else list(exposures)
+    assert len(ex) == len(cameras)
+    if not cameras:
+        return []
+    return list(_SplatBatch.apply(means, log_scales, quats, opacity_logits, kd, ks, normals, envmap.data, lut, meta,
+                                  cameras, int(n_streams), *ex))
+
+
+def splat_view(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
+               normals: Tensor, camera: PinholeCamera, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
+               min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
+               rasterize_mode: str = "antialiased") -> Tensor:
+    """[H,W,4] tone-mapped RGBA of one view on the caller's stream (a batch of one)."""
+    return splat_views(means, log_scales, quats, opacity_logits, kd, ks, normals, [camera], exposures=exposure,
+                       envmap=envmap, fg_lut=fg_lut, min_roughness=min_roughness, max_metallic=max_metallic, mode=mode,
+                       tone_type=tone_type, rasterize_mode=rasterize_mode, n_streams=1)[0]

@@ -29,7 +29,9 @@ _workspaces: Dict[Tuple[int, int], Tensor] = {}
 
 
 def _workspace(device: torch.device, nbytes: int) -> Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    """Scan / sort scratch, one buffer per (device, stream): views on different streams run concurrently."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
@@ -99,7 +101,7 @@ class _Project(torch.autograd.Function):
         v_scales = torch.empty(N, 3, dtype=torch.float32, device=dev)
         call("gsb_project_bwd", dev, C.c_int32(N), ptr(means), ptr(quats), ptr(scales), C.byref(cam), ptr(radii),
                                   ptr(v_means2d), ptr(v_depths_c), ptr(v_conics), ptr(v_comps_c), ptr(v_means),
-                                  ptr(v_quats), ptr(v_scales), None, None, None, stream_ptr(dev))
+                                  ptr(v_quats), ptr(v_scales), None, None, None, C.c_int32(0), stream_ptr(dev))
         return v_means, v_quats, v_scales, None
 
 
@@ -107,9 +109,10 @@ _total_slots: Dict[int, list] = {}
 
 
 def _total_slot(device: torch.device) -> Tensor:
-    """A pinned host int64 the device writes M into (ring of 8 per device: a slot is read before it is reused)."""
+    """A pinned host int64 the device writes M into (ring of 64 per device: a slot is read before it is reused --
+    at most a batch of views is outstanding at a time)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
-    ring = _total_slots.setdefault(key, [[torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(8)], 0])
+    ring = _total_slots.setdefault(key, [[torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(64)], 0])
     ring[1] = (ring[1] + 1) % len(ring[0])
     return ring[0][ring[1]]
 

@@ -87,8 +87,9 @@ _shade_ws: dict = {}
 
 def shade_workspace(dev: torch.device, R0: int, L: int, Rb: int) -> Tensor:
     """Scratch for gsb_shade_bwd's private copies of the coarse env levels (zeroed by the call itself, so one
-    buffer per device and stack shape is shared by every view)."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), R0, L, Rb)
+    buffer per device, stream and stack shape is shared by every view on that stream)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream, R0, L, Rb)
     ws = _shade_ws.get(key)
     if ws is None:
         n = C.c_size_t(0)
@@ -129,7 +130,8 @@ class _Shade(torch.autograd.Function):
         call("gsb_shade_bwd", dev, C.c_int32(N), ptr(means), ptr(normals), ptr(kd), ptr(ks), ctx.cam, ptr(lut),
              C.c_int32(lut.shape[0]), ptr(stack), C.c_int32(R0), C.c_int32(L), C.c_int32(Rb), C.c_float(min_r),
              C.c_float(max_m), C.c_float(emin), C.c_float(emax), C.c_int32(mode), ptr(v_colors), ptr(v_means),
-             ptr(v_normals), ptr(v_kd), ptr(v_ks), ptr(v_stack), ptr(ws), C.c_size_t(ws.numel()), stream_ptr(dev))
+             ptr(v_normals), ptr(v_kd), ptr(v_ks), ptr(v_stack), ptr(ws), C.c_size_t(ws.numel()), C.c_int32(0),
+             stream_ptr(dev))
         return v_means, v_normals, v_kd, v_ks, v_stack, None, None, None
 
 

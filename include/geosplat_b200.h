@@ -62,7 +62,9 @@ int gsb_project_fwd(int32_t N, const float *means, const float *quats, const flo
                     float *comps, int32_t *tiles_per_gauss, void *stream);
 
 /* VJP of gsb_project_fwd.  v_depths may be NULL; v_comps is ignored in classic mode (may be NULL).
- * Writes (not accumulates) v_means[N,3] v_quats[N,4] v_scales[N,3]; culled rows get zeros.
+ * accumulate == 0: writes v_means[N,3] v_quats[N,4] v_scales[N,3] (and v_opacity_logits); culled rows get zeros.
+ * accumulate != 0: adds to them (plain read-modify-write: the views of a batch that share a buffer must be on one
+ * stream).
  * Fused opacity activation (all three NULL to disable): when gsb_composite_fwd was given opacity logits and comps,
  * pass the logits and gsb_composite_bwd's v_opacities here; the kernel adds d(opacity)/d(comp) to v_comps and writes
  * v_opacity_logits[N] (the backward of torch.sigmoid(opacities) * compensations, rfstudio/model/gsplat.py:338 +
@@ -71,7 +73,7 @@ int gsb_project_bwd(int32_t N, const float *means, const float *quats, const flo
                     const gsb_camera *cam, const int32_t *radii, const float *v_means2d,
                     const float *v_depths, const float *v_conics, const float *v_comps, float *v_means,
                     float *v_quats, float *v_scales, const float *opacity_logits, const float *v_opacities_eff,
-                    float *v_opacity_logits, void *stream);
+                    float *v_opacity_logits, int32_t accumulate, void *stream);
 
 /* Bytes of scratch the scan / sort calls below need for N Gaussians and up to M intersections. */
 int gsb_bin_workspace_bytes(int32_t N, int64_t M, size_t *bytes_host);
@@ -176,7 +178,8 @@ int gsb_shade_fwd(int32_t N, const float *means, const float *normals, const flo
  * texels take the gradients of every rough Gaussian; same-address reductions serialise in L2). */
 int gsb_shade_workspace_bytes(int32_t R0, int32_t L, int32_t Rb, size_t *bytes_host);
 
-/* VJP of gsb_shade_fwd.  Writes v_means/v_normals/v_kd/v_ks; ACCUMULATES texel gradients into
+/* VJP of gsb_shade_fwd.  Writes (accumulate == 0) or adds to (accumulate != 0, same-stream read-modify-write)
+ * v_means/v_normals/v_kd/v_ks; always ACCUMULATES texel gradients into
  * v_env_stack (same layout as env_stack; lets one buffer collect all views of a step).  `workspace` (16-byte
  * aligned, gsb_shade_workspace_bytes) may be NULL: every texel gradient then goes straight to v_env_stack. */
 int gsb_shade_bwd(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
@@ -184,7 +187,7 @@ int gsb_shade_bwd(int32_t N, const float *means, const float *normals, const flo
                   int32_t R0, int32_t L, int32_t Rb, float min_roughness, float max_metallic,
                   float env_min_roughness, float env_max_roughness, int32_t mode, const float *v_colors,
                   float *v_means, float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, void *workspace,
-                  size_t workspace_bytes, void *stream);
+                  size_t workspace_bytes, int32_t accumulate, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone texture sampling: replaces nvdiffrast.torch.texture (third-party, unpinned, README.md:36)
