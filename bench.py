@@ -15,6 +15,7 @@ timed region), so `scaling` is "weak".  Prints ONE JSON line; keys are documente
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -178,7 +179,7 @@ def run_b200(a):
     v_img = v_img_host.to(dev)
     stats = {}
 
-    from geosplatting_b200.fused import splat_views
+    from geosplatting_b200.fused import splat_view, splat_views
 
     def render(p, env_, ex, cam):
         gs = GSplatter(gaussians=Splats(p["means"], p["scales"], p["quats"], p["normals"], p["opacities"]),
@@ -220,8 +221,12 @@ def run_b200(a):
                 marks.append((n, e0, e1, time.perf_counter() - h0))
             i += n
 
-    def step(i):                               # one view at a time on the current stream (instrumented pass)
-        img = render(params, env, exposure, cams[i % len(cams)])
+    def step(i):
+        """One view at a time on the current stream, every kernel group launched from Python (native=False) so that
+        each C-ABI entry point can be bracketed by CUDA events: the instrumented pass."""
+        img = splat_view(params["means"], params["scales"], params["quats"], params["opacities"], params["kd"],
+                         params["ks"], params["normals"], cams[i % len(cams)], exposure=exposure, envmap=env, fg_lut=lut,
+                         min_roughness=0.1, max_metallic=1.0, native=False)
         return img, torch.autograd.grad(img, grad_inputs, grad_outputs=v_img)
 
     def barrier():
@@ -240,31 +245,32 @@ def run_b200(a):
     barrier()
 
     # ---- timed region: EXACTLY K steps (views), device-timed ----------------------------------------------------
-    DOMINANT = {"gsb_composite_fwd", "gsb_composite_bwd"}
     sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
+    if rank == 0:
         sampler.start()
-    if os.environ.get("BENCH_NO_LIVE"):
-        DOMINANT = set()
+    gc.collect()
     run_steps(B)                               # the sampler's start-up left the GPU idle for 0.3 s: clocks back up
     if bucket is not None:
         bucket.wait()
-    _lib.CallStats.reset(timing=DOMINANT)      # live events around the dominant kernels only (host cost matters)
+    _lib.CallStats.reset(timing=False)         # launch counters only: the timed region carries no per-kernel events
     barrier()
     wall0 = time.perf_counter()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+    # CPython's cyclic collector walks every live object when its generation-2 threshold trips (~30 ms with torch
+    # loaded): a stop-the-world pause longer than four views.  Nothing in a view creates reference cycles.
+    gc.disable()
     t_begin.record()
     run_steps(a.steps, batch_marks)
     if bucket is not None:
         bucket.wait()                          # the last collective completes inside the timed region
     t_end.record()
     barrier()
+    gc.enable()
     wall = time.perf_counter() - wall0
     batches = {"views": [m[0] for m in batch_marks], "device_ms": [round(m[1].elapsed_time(m[2]), 3) for m in batch_marks],
                "host_enqueue_ms": [round(m[3] * 1e3, 3) for m in batch_marks],
                "cuda_mallocs_in_region": torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0}
-    live = _lib.CallStats.durations_ms()
     launches = _lib.CallStats.launches()
     clocks = sampler.stop() if rank == 0 else None
     # the L2-flush writes are not part of a step: measure them once, outside, and take them off the region
@@ -356,12 +362,15 @@ def run_b200(a):
         barrier()
         upload(2)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()
         s.record()
         for i in range(2, 2 + n_e2e):
             e2e_step(i)
         s_cmp.wait_stream(s_out)                          # the last view's results have landed in host memory
         e.record()
         barrier()
+        gc.enable()
         te = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -441,11 +450,11 @@ def run_b200(a):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_kind,
                 "alg_bytes_per_launch": alg[dom], "avg_ms": per_kernel[dom]["avg_ms"],
-                "avg_ms_in_timed_region": (round(live[dom][1] / live[dom][0], 4) if dom in live and live[dom][0] else None),
-                "note": "avg_ms: the kernel alone (instrumented sequential pass of the same K views); "
-                        "avg_ms_in_timed_region: live events in the timed region, where the kernels of two views share "
-                        "the SMs.  The composite kernels are FP32/MUFU issue bound, not HBM bound (DESIGN.md section 4): "
-                        "a tile's 16x16 pixels each evaluate every listed Gaussian",
+                "note": "avg_ms: CUDA events around the entry point in the instrumented pass of bench.py (the same K views, "
+                        "one at a time on one stream, each kernel group launched from Python); in the timed region the "
+                        "kernels of up to three views share the SMs and a view is three native calls.  The composite "
+                        "kernels are FP32/MUFU issue bound, not HBM bound (DESIGN.md section 4): a tile's 16x16 pixels "
+                        "each evaluate every listed Gaussian",
                 "pix_gauss_evals_upper_per_launch": 256.0 * M}
 
     out = None

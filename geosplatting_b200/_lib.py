@@ -20,6 +20,18 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "geosplat_b200.h")
 _lib: Optional[C.CDLL] = None
 
 
+class GsbViewConfig(C.Structure):
+    """Mirror of `struct gsb_view_config` (include/geosplat_b200.h)."""
+
+    _fields_ = [
+        ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("lut_res", C.c_int32), ("R0", C.c_int32), ("L", C.c_int32), ("Rb", C.c_int32),
+        ("min_roughness", C.c_float), ("max_metallic", C.c_float),
+        ("env_min_roughness", C.c_float), ("env_max_roughness", C.c_float),
+        ("mode", C.c_int32), ("naive_tonemap", C.c_int32),
+    ]
+
+
 class GsbCamera(C.Structure):
     """Mirror of `struct gsb_camera` (include/geosplat_b200.h)."""
 
@@ -50,6 +62,12 @@ def load() -> C.CDLL:
                 "There is no CPU or PyTorch fallback for this path.")
         _lib = C.CDLL(LIB_PATH)
         _lib.gsb_last_error.restype = C.c_char_p
+        # the per-view driver is called with raw integers (tensor.data_ptr()): declare the pointer widths
+        vp, i64 = C.c_void_p, C.c_int64
+        _lib.gsb_view_bytes.argtypes = [vp, i64, vp]
+        _lib.gsb_view_prepare.argtypes = [vp] * 15
+        _lib.gsb_view_finish.argtypes = [vp, vp, i64] + [vp] * 8
+        _lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 24
     return _lib
 
 
@@ -65,7 +83,11 @@ class CallStats:
     KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0, "gsb_envstack_texels": 0,
                "gsb_composite_workspace_bytes": 0, "gsb_specular_workspace_bytes": 0, "gsb_specular_cubemap_fwd": 3,
                "gsb_specular_cubemap_bwd": 3, "gsb_composite_fwd": 4, "gsb_composite_bwd": 2, "gsb_shade_bwd": 2,
-               "gsb_shade_workspace_bytes": 0, "gsb_vertex_normals_fwd": 2, "gsb_vertex_normals_bwd": 2}
+               "gsb_shade_workspace_bytes": 0, "gsb_vertex_normals_fwd": 2, "gsb_vertex_normals_bwd": 2,
+               "gsb_bin2_workspace_bytes": 0, "gsb_bin2_count": 2, "gsb_bin2_sort": 2,
+               # the native per-view driver: prepare = project + iota + total + shade; finish = emit + offsets + pack +
+               # build + order + composite + tone map; backward = tone map + order + composite + project + shade + sum
+               "gsb_view_bytes": 0, "gsb_view_prepare": 4, "gsb_view_finish": 7, "gsb_view_backward": 6}
     timing = False        # False, True (every entry point) or a set of entry-point names
     counts: dict = {}
     events: dict = {}

@@ -25,8 +25,8 @@ from typing import List, NamedTuple, Sequence
 import torch
 from torch import Tensor
 
-from ._lib import call, f32c, ptr, stream_ptr
-from .rasterization import BinCount, bin_finish, make_camera
+from ._lib import GsbViewConfig, call, f32c, ptr, stream_ptr
+from .rasterization import BinCount, _total_slot, bin_finish, make_camera
 from .scenes import PinholeCamera
 from .shade import MODES, EnvStack, shade_workspace
 
@@ -102,7 +102,7 @@ def _prepare(sh: _Shared, camera: PinholeCamera, exposure: Tensor) -> _View:
     return v
 
 
-def _finish(sh: _Shared, v: _View) -> Tensor:
+def _finish(sh: _Shared, v: _View, out: Tensor) -> Tensor:
     """Binning, compositing, tone map of a prepared view (the host waits for M here)."""
     dev, N, meta = sh.dev, sh.N, sh.meta
     W, H = v.cam.width, v.cam.height
@@ -120,11 +120,78 @@ def _finish(sh: _Shared, v: _View) -> Tensor:
          ptr(v.conics), ptr(v.colors), ptr(sh.logits), C.c_int32(1), ptr(v.comps) if meta.antialiased else None, None,
          ptr(v.offsets), ptr(flatten_ids), C.c_int64(M), ptr(v.render), ptr(v.alphas), ptr(v.last_ids), ptr(v.ws),
          C.c_size_t(v.ws.numel()), st)
-    out = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
     call("gsb_tonemap_planar_fwd", dev, C.c_int64(H * W), ptr(v.render), ptr(v.alphas), ptr(v.exposure),
          C.c_int32(meta.naive_tonemap), ptr(out), st)
     v.means2d = v.depths = v.conics = v.comps = None          # only radii / colors / lists are needed again
     return out
+
+
+# ---- native orchestration: three C-ABI calls per view (csrc/view.cu) -----------------------------------------------
+def _u8(n: int, dev) -> Tensor:
+    return torch.empty(n, dtype=torch.uint8, device=dev)
+
+
+def _view_config(sh: _Shared, cam) -> GsbViewConfig:
+    m = sh.meta
+    return GsbViewConfig(sh.N, cam.width, cam.height, sh.lut.shape[0], m.R0, m.L, m.Rb, m.min_roughness, m.max_metallic,
+                         m.env_min_roughness, m.env_max_roughness, m.mode, m.naive_tonemap)
+
+
+class _NativeView:
+    __slots__ = ("cam", "cam_pos", "cfg", "sizes", "exposure", "keep1", "tmp1", "keep2", "slot", "event", "M", "stream")
+
+
+def _prepare_native(sh: _Shared, camera: PinholeCamera, exposure: Tensor, cfgs: dict) -> _NativeView:
+    v = _NativeView()
+    dev = sh.dev
+    v.cam, v.cam_pos = _camera_struct(camera, sh.meta.antialiased)
+    v.exposure = f32c(exposure).reshape(1)
+    key = (v.cam.width, v.cam.height)
+    hit = cfgs.get(key)
+    if hit is None:
+        cfg = _view_config(sh, v.cam)
+        sizes = (C.c_size_t * 5)()
+        call("gsb_view_bytes", dev, C.addressof(cfg), 0, C.addressof(sizes))
+        hit = cfgs[key] = (cfg, tuple(sizes))
+    v.cfg, v.sizes = hit
+    v.keep1, v.tmp1 = _u8(v.sizes[0], dev), _u8(v.sizes[1], dev)
+    v.slot = _total_slot(dev)
+    stream = torch.cuda.current_stream(dev)
+    call("gsb_view_prepare", dev, C.addressof(v.cfg), C.addressof(v.cam), C.addressof(v.cam_pos), sh.means.data_ptr(),
+         sh.quats.data_ptr(), sh.scales.data_ptr(), sh.normals.data_ptr(), sh.kd.data_ptr(), sh.ks.data_ptr(),
+         sh.lut.data_ptr(), sh.env.data_ptr(), v.keep1.data_ptr(), v.tmp1.data_ptr(), v.slot.data_ptr(),
+         stream.cuda_stream)
+    v.event = torch.cuda.Event()
+    v.event.record(stream)
+    return v
+
+
+def _finish_native(sh: _Shared, v: _NativeView, out: Tensor) -> Tensor:
+    dev = sh.dev
+    v.event.synchronize()                                     # M was stored straight into pinned memory
+    v.M = M = int(v.slot[0])
+    v.event = v.slot = None
+    sizes = (C.c_size_t * 5)()
+    call("gsb_view_bytes", dev, C.addressof(v.cfg), M, C.addressof(sizes))
+    v.keep2 = _u8(sizes[2], dev)
+    tmp2 = _u8(sizes[3], dev)
+    call("gsb_view_finish", dev, C.addressof(v.cfg), C.addressof(v.cam), M, sh.logits.data_ptr(), v.exposure.data_ptr(),
+         v.keep1.data_ptr(), v.tmp1.data_ptr(), v.keep2.data_ptr(), tmp2.data_ptr(), out.data_ptr(),
+         torch.cuda.current_stream(dev).cuda_stream)
+    v.tmp1 = None
+    return out
+
+
+def _view_backward_native(sh: _Shared, v: _NativeView, v_out: Tensor, g: "_Grads", v_exp: Tensor) -> None:
+    dev = sh.dev
+    v_out = f32c(v_out)
+    tmp3 = _u8(v.sizes[4], dev)
+    call("gsb_view_backward", dev, C.addressof(v.cfg), C.addressof(v.cam), C.addressof(v.cam_pos), v.M,
+         sh.means.data_ptr(), sh.quats.data_ptr(), sh.scales.data_ptr(), sh.logits.data_ptr(), sh.normals.data_ptr(),
+         sh.kd.data_ptr(), sh.ks.data_ptr(), sh.lut.data_ptr(), sh.env.data_ptr(), v.exposure.data_ptr(),
+         v.keep1.data_ptr(), v.keep2.data_ptr(), tmp3.data_ptr(), v_out.data_ptr(), g.means.data_ptr(),
+         g.quats.data_ptr(), g.scales.data_ptr(), g.logits.data_ptr(), g.normals.data_ptr(), g.kd.data_ptr(),
+         g.ks.data_ptr(), g.env.data_ptr(), v_exp.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
 
 
 class _Grads:
@@ -175,7 +242,7 @@ def _view_backward(sh: _Shared, v: _View, v_out: Tensor, g: _Grads, v_exp: Tenso
 class _SplatBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, log_scales, quats, logits, kd, ks, normals, env_data, lut, meta, cameras, n_streams,
-                *exposures):
+                native, *exposures):
         sh = _Shared()
         sh.means, sh.quats, sh.kd, sh.ks, sh.normals = f32c(means), f32c(quats), f32c(kd), f32c(ks), f32c(normals)
         sh.env, sh.lut, sh.meta = f32c(env_data), lut, meta
@@ -185,25 +252,25 @@ class _SplatBatch(torch.autograd.Function):
         sh.scales = f32c(log_scales).exp()                    # rfstudio/model/gsplat.py:337, once per batch
         main = torch.cuda.current_stream(dev)
         side = _streams(dev, n_streams) if n_streams > 1 and len(cameras) > 1 else []
+        # what outlives the side streams' work (the images here, the gradient buffers in the backward) is allocated
+        # on the CALLER's stream before the side streams wait for it: the caching allocator then recycles it in plain
+        # stream order, with no record_stream() events that would delay reuse and grow the pool
+        outs = [torch.empty(c.height, c.width, 4, dtype=torch.float32, device=dev) for c in cameras]
         for s in side:
             s.wait_stream(main)
         where = [side[i % len(side)] if side else main for i in range(len(cameras))]
-        views = []
+        views, cfgs = [], {}
         for cam, ex, s in zip(cameras, exposures, where):
             with torch.cuda.stream(s):
-                v = _prepare(sh, cam, ex)
+                v = _prepare_native(sh, cam, ex, cfgs) if native else _prepare(sh, cam, ex)
                 v.stream = s
                 views.append(v)
-        outs = []
-        for v in views:
+        for v, out in zip(views, outs):
             with torch.cuda.stream(v.stream):
-                outs.append(_finish(sh, v))
+                (_finish_native if native else _finish)(sh, v, out)
         for s in side:
             main.wait_stream(s)
-        if side:
-            for o in outs:
-                o.record_stream(main)
-        ctx.sh, ctx.views, ctx.side = sh, views, side
+        ctx.sh, ctx.views, ctx.side, ctx.native = sh, views, side, native
         ctx.shapes = (tuple(logits.shape), [tuple(e.shape) for e in exposures], env_data.shape[0])
         return tuple(outs)
 
@@ -213,38 +280,36 @@ class _SplatBatch(torch.autograd.Function):
         logits_shape, exposure_shapes, T = ctx.shapes
         dev, N = sh.dev, sh.N
         main = torch.cuda.current_stream(dev)
+        v_exps = []
+        # one zero-filled gradient buffer per stream in use, every view on that stream adds into it (allocated on the
+        # caller's stream, see forward)
+        bufs = {v.stream: None for v, v_out in zip(views, v_outs) if v_out is not None}
+        for k in bufs:
+            bufs[k] = _Grads(N, T, dev)
+        v_exp_all = torch.zeros(len(views), dtype=torch.float32, device=dev)
         for s in side:
             s.wait_stream(main)
-        bufs = {}
-        v_exps = []
-        for v, v_out in zip(views, v_outs):
+        for i, (v, v_out) in enumerate(zip(views, v_outs)):
             if v_out is None:
                 v_exps.append(None)
                 continue
             with torch.cuda.stream(v.stream):
-                g = bufs.get(v.stream)
-                if g is None:
-                    g = bufs[v.stream] = _Grads(N, T, dev)     # zero-filled once; every view on this stream adds
-                v_exp = torch.zeros(1, dtype=torch.float32, device=dev)
-                _view_backward(sh, v, v_out, g, v_exp)
+                g = bufs[v.stream]
+                v_exp = v_exp_all[i:i + 1]
+                (_view_backward_native if ctx.native else _view_backward)(sh, v, v_out, g, v_exp)
                 v_exps.append(v_exp)
         for s in side:
             main.wait_stream(s)
         if not bufs:
-            return (None,) * (12 + len(views))
+            return (None,) * (13 + len(views))
         gs = list(bufs.values())
         total = gs[0]
-        for g in gs:
-            g.flat.record_stream(main)
         for g in gs[1:]:
             total.flat.add_(g.flat)                            # one add per extra stream for the whole batch
         total.scales.mul_(sh.scales.reshape(-1))               # d exp(s) / d s
-        for e in v_exps:
-            if e is not None:
-                e.record_stream(main)
         return (total.means.view(N, 3), total.scales.view(N, 3), total.quats.view(N, 4), total.logits.view(logits_shape),
                 total.kd.view(N, 3), total.ks.view(N, 2), total.normals.view(N, 3), total.env.view(T, 4), None, None,
-                None, None, *[None if e is None else e.reshape(shp) for e, shp in zip(v_exps, exposure_shapes)])
+                None, None, None, *[None if e is None else e.reshape(shp) for e, shp in zip(v_exps, exposure_shapes)])
 
 
 def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic, mode, tone_type, rasterize_mode):
@@ -263,12 +328,13 @@ def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic,
 def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
                 normals: Tensor, cameras: Sequence[PinholeCamera], *, exposures, envmap: EnvStack, fg_lut: Tensor,
                 min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-                rasterize_mode: str = "antialiased", n_streams: int = 3) -> List[Tensor]:
+                rasterize_mode: str = "antialiased", n_streams: int = 3, native: bool = True) -> List[Tensor]:
     """The per-view loop of GeoSplatter.render_report for a batch of cameras: list of [H,W,4] tone-mapped RGBA images,
     ready on the caller's stream, differentiable w.r.t. every tensor argument and `envmap.data`.
 
     `exposures`: one tensor shared by all views or a sequence of one per view.  `n_streams` <= 1 keeps everything on
-    the caller's stream."""
+    the caller's stream.  `native`: sequence the kernels of a view in the library's per-view driver (three C-ABI calls
+    per view, csrc/view.cu) rather than call by call from Python (what per-kernel instrumentation needs)."""
     if not means.is_cuda:
         raise RuntimeError("geosplatting_b200.splat_views needs CUDA tensors; there is no CPU path")
     meta, lut = _meta_and_lut(envmap, fg_lut, min_roughness, max_metallic, mode, tone_type, rasterize_mode)
@@ -278,14 +344,14 @@ def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits
     if not cameras:
         return []
     return list(_SplatBatch.apply(means, log_scales, quats, opacity_logits, kd, ks, normals, envmap.data, lut, meta,
-                                  cameras, int(n_streams), *ex))
+                                  cameras, int(n_streams), bool(native), *ex))
 
 
 def splat_view(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
                normals: Tensor, camera: PinholeCamera, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
                min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-               rasterize_mode: str = "antialiased") -> Tensor:
+               rasterize_mode: str = "antialiased", native: bool = True) -> Tensor:
     """[H,W,4] tone-mapped RGBA of one view on the caller's stream (a batch of one)."""
     return splat_views(means, log_scales, quats, opacity_logits, kd, ks, normals, [camera], exposures=exposure,
                        envmap=envmap, fg_lut=fg_lut, min_roughness=min_roughness, max_metallic=max_metallic, mode=mode,
-                       tone_type=tone_type, rasterize_mode=rasterize_mode, n_streams=1)[0]
+                       tone_type=tone_type, rasterize_mode=rasterize_mode, n_streams=1, native=native)[0]

@@ -284,6 +284,42 @@ int gsb_tonemap_planar_fwd(int64_t P, const float *render, const float *alphas, 
 int gsb_tonemap_planar_bwd(int64_t P, const float *render, const float *exposure, int32_t naive,
                            const float *v_out, float *v_render, float *v_alphas, float *v_exposure, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native per-view driver: one training view of RenderableAttrs.splat (rfstudio/model/geosplat.py:53-132, culling
+ * off, tone_type 'naive' / 'none') + GSplatter.render_rgba (rfstudio/model/gsplat.py:284-358) as three calls that
+ * sequence the stage entry points above on caller-provided arenas.  The host keeps three calls and a handful of
+ * allocations per view instead of ~40 framework calls; the kernels and the results are the same.
+ *   prepare  : projection, depth order + intersection count (M -> *total_out, device or pinned host), shade;
+ *   finish   : binning by tile, compositing, tone map -> out[H,W,4]        (needs M on the host);
+ *   backward : tone map / compositing / projection / shade VJPs; ADDS the per-Gaussian gradients, the env-stack
+ *              texel gradients and v_exposure[1] into the caller's buffers (the views of a batch that share them
+ *              must be on one stream; the caller zero-fills once per batch).  v_scales is w.r.t. the LINEAR scales.
+ * Arenas: gsb_view_bytes -> {keep1, tmp1, keep2, tmp2, tmp3}; keep1 lives prepare..backward, tmp1 prepare..finish,
+ * keep2 finish..backward, tmp2 inside finish, tmp3 inside backward (layouts: csrc/view.cu).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gsb_view_config {
+    int32_t N, width, height;
+    int32_t lut_res, R0, L, Rb;                 /* FG LUT resolution; env stack shape */
+    float min_roughness, max_metallic;          /* geosplat.py:85-86 */
+    float env_min_roughness, env_max_roughness; /* TextureSplitSum.min/max_roughness */
+    int32_t mode;                               /* 0 pbr, 1 diffuse, 2 specular */
+    int32_t naive_tonemap;                      /* 1: _tone_mapping_naive, 0: rgb * exposure */
+} gsb_view_config;
+
+int gsb_view_bytes(const gsb_view_config *cfg, int64_t M, size_t *bytes5_host);
+int gsb_view_prepare(const gsb_view_config *cfg, const gsb_camera *cam, const float *cam_pos_host, const float *means,
+                     const float *quats, const float *scales, const float *normals, const float *kd, const float *ks,
+                     const float *fg_lut, const float *env_stack, void *keep1, void *tmp1, int64_t *total_out,
+                     void *stream);
+int gsb_view_finish(const gsb_view_config *cfg, const gsb_camera *cam, int64_t M, const float *opacity_logits,
+                    const float *exposure, void *keep1, void *tmp1, void *keep2, void *tmp2, float *out, void *stream);
+int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const float *cam_pos_host, int64_t M,
+                      const float *means, const float *quats, const float *scales, const float *opacity_logits,
+                      const float *normals, const float *kd, const float *ks, const float *fg_lut,
+                      const float *env_stack, const float *exposure, const void *keep1, const void *keep2, void *tmp3,
+                      const float *v_out, float *v_means, float *v_quats, float *v_scales, float *v_opacity_logits,
+                      float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, float *v_exposure, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

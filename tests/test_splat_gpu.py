@@ -181,7 +181,7 @@ def test_multi_stream_batch_equals_sequential_views():
     cots = [torch.randn(192, 256, 4, generator=gen).to(DEV) for _ in cams]
     names = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
     results = []
-    for n_streams in (3, 2, 0):
+    for n_streams, native in ((3, True), (2, False), (1, True), (0, False)):
         t = {"means": sg["means"], "scales": sg["scales"].log(), "quats": sg["quats"],
              "opacities": torch.logit(sg["opacities"])[:, None], "kd": sg["kd"], "ks": sg["ks"], "normals": sg["normals"]}
         t = {k: v.to(DEV).requires_grad_(True) for k, v in t.items()}
@@ -190,10 +190,10 @@ def test_multi_stream_batch_equals_sequential_views():
         exs = [torch.tensor([0.9 + 0.05 * i], device=DEV, requires_grad=True) for i in range(len(cams))]
         kw = dict(envmap=env, fg_lut=lut, min_roughness=0.1, max_metallic=1.0)
         args = [t[k] for k in names]
-        if n_streams:
-            imgs = splat_views(*args, cams, exposures=exs, n_streams=n_streams, **kw)
+        if n_streams:      # one batch node; kernels sequenced by the native per-view driver or call by call from Python
+            imgs = splat_views(*args, cams, exposures=exs, n_streams=n_streams, native=native, **kw)
         else:
-            imgs = [splat_view(*args, c, exposure=e, **kw) for c, e in zip(cams, exs)]
+            imgs = [splat_view(*args, c, exposure=e, native=native, **kw) for c, e in zip(cams, exs)]
         loss = sum((i * c).sum() for i, c in zip(imgs, cots))
         grads = torch.autograd.grad(loss, args + [env_leaf] + exs)
         torch.cuda.synchronize()
