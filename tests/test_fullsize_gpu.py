@@ -1,0 +1,129 @@
+"""Size-independent properties of the hot path at BASELINE.json's full sizes (1 M MGAdaptor Gaussians at 800x800;
+5 M random Gaussians at 1600x1600), where the CPU oracle would take minutes: sortedness of the tile lists, linearity of
+the image in the colours, front-to-back consistency of alpha, determinism, finite gradients, and agreement of the
+batched multi-stream path with itself across stream counts."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from geosplatting_b200 import rasterization, scenes, splitsum
+from geosplatting_b200.fused import splat_views
+from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
+from geosplatting_b200.shade import synthetic_fg_lut
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _check_lists(info, depths_packed, n_tiles):
+    """flatten_ids / offsets must describe, per tile, a run sorted by (depth, Gaussian index)."""
+    ids = info["isect_ids"]
+    assert bool((ids[1:] >= ids[:-1]).all()), "isect_ids not sorted"
+    tile = (ids >> 32).long()
+    offs = info["isect_offsets"].reshape(-1).long()
+    M = ids.shape[0]
+    # offsets[t] = first position of tile t
+    first = torch.searchsorted(tile, torch.arange(n_tiles, device=tile.device))
+    assert torch.equal(first, offs)
+    # equal keys keep ascending Gaussian order (stable sort of Gaussian-major pairs)
+    flat = info["flatten_ids"].long()
+    same = ids[1:] == ids[:-1]
+    assert bool((flat[1:][same] > flat[:-1][same]).all())
+    # the depth bits in the keys are the depths of the listed Gaussians
+    dbits = depths_packed.contiguous().view(torch.int32)[flat].long() & 0xFFFFFFFF
+    assert torch.equal(ids & 0xFFFFFFFF, dbits)
+    return M
+
+
+def test_config3_1m_gaussians_800_properties():
+    verts, faces = scenes.cube_sphere(118)                       # 167 088 faces -> 1 002 528 Gaussians (bench.py)
+    with torch.no_grad():
+        vd, fd = verts.to(DEV), faces.to(DEV)
+        sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+    N = sp.means.shape[0]
+    assert N == 1_002_528
+    cam = scenes.orbit_cameras(1, 800, 800, seed=1)[0]
+    vm = torch.from_numpy(cam.view_matrix)[None].to(DEV)
+    K = torch.from_numpy(cam.intrinsic_matrix)[None].to(DEV)
+    gen = torch.Generator().manual_seed(0)
+    c1 = torch.rand(N, 3, generator=gen).to(DEV)
+    c2 = torch.rand(N, 3, generator=gen).to(DEV)
+    args = (sp.means, sp.quats, sp.scales.exp(), torch.sigmoid(sp.opacities)[:, 0])
+    r1, a1, info = rasterization(*args, c1, vm, K, 800, 800, rasterize_mode="antialiased")
+    r2, a2, _ = rasterization(*args, c2, vm, K, 800, 800, rasterize_mode="antialiased")
+    r12, a12, _ = rasterization(*args, c1 + c2, vm, K, 800, 800, rasterize_mode="antialiased")
+    M = _check_lists(info, info["depths"], 2500)
+    assert 2_000_000 < M < 2_600_000
+    assert torch.equal(a1, a2) and torch.equal(a1, a12)          # alpha does not depend on the colours
+    assert float(a1.min()) >= 0.0 and float(a1.max()) <= 1.0
+    assert float((r12 - (r1 + r2)).abs().max()) <= 1e-5          # the image is linear in the colours
+    white, _, _ = rasterization(*args, torch.ones(N, 3, device=DEV), vm, K, 800, 800, rasterize_mode="antialiased")
+    assert float((white[..., 0] - a1[..., 0]).abs().max()) <= 1e-5   # unit colours composite to alpha
+    r1b, a1b, _ = rasterization(*args, c1, vm, K, 800, 800, rasterize_mode="antialiased")
+    assert torch.equal(r1, r1b) and torch.equal(a1, a1b)         # deterministic forward
+    # gradient w.r.t. the colours of <render, cot> is the render of ... its transpose: check against linearity
+    cot = torch.randn(1, 800, 800, 3, generator=gen).to(DEV)
+    c = c1.clone().requires_grad_(True)
+    r, _, _ = rasterization(*args, c, vm, K, 800, 800, rasterize_mode="antialiased")
+    (g,) = torch.autograd.grad((r * cot).sum(), [c])
+    lhs = float((g * c2).sum())                                   # <J^T cot, c2>
+    rhs = float((r2 * cot).sum())                                 # <cot, J c2>
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(rhs), 1.0), (lhs, rhs)
+
+
+def test_config3_batch_of_views_stream_counts_agree():
+    """The bench configuration through fused.splat_views: 1, 2 and 3 streams give identical images and gradients that
+    agree to the order of additions; everything finite."""
+    verts, faces = scenes.cube_sphere(118)
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        vd, fd = verts.to(DEV), faces.to(DEV)
+        sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+        cube = torch.exp(torch.randn(6, 512, 512, 3, generator=gen)).clamp_min(1e-2).to(DEV)
+        env0 = splitsum.as_envstack(cube)
+    N = sp.means.shape[0]
+    kd = (torch.rand(N, 3, generator=gen) * 0.8 + 0.1).to(DEV)
+    ks = torch.rand(N, 2, generator=gen).to(DEV)
+    cams = scenes.orbit_cameras(4, 800, 800, seed=1)
+    lut = synthetic_fg_lut(torch.device(DEV))
+    cot = torch.randn(800, 800, 4, generator=gen).to(DEV)
+    out = []
+    from geosplatting_b200.shade import EnvStack
+    for ns in (1, 2, 3):
+        p = [t.detach().clone().requires_grad_(True) for t in (sp.means, sp.scales, sp.quats, sp.opacities, kd, ks, sp.colors)]
+        env_leaf = env0.data.detach().clone().requires_grad_(True)
+        env = EnvStack(env_leaf, env0.R0, env0.L, env0.Rb, env0.min_roughness, env0.max_roughness)
+        ex = torch.ones(1, device=DEV, requires_grad=True)
+        imgs = splat_views(*p, cams, exposures=ex, envmap=env, fg_lut=lut, min_roughness=0.1, max_metallic=1.0, n_streams=ns)
+        grads = torch.autograd.grad(imgs, p + [env_leaf, ex], grad_outputs=[cot] * len(cams))
+        torch.cuda.synchronize()
+        assert all(bool(torch.isfinite(i).all()) for i in imgs) and all(bool(torch.isfinite(g).all()) for g in grads)
+        assert 0.2 < float(imgs[0][..., 3].mean()) < 0.6          # the object covers about a third of the frame
+        out.append((imgs, grads))
+    for imgs, grads in out[1:]:
+        for a, b in zip(imgs, out[0][0]):
+            assert torch.equal(a, b)
+        for a, b in zip(grads, out[0][1]):
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
+
+
+def test_config5_5m_gaussians_1600_lists_and_memory():
+    """BASELINE.json configs[4] scale: 5 M Gaussians, 1600x1600 (10 000 tiles, 14 tile bits)."""
+    g = scenes.random_gaussians(5_000_000, seed=1, extent=0.8, scale_lo=0.001, scale_hi=0.006)
+    cam = scenes.orbit_cameras(1, 1600, 1600, seed=2)[0]
+    t = {k: v.to(DEV) for k, v in g.items()}
+    t["colors"].requires_grad_(True)
+    t["means"].requires_grad_(True)
+    vm = torch.from_numpy(cam.view_matrix)[None].to(DEV)
+    K = torch.from_numpy(cam.intrinsic_matrix)[None].to(DEV)
+    torch.cuda.reset_peak_memory_stats()
+    render, alpha, info = rasterization(t["means"], t["quats"], t["scales"], t["opacities"], t["colors"], vm, K, 1600,
+                                        1600, rasterize_mode="antialiased")
+    M = _check_lists(info, info["depths"], 10_000)
+    assert M > 5_000_000
+    (render.sum() + alpha.sum()).backward()
+    assert bool(torch.isfinite(t["means"].grad).all()) and bool(torch.isfinite(t["colors"].grad).all())
+    assert float(t["colors"].grad.abs().sum()) > 0
+    assert torch.cuda.max_memory_allocated() < 20e9              # sized for 180 GB, nowhere near it
