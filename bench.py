@@ -35,7 +35,7 @@ PARAM_NAMES = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=80)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh-n", type=int, default=118, help="cube-sphere subdivision: 72*n*n Gaussians (118 -> 1.0M)")
