@@ -1,0 +1,192 @@
+// Multi-resolution hash-grid encoding, forward and backward: the fields behind kd / ks / z of the hot path
+// (SURVEY.md section 8f rank 1).  Semantics are those of the reference's own `torch` backend of HashEncoding
+// (rfstudio/model/components/encoding.py:124-138 scalings/offsets, :164-180 hash_fn, :182-229 pytorch_fwd): every level
+// is hashed (primes 1, 2654435761, 805459861, modulo 2^log2), corners are ceil/floor of x01 * scaling, trilinear blend
+// in the reference's operation order.  THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false so that the features are
+// bit-identical to that code (oracle/encoding.py); tinycudann -- the reference's default backend, unpinned and absent
+// here -- uses a different level layout and fp16 storage.
+//
+// One thread per (point, level): the 16 threads of a point share its coordinates through L1, the feature pair is one
+// float2, the 8 corner gathers hit the L2-resident table (2^18 entries x 16 levels x 8 B = 33.5 MB).  Algorithmic
+// bytes: 12 B in + 8 B/level out per point (+ 64 B/level of L2 gathers).  The backward scatters with one
+// red.global.add.v2.f32 per corner and writes d/dx once per point after a 16-lane segmented reduction.
+#include "gsb_common.cuh"
+
+namespace {
+
+constexpr int MAX_LEVELS = 32;
+
+struct Scalings {
+    float s[MAX_LEVELS];
+};
+
+__device__ __forceinline__ uint32_t hash3(int x, int y, int z, uint32_t mask) {
+    // low bits of the reference's int64 products / xor / modulo 2^k: 32-bit wrap-around arithmetic keeps them
+    return ((uint32_t)x ^ ((uint32_t)y * 2654435761u) ^ ((uint32_t)z * 805459861u)) & mask;
+}
+
+struct Cell {
+    uint32_t idx[8];   // f0..f7 in the reference's naming (c = ceil corner, f = floor corner)
+    float ox, oy, oz;
+};
+
+__device__ __forceinline__ Cell locate(const float *__restrict__ x, int n, float scaling, uint32_t level_base,
+                                       uint32_t mask) {
+    Cell c;
+    const float sx = (x[3 * n] * 0.5f + 0.5f) * scaling;
+    const float sy = (x[3 * n + 1] * 0.5f + 0.5f) * scaling;
+    const float sz = (x[3 * n + 2] * 0.5f + 0.5f) * scaling;
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const int ifx = (int)fx, ify = (int)fy, ifz = (int)fz;
+    const int icx = (int)ceilf(sx), icy = (int)ceilf(sy), icz = (int)ceilf(sz);
+    c.ox = sx - fx; c.oy = sy - fy; c.oz = sz - fz;
+    c.idx[0] = level_base + hash3(icx, icy, icz, mask);
+    c.idx[1] = level_base + hash3(icx, ify, icz, mask);
+    c.idx[2] = level_base + hash3(ifx, ify, icz, mask);
+    c.idx[3] = level_base + hash3(ifx, icy, icz, mask);
+    c.idx[4] = level_base + hash3(icx, icy, ifz, mask);
+    c.idx[5] = level_base + hash3(icx, ify, ifz, mask);
+    c.idx[6] = level_base + hash3(ifx, ify, ifz, mask);
+    c.idx[7] = level_base + hash3(ifx, icy, ifz, mask);
+    return c;
+}
+
+__global__ void __launch_bounds__(256) hashgrid_fwd_kernel(long long total, int L, int log2_T, Scalings sc,
+                                                            const float *__restrict__ x,
+                                                            const float2 *__restrict__ table,
+                                                            float2 *__restrict__ feats) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int n = (int)(t / L), l = (int)(t % L);
+    const Cell c = locate(x, n, sc.s[l], (uint32_t)l << log2_T, (1u << log2_T) - 1u);
+    float2 f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __ldg(table + c.idx[k]);
+    const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.0f - ox, ry = 1.0f - oy, rz = 1.0f - oz;
+    float2 out;
+    {
+        const float f03 = f[0].x * ox + f[3].x * rx, f12 = f[1].x * ox + f[2].x * rx;
+        const float f56 = f[5].x * ox + f[6].x * rx, f47 = f[4].x * ox + f[7].x * rx;
+        out.x = (f03 * oy + f12 * ry) * oz + (f47 * oy + f56 * ry) * rz;
+    }
+    {
+        const float f03 = f[0].y * ox + f[3].y * rx, f12 = f[1].y * ox + f[2].y * rx;
+        const float f56 = f[5].y * ox + f[6].y * rx, f47 = f[4].y * ox + f[7].y * rx;
+        out.y = (f03 * oy + f12 * ry) * oz + (f47 * oy + f56 * ry) * rz;
+    }
+    feats[t] = out;
+}
+
+// v_table += (corner weight) * v_feats * table_grad_scale;  v_x[n] = sum over levels of d feats / d x . v_feats.
+// L must divide 32 or be a multiple of it for the segmented reduction; otherwise v_x goes through atomics.
+__global__ void __launch_bounds__(256) hashgrid_bwd_kernel(long long total, int L, int log2_T, Scalings sc,
+                                                            const float *__restrict__ x,
+                                                            const float2 *__restrict__ table,
+                                                            const float2 *__restrict__ v_feats, float table_grad_scale,
+                                                            float2 *__restrict__ v_table, float *__restrict__ v_x,
+                                                            int segmented) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < total;
+    const int n = live ? (int)(t / L) : 0, l = live ? (int)(t % L) : 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (live) {
+        const float scaling = sc.s[l];
+        const Cell c = locate(x, n, scaling, (uint32_t)l << log2_T, (1u << log2_T) - 1u);
+        const float2 v = v_feats[t];
+        const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.0f - ox, ry = 1.0f - oy, rz = 1.0f - oz;
+        // value = ((f0 ox + f3 rx) oy + (f1 ox + f2 rx) ry) oz + ((f4 ox + f7 rx) oy + (f5 ox + f6 rx) ry) rz
+        const float w[8] = {ox * oy * oz, ox * ry * oz, rx * ry * oz, rx * oy * oz,
+                            ox * oy * rz, ox * ry * rz, rx * ry * rz, rx * oy * rz};
+        if (v_table) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float s = w[k] * table_grad_scale;
+                atomicAdd(v_table + c.idx[k], make_float2(s * v.x, s * v.y));
+            }
+        }
+        if (v_x) {
+            float2 f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __ldg(table + c.idx[k]);
+            float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float a[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = ch ? f[k].y : f[k].x;
+                const float vv = ch ? v.y : v.x;
+                const float f03 = a[0] * ox + a[3] * rx, f12 = a[1] * ox + a[2] * rx;
+                const float f56 = a[5] * ox + a[6] * rx, f47 = a[4] * ox + a[7] * rx;
+                const float d03 = a[0] - a[3], d12 = a[1] - a[2], d56 = a[5] - a[6], d47 = a[4] - a[7];
+                d[0] += vv * ((d03 * oy + d12 * ry) * oz + (d47 * oy + d56 * ry) * rz);
+                d[1] += vv * ((f03 - f12) * oz + (f47 - f56) * rz);
+                d[2] += vv * ((f03 * oy + f12 * ry) - (f47 * oy + f56 * ry));
+            }
+            const float j = 0.5f * scaling;   // d offset / d x  (floor and ceil carry no gradient)
+            gx = d[0] * j; gy = d[1] * j; gz = d[2] * j;
+        }
+    }
+    if (!v_x) return;
+    if (segmented) {   // L consecutive lanes hold one point: xor-butterfly inside the segment
+        for (int o = 1; o < L && o < 32; o <<= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (live && (l % 32) == 0) {
+            if (L <= 32) { v_x[3 * n] = gx; v_x[3 * n + 1] = gy; v_x[3 * n + 2] = gz; }
+            else { atomicAdd(v_x + 3 * n, gx); atomicAdd(v_x + 3 * n + 1, gy); atomicAdd(v_x + 3 * n + 2, gz); }
+        }
+    } else if (live) {
+        atomicAdd(v_x + 3 * n, gx); atomicAdd(v_x + 3 * n + 1, gy); atomicAdd(v_x + 3 * n + 2, gz);
+    }
+}
+
+int check(int64_t N, int32_t L, int32_t F, int32_t log2_T, const float *scalings_host) {
+    GSB_CHECK_ARG(N >= 0 && L >= 1 && L <= MAX_LEVELS && log2_T >= 1 && log2_T <= 24 && scalings_host != nullptr);
+    if (F != 2) {
+        gsb_set_error("gsb_hashgrid: features_per_level must be 2 (GeoSplatting's fields, geosplat.py:485-518), got %d", F);
+        return GSB_EINVAL;
+    }
+    GSB_CHECK_ARG((int64_t)L << log2_T < (int64_t)1 << 31);
+    return GSB_OK;
+}
+
+}  // namespace
+
+#define GSB_API extern "C" __attribute__((visibility("default")))
+
+GSB_API int gsb_hashgrid_fwd(int64_t N, const float *x, const float *table, int32_t L, int32_t F, int32_t log2_T,
+                             const float *scalings_host, float *feats, void *stream) {
+    int rc = check(N, L, F, log2_T, scalings_host);
+    if (rc != GSB_OK) return rc;
+    if (N == 0) return GSB_OK;
+    GSB_CHECK_ARG(x && table && feats);
+    Scalings sc;
+    for (int l = 0; l < L; ++l) sc.s[l] = scalings_host[l];
+    const long long total = (long long)N * L;
+    hashgrid_fwd_kernel<<<gsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        total, L, log2_T, sc, x, reinterpret_cast<const float2 *>(table), reinterpret_cast<float2 *>(feats));
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_hashgrid_bwd(int64_t N, const float *x, const float *table, int32_t L, int32_t F, int32_t log2_T,
+                             const float *scalings_host, const float *v_feats, float table_grad_scale, float *v_table,
+                             float *v_x, void *stream) {
+    int rc = check(N, L, F, log2_T, scalings_host);
+    if (rc != GSB_OK) return rc;
+    if (N == 0) return GSB_OK;
+    GSB_CHECK_ARG(x && table && v_feats && (v_table || v_x));
+    Scalings sc;
+    for (int l = 0; l < L; ++l) sc.s[l] = scalings_host[l];
+    const long long total = (long long)N * L;
+    const int segmented = (L <= 32) ? ((32 % L) == 0) : ((L % 32) == 0);
+    if (v_x && (!segmented || L > 32))
+        GSB_CHECK_CUDA(cudaMemsetAsync(v_x, 0, sizeof(float) * 3 * (size_t)N, (cudaStream_t)stream));
+    hashgrid_bwd_kernel<<<gsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        total, L, log2_T, sc, x, reinterpret_cast<const float2 *>(table), reinterpret_cast<const float2 *>(v_feats),
+        table_grad_scale, reinterpret_cast<float2 *>(v_table), v_x, segmented);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}

@@ -1,0 +1,145 @@
+"""Hash-grid fields that produce kd / ks / z for the hot path, over the C ABI
+(gsb_hashgrid_fwd / gsb_hashgrid_bwd).
+
+Mirrors, with the same field names and argument meaning:
+    HashEncoding          rfstudio/model/components/encoding.py:96-241   (backend='torch' semantics)
+    MLP                   rfstudio/nn/mlp.py:27-145                       (bias / skip connections / weight norm are not
+                                                                          used by GeoSplatting's fields and raise)
+    GaussianField configs rfstudio/model/geosplat.py:485-518              -> kd_field(), ks_field(), z_field()
+The gather / scatter over the table is the hand-written part (L2-bound random access); the MLP is three bias-free
+GEMMs on cuBLAS through torch.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from ._lib import call, f32c, ptr, stream_ptr
+
+
+def level_scalings(num_levels: int, min_res: int, max_res: int) -> List[float]:
+    """encoding.py:129-135: floor(min_res * growth ** level) (computed like the reference, in fp32 torch ops)."""
+    levels = torch.arange(num_levels)
+    growth = math.exp((math.log(max_res) - math.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1
+    return [float(v) for v in torch.floor(min_res * growth ** levels)]
+
+
+class _HashGrid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, table: Tensor, scalings, log2_T: int, table_grad_scale: float):
+        x_c, table_c = f32c(x), f32c(table)
+        dev = x_c.device
+        N, L, F = x_c.shape[0], len(scalings), table_c.shape[1]
+        feats = torch.empty(N, L * F, dtype=torch.float32, device=dev)
+        sc = (C.c_float * L)(*scalings)
+        call("gsb_hashgrid_fwd", dev, C.c_int64(N), ptr(x_c), ptr(table_c), C.c_int32(L), C.c_int32(F), C.c_int32(log2_T),
+             sc, ptr(feats), stream_ptr(dev))
+        ctx.save_for_backward(x_c, table_c)
+        ctx.misc = (sc, L, F, log2_T, float(table_grad_scale))
+        return feats
+
+    @staticmethod
+    def backward(ctx, v_feats):
+        x, table = ctx.saved_tensors
+        sc, L, F, log2_T, gscale = ctx.misc
+        dev = x.device
+        N = x.shape[0]
+        v_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        v_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        if v_table is None and v_x is None:
+            return None, None, None, None, None
+        call("gsb_hashgrid_bwd", dev, C.c_int64(N), ptr(x), ptr(table), C.c_int32(L), C.c_int32(F), C.c_int32(log2_T), sc,
+             ptr(f32c(v_feats)), C.c_float(gscale), ptr(v_table), ptr(v_x), stream_ptr(dev))
+        return v_x, v_table, None, None, None
+
+
+class MLP(nn.Module):
+    """rfstudio/nn/mlp.py: `layers` [in, hidden..., out] (in may be -1 = inferred), ReLU between layers, `activation`
+    after the last, kaiming-uniform weights, no bias."""
+
+    def __init__(self, layers: Sequence[int], activation: str = "none", bias: bool = False,
+                 initialization: str = "kaiming-uniform", skip_connections: Sequence[int] = (), weight_norm: bool = False,
+                 in_dim: Optional[int] = None):
+        super().__init__()
+        if bias or skip_connections or weight_norm:
+            raise NotImplementedError("geosplatting_b200.MLP: GeoSplatting's fields use bias=False, no skip connections, "
+                                      "no weight norm (rfstudio/model/geosplat.py:485-518)")
+        if activation not in ("none", "sigmoid", "relu", "tanh", "softplus"):
+            raise ValueError(activation)
+        if initialization != "kaiming-uniform":
+            raise NotImplementedError(initialization)
+        layers = list(layers)
+        if layers[0] == -1:
+            if in_dim is None:
+                raise ValueError("MLP(layers=[-1, ...]) needs in_dim")
+            layers[0] = in_dim
+        self.layers, self.activation = layers, activation
+        self.weights = nn.ParameterList()
+        for i, o in zip(layers[:-1], layers[1:]):
+            w = torch.empty(o, i)
+            nn.init.kaiming_uniform_(w, nonlinearity="relu")              # mlp.py:99-100
+            self.weights.append(nn.Parameter(w))
+
+    def forward(self, x: Tensor) -> Tensor:
+        n = len(self.weights)
+        for i, w in enumerate(self.weights):
+            x = torch.nn.functional.linear(x, w)
+            if i < n - 1:
+                x = torch.relu(x)
+        return {"none": lambda t: t, "sigmoid": torch.sigmoid, "relu": torch.relu, "tanh": torch.tanh,
+                "softplus": torch.nn.functional.softplus}[self.activation](x)
+
+
+class HashEncoding(nn.Module):
+    """rfstudio/model/components/encoding.py:96-241 (backend='torch' semantics, interpolation 'linear')."""
+
+    def __init__(self, mlp: MLP, num_levels: int = 16, min_res: int = 16, max_res: int = 1024,
+                 log2_hashmap_size: int = 19, features_per_level: int = 2, hash_init_scale: float = 0.001,
+                 interpolation: str = "linear", grad_scaling: Optional[float] = None):
+        super().__init__()
+        assert grad_scaling is None or grad_scaling > 0                                    # encoding.py:126
+        if interpolation != "linear":
+            raise NotImplementedError(f"interpolation '{interpolation}' is not supported")  # as the torch backend, :139-143
+        if features_per_level != 2:
+            raise NotImplementedError("geosplatting_b200.HashEncoding: features_per_level must be 2")
+        self.mlp, self.num_levels, self.min_res, self.max_res = mlp, num_levels, min_res, max_res
+        self.log2_hashmap_size, self.features_per_level, self.grad_scaling = log2_hashmap_size, features_per_level, grad_scaling
+        self.hash_table_size = 2 ** log2_hashmap_size
+        self.scalings = level_scalings(num_levels, min_res, max_res)
+        self.hash_table = nn.Parameter((torch.rand(self.hash_table_size * num_levels, features_per_level) * 2 - 1)
+                                       * hash_init_scale)                                   # encoding.py:144-147
+
+    def encode(self, in_tensor: Tensor) -> Tensor:
+        """pytorch_fwd (encoding.py:182-229): [..., 3] in [-1, 1] -> [..., num_levels * features_per_level]."""
+        if not in_tensor.is_cuda:
+            raise RuntimeError("geosplatting_b200.HashEncoding needs CUDA tensors; there is no CPU path")
+        assert in_tensor.shape[-1] == 3
+        flat = in_tensor.reshape(-1, 3)
+        feats = _HashGrid.apply(flat, self.hash_table, self.scalings, self.log2_hashmap_size,
+                                1.0 if self.grad_scaling is None else float(self.grad_scaling))
+        return feats.view(*in_tensor.shape[:-1], self.num_levels * self.features_per_level)
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        """encoding.py:231-241.  The two straight-through expressions of the reference (`x/s + x.detach()(1-1/s)`,
+        `f*s + f.detach()(1-s)`) leave values unchanged and multiply the gradient that reaches the table by s while the
+        one that reaches x stays as it is: that factor is applied inside the backward kernel."""
+        return self.mlp(self.encode(in_tensor))
+
+
+def kd_field() -> HashEncoding:
+    """GaussianField.kd_enc (geosplat.py:485-495)."""
+    return HashEncoding(MLP([32, 32, 32, 3], activation="sigmoid"), grad_scaling=16.0, max_res=4096, log2_hashmap_size=18)
+
+
+def ks_field() -> HashEncoding:
+    """GaussianField.ks_enc (geosplat.py:497-507)."""
+    return HashEncoding(MLP([32, 32, 2], activation="none"), grad_scaling=16.0, max_res=4096, log2_hashmap_size=18)
+
+
+def z_field() -> HashEncoding:
+    """GaussianField.z_enc (geosplat.py:508-518)."""
+    return HashEncoding(MLP([32, 32, 1], activation="none"), grad_scaling=16.0, max_res=4096, log2_hashmap_size=18)

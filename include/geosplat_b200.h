@@ -285,6 +285,23 @@ int gsb_tonemap_planar_bwd(int64_t P, const float *render, const float *exposure
                            const float *v_out, float *v_render, float *v_alphas, float *v_exposure, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Hash-grid encoding of the fields that produce kd / ks / z: replaces
+ * HashEncoding.pytorch_fwd / tcnn.Encoding("HashGrid") behind rfstudio/model/components/encoding.py:231-241, used at
+ * rfstudio/model/geosplat.py:579-598,:644-669.  Semantics = the reference's own `torch` backend (encoding.py:124-229):
+ * x[N,3] in [-1,1]; table[L * 2^log2_T, F] (level-major, F must be 2); scalings_host[L] = floor(min_res * growth^l)
+ * (HOST array); feats[N, L*F] level-major.  Features are bit-identical to that code (the file is built -fmad=false).
+ * The MLP behind the encoding (rfstudio/nn/mlp.py) is three bias-free GEMMs and stays on the BLAS library.
+ * ------------------------------------------------------------------------------------------- */
+int gsb_hashgrid_fwd(int64_t N, const float *x, const float *table, int32_t L, int32_t F, int32_t log2_T,
+                     const float *scalings_host, float *feats, void *stream);
+/* VJP: ACCUMULATES table_grad_scale * d feats/d table . v_feats into v_table (same shape as table; may be NULL) and
+ * WRITES v_x[N,3] (may be NULL).  table_grad_scale carries HashEncoding.grad_scaling (encoding.py:232-240: the
+ * gradient reaching the table is multiplied by it, the one reaching x is not). */
+int gsb_hashgrid_bwd(int64_t N, const float *x, const float *table, int32_t L, int32_t F, int32_t log2_T,
+                     const float *scalings_host, const float *v_feats, float table_grad_scale, float *v_table,
+                     float *v_x, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Native per-view driver: one training view of RenderableAttrs.splat (rfstudio/model/geosplat.py:53-132, culling
  * off, tone_type 'naive' / 'none') + GSplatter.render_rgba (rfstudio/model/gsplat.py:284-358) as three calls that
  * sequence the stage entry points above on caller-provided arenas.  The host keeps three calls and a handful of

@@ -211,6 +211,63 @@ def main():
     save("ref_fg_lut_sub.npz", sha256=hashlib.sha256(raw).hexdigest(), sub=full[::8, ::8].copy(),
          corners=np.stack([full[0, 0], full[0, 255], full[255, 0], full[255, 255]]))
 
+    # ---- H. HashEncoding (torch backend) + MLP: the fields that produce kd / ks / z (SURVEY section 8f rank 1;
+    #         rfstudio/model/components/encoding.py:124-241, rfstudio/nn/mlp.py:125-145, configs geosplat.py:485-518).
+    #         The reference's Module framework does not initialise under this Python, so its METHODS are run on plain
+    #         namespaces: __setup__ (scalings, offsets, table init), hash_fn, pytorch_fwd, __call__ (grad scaling) and
+    #         MLP.__call__ are the reference's own code; only the nn.Linear containers are built here.
+    import functools
+    import importlib.machinery
+    import types
+    for name, path_ in (("rfstudio.model", "/root/reference/rfstudio/model"),
+                        ("rfstudio.model.components", "/root/reference/rfstudio/model/components")):
+        m = types.ModuleType(name)
+        m.__path__ = [path_]
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True)
+        sys.modules[name] = m
+    import rfstudio.model.components.encoding as RE
+    from rfstudio.nn import mlp as RMLP
+
+    class _Holder:
+        @staticmethod
+        def from_tensor(t):
+            return types.SimpleNamespace(params=t.clone().requires_grad_(True))
+
+    RE.ParameterModule = _Holder
+    enc_out = {}
+    for tag, layers, act, log2 in (("kd", [32, 32, 32, 3], "sigmoid", 10), ("ks", [32, 32, 2], "none", 12),
+                                   ("z", [32, 32, 1], "none", 9)):
+        torch.manual_seed({"kd": 11, "ks": 12, "z": 13}[tag])
+        e = types.SimpleNamespace(num_levels=16, min_res=16, max_res=4096, log2_hashmap_size=log2, features_per_level=2,
+                                  hash_init_scale=0.001, backend="torch", interpolation="linear", grad_scaling=16.0)
+        RE.HashEncoding.__setup__(e)
+        e.hash_fn = functools.partial(RE.HashEncoding.hash_fn, e)
+        e.pytorch_fwd = functools.partial(RE.HashEncoding.pytorch_fwd, e)
+        with torch.no_grad():   # a 1e-3 table gives nearly constant outputs: use O(1) features for a meaningful check
+            e.hash_table.mul_(1000.0)
+        lin = [torch.nn.Linear(i, o, bias=False) for i, o in zip(layers[:-1], layers[1:])]
+        for l in lin:
+            torch.nn.init.kaiming_uniform_(l.weight, nonlinearity="relu")           # rfstudio/nn/mlp.py:99-100
+        mlp_ns = types.SimpleNamespace(nn_layers=lin, skip_connection_set=set(), activation=act,
+                                       initialize_weights=lambda d: None)
+        e.mlp = functools.partial(RMLP.MLP.__call__, mlp_ns)
+        x = (torch.rand(1500, 3, generator=g) * 2 - 1)
+        x[:8] = torch.tensor([[-1.0, -1, -1], [1, 1, 1], [0, 0, 0], [1, -1, 0.5], [0.25, 0.5, -0.75], [-1, 1, 1],
+                              [0.999999, -0.999999, 0], [0.0625, 0.0625, 0.0625]])      # cell corners / exact lattice points
+        x = x.requires_grad_(True)
+        feats = e.pytorch_fwd(x)
+        y = RE.HashEncoding.__call__(e, x)
+        coty = torch.randn(y.shape, generator=g)
+        grads = torch.autograd.grad((y * coty).sum(), [x, e.hash_table] + [l.weight for l in lin])
+        idx = torch.nonzero(grads[1].abs().sum(-1)).reshape(-1)
+        enc_out.update({f"{tag}_x": x, f"{tag}_table": e.hash_table, f"{tag}_feats": feats, f"{tag}_y": y, f"{tag}_cot": coty,
+                        f"{tag}_v_x": grads[0], f"{tag}_v_table_idx": idx.to(torch.int32), f"{tag}_v_table_val": grads[1][idx],
+                        f"{tag}_scalings": e.scalings, f"{tag}_log2": log2})
+        for k, (l, gw) in enumerate(zip(lin, grads[2:])):
+            enc_out[f"{tag}_w{k}"] = l.weight
+            enc_out[f"{tag}_v_w{k}"] = gw
+    save("ref_encoding.npz", **enc_out)
+
 
 if __name__ == "__main__":
     main()

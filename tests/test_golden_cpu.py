@@ -118,3 +118,28 @@ def test_mgadapter_oracle_matches_reference_code():
                (("means", means), ("scales", scales), ("quats", quats), ("colors", colors), ("opacities", opac)))
     gv, = torch.autograd.grad(loss, verts)
     assert np.abs(gv.numpy() - g["v_vertices"]).max() <= 1e-4 * np.abs(g["v_vertices"]).max()
+
+
+def test_encoding_oracle_matches_reference_code():
+    """oracle/encoding.py against the reference's own HashEncoding (torch backend) + MLP code
+    (tests/golden/ref_encoding.npz, scripts/make_golden.py section H): features, outputs and every gradient."""
+    from oracle import encoding as OE
+    g = load("ref_encoding.npz")
+    for tag, act, n_w in (("kd", "sigmoid", 3), ("ks", "none", 2), ("z", "none", 2)):
+        log2 = int(g[f"{tag}_log2"])
+        scal = OE.level_scalings(16, 16, 4096)
+        assert np.array_equal(scal.numpy(), g[f"{tag}_scalings"])
+        x = torch.from_numpy(g[f"{tag}_x"]).requires_grad_(True)
+        table = torch.from_numpy(g[f"{tag}_table"]).requires_grad_(True)
+        ws = [torch.from_numpy(g[f"{tag}_w{k}"]).requires_grad_(True) for k in range(n_w)]
+        feats = OE.hash_encode(x, table, scal, log2)
+        assert np.array_equal(feats.detach().numpy(), g[f"{tag}_feats"])          # same op order: bit-identical
+        y = OE.field(x, table, ws, scal, log2, act, grad_scaling=16.0)
+        assert np.abs(y.detach().numpy() - g[f"{tag}_y"]).max() <= 1e-6
+        grads = torch.autograd.grad((y * torch.from_numpy(g[f"{tag}_cot"])).sum(), [x, table] + ws)
+        assert np.abs(grads[0].numpy() - g[f"{tag}_v_x"]).max() <= 1e-5 * np.abs(g[f"{tag}_v_x"]).max()
+        vt = np.zeros_like(g[f"{tag}_table"])
+        vt[g[f"{tag}_v_table_idx"]] = g[f"{tag}_v_table_val"]
+        assert np.abs(grads[1].numpy() - vt).max() <= 1e-5 * np.abs(vt).max()
+        for k in range(n_w):
+            assert np.abs(grads[2 + k].numpy() - g[f"{tag}_v_w{k}"]).max() <= 1e-5 * np.abs(g[f"{tag}_v_w{k}"]).max()
