@@ -92,11 +92,14 @@ class GSplatter:
 
 @dataclass
 class RenderableAttrs:
-    """rfstudio/model/geosplat.py:43-51 (occ / *_jitter belong to stages outside this path)."""
+    """rfstudio/model/geosplat.py:43-51.  `occ` and the jittered copies feed regularisers / later stages, not `splat`."""
 
     kd: Tensor        # [N,3]
     ks: Tensor        # [N,2]
     normals: Tensor   # [N,3]
+    occ: Optional[Tensor] = None
+    kd_jitter: Optional[Tensor] = None
+    ks_jitter: Optional[Tensor] = None
 
     def splat(self, gsplat: GSplatter, cameras, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
               min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",

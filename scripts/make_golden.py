@@ -268,6 +268,74 @@ def main():
             enc_out[f"{tag}_v_w{k}"] = gw
     save("ref_encoding.npz", **enc_out)
 
+    # ---- I. GaussianField.get_patches / get_gaussians_from_vertex / get_gaussians_from_face (SURVEY 8a row a3;
+    #         geosplat.py:520-674).  The class itself cannot be created under Python 3.12 (mutable dataclass default at
+    #         :482), so the three method bodies are cut out of the source by line range and exec'd as plain functions in
+    #         the namespace of the module head; `self` is a namespace holding the encoders of section H's kind.
+    import ast
+    import textwrap
+    src_lines = open("/root/reference/rfstudio/model/geosplat.py").read().split("\n")
+    tree = ast.parse("\n".join(src_lines))
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "GaussianField")
+    fns = {}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("get_patches", "get_gaussians_from_vertex",
+                                                           "get_gaussians_from_face"):
+            code = textwrap.dedent("\n".join(src_lines[fn.lineno - 1:fn.end_lineno]))
+            exec(compile(code, "/root/reference/rfstudio/model/geosplat.py", "exec"), ns)
+            fns[fn.name] = ns[fn.name]
+
+    def make_enc(layers, act, log2, seed):
+        torch.manual_seed(seed)
+        e = types.SimpleNamespace(num_levels=16, min_res=16, max_res=4096, log2_hashmap_size=log2, features_per_level=2,
+                                  hash_init_scale=0.001, backend="torch", interpolation="linear", grad_scaling=16.0)
+        RE.HashEncoding.__setup__(e)
+        e.hash_fn = functools.partial(RE.HashEncoding.hash_fn, e)
+        e.pytorch_fwd = functools.partial(RE.HashEncoding.pytorch_fwd, e)
+        with torch.no_grad():
+            e.hash_table.mul_(1000.0)
+        lin = [torch.nn.Linear(i, o, bias=False) for i, o in zip(layers[:-1], layers[1:])]
+        for l in lin:
+            torch.nn.init.kaiming_uniform_(l.weight, nonlinearity="relu")
+        mlp_ns = types.SimpleNamespace(nn_layers=lin, skip_connection_set=set(), activation=act,
+                                       initialize_weights=lambda d: None)
+        e.mlp = functools.partial(RMLP.MLP.__call__, mlp_ns)
+        return (lambda x: RE.HashEncoding.__call__(e, x)), e.hash_table, [l.weight for l in lin]
+
+    kd_f, kd_t, kd_w = make_enc([32, 32, 32, 3], "sigmoid", 9, 21)
+    ks_f, ks_t, ks_w = make_enc([32, 32, 2], "none", 9, 22)
+    z_f, z_t, z_w = make_enc([32, 32, 1], "none", 9, 23)
+    field = types.SimpleNamespace(kd_enc=kd_f, ks_enc=ks_f, z_enc=z_f, occ_enc=None, device=torch.device("cpu"))
+    field.get_patches = functools.partial(fns["get_patches"], field)
+    verts2, faces2 = scenes.icosphere(1, radius=0.6)
+    verts2 = (verts2 * (1.0 + 0.1 * torch.randn(verts2.shape[0], 1, generator=g))).requires_grad_(True)
+    guess = torch.tensor([0.3, -0.2])
+    fout = {"vertices": verts2, "indices": faces2, "initial_guess": guess, "scale": 0.9}
+    for k, (t_, w_) in (("kd", (kd_t, kd_w)), ("ks", (ks_t, ks_w)), ("z", (z_t, z_w))):
+        fout[f"{k}_table"] = t_
+        for i, w in enumerate(w_):
+            fout[f"{k}_w{i}"] = w
+    mesh2 = G.TriangleMesh(vertices=verts2, indices=faces2)
+    pts, areas = fns["get_patches"](field, mesh2)
+    fout.update(patch_normals=pts.normals, patch_areas=areas)
+    sp_v, at_v = fns["get_gaussians_from_vertex"](field, 0.0, 0.0, 0.9, mesh2, guess)
+    outs_v = dict(v_means=sp_v.means, v_scales=sp_v.scales, v_quats=sp_v.quats, v_opacities=sp_v.opacities, v_kd=at_v.kd,
+                  v_ks=at_v.ks, v_normals=at_v.normals)
+    cot_v = {k: torch.randn(v.shape, generator=g) for k, v in outs_v.items()}
+    gv = torch.autograd.grad(sum((outs_v[k] * cot_v[k]).sum() for k in outs_v), [verts2, kd_t, z_t], allow_unused=True)
+    fout.update(outs_v)
+    fout.update({"cot_" + k: v for k, v in cot_v.items()})
+    fout.update(vertexpath_grad_vertices=gv[0], vertexpath_grad_kd_table=gv[1], vertexpath_grad_z_table=gv[2])
+    sp_f, at_f, off_f = fns["get_gaussians_from_face"](field, mesh2, 0.0, 0.0, scale=0.9, initial_guess=guess)
+    outs_f = dict(f_means=sp_f.means, f_scales=sp_f.scales, f_quats=sp_f.quats, f_opacities=sp_f.opacities, f_kd=at_f.kd,
+                  f_ks=at_f.ks, f_normals=at_f.normals)
+    cot_f = {k: torch.randn(v.shape, generator=g) for k, v in outs_f.items()}
+    gf = torch.autograd.grad(sum((outs_f[k] * cot_f[k]).sum() for k in outs_f), [verts2, kd_t, z_t], allow_unused=True)
+    fout.update(outs_f)
+    fout.update({"cot_" + k: v for k, v in cot_f.items()})
+    fout.update(f_offsets=off_f, facepath_grad_vertices=gf[0], facepath_grad_kd_table=gf[1], facepath_grad_z_table=gf[2])
+    save("ref_field.npz", **fout)
+
 
 if __name__ == "__main__":
     main()
