@@ -568,19 +568,16 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 
 struct Workspace {
     Rec *rec;
-    int32_t *counts, *unit_ids, *sorted_counts, *order;
-    void *cub_temp;
-    size_t cub_bytes;
+    int32_t *counts, *work, *order;   // sub-list lengths, entries the forward walked (the backward's LPT key), tile order
     int2 *entries;
 };
 
-constexpr size_t CUB_TEMP_BYTES = 1 << 20;
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t workspace_bytes(int64_t N, int64_t M, int n_tiles) {
-    return align256(sizeof(Rec) * (size_t)N) + 4 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
-           align256(CUB_TEMP_BYTES + 64 * (size_t)n_tiles * SUBS) + align256(sizeof(int2) * (size_t)SUBS * (size_t)M) +
+    return align256(sizeof(Rec) * (size_t)N) + 3 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
+           align256(sizeof(int2) * (size_t)SUBS * (size_t)M) +
            256;
 }
 
@@ -591,12 +588,8 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
     p += align256(sizeof(Rec) * (size_t)N);
     const size_t ub = align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
     w.counts = reinterpret_cast<int32_t *>(p); p += ub;
-    w.unit_ids = reinterpret_cast<int32_t *>(p); p += ub;
-    w.sorted_counts = reinterpret_cast<int32_t *>(p); p += ub;
+    w.work = reinterpret_cast<int32_t *>(p); p += ub;
     w.order = reinterpret_cast<int32_t *>(p); p += ub;
-    w.cub_temp = p;
-    w.cub_bytes = align256(CUB_TEMP_BYTES + 64 * (size_t)n_tiles * SUBS);
-    p += w.cub_bytes;
     w.entries = reinterpret_cast<int2 *>(p);
     (void)M;
     return w;
@@ -619,7 +612,7 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
         W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order,
-        w.sorted_counts, render, alphas, last_ids);
+        w.work, render, alphas, last_ids);
     return 0;
 }
 
@@ -630,7 +623,7 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
-    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.sorted_counts, w.order);   // order by the forward's measured work
+    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.work, w.order);   // order by the forward's measured work
     composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB_B), 32 * WPB_B, 0, st>>>(
         W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order, alphas,
         last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
