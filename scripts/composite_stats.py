@@ -50,3 +50,29 @@ for (sw, sh) in ((8, 4), (8, 8), (16, 4), (4, 4), (16, 8), (16, 16)):
     lens = np.stack(lens, 1).reshape(-1)
     print(f"sub-rect {sw}x{sh}: entries={tot} ({tot/M:.2f} x M) pixel-evals={tot*sw*sh/1e6:.0f} M  sub-list max={lens.max()} "
           f"p99={np.percentile(lens,99):.0f} mean(nonempty)={lens[lens>0].mean():.0f}")
+
+# ---- how much tighter than the AABB test is the exact ellipse-vs-rectangle test (min of the quadratic form over the
+#      rectangle of pixel centres <= tau)?  8x4 sub-rectangles.
+a_, b_, c_ = conics[:, 0], conics[:, 1], conics[:, 2]
+tau = np.log(np.maximum(255.0 * op, 1.0 + 1e-9))
+tot_aabb = tot_exact = 0
+sw, sh = 8, 4
+for sy in range(16 // sh):
+    for sx in range(16 // sw):
+        rcx = tx * 16 + sx * sw + 0.5 * sw
+        rcy = ty * 16 + sy * sh + 0.5 * sh
+        hit = (np.abs(m2d[g, 0] - rcx) <= hx[g] + 0.5 * (sw - 1)) & (np.abs(m2d[g, 1] - rcy) <= hy[g] + 0.5 * (sh - 1))
+        gi = g[hit]
+        lx = (rcx[hit] - 0.5 * (sw - 1)) - m2d[gi, 0]; ux = (rcx[hit] + 0.5 * (sw - 1)) - m2d[gi, 0]
+        ly = (rcy[hit] - 0.5 * (sh - 1)) - m2d[gi, 1]; uy = (rcy[hit] + 0.5 * (sh - 1)) - m2d[gi, 1]
+        A, B, Cc = a_[gi], b_[gi], c_[gi]
+        def q(dx, dy): return 0.5 * (A * dx * dx + Cc * dy * dy) + B * dx * dy
+        inside = (lx <= 0) & (ux >= 0) & (ly <= 0) & (uy >= 0)
+        cands = []
+        for X in (lx, ux):
+            dy = np.clip(-B * X / Cc, ly, uy); cands.append(q(X, dy))
+        for Y in (ly, uy):
+            dx = np.clip(-B * Y / A, lx, ux); cands.append(q(dx, Y))
+        qmin = np.where(inside, 0.0, np.minimum.reduce(cands))
+        tot_aabb += hit.sum(); tot_exact += (qmin <= tau[gi]).sum()
+print(f"8x4: AABB test keeps {tot_aabb} entries, exact ellipse-vs-rectangle test keeps {tot_exact} ({tot_exact / tot_aabb:.3f})")
