@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(TILE *TILE) loss_fwd_kernel(int H, int W, Wind
     if (tid == 0) atomicAdd(sums + 2, t2);
 }
 
+__global__ void loss_finalize_kernel(int H, int W, float ssim_lambda, float mask_coeff, float *__restrict__ sums) {
+    const float n_ssim = 3.0f * (float)(H - 2 * HALO) * (float)(W - 2 * HALO), n_pix = (float)H * (float)W;
+    sums[3] = ssim_lambda * (1.0f - sums[0] / n_ssim) + (1.0f - ssim_lambda) * sums[1] / (3.0f * n_pix) +
+              mask_coeff * sums[2] / n_pix;
+}
+
 // v_rgba = v_loss * d loss / d rgba
 __global__ void __launch_bounds__(TILE *TILE) loss_bwd_kernel(int H, int W, Window win, const float4 *__restrict__ rgba,
                                                               const float4 *__restrict__ gt, const float *__restrict__ bg,
@@ -213,14 +219,16 @@ __global__ void __launch_bounds__(TILE *TILE) loss_bwd_kernel(int H, int W, Wind
 
 #define GSB_API extern "C" __attribute__((visibility("default")))
 
-GSB_API int gsb_loss_fwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, const float *bg, float *sums3,
-                         float *maps, void *stream) {
-    GSB_CHECK_ARG(H > 2 * HALO && W > 2 * HALO && rgba && gt_rgba && bg && sums3 && maps);
+GSB_API int gsb_loss_fwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, const float *bg,
+                         float ssim_lambda, float mask_coeff, float *sums4, float *maps, void *stream) {
+    GSB_CHECK_ARG(H > 2 * HALO && W > 2 * HALO && rgba && gt_rgba && bg && sums4 && maps);
     cudaStream_t st = (cudaStream_t)stream;
-    GSB_CHECK_CUDA(cudaMemsetAsync(sums3, 0, 3 * sizeof(float), st));
+    float *sums3 = sums4;
+    GSB_CHECK_CUDA(cudaMemsetAsync(sums4, 0, 4 * sizeof(float), st));
     dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE), block(TILE, TILE);
     loss_fwd_kernel<<<grid, block, 0, st>>>(H, W, make_window(), reinterpret_cast<const float4 *>(rgba),
                                             reinterpret_cast<const float4 *>(gt_rgba), bg, sums3, maps);
+    loss_finalize_kernel<<<1, 1, 0, st>>>(H, W, ssim_lambda, mask_coeff, sums4);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

@@ -29,16 +29,15 @@ class _ViewLoss(torch.autograd.Function):
         H, W = r.shape[0], r.shape[1]
         if H <= 10 or W <= 10:
             raise ValueError("view_loss: the SSIM window needs images larger than 10 x 10")
-        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        sums = torch.empty(4, dtype=torch.float32, device=dev)
         maps = torch.empty(9, H, W, dtype=torch.float32, device=dev)
-        call("gsb_loss_fwd", dev, C.c_int32(H), C.c_int32(W), ptr(r), ptr(g), ptr(b), ptr(sums), ptr(maps), stream_ptr(dev))
-        scale = sums.new_tensor([-ssim_lambda / (3.0 * (H - 10) * (W - 10)), (1.0 - ssim_lambda) / (3.0 * H * W),
-                                 mask_coeff / (H * W)])
-        loss = (sums * scale).sum() + ssim_lambda
+        call("gsb_loss_fwd", dev, C.c_int32(H), C.c_int32(W), ptr(r), ptr(g), ptr(b), C.c_float(ssim_lambda),
+             C.c_float(mask_coeff), ptr(sums), ptr(maps), stream_ptr(dev))
         ctx.save_for_backward(r, g, b, maps)
         ctx.misc = (H, W, float(ssim_lambda), float(mask_coeff))
-        ctx.mark_non_differentiable(sums)
-        return loss, sums
+        terms = sums[:3]
+        ctx.mark_non_differentiable(terms)
+        return sums[3], terms
 
     @staticmethod
     def backward(ctx, v_loss, _v_sums):

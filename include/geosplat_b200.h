@@ -306,13 +306,13 @@ int gsb_hashgrid_bwd(int64_t N, const float *x, const float *table, int32_t L, i
  * rfstudio/trainer/geosplat_trainer.py:171-180 (random-background composite, SSIML1Loss of
  * rfstudio/loss/photometric_loss.py:72-112 over torchmetrics' SSIM, mask MSE).  rgba[H,W,4] rendered (tone-mapped
  * linear rgb + alpha), gt_rgba[H,W,4] ground truth (linear rgb + mask), bg[H,W,3] random background.
- *   gsb_loss_fwd: sums3 (device, overwritten) = {sum of the SSIM map over the interior and 3 channels,
- *                 sum |img1 - img2|, sum (mask - alpha)^2}; maps[9,H,W] derivative maps for the backward.
- *                 loss = l (1 - sums3[0] / (3 (H-10)(W-10))) + (1 - l) sums3[1] / (3 H W) + c sums3[2] / (H W).
+ *   gsb_loss_fwd: sums4 (device, overwritten) = {sum of the SSIM map over the interior and 3 channels,
+ *                 sum |img1 - img2|, sum (mask - alpha)^2, loss}; maps[9,H,W] derivative maps for the backward.
+ *                 loss = l (1 - sums4[0] / (3 (H-10)(W-10))) + (1 - l) sums4[1] / (3 H W) + c sums4[2] / (H W).
  *   gsb_loss_bwd: v_rgba[H,W,4] = *v_loss (device scalar) * d loss / d rgba.
  * ------------------------------------------------------------------------------------------- */
-int gsb_loss_fwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, const float *bg, float *sums3,
-                 float *maps, void *stream);
+int gsb_loss_fwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, const float *bg, float ssim_lambda,
+                 float mask_coeff, float *sums4, float *maps, void *stream);
 int gsb_loss_bwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, const float *bg, const float *maps,
                  float ssim_lambda, float mask_coeff, const float *v_loss, float *v_rgba, void *stream);
 

@@ -210,3 +210,32 @@ def test_multi_stream_batch_equals_sequential_views():
             assert scale > 0, name
             tol = 1e-3 if name in ("scales", "quats") else 1e-4      # thin discs, see above
             assert float((a - b).abs().max()) <= tol * scale, (name, float((a - b).abs().max()), scale)
+
+
+def test_batch_edge_cases_empty_scene_and_mixed_resolutions():
+    """splat_views with no Gaussians at all (every arena empty) and with cameras of different sizes in one batch."""
+    from geosplatting_b200.fused import splat_views
+    cube = torch.full((6, 64, 64, 3), 0.5, device=DEV)
+    env = splitsum.as_envstack(cube)
+    lut = torch.from_numpy(synthetic_fg_lut()).to(DEV)
+    ex = torch.ones(1, device=DEV, requires_grad=True)
+    kw = dict(exposures=ex, envmap=env, fg_lut=lut, min_roughness=0.1, max_metallic=1.0)
+    z = lambda *s: torch.zeros(*s, device=DEV, requires_grad=True)
+    cams = [scenes.look_at_camera((0, 0, 2.5), 64, 48), scenes.look_at_camera((0, 1, 2.5), 80, 80)]
+    empty = [z(0, 3), z(0, 3), z(0, 4), z(0, 1), z(0, 3), z(0, 2), z(0, 3)]
+    imgs = splat_views(*empty, cams, **kw)
+    assert imgs[0].shape == (48, 64, 4) and imgs[1].shape == (80, 80, 4)
+    assert all(float(i.abs().max()) == 0.0 for i in imgs)
+    grads = torch.autograd.grad(sum(i.sum() for i in imgs), empty + [ex], allow_unused=True)
+    assert grads[0].shape == (0, 3) and float(grads[-1].abs().max()) == 0.0
+    # a real scene seen by cameras of different resolutions in one batch == the same views one by one
+    sg = scenes.surface_gaussians(5_000, seed=4)
+    p = [sg["means"], sg["scales"].log(), sg["quats"], torch.logit(sg["opacities"])[:, None], sg["kd"], sg["ks"], sg["normals"]]
+    p = [t.to(DEV) for t in p]
+    cams = [scenes.look_at_camera((0.5, 0.4, 2.4), 96, 64), scenes.look_at_camera((-1.0, 0.3, 2.2), 200, 120),
+            scenes.look_at_camera((0.0, 2.0, 1.5), 33, 47)]
+    with torch.no_grad():
+        batch = splat_views(*p, cams, **kw)
+        single = [splat_views(*p, [c], **kw)[0] for c in cams]
+    for a, b, c in zip(batch, single, cams):
+        assert a.shape == (c.height, c.width, 4) and torch.equal(a, b) and float(a[..., 3].max()) > 0.5
