@@ -26,7 +26,7 @@ import torch
 from torch import Tensor
 
 from ._lib import GsbViewConfig, call, f32c, ptr, stream_ptr
-from .rasterization import BinCount, _total_slot, bin_finish, make_camera
+from .rasterization import BinCount, _release_slot, _total_slot, bin_finish, make_camera
 from .scenes import PinholeCamera
 from .shade import MODES, EnvStack, shade_workspace
 
@@ -170,6 +170,7 @@ def _finish_native(sh: _Shared, v: _NativeView, out: Tensor) -> Tensor:
     dev = sh.dev
     v.event.synchronize()                                     # M was stored straight into pinned memory
     v.M = M = int(v.slot[0])
+    _release_slot(v.slot)
     v.event = v.slot = None
     sizes = (C.c_size_t * 5)()
     call("gsb_view_bytes", dev, C.addressof(v.cfg), M, C.addressof(sizes))

@@ -105,16 +105,17 @@ class _Project(torch.autograd.Function):
         return v_means, v_quats, v_scales, None
 
 
-_total_slots: Dict[int, list] = {}
+_free_slots: list = []
 
 
 def _total_slot(device: torch.device) -> Tensor:
-    """A pinned host int64 the device writes M into (ring of 64 per device: a slot is read before it is reused --
-    at most a batch of views is outstanding at a time)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    ring = _total_slots.setdefault(key, [[torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(64)], 0])
-    ring[1] = (ring[1] + 1) % len(ring[0])
-    return ring[0][ring[1]]
+    """A pinned host int64 the device writes M into.  Slots come from a free list and go back to it once read
+    (`_release_slot`), so any number of views can be outstanding; pinned memory is addressable from every device."""
+    return _free_slots.pop() if _free_slots else torch.zeros(1, dtype=torch.int64).pin_memory()
+
+
+def _release_slot(slot: Tensor) -> None:
+    _free_slots.append(slot)
 
 
 class BinCount:
@@ -144,6 +145,8 @@ class BinCount:
         if self._M is None:
             self._event.synchronize()     # no device->host copy: the kernel stored M straight into pinned memory
             self._M = int(self._slot[0])
+            _release_slot(self._slot)
+            self._slot = None
         return self._M
 
 
@@ -201,6 +204,7 @@ def bin_sort(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Te
         call("gsb_isect_total", dev, C.c_int32(N), ptr(cum), C.c_void_p(slot.data_ptr()), st)
         torch.cuda.current_stream(dev).synchronize()
         M = int(slot[0])
+        _release_slot(slot)
     if M == 0:
         offsets.zero_()
         e64 = torch.empty(0, dtype=torch.int64, device=dev)
