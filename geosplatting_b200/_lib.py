@@ -67,7 +67,7 @@ def load() -> C.CDLL:
         _lib.gsb_view_bytes.argtypes = [vp, i64, vp]
         _lib.gsb_view_prepare.argtypes = [vp] * 15
         _lib.gsb_view_finish.argtypes = [vp, vp, i64] + [vp] * 8
-        _lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 24
+        _lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 26
     return _lib
 
 

@@ -163,7 +163,8 @@ GSB_API int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam,
                               const float *fg_lut, const float *env_stack, const float *exposure, const void *keep1,
                               const void *keep2, void *tmp3, const float *v_out, float *v_means, float *v_quats,
                               float *v_scales, float *v_opacity_logits, float *v_normals, float *v_kd, float *v_ks,
-                              float *v_env_stack, float *v_exposure, void *stream) {
+                              float *v_env_stack, float *v_exposure, void *probe_start, void *probe_stop,
+                              void *stream) {
     VIEW_CHECK_CFG(cfg);
     GSB_CHECK_ARG(cam && cam_pos_host && M >= 0 && keep1 && keep2 && tmp3 && v_out && v_exposure);
     Sizes s;
@@ -181,8 +182,11 @@ GSB_API int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam,
     VIEW_TRY(gsb_tonemap_planar_bwd((int64_t)P, k2.render, exposure, cfg->naive_tonemap, v_out, v_render, v_alphas,
                                     v_exposure, stream));
     GSB_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 9 * N, (cudaStream_t)stream));
+    // optional probe: two caller-owned cudaEvent_t recorded around the dominant stage (bench.py's live roofline timing)
+    if (probe_start) GSB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)probe_start, (cudaStream_t)stream));
     VIEW_TRY(gsb_composite_bwd(cfg->width, cfg->height, 3, cfg->N, k1.colors, nullptr, k2.offsets, M, k2.alphas,
                                k2.last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opac, k2.comp_ws, stream));
+    if (probe_stop) GSB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)probe_stop, (cudaStream_t)stream));
     // both ADD into the caller's gradient buffers (views of a batch on one stream share them)
     VIEW_TRY(gsb_project_bwd(cfg->N, means, quats, scales, cam, k1.radii, v_means2d, nullptr, v_conics, nullptr, v_means,
                              v_quats, v_scales, opacity_logits, v_opac, v_opacity_logits, 1, stream));

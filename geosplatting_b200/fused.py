@@ -183,16 +183,30 @@ def _finish_native(sh: _Shared, v: _NativeView, out: Tensor) -> Tensor:
     return out
 
 
+# bench.py sets this to a list to time the compositing backward of every view live, inside the running batches:
+# (start, stop) CUDA-event pairs are appended to it
+PROBES = None
+
+
 def _view_backward_native(sh: _Shared, v: _NativeView, v_out: Tensor, g: "_Grads", v_exp: Tensor) -> None:
     dev = sh.dev
     v_out = f32c(v_out)
     tmp3 = _u8(v.sizes[4], dev)
+    p0 = p1 = 0
+    if PROBES is not None:
+        stream = torch.cuda.current_stream(dev)
+        pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for e in pair:
+            e.record(stream)          # materialises the cudaEvent_t; the driver re-records it around the stage
+        PROBES.append(pair)
+        p0, p1 = pair[0].cuda_event, pair[1].cuda_event
     call("gsb_view_backward", dev, C.addressof(v.cfg), C.addressof(v.cam), C.addressof(v.cam_pos), v.M,
          sh.means.data_ptr(), sh.quats.data_ptr(), sh.scales.data_ptr(), sh.logits.data_ptr(), sh.normals.data_ptr(),
          sh.kd.data_ptr(), sh.ks.data_ptr(), sh.lut.data_ptr(), sh.env.data_ptr(), v.exposure.data_ptr(),
          v.keep1.data_ptr(), v.keep2.data_ptr(), tmp3.data_ptr(), v_out.data_ptr(), g.means.data_ptr(),
          g.quats.data_ptr(), g.scales.data_ptr(), g.logits.data_ptr(), g.normals.data_ptr(), g.kd.data_ptr(),
-         g.ks.data_ptr(), g.env.data_ptr(), v_exp.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+         g.ks.data_ptr(), g.env.data_ptr(), v_exp.data_ptr(), p0 or None, p1 or None,
+         torch.cuda.current_stream(dev).cuda_stream)
 
 
 class _Grads:

@@ -350,7 +350,10 @@ int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const f
                       const float *normals, const float *kd, const float *ks, const float *fg_lut,
                       const float *env_stack, const float *exposure, const void *keep1, const void *keep2, void *tmp3,
                       const float *v_out, float *v_means, float *v_quats, float *v_scales, float *v_opacity_logits,
-                      float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, float *v_exposure, void *stream);
+                      float *v_normals, float *v_kd, float *v_ks, float *v_env_stack, float *v_exposure,
+                      void *probe_start, void *probe_stop, void *stream);
+/* probe_start / probe_stop: optional caller-owned cudaEvent_t (NULL to skip) recorded on `stream` right before and
+ * after the compositing backward, the dominant stage, so that a benchmark can time it inside a running batch. */
 
 #ifdef __cplusplus
 }
