@@ -249,19 +249,64 @@ __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float
     const float kscale = alphaSqr * (0.25f / 3.14159265358979323846f);
     const float e_scale = 0.25f * (1.0f - alphaSqr);
     const int s_begin = SPLIT ? blockIdx.y : 0, s_end = SPLIT ? blockIdx.y + 1 : 6;
+    // conservative copy of the cone test for the per-row spans below (the exact test on d decides membership)
+    const float cs = cutoff * (1.0f - 1e-5f) - 1e-6f;
+    const float halfR = 0.5f * (float)R, twoOverR = 2.0f / (float)R;
     for (int s = s_begin; s < s_end; ++s) {
         const float4 b = __ldg(bounds + (size_t)t * 6 + s);
-        int xmin = (int)b.x, xmax = (int)b.y, ymin = (int)b.z, ymax = (int)b.w;
-        if (xmin > xmax) { xmin = ymin = 1 << 30; xmax = ymax = -1; }   // this lane's cone misses face s
+        const int lxmin = (int)b.x, lxmax = (int)b.y, lymin = (int)b.z, lymax = (int)b.w;   // this lane's cone AABB
+        int ymin = lymin, ymax = lymax;
+        if (lxmin > lxmax) { ymin = 1 << 30; ymax = -1; }   // this lane's cone misses face s
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
             ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
             ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
         }
-        if (xmax < xmin) continue;   // warp-uniform
+        if (ymax < ymin) continue;   // warp-uniform
+        // face frame: p(gx, gy) = n + gx u + gy w, so p.V = a gx + (gy bw + cn)
+        float nx, ny, nz, ux, uy, uz, wx, wy, wz;
+        gsb_face_point(s, 0.f, 0.f, nx, ny, nz);
+        gsb_face_point(s, 1.f, 0.f, ux, uy, uz);
+        gsb_face_point(s, 0.f, 1.f, wx, wy, wz);
+        const float a = (ux - nx) * V.x + (uy - ny) * V.y + (uz - nz) * V.z;
+        const float bw = (wx - nx) * V.x + (wy - ny) * V.y + (wz - nz) * V.z;
+        const float cn = nx * V.x + ny * V.y + nz * V.z;
+        const float A = a * a - cs * cs;
         for (int y = ymin; y <= ymax; ++y) {
+            // Row span of THIS lane's cone: the texels with (a gx + b0)^2 >= cs^2 (gx^2 + gy^2 + 1), a gx + b0 >= 0 -- a
+            // chord of a conic, far tighter than the AABB (the AABB of a disc wastes 1 - pi/4 of its taps).  The
+            // span only has to be a superset (one texel of margin); where the quadratic does not describe a bounded
+            // interval (A >= 0: the face is steep against the cone axis) the AABB span is kept.
+            int xlo = 1 << 30, xhi = -1;
+            if (y >= lymin && y <= lymax && lxmin <= lxmax) {
+                xlo = lxmin; xhi = lxmax;
+                if (cs > 0.f && A < -1e-6f) {
+                    const float gy = ((float)y + 0.5f) * twoOverR - 1.0f;
+                    const float b0 = gy * bw + cn;
+                    const float Bq = 2.0f * a * b0, Cq = b0 * b0 - cs * cs * (gy * gy + 1.0f);
+                    const float disc = Bq * Bq - 4.0f * A * Cq;
+                    if (disc < 0.f) {
+                        xlo = 1 << 30; xhi = -1;
+                    } else {
+                        const float sq = sqrtf(disc), inv2A = 0.5f / A;
+                        const float r1 = (-Bq - sq) * inv2A, r2 = (-Bq + sq) * inv2A;
+                        const float glo = fminf(r1, r2), ghi = fmaxf(r1, r2);
+                        if (a * (0.5f * (glo + ghi)) + b0 < 0.f) {
+                            xlo = 1 << 30; xhi = -1;                       // the mirror branch of the squared test
+                        } else {
+                            xlo = max(xlo, (int)floorf((glo + 1.0f) * halfR - 0.5f) - 1);
+                            xhi = min(xhi, (int)ceilf((ghi + 1.0f) * halfR - 0.5f) + 1);
+                        }
+                    }
+                }
+            }
+            int xmin = xlo, xmax = xhi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+                xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            }
+            if (xmax < xmin) continue;   // warp-uniform
             const float4 *drow = dirs + ((size_t)s * R + y) * R;
             const float4 *prow = pre + ((size_t)s * R + y) * R;
             // branch-free body, 4 taps in flight: the loads are warp-broadcast L1 hits and the four weight
