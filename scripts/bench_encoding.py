@@ -32,4 +32,17 @@ for name, mk in (("kd", E.kd_field), ("ks", E.ks_field), ("z", E.z_field)):
     out[name] = {"encode_fwd_ms": round(t_enc, 4), "encode_fwd_gbs": round(N * 140 / t_enc / 1e6, 1),
                  "encode_fwd_frac_of_measured_hbm": round(N * 140 / t_enc / 1e6 / peak, 3),
                  "encode_fwd_bwd_ms": round(t_enc_bwd, 4), "field_fwd_bwd_ms": round(t_all, 4)}
+# the same kd field on mesh-ordered points (the bench scene's MGAdaptor means): neighbouring threads share cells
+from geosplatting_b200 import scenes
+from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
+with torch.no_grad():
+    verts, faces = scenes.cube_sphere(118)
+    vd, fd = verts.to(dev), faces.to(dev)
+    sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+xm = (sp.means / 0.9).clamp(-1, 1).detach().requires_grad_(True)
+enc = E.kd_field().to(dev)
+cotm = torch.randn(xm.shape[0], 32, device=dev)
+out["kd_mesh_ordered_points"] = {
+    "encode_fwd_ms": round(timed(lambda: enc.encode(xm)), 4),
+    "encode_fwd_bwd_ms": round(timed(lambda: torch.autograd.grad(enc.encode(xm), [xm, enc.hash_table], grad_outputs=cotm)), 4)}
 print(json.dumps({"N": N, "fields": out}))
