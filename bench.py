@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--light-res", type=int, default=512, help="env cube-map resolution (GeoSplatter.light_resolution)")
     ap.add_argument("--views", type=int, default=8, help="batch: distinct cameras per rank, forwarded then back-propagated together (the trainer's batch of 8); one gradient all-reduce per batch when N > 1")
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a batch are spread over")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a batch are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")

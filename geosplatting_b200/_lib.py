@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgeosplat_b200.so")
+LIB_PATH = os.environ.get("GSB_LIB_PATH") or os.path.join(_HERE, "lib", "libgeosplat_b200.so")   # override: tuning builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "geosplat_b200.h")
 

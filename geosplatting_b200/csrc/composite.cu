@@ -25,8 +25,20 @@ namespace {
 
 constexpr int SUB_W = 8, SUB_H = 4;                       // pixel footprint of one warp
 constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 8 sub-rectangles per tile
-constexpr int WPB = 2;                                    // warps (units) per CTA in the composite kernels
-constexpr int FG = 8;                                     // entries evaluated together in the forward
+#ifndef GSB_WPB
+#define GSB_WPB 2
+#endif
+#ifndef GSB_FG
+#define GSB_FG 8
+#endif
+#ifndef GSB_BG
+#define GSB_BG 8
+#endif
+#ifndef GSB_WPB_B
+#define GSB_WPB_B 2
+#endif
+constexpr int WPB = GSB_WPB;                              // warps (units) per CTA in the composite kernels
+constexpr int FG = GSB_FG;                                // entries evaluated together in the forward
 
 struct Rec {
     float4 k;  // x, y, hx, hy
@@ -371,8 +383,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
 // (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
 constexpr int BSTRIDE = 33;
-constexpr int BG = 8;      // entries evaluated together in phase A
-constexpr int WPB_B = 2;   // warps per CTA in the backward (15 KB of shared memory per warp)
+constexpr int BG = GSB_BG;   // entries evaluated together in phase A
+constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (15 KB of shared memory per warp)
 
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB_B)

@@ -8,10 +8,10 @@ what it removes is host work, glue kernels and idle SMs:
   * one autograd node instead of ~15 per view; no torch.cat / stack / slice copies of the image
     (gsb_tonemap_planar_*); sigmoid(opacity) * compensation folded into the record packing and its chain rule into
     gsb_project_bwd; cached camera structs; exp(log-scales) once per batch;
-  * the views of a batch are spread round-robin over CUDA streams.  Every view is PREPARED (projection, count, shade)
-    before the first one waits for its intersection count, and binning / compositing -- forward and backward -- of
-    neighbouring views overlap on the device: the composite kernels end in a long, poorly occupied tail (one warp per
-    sub-list) that a second view fills;
+  * the views of a batch are spread round-robin over CUDA streams and software-pipelined: a view is PREPARED
+    (projection, count, shade) one stream-round before it is finished, so the host's wait for its intersection count
+    never leaves the device idle, and binning / compositing -- forward and backward -- of neighbouring views overlap:
+    the composite kernels end in a long, poorly occupied tail (one warp per sub-list) that other views fill;
   * the backward kernels of the views on one stream ADD into that stream's gradient buffer (accumulate flag of
     gsb_project_bwd / gsb_shade_bwd), so a batch costs one zero-fill and one add per stream instead of one add per
     view and tensor in the autograd engine.
@@ -274,15 +274,27 @@ class _SplatBatch(torch.autograd.Function):
         for s in side:
             s.wait_stream(main)
         where = [side[i % len(side)] if side else main for i in range(len(cameras))]
-        views, cfgs = [], {}
-        for cam, ex, s in zip(cameras, exposures, where):
-            with torch.cuda.stream(s):
-                v = _prepare_native(sh, cam, ex, cfgs) if native else _prepare(sh, cam, ex)
-                v.stream = s
-                views.append(v)
-        for v, out in zip(views, outs):
-            with torch.cuda.stream(v.stream):
-                (_finish_native if native else _finish)(sh, v, out)
+        # Software pipeline over the views: one view per stream is prepared up front; after view i is finished (the
+        # only point where the host waits, for M_i), view i + n_streams is prepared on the same stream.  The host never
+        # waits on an idle device, and at any time the streams are in different phases, so the big compositing
+        # kernels of one view share the SMs with the small sort / scan kernels of its neighbours.
+        n = len(cameras)
+        views, cfgs = [None] * n, {}
+
+        def prep(i):
+            with torch.cuda.stream(where[i]):
+                v = _prepare_native(sh, cameras[i], exposures[i], cfgs) if native else _prepare(sh, cameras[i], exposures[i])
+                v.stream = where[i]
+                views[i] = v
+
+        ahead = max(2, len(side))
+        for i in range(min(ahead, n)):
+            prep(i)
+        for i in range(n):
+            with torch.cuda.stream(where[i]):
+                (_finish_native if native else _finish)(sh, views[i], outs[i])
+            if i + ahead < n:
+                prep(i + ahead)
         for s in side:
             main.wait_stream(s)
         ctx.sh, ctx.views, ctx.side, ctx.native = sh, views, side, native
@@ -343,7 +355,7 @@ def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic,
 def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
                 normals: Tensor, cameras: Sequence[PinholeCamera], *, exposures, envmap: EnvStack, fg_lut: Tensor,
                 min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-                rasterize_mode: str = "antialiased", n_streams: int = 3, native: bool = True) -> List[Tensor]:
+                rasterize_mode: str = "antialiased", n_streams: int = 4, native: bool = True) -> List[Tensor]:
     """The per-view loop of GeoSplatter.render_report for a batch of cameras: list of [H,W,4] tone-mapped RGBA images,
     ready on the caller's stream, differentiable w.r.t. every tensor argument and `envmap.data`.
 
