@@ -143,3 +143,25 @@ def test_encoding_oracle_matches_reference_code():
         assert np.abs(grads[1].numpy() - vt).max() <= 1e-5 * np.abs(vt).max()
         for k in range(n_w):
             assert np.abs(grads[2 + k].numpy() - g[f"{tag}_v_w{k}"]).max() <= 1e-5 * np.abs(g[f"{tag}_v_w{k}"]).max()
+
+
+def test_field_host_glue_matches_reference_code():
+    """The torch-only pieces of geosplatting_b200.field (host glue: get_patches, rot2quat, the rotation helper, the level
+    scalings) against the reference's own code (ref_field.npz / ref_math.npz / ref_encoding.npz); they need no GPU."""
+    from geosplatting_b200 import encoding as E
+    from geosplatting_b200.field import GaussianField, get_rotation_from_relative_vectors, rot2quat, safe_normalize
+    g = load("ref_field.npz")
+    verts, faces = torch.from_numpy(g["vertices"]), torch.from_numpy(g["indices"])
+    normals, areas = GaussianField.get_patches(None, verts, faces)
+    assert np.abs(normals.numpy() - g["patch_normals"]).max() <= 1e-6
+    assert np.abs(areas.numpy() - g["patch_areas"]).max() <= 1e-6 * np.abs(g["patch_areas"]).max()
+    # the vertex path's quaternions are rot2quat(rotation from +z to the patch normal)
+    R = get_rotation_from_relative_vectors(torch.tensor([0.0, 0.0, 1.0]), normals)
+    assert np.abs(rot2quat(R).numpy() - g["v_quats"]).max() <= 2e-6
+    m = load("ref_math.npz")
+    assert np.abs(rot2quat(torch.from_numpy(m["rots"])).numpy() - m["quats"]).max() <= 1e-6
+    assert np.abs(safe_normalize(torch.from_numpy(m["vecs"])).numpy() - m["safe_normalized"]).max() <= 1e-6
+    e = load("ref_encoding.npz")
+    assert np.array_equal(np.asarray(E.level_scalings(16, 16, 4096), np.float32), e["kd_scalings"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        E.HashEncoding(E.MLP([32, 3]), log2_hashmap_size=4).encode(torch.zeros(2, 3))
