@@ -219,3 +219,23 @@ def test_two_stage_binning_equals_single_sort():
     count = Rz.BinCount(empty, torch.zeros(0, device=DEV))
     flat, offs = Rz.bin_finish(count, torch.zeros(0, 2, device=DEV), empty, gcam)
     assert flat.numel() == 0 and int(offs.abs().max()) == 0
+
+
+def test_two_cameras_in_one_call():
+    """gsplat's signature takes viewmats[C,4,4]; the reference always passes C = 1 (gsplat.py:293), but the drop-in keeps
+    the batched form: C = 2 equals two single-camera calls, info is concatenated per camera."""
+    g = scenes.random_gaussians(4_000, seed=19, scale_lo=0.02, scale_hi=0.12)
+    cams = scenes.orbit_cameras(2, 160, 96, seed=9)
+    t = {k: v.to(DEV) for k, v in g.items()}
+    vms = torch.stack([torch.from_numpy(c.view_matrix) for c in cams]).to(DEV)
+    Ks = torch.stack([torch.from_numpy(c.intrinsic_matrix) for c in cams]).to(DEV)
+    args = (t["means"], t["quats"], t["scales"], t["opacities"], t["colors"])
+    render, alpha, info = rasterization(*args, vms, Ks, 160, 96, rasterize_mode="antialiased")
+    assert render.shape == (2, 96, 160, 3) and alpha.shape == (2, 96, 160, 1) and info["n_cameras"] == 2
+    n_ids = 0
+    for c in range(2):
+        r1, a1, i1 = rasterization(*args, vms[c:c + 1], Ks[c:c + 1], 160, 96, rasterize_mode="antialiased")
+        assert torch.equal(render[c], r1[0]) and torch.equal(alpha[c], a1[0])
+        n_ids += i1["gaussian_ids"].numel()
+    assert info["gaussian_ids"].numel() == n_ids and set(info["camera_ids"].unique().tolist()) == {0, 1}
+    assert info["isect_offsets"].shape == (2, 6, 10)
