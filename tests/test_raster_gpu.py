@@ -58,6 +58,10 @@ def _check(g, cam, mode, check_grads=True, seed=1, grad_rel_l2=2e-4, grad_linf=1
     assert np.abs(render - o_render)[ok].max() <= 1e-4
     assert np.abs(alpha - o_alpha)[ok].max() <= 1e-4
     assert np.abs(render - o_render)[frag].max(initial=0) <= 1.0  # a flipped decision moves a pixel by < 1 colour unit
+    # BASELINE.json north_star: PSNR within 0.05 dB of the reference -- over ALL pixels, fragile ones included, the
+    # image is the oracle's to better than 70 dB
+    mse = float(np.mean((render.astype(np.float64) - o_render) ** 2))
+    assert mse == 0.0 or 10.0 * np.log10(1.0 / mse) >= 70.0, 10.0 * np.log10(1.0 / mse)
     if check_grads:
         o_grads = R.rasterization_bwd(gn["means"], gn["quats"], gn["scales"], gn["opacities"], gn["colors"], ocam,
                                       o_info, o_alpha, vr, va, rasterize_mode=mode)
