@@ -4,13 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the CPU oracle on the box's host cores
 
-A "step" is one training view of BASELINE.json's metric configuration (1M Gaussians, 800x800): split-sum
-shade -> EWA projection -> tile bin / radix sort -> alpha composite -> tone map, then the backward of all of
-them for a fixed random image cotangent (gradients to means / log-scales / quats / opacities / kd / ks /
-normals / env-map texels / exposure).  The Gaussians come from the MGAdaptor kernel on a 167k-face mesh.
-Views are sharded over ranks (one process per GPU, no data-path collective inside a view; every
-`--allreduce-every` views the packed per-Gaussian gradients are summed with ONE NCCL all-reduce, inside the
-timed region), so `scaling` is "weak".  Prints ONE JSON line; keys are documented in DESIGN.md section 7.
+A "step" is one training view of BASELINE.json's metric configuration (1M Gaussians, 800x800): EWA projection -> depth
+order / intersection count -> split-sum shade -> tile binning -> alpha composite -> tone map, then the backward of all of
+them for a fixed random image cotangent (gradients to means / log-scales / quats / opacities / kd / ks / normals /
+env-map texels / exposure).  The Gaussians come from the MGAdaptor kernel on a 167k-face mesh.  The K views run the way
+the reference's trainer runs them -- batches of `--views` (8): all forwards, one backward over the batch -- through
+fused.splat_views (one autograd node per batch, views software-pipelined over `--streams` CUDA streams, three native
+calls per view).  Views are sharded over ranks (one process per GPU, no data-path collective inside a view; once per
+batch the packed per-Gaussian gradients are summed with ONE asynchronous NCCL all-reduce, inside the timed region), so
+`scaling` is "weak".  Prints ONE JSON line; keys are documented in DESIGN.md section 7.
 """
 from __future__ import annotations
 
@@ -177,7 +179,6 @@ def run_b200(a):
     gen = torch.Generator().manual_seed(1234 + rank)
     v_img_host = torch.randn(H, W, 4, generator=gen).pin_memory()
     v_img = v_img_host.to(dev)
-    stats = {}
 
     from geosplatting_b200.fused import splat_view, splat_views
 
