@@ -524,6 +524,12 @@ def run_oracle(a, steps, warmup, budget_s=150.0):
     from oracle import raster as R
     from oracle import shade as OS
 
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    R.set_num_threads(cores)
     cores = R.num_threads()
     torch.set_num_threads(cores)
     sc = build_scene_host(a)
