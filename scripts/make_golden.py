@@ -336,6 +336,29 @@ def main():
     fout.update(f_offsets=off_f, facepath_grad_vertices=gf[0], facepath_grad_kd_table=gf[1], facepath_grad_z_table=gf[2])
     save("ref_field.npz", **fout)
 
+    # ---- J. FlexiCubes.dual_marching_cubes + compute_entropy (_flexicubes.py:559-725), as
+    #         GeoSplatter.get_geometry drives it (geosplat.py:751-769): fixtures for the row that is NOT built yet, so
+    #         that a CUDA implementation can be held to the reference's own outputs (vertex / face ORDER included).
+    R = 10
+    fc0 = G.FlexiCubes.from_resolution(R, random_sdf=False, scale=0.9)
+    gv = fc0.vertices
+    # a bumpy sphere's SDF (the same family bench.py meshes come from) on the grid vertices
+    sdf = (gv.norm(dim=-1, keepdim=True) - 0.55 + 0.08 * torch.sin(5.0 * gv[:, :1]) * torch.cos(4.0 * gv[:, 1:2]))
+    sdf = sdf.clone().requires_grad_(True)
+    deform = (0.3 * torch.randn(gv.shape, generator=g)).requires_grad_(True)
+    weights = (0.2 * torch.randn(fc0.indices.shape[0], 21, generator=g)).requires_grad_(True)
+    verts_fc = gv + deform.tanh() * (0.5 * 0.9 / R)                                   # geosplat.py:756
+    fc = fc0.replace(vertices=verts_fc, sdf_values=sdf, alpha=weights[:, :8], beta=weights[:, 8:20],
+                     gamma=weights[:, 20:])
+    mesh_fc, L_dev = fc.dual_marching_cubes()
+    entropy = fc.compute_entropy()
+    cot_v = torch.randn(mesh_fc.vertices.shape, generator=g)
+    loss_fc = (mesh_fc.vertices * cot_v).sum() + L_dev.mean() * 0.5 + entropy * 0.3
+    g_sdf, g_def, g_w = torch.autograd.grad(loss_fc, [sdf, deform, weights])
+    save("ref_flexicubes.npz", resolution=R, scale=0.9, grid_vertices=gv, cube_indices=fc0.indices, sdf=sdf,
+         deform=deform, weights=weights, mesh_vertices=mesh_fc.vertices, mesh_indices=mesh_fc.indices, L_dev=L_dev,
+         entropy=entropy, cot_vertices=cot_v, v_sdf=g_sdf, v_deform=g_def, v_weights=g_w)
+
 
 if __name__ == "__main__":
     main()
