@@ -55,3 +55,32 @@ def test_cpu_tensors_are_rejected():
     z = torch.zeros(4, 3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         rasterization(z, torch.zeros(4, 4), z, torch.zeros(4), z, torch.eye(4)[None], torch.eye(3)[None], 32, 32)
+
+
+def test_header_is_plain_c_and_every_error_path_answers_without_a_gpu():
+    """include/geosplat_b200.h compiles as C99 (no torch / C++ types in the ABI), and argument validation of the newer
+    entry points (two-stage binning, per-view driver, hash grid, loss) answers with GSB_EINVAL before touching a device."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc:
+        subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c",
+                               _lib.HEADER_PATH])
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    assert lib.gsb_bin2_workspace_bytes(ctypes.c_int32(-1), ctypes.c_int64(0), ctypes.byref(n)) == -1
+    assert lib.gsb_bin2_workspace_bytes(ctypes.c_int32(1000), ctypes.c_int64(5000), ctypes.byref(n)) == 0 and n.value > 0
+    assert lib.gsb_view_bytes(None, ctypes.c_int64(0), None) == -1
+    cfg = _lib.GsbViewConfig(1000, 64, 48, 256, 64, 3, 16, 0.1, 1.0, 0.08, 0.5, 0, 1)
+    sizes = (ctypes.c_size_t * 5)()
+    assert lib.gsb_view_bytes(ctypes.addressof(cfg), 4000, ctypes.addressof(sizes)) == 0 and all(s > 0 for s in sizes)
+    bad = _lib.GsbViewConfig(1000, 64, 48, 256, 64, 3, 16, 0.1, 1.0, 0.08, 0.5, 7, 1)      # mode out of range
+    assert lib.gsb_view_bytes(ctypes.addressof(bad), 0, ctypes.addressof(sizes)) == -1
+    sc = (ctypes.c_float * 16)(*range(16, 32))
+    assert lib.gsb_hashgrid_fwd(ctypes.c_int64(10), None, None, ctypes.c_int32(16), ctypes.c_int32(4), ctypes.c_int32(18),
+                                sc, None, None) == -1
+    assert b"features_per_level must be 2" in lib.gsb_last_error()
+    assert lib.gsb_loss_fwd(ctypes.c_int32(8), ctypes.c_int32(8), None, None, None, ctypes.c_float(0.2),
+                            ctypes.c_float(5.0), None, None, None) == -1
+    assert lib.gsb_shade_workspace_bytes(ctypes.c_int32(512), ctypes.c_int32(6), ctypes.c_int32(16), ctypes.byref(n)) == 0
+    assert n.value == 16 * (6 * 32 * 32 + 6 * 16 * 16 + 6 * 16 * 16) * 32
