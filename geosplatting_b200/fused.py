@@ -298,12 +298,16 @@ class _SplatBatch(torch.autograd.Function):
         for s in side:
             main.wait_stream(s)
         ctx.sh, ctx.views, ctx.side, ctx.native = sh, views, side, native
+        # the kernels of the backward read the inputs again: registering them lets autograd's version counters catch
+        # an in-place update (an optimiser step) between this forward and its backward
+        ctx.save_for_backward(sh.means, sh.quats, sh.logits, sh.kd, sh.ks, sh.normals, sh.env)
         ctx.shapes = (tuple(logits.shape), [tuple(e.shape) for e in exposures], env_data.shape[0])
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *v_outs):
         sh, views, side = ctx.sh, ctx.views, ctx.side
+        _ = ctx.saved_tensors                                  # raises if an input was modified in place since the forward
         logits_shape, exposure_shapes, T = ctx.shapes
         dev, N = sh.dev, sh.N
         main = torch.cuda.current_stream(dev)

@@ -239,3 +239,21 @@ def test_batch_edge_cases_empty_scene_and_mixed_resolutions():
         single = [splat_views(*p, [c], **kw)[0] for c in cams]
     for a, b, c in zip(batch, single, cams):
         assert a.shape == (c.height, c.width, 4) and torch.equal(a, b) and float(a[..., 3].max()) > 0.5
+
+
+def test_inplace_update_between_forward_and_backward_is_caught():
+    """The batch node's backward re-reads its inputs; an optimiser-style in-place update in between must raise (autograd's
+    version counters), not silently differentiate the wrong point."""
+    from geosplatting_b200.fused import splat_views
+    sg = scenes.surface_gaussians(2_000, seed=6)
+    p = [sg["means"], sg["scales"].log(), sg["quats"], torch.logit(sg["opacities"])[:, None], sg["kd"], sg["ks"], sg["normals"]]
+    p = [t.to(DEV).requires_grad_(True) for t in p]
+    env = splitsum.as_envstack(torch.full((6, 64, 64, 3), 0.5, device=DEV))
+    lut = torch.from_numpy(synthetic_fg_lut()).to(DEV)
+    cams = scenes.orbit_cameras(2, 64, 64, seed=1)
+    imgs = splat_views(*p, cams, exposures=torch.ones(1, device=DEV), envmap=env, fg_lut=lut, min_roughness=0.1,
+                       max_metallic=1.0)
+    with torch.no_grad():
+        p[0].add_(0.01)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        torch.autograd.grad(sum(i.sum() for i in imgs), p)
