@@ -3,7 +3,15 @@
 Python host code over a C-ABI CUDA library (include/geosplat_b200.h).  Public operators mirror the
 reference's interfaces for this path:
 
-    rasterization(...)                  <- gsplat.rasterization   (rfstudio/model/gsplat.py:334-355)
+    rasterization(...)                       <- gsplat.rasterization            (rfstudio/model/gsplat.py:334-355)
+    shade.texture(...)                       <- nvdiffrast.torch.texture        (geosplat.py:93, _texture.py:220,:596,:604)
+    splitsum.render_utils / as_splitsum      <- rfstudio_render_utils plugin, TextureCubeMap.as_splitsum
+    splat.RenderableAttrs / GSplatter        <- rfstudio/model/geosplat.py:43-132, rfstudio/model/gsplat.py:284-358
+    fused.splat_views(...)                   <- the per-view loop of GeoSplatter.render_report (geosplat.py:869-879)
+    mgadapter.MGAdapter / compute_vertex_normals
+    encoding.HashEncoding / MLP, field.GaussianField   <- the kd / ks / z fields and their glue (geosplat.py:482-674)
+    loss.view_loss(...)                      <- the per-view loss of GeoSplatTrainer.step (geosplat_trainer.py:171-180)
+    parallel.shard_views / GradientBucket    <- view sharding + one all-reduce per batch (new: the reference is single-GPU)
 
 There is no CPU, PyTorch-eager or Triton fallback anywhere in this package.
 """
