@@ -355,9 +355,33 @@ def main():
     cot_v = torch.randn(mesh_fc.vertices.shape, generator=g)
     loss_fc = (mesh_fc.vertices * cot_v).sum() + L_dev.mean() * 0.5 + entropy * 0.3
     g_sdf, g_def, g_w = torch.autograd.grad(loss_fc, [sdf, deform, weights])
-    save("ref_flexicubes.npz", resolution=R, scale=0.9, grid_vertices=gv, cube_indices=fc0.indices, sdf=sdf,
+    from rfstudio.graphics._mesh import _flexicubes as RFC
+    cpu = torch.device("cpu")
+    # the four lookup tables are DATA of the algorithm (published with the FlexiCubes paper): stored in the fixture
+    # by value, read from the reference at generation time
+    tables = dict(tbl_cube_edges=RFC._get_cube_edges(cpu), tbl_check=RFC._get_check_table(cpu),
+                  tbl_dmc=RFC._get_dmc_table(cpu), tbl_num_vd=RFC._get_num_vd_table(cpu))
+    save("ref_flexicubes.npz", **tables, resolution=R, scale=0.9, grid_vertices=gv, cube_indices=fc0.indices, sdf=sdf,
          deform=deform, weights=weights, mesh_vertices=mesh_fc.vertices, mesh_indices=mesh_fc.indices, L_dev=L_dev,
          entropy=entropy, cot_vertices=cot_v, v_sdf=g_sdf, v_deform=g_def, v_weights=g_w)
+
+    # a rough random SDF on a 7 x 6 x 5 grid: every topology case incl. the ambiguous ones that get inverted
+    # (_flexicubes.py:472-505), non-cubic resolution, cubes with 2-4 dual vertices
+    fr = G.FlexiCubes.from_resolution(7, 6, 5, random_sdf=False, scale=1.0)
+    sdf_r = (torch.rand(fr.vertices.shape[0], 1, generator=g) - 0.45).requires_grad_(True)
+    w_r = (0.5 * torch.randn(fr.indices.shape[0], 21, generator=g)).requires_grad_(True)
+    fcr = fr.replace(sdf_values=sdf_r, alpha=w_r[:, :8], beta=w_r[:, 8:20], gamma=w_r[:, 20:])
+    occ_r = (sdf_r < 0)[fr.indices.flatten()].view(-1, 8)
+    surf_r = (occ_r.sum(-1) > 0) & (occ_r.sum(-1) < 8)
+    plain_case = (occ_r[surf_r] * torch.pow(2, torch.arange(8))).sum(-1)
+    resolved_case = fcr._get_case_id(occ_r, surf_r)
+    mesh_r, L_r = fcr.dual_marching_cubes()
+    cot_r = torch.randn(mesh_r.vertices.shape, generator=g)
+    gr = torch.autograd.grad((mesh_r.vertices * cot_r).sum() + L_r.mean(), [sdf_r, w_r])
+    save("ref_flexicubes_rough.npz", **tables, resolution=torch.tensor([7, 6, 5]), grid_vertices=fr.vertices,
+         cube_indices=fr.indices, sdf=sdf_r, weights=w_r, mesh_vertices=mesh_r.vertices, mesh_indices=mesh_r.indices,
+         L_dev=L_r, entropy=fcr.compute_entropy(), cot_vertices=cot_r, v_sdf=gr[0], v_weights=gr[1],
+         n_inverted=(plain_case != resolved_case).sum())
 
 
 if __name__ == "__main__":
