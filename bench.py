@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")
+    ap.add_argument("--fc-res", type=int, default=0,
+                    help="with --full-step: the mesh comes from FlexiCubes on an R^3 SDF grid every step (8f rank 3)")
     return ap.parse_args()
 
 
@@ -398,8 +400,44 @@ def run_b200(a):
         cube = sc["cubemap"].to(dev).requires_grad_(True)
         guess = torch.zeros(2, device=dev)
         field_params = [t for t in field.parameters()]
+        fc_grid = None
+        if a.fc_res > 0:
+            # GeoSplatter.get_geometry (geosplat.py:751-769): SDF grid -> FlexiCubes mesh + regulariser, every step
+            from geosplatting_b200.flexicubes import FlexiCubes
+            R_ = a.fc_res
+            fc_grid = FlexiCubes.from_resolution(R_, random_sdf=False, scale=0.9, device=dev)
+            gv_ = fc_grid.vertices
+            sdf_p = (gv_.norm(dim=-1, keepdim=True) - 0.6 + 0.06 * torch.sin(5.0 * gv_[:, :1]) * torch.cos(4.0 * gv_[:, 1:2]))
+            sdf_p = sdf_p.clone().requires_grad_(True)
+            deform_p = torch.zeros_like(gv_).requires_grad_(True)
+            weight_p = torch.zeros(fc_grid.indices.shape[0], 21, device=dev).requires_grad_(True)
+            fc_stats = {}
+
+        def geometry():
+            vertices = fc_grid.vertices + deform_p.tanh() * (0.5 * 0.9 / a.fc_res)
+            fc_ = fc_grid.replace(vertices=vertices, sdf_values=sdf_p, alpha=weight_p[:, :8], beta=weight_p[:, 8:20],
+                                  gamma=weight_p[:, 20:])
+            mesh_, l_dev_ = fc_.dual_marching_cubes()
+            reg_ = l_dev_.mean() * 0.5 + weight_p[:, :20].abs().mean() * 0.1 + fc_.compute_entropy() * 0.3
+            fc_stats.update(mesh_vertices=mesh_.vertices.shape[0], faces=mesh_.indices.shape[0],
+                            gaussians=6 * mesh_.indices.shape[0])
+            return mesh_, reg_
 
         def full_step():
+            if fc_grid is not None:
+                mesh_, reg_ = geometry()
+                spl, at, _ = field.get_gaussians_from_face(mesh_.vertices, mesh_.indices, 0.0, 0.0, scale=0.9,
+                                                           initial_guess=guess)
+                e_ = splitsum.as_envstack(cube)
+                imgs = splat_views(spl.means, spl.scales, spl.quats, spl.opacities, at.kd, at.ks, at.normals, cams[:8],
+                                   exposures=exposure, envmap=e_, fg_lut=lut, min_roughness=0.1, max_metallic=1.0,
+                                   n_streams=a.streams)
+                torch.autograd.grad(list(imgs) + [reg_], [sdf_p, deform_p, weight_p, cube, exposure] + field_params,
+                                    grad_outputs=[v_img] * len(imgs) + [torch.ones_like(reg_)])
+                return
+            _full_step_fixed_mesh()
+
+        def _full_step_fixed_mesh():
             """One training step of stage 1 without the optimiser and the loss (a random image cotangent stands in):
             vertex normals + MGAdaptor + the three hash-grid fields (a1-a3), split-sum prefilter (a4/a5), the batch of
             8 views (a7-a12), and the backward of all of it down to vertices, tables, MLP weights, cube map, exposure."""
@@ -433,6 +471,9 @@ def run_b200(a):
                         "backward, one rank (entry points of overlapping streams share the SMs: their ms are elapsed, "
                         "not isolated)",
                 "entry_point_ms_per_step": fk}
+        if fc_grid is not None:
+            full["flexicubes"] = dict(resolution=a.fc_res, **fc_stats)
+            full["what"] = "FlexiCubes mesh extraction + regulariser (SDF grid -> mesh, every step) + " + full["what"]
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     M, Nv = stats_last_view(params, cams[0], W, H)

@@ -10,6 +10,7 @@ reference's interfaces for this path:
     fused.splat_views(...)                   <- the per-view loop of GeoSplatter.render_report (geosplat.py:869-879)
     mgadapter.MGAdapter / compute_vertex_normals
     encoding.HashEncoding / MLP, field.GaussianField   <- the kd / ks / z fields and their glue (geosplat.py:482-674)
+    flexicubes.FlexiCubes                    <- FlexiCubes.dual_marching_cubes / compute_entropy (_flexicubes.py:368-802)
     loss.view_loss(...)                      <- the per-view loss of GeoSplatTrainer.step (geosplat_trainer.py:171-180)
     parallel.shard_views / GradientBucket    <- view sharding + one all-reduce per batch (new: the reference is single-GPU)
 

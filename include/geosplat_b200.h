@@ -317,6 +317,47 @@ int gsb_loss_bwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, 
                  float ssim_lambda, float mask_coeff, const float *v_loss, float *v_rgba, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * FlexiCubes dual marching cubes: replaces FlexiCubes._get_case_id,
+ * _identify_surf_edges, dual_marching_cubes, _compute_reg_loss, _triangulate, compute_entropy
+ * (rfstudio/graphics/_mesh/_flexicubes.py:460-802) as GeoSplatter.get_geometry drives them (geosplat.py:751-769).
+ * The per-cube / per-group / per-quad arithmetic is here; the ordering bookkeeping between the calls (one stable
+ * radix sort of the edge keys, prefix sums) is the host's (geosplatting_b200/flexicubes.py), which also states every
+ * buffer's meaning.  cubes[F,8] int32 grid-vertex ids; tables: check[256,5], num_vd[256], dmc[256,4,7], cube_edges[12,2]
+ * (int32, device).  N surface cubes, E surface edges, Q dual vertices, K (group, edge) entries.
+ * ------------------------------------------------------------------------------------------- */
+int gsb_fc_classify(int32_t F, const float *sdf, const int32_t *cubes, int32_t *cases, int32_t *surf_flag, void *stream);
+int gsb_fc_resolve(int32_t N, int32_t R0, int32_t R1, int32_t R2, const int32_t *surf_ids, const int32_t *cases,
+                   const int32_t *surf_flag, const int32_t *check_table, const int32_t *num_vd_table,
+                   const int32_t *dmc_table, int32_t *case_ids, int32_t *num_vd, int32_t *n_entries, void *stream);
+int gsb_fc_edge_keys(int32_t N, int64_t V, const int32_t *surf_ids, const int32_t *cubes, const int32_t *cube_edges,
+                     int64_t *keys, void *stream);
+/* vd[Q,3] dual vertices, vd_gamma[Q] activated gamma of the owning cube, vd_of[N,12] dual vertex of every cube edge,
+ * l_dev[K] (_compute_reg_loss). */
+int gsb_fc_dual_fwd(int32_t N, const int32_t *surf_ids, const int32_t *case_ids, const int32_t *num_vd,
+                    const int32_t *vd_base, const int32_t *k_base, const int32_t *dmc_table, const int32_t *cube_edges,
+                    const int32_t *edge_of, const int32_t *surf_edges, const float *vertices, const float *sdf,
+                    const float *alpha, const float *beta, const float *gamma, float *vd, float *vd_gamma,
+                    int32_t *vd_of, float *l_dev, void *stream);
+/* VJP: ACCUMULATES into v_vertices[V,3] v_sdf[V] v_alpha[F,8] v_beta[F,12] v_gamma[F] (raw parameters). */
+int gsb_fc_dual_bwd(int32_t N, const int32_t *surf_ids, const int32_t *case_ids, const int32_t *num_vd,
+                    const int32_t *vd_base, const int32_t *k_base, const int32_t *dmc_table, const int32_t *cube_edges,
+                    const int32_t *edge_of, const int32_t *surf_edges, const float *vertices, const float *sdf,
+                    const float *alpha, const float *beta, const float *gamma, const float *v_vd,
+                    const float *v_vd_gamma, const float *v_l_dev, float *v_vertices, float *v_sdf, float *v_alpha,
+                    float *v_beta, float *v_gamma, void *stream);
+/* quad_vd[n_quads,4] in winding order -> centres[n_quads,3], faces[4 n_quads,3] int64 (centre of quad q = vertex Q + q). */
+int gsb_fc_quad_fwd(int32_t n_quads, int32_t Q, const int32_t *quad_vd, const float *vd, const float *vd_gamma,
+                    float *centres, int64_t *faces, void *stream);
+/* VJP: ACCUMULATES into v_vd[Q,3] and v_vd_gamma[Q]. */
+int gsb_fc_quad_bwd(int32_t n_quads, int32_t Q, const int32_t *quad_vd, const float *vd, const float *vd_gamma,
+                    const float *v_centres, float *v_vd, float *v_vd_gamma, void *stream);
+/* compute_entropy over grid_edges[U,2] int64 (every grid edge once): sums3 = {sum BCE(a|b), sum BCE(b|a), #sign-changing
+ * edges}; entropy = (sums3[0] + sums3[1]) / sums3[2].  bwd ACCUMULATES *v_loss * d entropy / d sdf into v_sdf[V]. */
+int gsb_fc_entropy_fwd(int64_t U, const int64_t *grid_edges, const float *sdf, float *sums3, void *stream);
+int gsb_fc_entropy_bwd(int64_t U, const int64_t *grid_edges, const float *sdf, const float *sums3, const float *v_loss,
+                       float *v_sdf, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Native per-view driver: one training view of RenderableAttrs.splat (rfstudio/model/geosplat.py:53-132, culling
  * off, tone_type 'naive' / 'none') + GSplatter.render_rgba (rfstudio/model/gsplat.py:284-358) as three calls that
  * sequence the stage entry points above on caller-provided arenas.  The host keeps three calls and a handful of

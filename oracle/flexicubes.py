@@ -1,6 +1,6 @@
 """CPU restatement of FlexiCubes dual marching cubes + the SDF entropy regulariser, the step that produces the mesh
-MGAdaptor samples.  TEST INFRASTRUCTURE ONLY; the product row is not built yet -- this file
-and tests/golden/ref_flexicubes.npz are what it will be held to.
+MGAdaptor samples.  TEST INFRASTRUCTURE ONLY: the checker of geosplatting_b200/flexicubes.py
++ csrc/flexicubes.cu (tests/test_flexicubes_cpu.py, tests/test_flexicubes_gpu.py); never imported by the product.
 
 Follows rfstudio/graphics/_mesh/_flexicubes.py:460-506 (ambiguity resolution), :508-538 (surface edges),
 :559-713 (dual vertices, L_dev), :715-725 (entropy), :727-802 (regulariser, triangulation) as GeoSplatter.get_geometry

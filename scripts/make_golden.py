@@ -337,7 +337,7 @@ def main():
     save("ref_field.npz", **fout)
 
     # ---- J. FlexiCubes.dual_marching_cubes + compute_entropy (_flexicubes.py:559-725), as
-    #         GeoSplatter.get_geometry drives it (geosplat.py:751-769): fixtures for the row that is NOT built yet, so
+    #         GeoSplatter.get_geometry drives it (geosplat.py:751-769): fixtures for flexicubes.py + csrc/flexicubes.cu, so
     #         that a CUDA implementation can be held to the reference's own outputs (vertex / face ORDER included).
     R = 10
     fc0 = G.FlexiCubes.from_resolution(R, random_sdf=False, scale=0.9)
@@ -361,6 +361,9 @@ def main():
     # by value, read from the reference at generation time
     tables = dict(tbl_cube_edges=RFC._get_cube_edges(cpu), tbl_check=RFC._get_check_table(cpu),
                   tbl_dmc=RFC._get_dmc_table(cpu), tbl_num_vd=RFC._get_num_vd_table(cpu))
+    # the same four tables, int32, as the product's data file (geosplatting_b200/data/flexicubes_tables.npz)
+    np.savez_compressed(os.path.join(os.path.dirname(OUT), "..", "geosplatting_b200", "data", "flexicubes_tables.npz"),
+                        **{k[4:]: v.numpy().astype(np.int32) for k, v in tables.items()})
     save("ref_flexicubes.npz", **tables, resolution=R, scale=0.9, grid_vertices=gv, cube_indices=fc0.indices, sdf=sdf,
          deform=deform, weights=weights, mesh_vertices=mesh_fc.vertices, mesh_indices=mesh_fc.indices, L_dev=L_dev,
          entropy=entropy, cot_vertices=cot_v, v_sdf=g_sdf, v_deform=g_def, v_weights=g_w)

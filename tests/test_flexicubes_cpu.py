@@ -1,0 +1,78 @@
+"""FlexiCubes without a GPU: the host module (geosplatting_b200/flexicubes.py) driving the REAL kernel source of
+csrc/flexicubes.cu compiled for the host by tests/emu (threads run one after another; see tests/emu/cuda_runtime.h).
+This checks the ordering bookkeeping, the kernels' index arithmetic and their gradient formulas against the reference's
+own outputs in this GPU-less container; the CUDA build of the same source is checked by tests/test_flexicubes_gpu.py.
+The emulation is wired in by monkeypatching here -- the product refuses CPU tensors (last test)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from geosplatting_b200 import _lib
+from geosplatting_b200 import flexicubes as FC
+from tests import fc_cases
+from tests.emu import build as emu
+
+
+@pytest.fixture()
+def host_kernels(monkeypatch):
+    so = emu.build("flexicubes")
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.is_contiguous() and t.device.type == "cpu"
+        return C.c_void_p(t.data_ptr())
+
+    monkeypatch.setattr(_lib, "load", lambda: so)
+    monkeypatch.setattr(FC, "ptr", ptr)
+    monkeypatch.setattr(FC, "stream_ptr", lambda dev: None)
+    monkeypatch.setattr(FC, "_require_cuda", lambda t, what: None)
+    saved = dict(_lib.CallStats.counts)
+    yield so
+    _lib.CallStats.counts = saved
+
+
+def test_kernel_source_on_host_smooth_fixture(host_kernels):
+    fc_cases.check_smooth_fixture("cpu")
+
+
+def test_kernel_source_on_host_rough_fixture(host_kernels):
+    fc_cases.check_rough_fixture("cpu")
+
+
+@pytest.mark.parametrize("res,noise", [((12, 9, 7), 0.05), ((16, 16, 16), 0.0), ((5, 11, 8), 0.2)])
+def test_kernel_source_on_host_against_oracle(host_kernels, res, noise):
+    assert fc_cases.check_against_oracle("cpu", res=res, seed=sum(res), noise=noise) > 0
+
+
+def test_absent_weights_and_no_surface(host_kernels):
+    """alpha / beta / gamma = None behave like the reference's defaults (uniform weights); an SDF without a sign change
+    raises like the reference's assert."""
+    fc0, sdf, _, _ = fc_cases.sphere_case((8, 8, 8), 1, "cpu")
+    mesh, l_dev = fc0.replace(sdf_values=sdf).dual_marching_cubes()
+    z = torch.zeros(fc0.indices.shape[0], 21)
+    mesh_z, l_dev_z = fc0.replace(sdf_values=sdf, alpha=z[:, :8], beta=z[:, 8:20], gamma=z[:, 20:]).dual_marching_cubes()
+    assert torch.equal(mesh.indices, mesh_z.indices) and torch.equal(mesh.vertices, mesh_z.vertices)
+    assert mesh.indices.max() == mesh.vertices.shape[0] - 1 and bool(torch.isfinite(l_dev).all())
+    with pytest.raises(AssertionError, match="no sign change"):
+        fc0.replace(sdf_values=torch.ones_like(sdf)).dual_marching_cubes()
+
+
+def test_product_has_no_cpu_path():
+    fc0, sdf, _, _ = fc_cases.sphere_case((4, 4, 4), 1, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fc0.replace(sdf_values=sdf).dual_marching_cubes()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fc0.replace(sdf_values=sdf).compute_entropy()
+
+
+def test_product_tables_are_the_reference_tables():
+    """geosplatting_b200/data/flexicubes_tables.npz (written by scripts/make_golden.py section J) holds the four lookup
+    tables by value; the fixtures carry the reference's own copies."""
+    import numpy as np
+    g = fc_cases.load("ref_flexicubes.npz")
+    tb = FC._tables(torch.device("cpu"))
+    assert set(tb) == {"cube_edges", "check", "dmc", "num_vd"}
+    for k, v in tb.items():
+        assert v.dtype == torch.int32 and np.array_equal(v.numpy(), g["tbl_" + k])

@@ -169,7 +169,7 @@ def test_field_host_glue_matches_reference_code():
 
 def test_flexicubes_fixture_is_a_closed_surface():
     """tests/golden/ref_flexicubes.npz (scripts/make_golden.py section J: the reference's own FlexiCubes code on a
-    10^3 grid, as GeoSplatter.get_geometry drives it) is the fixture the not-yet-built SURVEY 8f rank-3 row will be held
+    10^3 grid, as GeoSplatter.get_geometry drives it) is the fixture the SURVEY 8f rank-3 row (flexicubes.py) is held
     to.  Sanity of the fixture itself: a watertight, consistently oriented surface near the SDF's zero level set, finite
     gradients -- and it feeds the MGAdaptor oracle (6 Gaussians per face)."""
     from oracle import mgadapter as OMG
