@@ -3,19 +3,25 @@
 // dual_marching_cubes, _compute_reg_loss, _triangulate, compute_entropy) as GeoSplatter.get_geometry drives them
 // (rfstudio/model/geosplat.py:751-769).  The reference is ~100 torch kernels with row-wise unique() and boolean-mask
 // indexing per step; here the per-cube / per-edge-group / per-quad arithmetic is one kernel each, and the ordering
-// bookkeeping (one stable radix sort of the edge keys, a handful of prefix sums) is left to the host's library calls
-// (geosplatting_b200/flexicubes.py).  Every output ORDER of the reference is kept (oracle/flexicubes.py spells them out):
-// MGAdaptor emits its Gaussians in face order.
+// bookkeeping is one stable cub radix sort of the 12 N edge keys plus three cub scans, sequenced natively by
+// gsb_fc_surface / gsb_fc_topology (two device->host reads per call: N, then {E, n_quads, Q, K}).  Every output ORDER of
+// the reference is kept (oracle/flexicubes.py spells them out): MGAdaptor emits its Gaussians in face order.
 //
 // Kernels (all streaming / gather, HBM- and L2-bound integer and fp32 work; no reuse to tile for):
 //   fc_classify      per cube        : occupancy case (8 bits), surface flag
 //   fc_resolve       per surf cube   : ambiguity inversion against the neighbour across the ambiguous face, number of
 //                                      dual vertices, number of (group, edge) entries
 //   fc_edge_keys     per (surf cube, edge) : 64-bit key v_a * V + v_b in the cube-local orientation
+//   fc_edge_flags / fc_edge_assign  per sorted key : run heads (distinct grid edges), sign change, runs of four (quads);
+//                                      after the scan: surface-edge ids, endpoints, quad entries in winding order
+//   fc_class_flags / fc_number      per surf cube : dual-vertex and L_dev numbering "k = 1..4, cubes ascending"
 //   fc_dual_fwd/bwd  per (surf cube, group): dual vertex = beta-weighted mean of the alpha-weighted zero crossings of its
 //                                      edges, L_dev entries; VJP to grid vertices, SDF, alpha, beta, gamma
 //   fc_quad_fwd/bwd  per quad        : gamma-weighted centre, 4 faces; VJP to the 4 dual vertices and their gammas
 //   fc_entropy_fwd/bwd per grid edge : symmetric BCE between the endpoint SDF values of sign-changing edges
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "gsb_common.cuh"
 
 namespace {
@@ -74,12 +80,137 @@ __global__ void __launch_bounds__(256) fc_resolve_kernel(int N, int R0, int R1, 
 __global__ void __launch_bounds__(256) fc_edge_keys_kernel(int N, long long V, const int32_t *__restrict__ surf_ids,
                                                             const int32_t *__restrict__ cubes,
                                                             const int32_t *__restrict__ cube_edges,
-                                                            long long *__restrict__ keys) {
+                                                            long long *__restrict__ keys, int32_t *__restrict__ iota) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 12) return;
     const int n = i / 12, e = i % 12;
     const int32_t *cu = cubes + 8 * (size_t)surf_ids[n];
     keys[i] = (long long)cu[cube_edges[2 * e]] * V + cu[cube_edges[2 * e + 1]];
+    if (iota) iota[i] = i;
+}
+
+// ---- ordering bookkeeping ---------------------------------------------------------------------------------------
+// After the stable sort of the 12 N keys, the entries of one grid edge form a run of 1..4 equal keys in ascending
+// (cube, local edge) order -- the order the reference's stable sort of the quad entries gives (_flexicubes.py:761).
+struct I3 {
+    int32_t hc, qp, qn;   // run head of a sign-changing edge | ... shared by four cubes, first endpoint sdf > 0 | <= 0
+};
+struct I8 {
+    int32_t c[4], e[4];   // one-hot of the cube's dual-vertex count k = 1..4 | the same times its number of entries
+};
+struct AddI3 {
+    __host__ __device__ __forceinline__ I3 operator()(const I3 &a, const I3 &b) const {
+        return I3{a.hc + b.hc, a.qp + b.qp, a.qn + b.qn};
+    }
+};
+struct AddI8 {
+    __host__ __device__ __forceinline__ I8 operator()(const I8 &a, const I8 &b) const {
+        I8 r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { r.c[k] = a.c[k] + b.c[k]; r.e[k] = a.e[k] + b.e[k]; }
+        return r;
+    }
+};
+
+__device__ __forceinline__ int run_length(const long long *__restrict__ ks, int h, int n12) {
+    const long long key = ks[h];
+    int cnt = 1;
+    while (cnt < 4 && h + cnt < n12 && ks[h + cnt] == key) ++cnt;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(256) fc_edge_flags_kernel(int n12, long long V, const long long *__restrict__ ks,
+                                                             const float *__restrict__ sdf, I3 *__restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n12) return;
+    I3 f = {0, 0, 0};
+    const long long key = ks[i];
+    if (i == 0 || ks[i - 1] != key) {
+        const float a = sdf[key / V], b = sdf[key % V];
+        if ((a < 0.f) != (b < 0.f)) {
+            f.hc = 1;
+            if (run_length(ks, i, n12) == 4) { f.qp = a > 0.f; f.qn = !(a > 0.f); }
+        }
+    }
+    flags[i] = f;
+}
+
+// scan = inclusive scan of the flags.  edge_of[cube * 12 + local edge] = surface-edge id or -1; surf_edges[id] =
+// (v_a, v_b); quad_entry[q][0..3] = the (cube * 12 + local edge) entries around quad q in winding order, quads whose
+// first endpoint is positive first, each half by ascending edge; counts[0] = E, counts[1] = n_quads.
+__global__ void __launch_bounds__(256) fc_edge_assign_kernel(int n12, long long V, const long long *__restrict__ ks,
+                                                              const int32_t *__restrict__ perm,
+                                                              const float *__restrict__ sdf, const I3 *__restrict__ scan,
+                                                              int32_t *__restrict__ edge_of,
+                                                              int32_t *__restrict__ surf_edges,
+                                                              int32_t *__restrict__ quad_entry,
+                                                              int32_t *__restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n12) return;
+    const I3 last = scan[n12 - 1];
+    if (i == n12 - 1) { counts[0] = last.hc; counts[1] = last.qp + last.qn; }
+    const long long key = ks[i];
+    int h = i;
+    while (h > 0 && ks[h - 1] == key) --h;
+    const int ua = (int)(key / V), ub = (int)(key % V);
+    const float a = sdf[ua], b = sdf[ub];
+    if ((a < 0.f) == (b < 0.f)) { edge_of[perm[i]] = -1; return; }
+    const I3 s = scan[h];
+    const int id = s.hc - 1;
+    edge_of[perm[i]] = id;
+    if (i != h) return;
+    surf_edges[2 * id] = ua;
+    surf_edges[2 * id + 1] = ub;
+    if (run_length(ks, h, n12) != 4) return;
+    const bool fp = a > 0.f;
+    const int q = fp ? s.qp - 1 : last.qp + s.qn - 1;
+    const int e0 = perm[h], e1 = perm[h + 1], e2 = perm[h + 2], e3 = perm[h + 3];
+    int32_t *o = quad_entry + 4 * (size_t)q;
+    if (fp) { o[0] = e0; o[1] = e1; o[2] = e3; o[3] = e2; }     // [0, 1, 3, 2]   (_flexicubes.py:769)
+    else    { o[0] = e2; o[1] = e3; o[2] = e1; o[3] = e0; }     // [2, 3, 1, 0]   (_flexicubes.py:770)
+}
+
+__global__ void __launch_bounds__(256) fc_class_flags_kernel(int N, const int32_t *__restrict__ num_vd,
+                                                              const int32_t *__restrict__ n_entries,
+                                                              I8 *__restrict__ flags) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    I8 f;
+    const int k = num_vd[n], ne = n_entries[n];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f.c[j] = (k == j + 1); f.e[j] = (k == j + 1) ? ne : 0; }
+    flags[n] = f;
+}
+
+// Dual vertices and L_dev entries are numbered class by class (k = 1..4 dual vertices), cubes ascending within a class
+// (the num_vd loop, _flexicubes.py:640-690).  counts[2] = Q, counts[3] = K.
+__global__ void __launch_bounds__(256) fc_number_kernel(int N, const int32_t *__restrict__ num_vd,
+                                                         const int32_t *__restrict__ n_entries,
+                                                         const I8 *__restrict__ scan, int32_t *__restrict__ vd_base,
+                                                         int32_t *__restrict__ k_base, int32_t *__restrict__ counts) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const I8 tot = scan[N - 1];
+    const int k = num_vd[n];
+    int voff = 0, koff = 0, Q = 0, K = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j + 1 == k) { voff = Q; koff = K; }
+        Q += (j + 1) * tot.c[j];
+        K += tot.e[j];
+    }
+    if (n == 0) { counts[2] = Q; counts[3] = K; }
+    if (k < 1 || k > 4) { vd_base[n] = 0; k_base[n] = 0; return; }   // not reachable for a surface cube
+    const I8 s = scan[n];
+    vd_base[n] = voff + k * (s.c[k - 1] - 1);
+    k_base[n] = koff + s.e[k - 1] - n_entries[n];
+}
+
+__global__ void __launch_bounds__(256) fc_quad_gather_kernel(int n4, const int32_t *__restrict__ quad_entry,
+                                                              const int32_t *__restrict__ vd_of,
+                                                              int32_t *__restrict__ quad_vd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) quad_vd[i] = vd_of[quad_entry[i]];
 }
 
 struct Crossing {
@@ -376,7 +507,7 @@ GSB_API int gsb_fc_edge_keys(int32_t N, int64_t V, const int32_t *surf_ids, cons
     if (N == 0) return GSB_OK;
     GSB_CHECK_ARG(surf_ids && cubes && cube_edges && keys);
     fc_edge_keys_kernel<<<gsb_div_up((int64_t)N * 12, 256), 256, 0, (cudaStream_t)stream>>>(
-        N, (long long)V, surf_ids, cubes, cube_edges, reinterpret_cast<long long *>(keys));
+        N, (long long)V, surf_ids, cubes, cube_edges, reinterpret_cast<long long *>(keys), nullptr);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
@@ -457,6 +588,147 @@ GSB_API int gsb_fc_entropy_bwd(int64_t U, const int64_t *grid_edges, const float
     GSB_CHECK_ARG(grid_edges && sdf && sums3 && v_loss && v_sdf);
     fc_entropy_kernel<true><<<gsb_div_up(U, 256), 256, 0, (cudaStream_t)stream>>>(
         (long long)U, reinterpret_cast<const long long *>(grid_edges), sdf, const_cast<float *>(sums3), v_loss, v_sdf);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+// ---- native sequencing of the bookkeeping -----------------------------------------------------------------------
+static size_t fc_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int fc_key_bits(int64_t V) {
+    // keys are below V * V
+    int b = 1;
+    while (b < 63 && ((int64_t)1 << b) < V) ++b;
+    return 2 * b > 64 ? 64 : 2 * b;
+}
+
+struct FcTemp {
+    size_t select, sort, scan3, scan8;
+    size_t max() const {
+        size_t m = select;
+        if (sort > m) m = sort;
+        if (scan3 > m) m = scan3;
+        if (scan8 > m) m = scan8;
+        return m;
+    }
+};
+
+static FcTemp fc_temp_bytes(int32_t F, int32_t N) {
+    FcTemp t = {0, 0, 0, 0};
+    cub::DeviceSelect::Flagged((void *)nullptr, t.select, thrust::counting_iterator<int32_t>(0), (const int32_t *)nullptr,
+                               (int32_t *)nullptr, (int32_t *)nullptr, (int)F);
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, t.sort, (const long long *)nullptr, (long long *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, 12 * (int)N, 0, 64);
+    cub::DeviceScan::InclusiveScan((void *)nullptr, t.scan3, (const I3 *)nullptr, (I3 *)nullptr, AddI3(), 12 * (int)N);
+    cub::DeviceScan::InclusiveScan((void *)nullptr, t.scan8, (const I8 *)nullptr, (I8 *)nullptr, AddI8(), (int)N);
+    return t;
+}
+
+// Workspace of gsb_fc_surface (N = 0) and gsb_fc_topology: n_entries [N] i32, keys / sorted keys [12 N] i64, iota /
+// perm [12 N] i32, flags and their scan [12 N] I3, class flags and their scan [N] I8, 4 counters, cub temp.
+GSB_API int gsb_fc_workspace_bytes(int32_t F, int32_t N, size_t *bytes_host) {
+    GSB_CHECK_ARG(F >= 0 && N >= 0 && N <= F && (int64_t)N * 12 < 2147483647LL && bytes_host != nullptr);
+    const size_t n = (size_t)N, n12 = 12 * n;
+    *bytes_host = fc_align(4 * n) + 2 * fc_align(8 * n12) + 2 * fc_align(4 * n12) + 2 * fc_align(sizeof(I3) * n12) +
+                  2 * fc_align(sizeof(I8) * n) + 256 + fc_align(fc_temp_bytes(F, N).max()) + 256;
+    return GSB_OK;
+}
+
+GSB_API int gsb_fc_surface(int32_t F, const float *sdf, const int32_t *cubes, int32_t *cases, int32_t *surf_flag,
+                           int32_t *surf_ids, void *workspace, size_t workspace_bytes, int32_t *n_surf_host,
+                           void *stream) {
+    GSB_CHECK_ARG(F >= 0 && n_surf_host != nullptr);
+    *n_surf_host = 0;
+    if (F == 0) return GSB_OK;
+    GSB_CHECK_ARG(sdf && cubes && cases && surf_flag && surf_ids && workspace);
+    size_t need = 0;
+    GSB_CHECK_ARG(gsb_fc_workspace_bytes(F, 0, &need) == GSB_OK);
+    if (need > workspace_bytes) {
+        gsb_set_error("gsb_fc_surface: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GSB_ENOMEM;
+    }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    int32_t *d_count = reinterpret_cast<int32_t *>(p); p += 256;
+    fc_classify_kernel<<<gsb_div_up(F, 256), 256, 0, (cudaStream_t)stream>>>(F, sdf, cubes, cases, surf_flag);
+    GSB_CHECK_LAUNCH();
+    size_t tb = fc_temp_bytes(F, 0).select;
+    GSB_CHECK_CUDA(cub::DeviceSelect::Flagged(p, tb, thrust::counting_iterator<int32_t>(0), surf_flag, surf_ids, d_count,
+                                              (int)F, (cudaStream_t)stream));
+    GSB_CHECK_CUDA(cudaMemcpyAsync(n_surf_host, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GSB_OK;
+}
+
+GSB_API int gsb_fc_topology(int32_t F, int32_t N, int64_t V, int32_t R0, int32_t R1, int32_t R2, const float *sdf,
+                            const int32_t *cubes, const int32_t *surf_ids, const int32_t *cases, const int32_t *surf_flag,
+                            const int32_t *check_table, const int32_t *num_vd_table, const int32_t *dmc_table,
+                            const int32_t *cube_edges, int32_t *case_ids, int32_t *num_vd, int32_t *vd_base,
+                            int32_t *k_base, int32_t *edge_of, int32_t *surf_edges, int32_t *quad_entry, void *workspace,
+                            size_t workspace_bytes, int32_t *counts_host, void *stream) {
+    GSB_CHECK_ARG(N > 0 && N <= F && V > 0 && R0 > 0 && R1 > 0 && R2 > 0 && counts_host != nullptr);
+    GSB_CHECK_ARG(sdf && cubes && surf_ids && cases && surf_flag && check_table && num_vd_table && dmc_table &&
+                  cube_edges && case_ids && num_vd && vd_base && k_base && edge_of && surf_edges && quad_entry && workspace);
+    size_t need = 0;
+    GSB_CHECK_ARG(gsb_fc_workspace_bytes(F, N, &need) == GSB_OK);
+    if (need > workspace_bytes) {
+        gsb_set_error("gsb_fc_topology: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GSB_ENOMEM;
+    }
+    const size_t n = (size_t)N, n12 = 12 * n;
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(p); p += 256;
+    int32_t *n_entries = reinterpret_cast<int32_t *>(p); p += fc_align(4 * n);
+    long long *keys = reinterpret_cast<long long *>(p); p += fc_align(8 * n12);
+    long long *keys_sorted = reinterpret_cast<long long *>(p); p += fc_align(8 * n12);
+    int32_t *iota = reinterpret_cast<int32_t *>(p); p += fc_align(4 * n12);
+    int32_t *perm = reinterpret_cast<int32_t *>(p); p += fc_align(4 * n12);
+    I3 *flags3 = reinterpret_cast<I3 *>(p); p += fc_align(sizeof(I3) * n12);
+    I3 *scan3 = reinterpret_cast<I3 *>(p); p += fc_align(sizeof(I3) * n12);
+    I8 *flags8 = reinterpret_cast<I8 *>(p); p += fc_align(sizeof(I8) * n);
+    I8 *scan8 = reinterpret_cast<I8 *>(p); p += fc_align(sizeof(I8) * n);
+    void *temp = p;
+    const FcTemp tb = fc_temp_bytes(F, N);
+    size_t b;
+
+    fc_resolve_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+        N, R0, R1, R2, surf_ids, cases, surf_flag, check_table, num_vd_table, dmc_table, case_ids, num_vd, n_entries);
+    GSB_CHECK_LAUNCH();
+    // dual-vertex / L_dev numbering
+    fc_class_flags_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(N, num_vd, n_entries, flags8);
+    GSB_CHECK_LAUNCH();
+    b = tb.scan8;
+    GSB_CHECK_CUDA(cub::DeviceScan::InclusiveScan(temp, b, flags8, scan8, AddI8(), (int)N, (cudaStream_t)stream));
+    fc_number_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(N, num_vd, n_entries, scan8, vd_base, k_base,
+                                                                          d_counts);
+    GSB_CHECK_LAUNCH();
+    // surface edges and quads
+    fc_edge_keys_kernel<<<gsb_div_up((int64_t)n12, 256), 256, 0, (cudaStream_t)stream>>>(
+        N, (long long)V, surf_ids, cubes, cube_edges, keys, iota);
+    GSB_CHECK_LAUNCH();
+    b = tb.sort;
+    GSB_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, b, keys, keys_sorted, iota, perm, (int)n12, 0, fc_key_bits(V),
+                                                   (cudaStream_t)stream));
+    fc_edge_flags_kernel<<<gsb_div_up((int64_t)n12, 256), 256, 0, (cudaStream_t)stream>>>(
+        (int)n12, (long long)V, keys_sorted, sdf, flags3);
+    GSB_CHECK_LAUNCH();
+    b = tb.scan3;
+    GSB_CHECK_CUDA(cub::DeviceScan::InclusiveScan(temp, b, flags3, scan3, AddI3(), (int)n12, (cudaStream_t)stream));
+    fc_edge_assign_kernel<<<gsb_div_up((int64_t)n12, 256), 256, 0, (cudaStream_t)stream>>>(
+        (int)n12, (long long)V, keys_sorted, perm, sdf, scan3, edge_of, surf_edges, quad_entry, d_counts);
+    GSB_CHECK_LAUNCH();
+    GSB_CHECK_CUDA(cudaMemcpyAsync(counts_host, d_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                   (cudaStream_t)stream));
+    GSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GSB_OK;
+}
+
+GSB_API int gsb_fc_quad_gather(int32_t n_quads, const int32_t *quad_entry, const int32_t *vd_of, int32_t *quad_vd,
+                               void *stream) {
+    GSB_CHECK_ARG(n_quads >= 0);
+    if (n_quads == 0) return GSB_OK;
+    GSB_CHECK_ARG(quad_entry && vd_of && quad_vd);
+    fc_quad_gather_kernel<<<gsb_div_up(4 * (int64_t)n_quads, 256), 256, 0, (cudaStream_t)stream>>>(
+        4 * n_quads, quad_entry, vd_of, quad_vd);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

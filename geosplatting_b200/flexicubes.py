@@ -8,19 +8,19 @@ Mirrors:
 as GeoSplatter.get_geometry drives them (rfstudio/model/geosplat.py:751-769).  grad_func / sdf_eps (the non-differentiable
 QEF variant) are not on that path and are not mirrored.
 
-Division of labour.  The kernels (csrc/flexicubes.cu) do everything per cube / per dual vertex / per quad / per grid
-edge, forward and backward.  What is left here is ORDER bookkeeping, done with library calls on the device (torch.unique
-= one radix sort of the 64-bit edge keys, cumsum, one stable argsort of the quad entries); it decides the numbering of
-surface edges, dual vertices, L_dev entries and quads, which must match the reference because MGAdaptor emits Gaussians
-in face order (oracle/flexicubes.py lists the orders).  Three device->host reads per call size the outputs: the number
-of surface cubes, (Q, K, E) and the number of quad entries.
+Division of labour.  The library (csrc/flexicubes.cu) does everything: per cube / per dual vertex / per quad / per grid
+edge arithmetic, forward and backward, and the ORDER bookkeeping (one stable cub radix sort of the 64-bit edge keys,
+three cub scans) that decides the numbering of surface edges, dual vertices, L_dev entries and quads -- which must match
+the reference because MGAdaptor emits Gaussians in face order (oracle/flexicubes.py lists the orders).  This module
+allocates (scratch sized by upper bounds in N) and makes seven calls per forward; two device->host reads size the
+outputs: the number of surface cubes, then {E, n_quads, Q, K}.
 
 Buffers (N surface cubes, E surface edges, Q dual vertices, K (group, edge) entries, n_quads):
     cases[F] i32        occupancy bit mask of every cube         surf_flag[F] i32  1 for surface cubes
     surf_ids[N] i32     surface cubes ascending                  case_ids[N] i32   case after ambiguity resolution
     num_vd[N] i32       dual vertices of the cube (1..4)         n_entries[N] i32  (group, edge) entries of the cube
-    keys[N*12] i64      v_a * V + v_b of every cube edge         edge_of[N,12] i32 surface-edge id or -1
-    surf_edges[E,2] i32 endpoints, ascending (v_a, v_b)          vd_base[N] / k_base[N] i32  first dual vertex / entry
+    edge_of[N,12] i32   surface-edge id or -1                    vd_base[N] / k_base[N] i32  first dual vertex / entry
+    surf_edges[E,2] i32 endpoints, ascending (v_a, v_b)          quad_entry[n_quads,4] i32 positions into vd_of
     vd_of[N,12] i32     dual vertex of every (cube, edge)        quad_vd[n_quads,4] i32 in winding order
 """
 from __future__ import annotations
@@ -71,76 +71,48 @@ class Topology:
     Q: int
     K: int
     n_quads: int
-    surf_ids: Tensor
-    case_ids: Tensor
-    num_vd: Tensor
-    vd_base: Tensor
-    k_base: Tensor
-    edge_of: Tensor
-    shared: Tensor
-    surf_edges: Tensor
+    surf_ids: Tensor        # [N] (a view of an [F] buffer)
+    case_ids: Tensor        # [N]
+    num_vd: Tensor          # [N]
+    vd_base: Tensor         # [N]
+    k_base: Tensor          # [N]
+    edge_of: Tensor         # [N,12]
+    surf_edges: Tensor      # [12 N, 2], the first E rows are used
+    quad_entry: Tensor      # [3 N, 4], the first n_quads rows are used
+
+
+def _workspace(F: int, N: int, dev: torch.device) -> Tuple[Tensor, int]:
+    need = C.c_size_t(0)
+    call("gsb_fc_workspace_bytes", dev, C.c_int32(F), C.c_int32(N), C.byref(need))
+    return torch.empty(need.value, dtype=torch.uint8, device=dev), need.value
 
 
 def _topology(sdf: Tensor, cubes: Tensor, res: Tuple[int, int, int]) -> Topology:
-    """_get_case_id + _identify_surf_edges (_flexicubes.py:460-538) and the dual-vertex / L_dev numbering of the
-    num_vd loop (_flexicubes.py:640-690)."""
+    """_get_case_id + _identify_surf_edges (_flexicubes.py:460-538), the dual-vertex / L_dev numbering of the num_vd loop
+    (:640-690) and the quad list of _triangulate (:758-771), sequenced natively: two calls, one host read each."""
     dev = sdf.device
     tb = _tables(dev)
     F, V = cubes.shape[0], sdf.shape[0]
     st = stream_ptr(dev)
-    cases, flag = _i32(F, dev), _i32(F, dev)
-    call("gsb_fc_classify", dev, C.c_int32(F), ptr(sdf), ptr(cubes), ptr(cases), ptr(flag), st)
-    surf_ids = flag.nonzero().squeeze(1).int()                                      # read 1: N
-    N = surf_ids.shape[0]
+    cases, flag, surf_ids = _i32(F, dev), _i32(F, dev), _i32(F, dev)
+    ws, ws_bytes = _workspace(F, 0, dev)
+    n_surf = C.c_int32(0)
+    call("gsb_fc_surface", dev, C.c_int32(F), ptr(sdf), ptr(cubes), ptr(cases), ptr(flag), ptr(surf_ids), ptr(ws),
+         C.c_size_t(ws_bytes), C.byref(n_surf), st)                                  # read 1: N
+    N = n_surf.value
     if N == 0:
         raise AssertionError("FlexiCubes: the SDF has no sign change (the reference asserts N > 0, _flexicubes.py:605)")
-    case_ids, num_vd, n_ent = _i32(N, dev), _i32(N, dev), _i32(N, dev)
-    call("gsb_fc_resolve", dev, C.c_int32(N), C.c_int32(res[0]), C.c_int32(res[1]), C.c_int32(res[2]), ptr(surf_ids),
-         ptr(cases), ptr(flag), ptr(tb["check"]), ptr(tb["num_vd"]), ptr(tb["dmc"]), ptr(case_ids), ptr(num_vd),
-         ptr(n_ent), st)
-    keys = torch.empty(N * 12, dtype=torch.int64, device=dev)
-    call("gsb_fc_edge_keys", dev, C.c_int32(N), C.c_int64(V), ptr(surf_ids), ptr(cubes), ptr(tb["cube_edges"]),
-         ptr(keys), st)
-
-    # surface edges: rank of the sign-changing ones among the distinct grid edges, ascending (v_a, v_b)
-    uniq, inv, cnt = torch.unique(keys, return_inverse=True, return_counts=True)
-    ua, ub = uniq // V, uniq % V
-    neg = sdf < 0
-    crossing = neg[ua] != neg[ub]
-    rank = torch.where(crossing, torch.cumsum(crossing.long(), 0) - 1, -1)
-    edge_of = rank[inv].int().view(N, 12).contiguous()
-    shared = cnt[inv].view(N, 12)
-
-    # numbering: for k = 1..4, the cubes emitting k dual vertices (ascending), k vertices each; L_dev entries alike
-    nv, ne = num_vd.long(), n_ent.long()
-    vd_base, k_base = torch.zeros_like(nv), torch.zeros_like(nv)
-    voff = torch.zeros((), dtype=torch.int64, device=dev)
-    koff = torch.zeros((), dtype=torch.int64, device=dev)
-    for k in range(1, 5):
-        m = (nv == k).long()
-        vd_base += m * (voff + k * (torch.cumsum(m, 0) - m))
-        ek = ne * m
-        k_base += m * (koff + torch.cumsum(ek, 0) - ek)
-        voff = voff + k * m.sum()
-        koff = koff + ek.sum()
-    Q, K, E = (int(x) for x in torch.stack([voff, koff, crossing.sum()]).tolist())   # read 2: Q, K, E
-    order = torch.argsort((~crossing).to(torch.uint8), stable=True)[:E]              # crossing edges, ascending
-    surf_edges = torch.stack([ua[order], ub[order]], 1).int().contiguous()
-    return Topology(N=N, E=E, Q=Q, K=K, n_quads=0, surf_ids=surf_ids, case_ids=case_ids, num_vd=num_vd,
-                    vd_base=vd_base.int(), k_base=k_base.int(), edge_of=edge_of, shared=shared, surf_edges=surf_edges)
-
-
-def _quads(t: Topology, vd_of: Tensor, sdf: Tensor) -> Tensor:
-    """The with-no-grad part of _triangulate (_flexicubes.py:758-771): quads around the surface edges four surface cubes
-    share, ascending edge id, those whose first endpoint has sdf > 0 first; [n_quads,4] i32 in winding order."""
-    sel = ((t.shared == 4) & (t.edge_of >= 0)).view(-1).nonzero().squeeze(1)         # read 3: 4 * n_quads
-    e_id, v_id = t.edge_of.view(-1)[sel].long(), vd_of.view(-1)[sel]
-    order = torch.argsort(e_id, stable=True)
-    quad_edge = e_id[order].view(-1, 4)[:, 0]
-    quad = v_id[order].view(-1, 4)
-    first_positive = sdf[t.surf_edges[quad_edge, 0].long()] > 0
-    wound = torch.where(first_positive[:, None], quad[:, [0, 1, 3, 2]], quad[:, [2, 3, 1, 0]])
-    return wound[torch.argsort((~first_positive).to(torch.uint8), stable=True)].contiguous()
+    case_ids, num_vd, vd_base, k_base = (_i32(N, dev) for _ in range(4))
+    edge_of, surf_edges, quad_entry = _i32((N, 12), dev), _i32((12 * N, 2), dev), _i32((3 * N, 4), dev)
+    ws, ws_bytes = _workspace(F, N, dev)
+    counts = (C.c_int32 * 4)()
+    call("gsb_fc_topology", dev, C.c_int32(F), C.c_int32(N), C.c_int64(V), C.c_int32(res[0]), C.c_int32(res[1]),
+         C.c_int32(res[2]), ptr(sdf), ptr(cubes), ptr(surf_ids), ptr(cases), ptr(flag), ptr(tb["check"]),
+         ptr(tb["num_vd"]), ptr(tb["dmc"]), ptr(tb["cube_edges"]), ptr(case_ids), ptr(num_vd), ptr(vd_base), ptr(k_base),
+         ptr(edge_of), ptr(surf_edges), ptr(quad_entry), ptr(ws), C.c_size_t(ws_bytes), counts, st)   # read 2
+    E, n_quads, Q, K = (int(c) for c in counts)
+    return Topology(N=N, E=E, Q=Q, K=K, n_quads=n_quads, surf_ids=surf_ids[:N], case_ids=case_ids, num_vd=num_vd,
+                    vd_base=vd_base, k_base=k_base, edge_of=edge_of, surf_edges=surf_edges, quad_entry=quad_entry)
 
 
 class _DualMarchingCubes(torch.autograd.Function):
@@ -158,13 +130,13 @@ class _DualMarchingCubes(torch.autograd.Function):
         call("gsb_fc_dual_fwd", dev, C.c_int32(t.N), ptr(t.surf_ids), ptr(t.case_ids), ptr(t.num_vd), ptr(t.vd_base),
              ptr(t.k_base), ptr(tb["dmc"]), ptr(tb["cube_edges"]), ptr(t.edge_of), ptr(t.surf_edges), ptr(v), ptr(s),
              ptr(a), ptr(b), ptr(g), ptr(vd), ptr(vd_gamma), ptr(vd_of), ptr(l_dev), st)
-        quad = _quads(t, vd_of, s)
-        nq = quad.shape[0]
+        nq = t.n_quads
+        quad = _i32((nq, 4), dev)
+        call("gsb_fc_quad_gather", dev, C.c_int32(nq), ptr(t.quad_entry), ptr(vd_of), ptr(quad), st)
         centres = _f32((nq, 3), dev)
         faces = torch.empty(4 * nq, 3, dtype=torch.int64, device=dev)
         call("gsb_fc_quad_fwd", dev, C.c_int32(nq), C.c_int32(t.Q), ptr(quad), ptr(vd), ptr(vd_gamma), ptr(centres),
              ptr(faces), st)
-        t.n_quads = nq
         ctx.topo, ctx.cubes = t, cubes
         ctx.save_for_backward(v, s, a, b, g, vd, vd_gamma, quad)
         ctx.shapes = (sdf_values.shape, gamma.shape)

@@ -320,11 +320,29 @@ int gsb_loss_bwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, 
  * FlexiCubes dual marching cubes: replaces FlexiCubes._get_case_id,
  * _identify_surf_edges, dual_marching_cubes, _compute_reg_loss, _triangulate, compute_entropy
  * (rfstudio/graphics/_mesh/_flexicubes.py:460-802) as GeoSplatter.get_geometry drives them (geosplat.py:751-769).
- * The per-cube / per-group / per-quad arithmetic is here; the ordering bookkeeping between the calls (one stable
- * radix sort of the edge keys, prefix sums) is the host's (geosplatting_b200/flexicubes.py), which also states every
- * buffer's meaning.  cubes[F,8] int32 grid-vertex ids; tables: check[256,5], num_vd[256], dmc[256,4,7], cube_edges[12,2]
+ * Per-cube / per-group / per-quad arithmetic and the ordering bookkeeping (one stable radix sort of the edge keys,
+ * three prefix sums) are all here; geosplatting_b200/flexicubes.py allocates and states every buffer's meaning.  cubes[F,8] int32 grid-vertex ids; tables: check[256,5], num_vd[256], dmc[256,4,7], cube_edges[12,2]
  * (int32, device).  N surface cubes, E surface edges, Q dual vertices, K (group, edge) entries.
  * ------------------------------------------------------------------------------------------- */
+/* Native sequencing of the integer part (what _get_case_id, _identify_surf_edges, the num_vd loop and the no-grad part
+ * of _triangulate compute, _flexicubes.py:460-538, :640-690, :758-771).  Two calls, one device->host read each:
+ *   gsb_fc_surface : classify all F cubes, compact the surface cube ids (ascending) into surf_ids[F]; *n_surf_host = N.
+ *   gsb_fc_topology: for N surface cubes -- resolved cases, dual-vertex counts, numbering (vd_base, k_base), surface
+ *                    edges (edge_of[N,12], surf_edges[<=12N,2]), quads (quad_entry[<=3N,4]: positions cube*12+edge into
+ *                    vd_of, winding order, reference quad order); counts_host[4] = {E, n_quads, Q, K}.
+ * Both synchronise `stream` before returning.  workspace: gsb_fc_workspace_bytes(F, N) bytes (N = 0 for gsb_fc_surface).
+ * After gsb_fc_dual_fwd, gsb_fc_quad_gather turns quad_entry into quad_vd for gsb_fc_quad_fwd/bwd. */
+int gsb_fc_workspace_bytes(int32_t F, int32_t N, size_t *bytes_host);
+int gsb_fc_surface(int32_t F, const float *sdf, const int32_t *cubes, int32_t *cases, int32_t *surf_flag,
+                   int32_t *surf_ids, void *workspace, size_t workspace_bytes, int32_t *n_surf_host, void *stream);
+int gsb_fc_topology(int32_t F, int32_t N, int64_t V, int32_t R0, int32_t R1, int32_t R2, const float *sdf,
+                    const int32_t *cubes, const int32_t *surf_ids, const int32_t *cases, const int32_t *surf_flag,
+                    const int32_t *check_table, const int32_t *num_vd_table, const int32_t *dmc_table,
+                    const int32_t *cube_edges, int32_t *case_ids, int32_t *num_vd, int32_t *vd_base, int32_t *k_base,
+                    int32_t *edge_of, int32_t *surf_edges, int32_t *quad_entry, void *workspace, size_t workspace_bytes,
+                    int32_t *counts_host, void *stream);
+int gsb_fc_quad_gather(int32_t n_quads, const int32_t *quad_entry, const int32_t *vd_of, int32_t *quad_vd, void *stream);
+/* The same stages one kernel per call (the pieces gsb_fc_surface / gsb_fc_topology sequence). */
 int gsb_fc_classify(int32_t F, const float *sdf, const int32_t *cubes, int32_t *cases, int32_t *surf_flag, void *stream);
 int gsb_fc_resolve(int32_t N, int32_t R0, int32_t R1, int32_t R2, const int32_t *surf_ids, const int32_t *cases,
                    const int32_t *surf_flag, const int32_t *check_table, const int32_t *num_vd_table,

@@ -26,6 +26,9 @@ static const cudaError_t cudaSuccess = 0;
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 
 template <class T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 template <class T> static inline T __ldg(const T *p) { return *p; }

@@ -84,3 +84,28 @@ def test_header_is_plain_c_and_every_error_path_answers_without_a_gpu():
                             ctypes.c_float(5.0), None, None, None) == -1
     assert lib.gsb_shade_workspace_bytes(ctypes.c_int32(512), ctypes.c_int32(6), ctypes.c_int32(16), ctypes.byref(n)) == 0
     assert n.value == 16 * (6 * 32 * 32 + 6 * 16 * 16 + 6 * 16 * 16) * 32
+
+
+def test_flexicubes_entry_points_validate_arguments_without_a_gpu():
+    """gsb_fc_*: size queries answer on the host, bad arguments come back as GSB_EINVAL with a message."""
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    i32, i64 = ctypes.c_int32, ctypes.c_int64
+    assert lib.gsb_fc_workspace_bytes(i32(128 ** 3), i32(0), ctypes.byref(n)) == 0 and n.value > 0
+    small = n.value
+    assert lib.gsb_fc_workspace_bytes(i32(128 ** 3), i32(100000), ctypes.byref(n)) == 0 and n.value > small
+    # 12 N (number of cube edges) must fit the int32 the sort and the scans count in; more surface cubes than cubes
+    assert lib.gsb_fc_workspace_bytes(i32(2 ** 31 - 1), i32(2 ** 28), ctypes.byref(n)) == -1
+    assert lib.gsb_fc_workspace_bytes(i32(10), i32(11), ctypes.byref(n)) == -1
+    cnt = i32(7)
+    assert lib.gsb_fc_surface(i32(0), None, None, None, None, None, None, ctypes.c_size_t(0), ctypes.byref(cnt), None) == 0
+    assert cnt.value == 0                                                     # empty grid: no device work, N = 0
+    assert lib.gsb_fc_surface(i32(8), None, None, None, None, None, None, ctypes.c_size_t(0), ctypes.byref(cnt), None) == -1
+    assert b"gsb_fc_surface" in lib.gsb_last_error()
+    counts = (i32 * 4)()
+    assert lib.gsb_fc_topology(i32(8), i32(0), i64(27), i32(2), i32(2), i32(2), *([None] * 17), ctypes.c_size_t(0),
+                               counts, None) == -1
+    assert lib.gsb_fc_quad_gather(i32(0), None, None, None, None) == 0
+    assert lib.gsb_fc_quad_gather(i32(4), None, None, None, None) == -1
+    assert lib.gsb_fc_dual_fwd(i32(4), *([None] * 18), None) == -1
+    assert lib.gsb_fc_entropy_fwd(i64(-1), None, None, None, None) == -1

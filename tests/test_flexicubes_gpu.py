@@ -25,10 +25,10 @@ def test_rough_fixture_with_inverted_cases():
 def test_against_oracle(res, noise):
     _lib.CallStats.reset()
     assert fc_cases.check_against_oracle(DEV, res=res, seed=sum(res), noise=noise) > 0
-    # the CUDA kernels ran: classify, resolve, keys, dual fwd/bwd, quad fwd/bwd, entropy fwd/bwd
+    # the CUDA library did the work: native topology driver, dual fwd/bwd, quad gather/fwd/bwd, entropy fwd/bwd
     assert {k for k in _lib.CallStats.counts if k.startswith("gsb_fc_")} == {
-        "gsb_fc_classify", "gsb_fc_resolve", "gsb_fc_edge_keys", "gsb_fc_dual_fwd", "gsb_fc_dual_bwd",
-        "gsb_fc_quad_fwd", "gsb_fc_quad_bwd", "gsb_fc_entropy_fwd", "gsb_fc_entropy_bwd"}
+        "gsb_fc_workspace_bytes", "gsb_fc_surface", "gsb_fc_topology", "gsb_fc_dual_fwd", "gsb_fc_dual_bwd",
+        "gsb_fc_quad_gather", "gsb_fc_quad_fwd", "gsb_fc_quad_bwd", "gsb_fc_entropy_fwd", "gsb_fc_entropy_bwd"}
 
 
 def test_full_size_grid_is_watertight_and_feeds_mgadapter():
