@@ -90,7 +90,7 @@ class CallStats:
                "gsb_view_bytes": 0, "gsb_view_prepare": 4, "gsb_view_finish": 7, "gsb_view_backward": 6,
                # FlexiCubes: surface = classify (+ cub select); topology = resolve, class flags, numbering, edge keys,
                # edge flags, edge assignment (+ cub sort and two scans)
-               "gsb_fc_workspace_bytes": 0, "gsb_fc_surface": 1, "gsb_fc_topology": 6}
+               "gsb_fc_workspace_bytes": 0, "gsb_fc_surface": 1, "gsb_fc_topology": 6, "gsb_fc_entropy_fwd": 2}
     timing = False        # False, True (every entry point) or a set of entry-point names
     counts: dict = {}
     events: dict = {}

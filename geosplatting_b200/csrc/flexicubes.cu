@@ -18,7 +18,8 @@
 //   fc_dual_fwd/bwd  per (surf cube, group): dual vertex = beta-weighted mean of the alpha-weighted zero crossings of its
 //                                      edges, L_dev entries; VJP to grid vertices, SDF, alpha, beta, gamma
 //   fc_quad_fwd/bwd  per quad        : gamma-weighted centre, 4 faces; VJP to the 4 dual vertices and their gammas
-//   fc_entropy_fwd/bwd per grid edge : symmetric BCE between the endpoint SDF values of sign-changing edges
+//   fc_entropy_fwd/bwd per grid edge : symmetric BCE between the endpoint SDF values of sign-changing edges (8 B of
+//                                      int32 ids per edge, four edges per thread)
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -33,10 +34,17 @@ __global__ void __launch_bounds__(256) fc_classify_kernel(int F, const float *__
                                                            int32_t *__restrict__ surf_flag) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
+    // the eight corner ids as two 16-byte loads (rows of cubes[F,8] are 32-byte aligned), then eight independent gathers
+    const int4 lo = reinterpret_cast<const int4 *>(cubes)[2 * (size_t)f];
+    const int4 hi = reinterpret_cast<const int4 *>(cubes)[2 * (size_t)f + 1];
+    const int id[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = sdf[id[k]];
     int c = 0, n = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const bool in = sdf[cubes[8 * f + k]] < 0.f;
+        const bool in = v[k] < 0.f;
         c |= (int)in << k;
         n += in;
     }
@@ -437,24 +445,39 @@ __global__ void __launch_bounds__(256) fc_quad_kernel(int n_quads, int Q, const 
 // F.binary_cross_entropy_with_logits(x, t) = max(x, 0) - x t + log(1 + exp(-|x|)); sums[0..2] = {sum_a, sum_b, count}
 __device__ __forceinline__ float bce_logits(float x, float t) { return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x))); }
 
+// Four edges per thread, block-strided (every load instruction of a warp is one contiguous 256-byte request, four
+// independent requests in flight per thread before the dependent SDF gathers).
+constexpr int ENT_EPT = 4;
+constexpr int ENT_REPLICAS = GSB_FC_ENTROPY_REPLICAS;
+
 template <bool BWD>
-__global__ void __launch_bounds__(256) fc_entropy_kernel(long long U, const long long *__restrict__ edges,
+__global__ void __launch_bounds__(256) fc_entropy_kernel(long long U, const int2 *__restrict__ edges,
                                                           const float *__restrict__ sdf, float *__restrict__ sums,
                                                           const float *__restrict__ v_loss, float *__restrict__ v_sdf) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long base = (long long)blockIdx.x * (256 * ENT_EPT) + threadIdx.x;
+    int2 e[ENT_EPT];
+    float a[ENT_EPT], b[ENT_EPT];
+#pragma unroll
+    for (int k = 0; k < ENT_EPT; ++k) {
+        const long long i = base + k * 256;
+        e[k] = i < U ? edges[i] : make_int2(-1, -1);
+    }
+#pragma unroll
+    for (int k = 0; k < ENT_EPT; ++k) {
+        a[k] = e[k].x >= 0 ? sdf[e[k].x] : 1.f;
+        b[k] = e[k].x >= 0 ? sdf[e[k].y] : 1.f;
+    }
     float sa = 0.f, sb = 0.f, cnt = 0.f;
-    if (i < U) {
-        const long long va = edges[2 * i], vb = edges[2 * i + 1];
-        const float a = sdf[va], b = sdf[vb];
-        if ((a < 0.f) != (b < 0.f)) {
-            const float ta = (b > 0.f) ? 1.f : 0.f, tb = (a > 0.f) ? 1.f : 0.f;
-            if (!BWD) {
-                sa = bce_logits(a, ta); sb = bce_logits(b, tb); cnt = 1.f;
-            } else {
-                const float s = __ldg(v_loss) / sums[2];
-                atomicAdd(v_sdf + va, s * (1.0f / (1.0f + expf(-a)) - ta));
-                atomicAdd(v_sdf + vb, s * (1.0f / (1.0f + expf(-b)) - tb));
-            }
+#pragma unroll
+    for (int k = 0; k < ENT_EPT; ++k) {
+        if ((a[k] < 0.f) == (b[k] < 0.f)) continue;
+        const float ta = (b[k] > 0.f) ? 1.f : 0.f, tb = (a[k] > 0.f) ? 1.f : 0.f;
+        if (!BWD) {
+            sa += bce_logits(a[k], ta); sb += bce_logits(b[k], tb); cnt += 1.f;
+        } else {
+            const float s = __ldg(v_loss) / sums[2];
+            atomicAdd(v_sdf + e[k].x, s * (1.0f / (1.0f + expf(-a[k])) - ta));
+            atomicAdd(v_sdf + e[k].y, s * (1.0f / (1.0f + expf(-b[k])) - tb));
         }
     }
     if constexpr (!BWD) {
@@ -467,10 +490,20 @@ __global__ void __launch_bounds__(256) fc_entropy_kernel(long long U, const long
         }
         if ((threadIdx.x & 31) != 0) return;
 #endif
+        // same-address reductions serialise in L2 (the forward took 2.5x the backward's time on identical traffic with
+        // one set of three accumulators): spread the warps over ENT_REPLICAS private sets, summed by fc_entropy_finish
         if (cnt > 0.f) {
-            atomicAdd(sums, sa); atomicAdd(sums + 1, sb); atomicAdd(sums + 2, cnt);
+            float *o = sums + 3 * (blockIdx.x % ENT_REPLICAS);
+            atomicAdd(o, sa); atomicAdd(o + 1, sb); atomicAdd(o + 2, cnt);
         }
     }
+}
+
+__global__ void fc_entropy_finish_kernel(const float *__restrict__ partials, float *__restrict__ sums3) {
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int r = 0; r < ENT_REPLICAS; ++r)
+        for (int k = 0; k < 3; ++k) s[k] += partials[3 * r + k];
+    sums3[0] = s[0]; sums3[1] = s[1]; sums3[2] = s[2];
 }
 
 }  // namespace
@@ -481,7 +514,7 @@ GSB_API int gsb_fc_classify(int32_t F, const float *sdf, const int32_t *cubes, i
                             void *stream) {
     GSB_CHECK_ARG(F >= 0);
     if (F == 0) return GSB_OK;
-    GSB_CHECK_ARG(sdf && cubes && cases && surf_flag);
+    GSB_CHECK_ARG(sdf && cubes && cases && surf_flag && (reinterpret_cast<uintptr_t>(cubes) & 15) == 0);
     fc_classify_kernel<<<gsb_div_up(F, 256), 256, 0, (cudaStream_t)stream>>>(F, sdf, cubes, cases, surf_flag);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
@@ -570,24 +603,30 @@ GSB_API int gsb_fc_quad_bwd(int32_t n_quads, int32_t Q, const int32_t *quad_vd, 
     return GSB_OK;
 }
 
-GSB_API int gsb_fc_entropy_fwd(int64_t U, const int64_t *grid_edges, const float *sdf, float *sums3, void *stream) {
+GSB_API int gsb_fc_entropy_fwd(int64_t U, const int32_t *grid_edges, const float *sdf, float *sums3, float *partials,
+                               void *stream) {
     GSB_CHECK_ARG(U >= 0 && sums3 != nullptr);
-    GSB_CHECK_CUDA(cudaMemsetAsync(sums3, 0, 3 * sizeof(float), (cudaStream_t)stream));
-    if (U == 0) return GSB_OK;
-    GSB_CHECK_ARG(grid_edges && sdf);
-    fc_entropy_kernel<false><<<gsb_div_up(U, 256), 256, 0, (cudaStream_t)stream>>>(
-        (long long)U, reinterpret_cast<const long long *>(grid_edges), sdf, sums3, nullptr, nullptr);
+    if (U == 0) {
+        GSB_CHECK_CUDA(cudaMemsetAsync(sums3, 0, 3 * sizeof(float), (cudaStream_t)stream));
+        return GSB_OK;
+    }
+    GSB_CHECK_ARG(grid_edges && sdf && partials);
+    GSB_CHECK_CUDA(cudaMemsetAsync(partials, 0, 3 * ENT_REPLICAS * sizeof(float), (cudaStream_t)stream));
+    fc_entropy_kernel<false><<<gsb_div_up(U, 256 * ENT_EPT), 256, 0, (cudaStream_t)stream>>>(
+        (long long)U, reinterpret_cast<const int2 *>(grid_edges), sdf, partials, nullptr, nullptr);
+    GSB_CHECK_LAUNCH();
+    fc_entropy_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(partials, sums3);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 
-GSB_API int gsb_fc_entropy_bwd(int64_t U, const int64_t *grid_edges, const float *sdf, const float *sums3,
+GSB_API int gsb_fc_entropy_bwd(int64_t U, const int32_t *grid_edges, const float *sdf, const float *sums3,
                                const float *v_loss, float *v_sdf, void *stream) {
     GSB_CHECK_ARG(U >= 0);
     if (U == 0) return GSB_OK;
     GSB_CHECK_ARG(grid_edges && sdf && sums3 && v_loss && v_sdf);
-    fc_entropy_kernel<true><<<gsb_div_up(U, 256), 256, 0, (cudaStream_t)stream>>>(
-        (long long)U, reinterpret_cast<const long long *>(grid_edges), sdf, const_cast<float *>(sums3), v_loss, v_sdf);
+    fc_entropy_kernel<true><<<gsb_div_up(U, 256 * ENT_EPT), 256, 0, (cudaStream_t)stream>>>(
+        (long long)U, reinterpret_cast<const int2 *>(grid_edges), sdf, const_cast<float *>(sums3), v_loss, v_sdf);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
@@ -640,7 +679,8 @@ GSB_API int gsb_fc_surface(int32_t F, const float *sdf, const int32_t *cubes, in
     GSB_CHECK_ARG(F >= 0 && n_surf_host != nullptr);
     *n_surf_host = 0;
     if (F == 0) return GSB_OK;
-    GSB_CHECK_ARG(sdf && cubes && cases && surf_flag && surf_ids && workspace);
+    GSB_CHECK_ARG(sdf && cubes && cases && surf_flag && surf_ids && workspace &&
+                  (reinterpret_cast<uintptr_t>(cubes) & 15) == 0);
     size_t need = 0;
     GSB_CHECK_ARG(gsb_fc_workspace_bytes(F, 0, &need) == GSB_OK);
     if (need > workspace_bytes) {

@@ -38,6 +38,7 @@ from ._lib import call, f32c, ptr, stream_ptr
 
 _TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "flexicubes_tables.npz")
 _tables_cache: Dict[str, Dict[str, Tensor]] = {}
+ENTROPY_REPLICAS = 64          # GSB_FC_ENTROPY_REPLICAS (include/geosplat_b200.h)
 
 
 def _tables(dev: torch.device) -> Dict[str, Tensor]:
@@ -172,9 +173,9 @@ class _Entropy(torch.autograd.Function):
     def forward(ctx, sdf_values: Tensor, grid_edges: Tensor):
         s = f32c(sdf_values).view(-1)
         dev = s.device
-        sums = _f32(3, dev)
+        sums, partials = _f32(3, dev), _f32(3 * ENTROPY_REPLICAS, dev)
         call("gsb_fc_entropy_fwd", dev, C.c_int64(grid_edges.shape[0]), ptr(grid_edges), ptr(s), ptr(sums),
-             stream_ptr(dev))
+             ptr(partials), stream_ptr(dev))
         ctx.save_for_backward(s, grid_edges, sums)
         ctx.shape = sdf_values.shape
         return (sums[0] + sums[1]) / sums[2]
@@ -258,11 +259,11 @@ class FlexiCubes:
         return self._static["cubes"]
 
     def _grid_edges(self) -> Tensor:
-        """Every grid edge once, [U,2] int64 (the unique() of compute_entropy, _flexicubes.py:716-717; the edge set does
+        """Every grid edge once, [U,2] int32 (the unique() of compute_entropy, _flexicubes.py:716-717; the edge set does
         not depend on the SDF, so it is computed once per grid)."""
         if "grid_edges" not in self._static:
             ce = _tables(self.indices.device)["cube_edges"].long()
-            self._static["grid_edges"] = self.indices[:, ce].view(-1, 2).unique(dim=0).contiguous()
+            self._static["grid_edges"] = self.indices[:, ce].view(-1, 2).unique(dim=0).int().contiguous()
         return self._static["grid_edges"]
 
     # -- the two operators -----------------------------------------------------------------------------------------

@@ -321,7 +321,7 @@ int gsb_loss_bwd(int32_t H, int32_t W, const float *rgba, const float *gt_rgba, 
  * _identify_surf_edges, dual_marching_cubes, _compute_reg_loss, _triangulate, compute_entropy
  * (rfstudio/graphics/_mesh/_flexicubes.py:460-802) as GeoSplatter.get_geometry drives them (geosplat.py:751-769).
  * Per-cube / per-group / per-quad arithmetic and the ordering bookkeeping (one stable radix sort of the edge keys,
- * three prefix sums) are all here; geosplatting_b200/flexicubes.py allocates and states every buffer's meaning.  cubes[F,8] int32 grid-vertex ids; tables: check[256,5], num_vd[256], dmc[256,4,7], cube_edges[12,2]
+ * three prefix sums) are all here; geosplatting_b200/flexicubes.py allocates and states every buffer's meaning.  cubes[F,8] int32 grid-vertex ids (16-byte aligned); tables: check[256,5], num_vd[256], dmc[256,4,7], cube_edges[12,2]
  * (int32, device).  N surface cubes, E surface edges, Q dual vertices, K (group, edge) entries.
  * ------------------------------------------------------------------------------------------- */
 /* Native sequencing of the integer part (what _get_case_id, _identify_surf_edges, the num_vd loop and the no-grad part
@@ -369,10 +369,13 @@ int gsb_fc_quad_fwd(int32_t n_quads, int32_t Q, const int32_t *quad_vd, const fl
 /* VJP: ACCUMULATES into v_vd[Q,3] and v_vd_gamma[Q]. */
 int gsb_fc_quad_bwd(int32_t n_quads, int32_t Q, const int32_t *quad_vd, const float *vd, const float *vd_gamma,
                     const float *v_centres, float *v_vd, float *v_vd_gamma, void *stream);
-/* compute_entropy over grid_edges[U,2] int64 (every grid edge once): sums3 = {sum BCE(a|b), sum BCE(b|a), #sign-changing
- * edges}; entropy = (sums3[0] + sums3[1]) / sums3[2].  bwd ACCUMULATES *v_loss * d entropy / d sdf into v_sdf[V]. */
-int gsb_fc_entropy_fwd(int64_t U, const int64_t *grid_edges, const float *sdf, float *sums3, void *stream);
-int gsb_fc_entropy_bwd(int64_t U, const int64_t *grid_edges, const float *sdf, const float *sums3, const float *v_loss,
+/* compute_entropy over grid_edges[U,2] int32 (every grid edge once): sums3 = {sum BCE(a|b), sum BCE(b|a), #sign-changing
+ * edges}; entropy = (sums3[0] + sums3[1]) / sums3[2].  partials: scratch of 3 * GSB_FC_ENTROPY_REPLICAS floats.
+ * bwd ACCUMULATES *v_loss * d entropy / d sdf into v_sdf[V]. */
+#define GSB_FC_ENTROPY_REPLICAS 64
+int gsb_fc_entropy_fwd(int64_t U, const int32_t *grid_edges, const float *sdf, float *sums3, float *partials,
+                       void *stream);
+int gsb_fc_entropy_bwd(int64_t U, const int32_t *grid_edges, const float *sdf, const float *sums3, const float *v_loss,
                        float *v_sdf, void *stream);
 
 /* ---------------------------------------------------------------------------------------------

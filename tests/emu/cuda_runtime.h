@@ -20,6 +20,10 @@
 struct gsb_emu_dim3 { unsigned x, y, z; };
 static thread_local gsb_emu_dim3 blockIdx, blockDim, threadIdx, gridDim;
 
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
 typedef void *cudaStream_t;
 typedef int cudaError_t;
 static const cudaError_t cudaSuccess = 0;

@@ -108,4 +108,4 @@ def test_flexicubes_entry_points_validate_arguments_without_a_gpu():
     assert lib.gsb_fc_quad_gather(i32(0), None, None, None, None) == 0
     assert lib.gsb_fc_quad_gather(i32(4), None, None, None, None) == -1
     assert lib.gsb_fc_dual_fwd(i32(4), *([None] * 18), None) == -1
-    assert lib.gsb_fc_entropy_fwd(i64(-1), None, None, None, None) == -1
+    assert lib.gsb_fc_entropy_fwd(i64(-1), None, None, None, None, None) == -1

@@ -76,3 +76,31 @@ def test_product_tables_are_the_reference_tables():
     assert set(tb) == {"cube_edges", "check", "dmc", "num_vd"}
     for k, v in tb.items():
         assert v.dtype == torch.int32 and np.array_equal(v.numpy(), g["tbl_" + k])
+
+
+@pytest.mark.parametrize("res", [(1, 1, 1), (2, 1, 3), (3, 3, 3), (4, 2, 5)])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_tiny_random_grids_against_oracle(host_kernels, res, seed):
+    """Random SDF on grids down to a single cube (no quads at all: a mesh with dual vertices and zero faces), every
+    case of the ambiguity table reachable at the grid boundary: same faces, vertices, L_dev and SDF gradient."""
+    import numpy as np
+    from oracle import flexicubes as OF
+    gen = torch.Generator().manual_seed(100 * seed + sum(res))
+    fc0 = FC.FlexiCubes.from_resolution(*res, random_sdf=False, scale=1.0)
+    sdf0 = torch.rand(fc0.vertices.shape[0], 1, generator=gen) - 0.5
+    w0 = 0.5 * torch.randn(fc0.indices.shape[0], 21, generator=gen)
+    tbl = fc_cases.tables(fc_cases.load("ref_flexicubes.npz"))
+    got = {}
+    for which in ("ours", "oracle"):
+        sdf, w = sdf0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        if which == "ours":
+            mesh, l_dev = fc0.replace(sdf_values=sdf, alpha=w[:, :8], beta=w[:, 8:20], gamma=w[:, 20:]).dual_marching_cubes()
+            mv, mf = mesh.vertices, mesh.indices
+        else:
+            mv, mf, l_dev = OF.dual_marching_cubes(fc0.vertices, sdf, fc0.indices, res, w[:, :8], w[:, 8:20], w[:, 20:], tbl)
+        g = torch.autograd.grad(mv.square().sum() + l_dev.sum(), [sdf, w])
+        got[which] = [x.detach().numpy() for x in (mf, mv, l_dev, *g)]
+    a, b = got["ours"], got["oracle"]
+    assert a[0].shape == b[0].shape and np.array_equal(a[0], b[0])
+    for x, y in zip(a[1:], b[1:]):
+        assert x.shape == y.shape and np.abs(x - y).max(initial=0.0) <= 1e-4 * max(1.0, np.abs(y).max(initial=0.0))
