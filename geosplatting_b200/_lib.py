@@ -145,6 +145,13 @@ def ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    """The product has no CPU path: every public operator refuses CPU tensors through this one check (modules bind it
+    as `_require_cuda`, which is also the single point tests/emu patches to run kernel source compiled for the host)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"geosplatting_b200.{what} needs CUDA tensors; there is no CPU path")
+
+
 def stream_ptr(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 

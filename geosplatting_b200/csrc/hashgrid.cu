@@ -215,7 +215,11 @@ GSB_API int gsb_hashgrid_bwd(int64_t N, const float *x, const float *table, int3
     Scalings sc;
     for (int l = 0; l < L; ++l) sc.s[l] = scalings_host[l];
     const long long total = (long long)N * L;
+#ifdef GSB_HOST_EMULATION   // tests/emu runs the threads one after another: no warp to reduce over, d/dx through atomics
+    const int segmented = 0;
+#else
     const int segmented = (L <= 32) ? ((32 % L) == 0) : ((L % 32) == 0);
+#endif
     if (v_x && (!segmented || L > 32))
         GSB_CHECK_CUDA(cudaMemsetAsync(v_x, 0, sizeof(float) * 3 * (size_t)N, (cudaStream_t)stream));
     hashgrid_bwd_kernel<<<gsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(

@@ -15,6 +15,22 @@
 
 namespace {
 
+// Sum of `v` over the 256 threads of the block, added to *out by one atomic.
+__device__ __forceinline__ void block_add(float v, float *out) {
+#ifndef GSB_HOST_EMULATION   // tests/emu runs the threads one after another: every thread adds its own term
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s[w];
+#endif
+    atomicAdd(out, v);
+}
+
+
 template <int N>
 struct Dual {
     float v;
@@ -384,16 +400,7 @@ __global__ void __launch_bounds__(256) tonemap_bwd_kernel(long long P, const flo
         v_rgba[i] = make_float4(v.x * dx * e, v.y * dy * e, v.z * dz * e, v.w);
         ve = v.x * dx * p.x + v.y * dy * p.y + v.z * dz * p.z;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ve += __shfl_xor_sync(0xffffffffu, ve, o);
-    __shared__ float s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ve;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s[w];
-        atomicAdd(v_exposure, t);
-    }
+    block_add(ve, v_exposure);
 }
 
 // Planar variants: read the rasterizer's own outputs (render[P,3], alphas[P]) and write the RGBA image, so no
@@ -433,16 +440,7 @@ __global__ void __launch_bounds__(256) tonemap_planar_bwd_kernel(long long P, co
         v_alphas[i] = v.w;
         ve = v.x * dx * x + v.y * dy * y + v.z * dz * z;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ve += __shfl_xor_sync(0xffffffffu, ve, o);
-    __shared__ float s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ve;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s[w];
-        atomicAdd(v_exposure, t);
-    }
+    block_add(ve, v_exposure);
 }
 
 }  // namespace

@@ -19,6 +19,7 @@ import torch
 from torch import Tensor, nn
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 
 def level_scalings(num_levels: int, min_res: int, max_res: int) -> List[float]:
@@ -115,8 +116,7 @@ class HashEncoding(nn.Module):
 
     def encode(self, in_tensor: Tensor) -> Tensor:
         """pytorch_fwd (encoding.py:182-229): [..., 3] in [-1, 1] -> [..., num_levels * features_per_level]."""
-        if not in_tensor.is_cuda:
-            raise RuntimeError("geosplatting_b200.HashEncoding needs CUDA tensors; there is no CPU path")
+        _require_cuda(in_tensor, "HashEncoding")
         assert in_tensor.shape[-1] == 3
         flat = in_tensor.reshape(-1, 3)
         feats = _HashGrid.apply(flat, self.hash_table, self.scalings, self.log2_hashmap_size,

@@ -35,6 +35,7 @@ import torch
 from torch import Tensor
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 _TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "flexicubes_tables.npz")
 _tables_cache: Dict[str, Dict[str, Tensor]] = {}
@@ -49,11 +50,6 @@ def _tables(dev: torch.device) -> Dict[str, Tensor]:
         with np.load(_TABLE_PATH) as z:
             _tables_cache[key] = {k: torch.from_numpy(z[k].astype(np.int32)).contiguous().to(dev) for k in z.files}
     return _tables_cache[key]
-
-
-def _require_cuda(t: Tensor, what: str) -> None:
-    if not t.is_cuda:
-        raise RuntimeError(f"geosplatting_b200.{what} needs CUDA tensors; there is no CPU path")
 
 
 def _i32(shape, dev) -> Tensor:

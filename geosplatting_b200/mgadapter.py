@@ -16,6 +16,7 @@ import torch
 from torch import Tensor
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 
 def _i64c(t: Tensor) -> Tensor:
@@ -52,8 +53,7 @@ class _VertexNormals(torch.autograd.Function):
 
 def compute_vertex_normals(vertices: Tensor, faces: Tensor) -> Tensor:
     """Area-weighted vertex normals with the `fix=True` fallback (0,0,1) for degenerate vertices."""
-    if not vertices.is_cuda:
-        raise RuntimeError("geosplatting_b200.compute_vertex_normals needs CUDA tensors; there is no CPU path")
+    _require_cuda(vertices, "compute_vertex_normals")
     return _VertexNormals.apply(vertices, faces)
 
 
@@ -114,8 +114,7 @@ class MGAdapter:
 
     def make(self, vertices: Tensor, faces: Tensor, vertex_normals: Optional[Tensor] = None, *,
              normal_interpolation: bool = True) -> Tuple[MGSplats, Tensor]:
-        if not vertices.is_cuda:
-            raise RuntimeError("geosplatting_b200.MGAdapter needs CUDA tensors; there is no CPU path")
+        _require_cuda(vertices, "MGAdapter")
         if normal_interpolation and vertex_normals is None:
             raise ValueError("normal_interpolation=True needs vertex normals (mesh.compute_vertex_normals(fix=True))")
         vn = vertex_normals if normal_interpolation else None
@@ -145,7 +144,6 @@ class _ToneMap(torch.autograd.Function):
 
 def tone_mapping_naive(rgba: Tensor, exposure: Tensor) -> Tensor:
     """rgba[...,4], exposure[1] (device tensor) -> [...,4]."""
-    if not rgba.is_cuda:
-        raise RuntimeError("geosplatting_b200.tone_mapping_naive needs CUDA tensors; there is no CPU path")
+    _require_cuda(rgba, "tone_mapping_naive")
     assert rgba.shape[-1] == 4
     return _ToneMap.apply(rgba, exposure)

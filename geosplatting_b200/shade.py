@@ -18,6 +18,7 @@ import torch
 from torch import Tensor
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 MODES = {"pbr": 0, "diffuse": 1, "specular": 2}
 
@@ -141,8 +142,7 @@ def shade(means: Tensor, normals: Tensor, kd: Tensor, ks: Tensor, camera_pos: Se
     host floats; `fg_lut` is the [R,R,2] (or [1,R,R,2]) DFG table on the device."""
     if mode not in MODES:
         raise ValueError(mode)
-    if not means.is_cuda:
-        raise RuntimeError("geosplatting_b200.shade needs CUDA tensors; there is no CPU path")
+    _require_cuda(means, "shade")
     lut = f32c(fg_lut).reshape(fg_lut.shape[-3], fg_lut.shape[-2], 2)
     cam = tuple(float(x) for x in camera_pos)
     meta = (env.R0, env.L, env.Rb, float(min_roughness), float(max_metallic), env.min_roughness, env.max_roughness,
@@ -227,8 +227,7 @@ def texture(tex: Tensor, uv: Tensor, uv_da=None, mip_level_bias: Optional[Tensor
     """
     if uv_da is not None or max_mip_level is not None:
         raise NotImplementedError("geosplatting_b200.texture: uv_da / max_mip_level are not used on this path")
-    if not uv.is_cuda:
-        raise RuntimeError("geosplatting_b200.texture needs CUDA tensors; there is no CPU path")
+    _require_cuda(uv, "texture")
     lead = uv.shape[:-1]
     if boundary_mode == "clamp":
         if filter_mode != "linear" or tex.dim() != 4 or tex.shape[0] != 1 or tex.shape[-1] != 2:

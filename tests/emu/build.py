@@ -13,24 +13,27 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "geosplatting_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-_LAUNCH = re.compile(r"(\w+(?:<\w+>)?)<<<(.+?), (\d+), 0, \(cudaStream_t\)stream>>>\(")
+_LAUNCH = re.compile(r"(\w+(?:<[\w, ]+>)?)<<<(.+?), (\d+), 0, (?:\(cudaStream_t\)stream|st)>>>\(")
 
 
-def build(name: str) -> C.CDLL:
-    """`name`.cu -> tests/emu/_build/lib`name`_emu.so (rebuilt when the source is newer)."""
+def build(*names: str) -> C.CDLL:
+    """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu.so (rebuilt when a source is newer)."""
     os.makedirs(OUT, exist_ok=True)
-    src = os.path.join(CSRC, name + ".cu")
-    cpp = os.path.join(OUT, name + "_emu.cpp")
-    lib = os.path.join(OUT, f"lib{name}_emu.so")
-    deps = [src, os.path.join(CSRC, "gsb_common.cuh"), os.path.join(HERE, "cuda_runtime.h"), __file__]
+    srcs = [os.path.join(CSRC, n + ".cu") for n in names]
+    lib = os.path.join(OUT, "lib" + "_".join(names) + "_emu.so")
+    deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \
+        [os.path.join(d, f) for d, _, fs in os.walk(HERE) if "_build" not in d for f in fs if f.endswith((".h", ".cuh"))]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        text = open(src).read()
-        text, n = _LAUNCH.subn(r"gsb_emu::launch(\2, \3, [](auto... a) { \1(a...); })(", text)
-        assert n > 0 and "<<<" not in text, "a launch site the emulation rewrite does not understand"
-        with open(cpp, "w") as f:
-            f.write(text)
+        cpps = []
+        for n, src in zip(names, srcs):
+            text = open(src).read()
+            text, k = _LAUNCH.subn(r"gsb_emu::launch(\2, \3, [](auto... a) { \1(a...); })(", text)
+            assert k > 0 and "<<<" not in text, f"{n}.cu: a launch site the emulation rewrite does not understand"
+            cpps.append(os.path.join(OUT, n + "_emu.cpp"))
+            with open(cpps[-1], "w") as f:
+                f.write(text)
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", HERE, "-I", CSRC,
-                               "-o", lib, cpp, "-x", "c++", os.path.join(CSRC, "error.cu")])
+                               "-o", lib, *cpps, "-x", "c++", os.path.join(CSRC, "error.cu")])
     so = C.CDLL(lib)
     so.gsb_last_error.restype = C.c_char_p
     return so

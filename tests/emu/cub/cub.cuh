@@ -24,20 +24,30 @@ struct DeviceSelect {
 
 struct DeviceRadixSort {
     template <class K, class V>
-    static cudaError_t SortPairs(void *temp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, int n,
+    static cudaError_t SortPairs(void *temp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, long long n,
                                  int begin_bit = 0, int end_bit = sizeof(K) * 8, cudaStream_t = 0) {
         if (!temp) { bytes = 1; return cudaSuccess; }
         using U = unsigned long long;
         const U mask = (end_bit - begin_bit >= 64) ? ~0ull : (((1ull << (end_bit - begin_bit)) - 1) << begin_bit);
-        std::vector<int> idx(n);
+        std::vector<long long> idx(n);
         std::iota(idx.begin(), idx.end(), 0);
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return ((U)kin[a] & mask) < ((U)kin[b] & mask); });
-        for (int i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+        std::stable_sort(idx.begin(), idx.end(), [&](long long a, long long b) { return ((U)kin[a] & mask) < ((U)kin[b] & mask); });
+        for (long long i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
         return cudaSuccess;
     }
 };
 
 struct DeviceScan {
+    template <class In, class Out>
+    static cudaError_t InclusiveSum(void *temp, size_t &bytes, In in, Out out, int n, cudaStream_t = 0) {
+        if (!temp) { bytes = 1; return cudaSuccess; }
+        if (n <= 0) return cudaSuccess;
+        auto acc = in[0];
+        out[0] = acc;
+        for (int i = 1; i < n; ++i) { acc = acc + in[i]; out[i] = acc; }
+        return cudaSuccess;
+    }
+
     template <class In, class Out, class Op>
     static cudaError_t InclusiveScan(void *temp, size_t &bytes, In in, Out out, Op op, int n, cudaStream_t = 0) {
         if (!temp) { bytes = 1; return cudaSuccess; }

@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define GSB_HOST_EMULATION 1
@@ -22,7 +23,44 @@ static thread_local gsb_emu_dim3 blockIdx, blockDim, threadIdx, gridDim;
 
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __fdividef(float a, float b) { return a / b; }
+#define __expf(x) expf(x)
+static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline float __fsqrt_rn(float x) { return sqrtf(x); }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline float min(float a, float b) { return fminf(a, b); }
+static inline float max(float a, float b) { return fmaxf(a, b); }
+// warp intrinsics have no sequential meaning: kernels route around them under GSB_HOST_EMULATION; reaching one is a bug
+template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { abort(); }
+static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 
 typedef void *cudaStream_t;
 typedef int cudaError_t;
@@ -35,6 +73,16 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 
 template <class T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
+static inline float2 atomicAdd(float2 *p, float2 v) {   // red.global.add.v2.f32
+    float2 old = *p;
+    p->x += v.x; p->y += v.y;
+    return old;
+}
+static inline float4 atomicAdd(float4 *p, float4 v) {   // sm_90+ vector reduction (red.global.add.v4.f32)
+    float4 old = *p;
+    p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+    return old;
+}
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
 namespace gsb_emu {

@@ -3,34 +3,18 @@ csrc/flexicubes.cu compiled for the host by tests/emu (threads run one after ano
 This checks the ordering bookkeeping, the kernels' index arithmetic and their gradient formulas against the reference's
 own outputs in this GPU-less container; the CUDA build of the same source is checked by tests/test_flexicubes_gpu.py.
 The emulation is wired in by monkeypatching here -- the product refuses CPU tensors (last test)."""
-import ctypes as C
-
 import pytest
 import torch
 
-from geosplatting_b200 import _lib
 from geosplatting_b200 import flexicubes as FC
 from tests import fc_cases
 from tests.emu import build as emu
+from tests.emu.patch import route
 
 
 @pytest.fixture()
 def host_kernels(monkeypatch):
-    so = emu.build("flexicubes")
-
-    def ptr(t):
-        if t is None:
-            return None
-        assert t.is_contiguous() and t.device.type == "cpu"
-        return C.c_void_p(t.data_ptr())
-
-    monkeypatch.setattr(_lib, "load", lambda: so)
-    monkeypatch.setattr(FC, "ptr", ptr)
-    monkeypatch.setattr(FC, "stream_ptr", lambda dev: None)
-    monkeypatch.setattr(FC, "_require_cuda", lambda t, what: None)
-    saved = dict(_lib.CallStats.counts)
-    yield so
-    _lib.CallStats.counts = saved
+    route(monkeypatch, emu.build("flexicubes"), FC)
 
 
 def test_kernel_source_on_host_smooth_fixture(host_kernels):
