@@ -10,7 +10,9 @@ into the C-ABI library through the operator mirrors of this package):
 What it drives per step: FlexiCubes mesh + regulariser (flexicubes.py) -> vertex normals + MGAdaptor + kd / ks / z
 hash-grid fields (field.py) -> split-sum prefilter (splitsum.py) -> the batch of views (fused.splat_views: shade,
 rasterize, tone map) -> per-view loss (loss.py).  `smooth_type` 'grad' / 'tv' (extra render_rgb passes per view, off in
-every shipped stage-1 recipe until their weights are raised) are not mirrored; 'jitter' (the default) is.
+every shipped stage-1 recipe until their weights are raised) and the normal smoothness term run through
+GSplatter.render_rgb like the reference's; their Sobel filter restates kornia.filters.spatial_gradient (third-party,
+absent here: PARITY UNPINNED for that filter, |.| is taken so its sign conventions do not matter).
 """
 from __future__ import annotations
 
@@ -38,6 +40,28 @@ def srgb2rgb(rgba: Tensor) -> Tensor:
     return torch.cat((lin, rgba[..., 3:]), dim=-1)
 
 
+def spatial_gradient(x: Tensor) -> Tensor:
+    """kornia.filters.spatial_gradient(x, mode='sobel', order=1, normalized=True): [B,C,H,W] -> [B,C,2,H,W] (d/dx, d/dy),
+    3x3 Sobel kernels divided by 8, replicate padding."""
+    B, Cn, H, W = x.shape
+    kx = x.new_tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
+    k = torch.stack((kx, kx.t()))[:, None]                                         # [2,1,3,3]
+    y = torch.nn.functional.conv2d(torch.nn.functional.pad(x.reshape(B * Cn, 1, H, W), (1, 1, 1, 1), mode="replicate"), k)
+    return y.view(B, Cn, 2, H, W)
+
+
+def _edge_aware(rendered: Tensor, gt_rgb: Tensor) -> Tensor:
+    """geosplat.py:885-888: |grad(render)| * exp(-|grad(gt)|), summed over channels, averaged."""
+    a = spatial_gradient(rendered[None].permute(0, 3, 1, 2))[0].abs()
+    b = (-spatial_gradient(gt_rgb[None].permute(0, 3, 1, 2))[0].abs()).exp()
+    return (a * b).sum(1).mean()
+
+
+def _tv(rendered: Tensor) -> Tensor:
+    """geosplat.py:907-910."""
+    return (rendered[1:, :] - rendered[:-1, :]).square().mean() + (rendered[:, 1:] - rendered[:, :-1]).square().mean()
+
+
 class GeoSplatter(nn.Module):
     def __init__(self, *, background_color: str = "random", resolution: int = 32, light_resolution: int = 512,
                  field: Optional[GaussianField] = None, gaussian_limits_hard: int = 1500000,
@@ -45,8 +69,8 @@ class GeoSplatter(nn.Module):
                  max_metallic: float = 1.0, smooth_type: str = "jitter", initial_guess: str = "hybrid",
                  fg_lut: Optional[Tensor] = None, n_streams: int = 4):
         super().__init__()
-        if smooth_type != "jitter":
-            raise NotImplementedError("smooth_type 'grad' / 'tv' are not mirrored (module docstring)")
+        if smooth_type not in ("jitter", "grad", "tv"):
+            raise ValueError(smooth_type)
         if initial_guess not in _GUESS:
             raise ValueError(initial_guess)
         self.background_color, self.resolution, self.light_resolution = background_color, resolution, light_resolution
@@ -62,7 +86,7 @@ class GeoSplatter(nn.Module):
         self.sdf_params = nn.Parameter(self.geometric_repr.sdf_values.clone())
         self.weight_params = nn.Parameter(torch.zeros(self.geometric_repr.indices.shape[0], 21))
         self.sdf_weight = self.occ_weight = self.light_weight = 0.0
-        self.kd_grad_weight = self.ks_grad_weight = 0.0
+        self.kd_grad_weight = self.ks_grad_weight = self.normal_grad_weight = 0.0
         self.kd_regualr_perturb_std = self.ks_regualr_perturb_std = 0.0          # (sic: the reference's spelling)
         self.sample_method = "face"
         self.initial_guess_bias = nn.Parameter(torch.tensor(_GUESS[initial_guess]), requires_grad=False)
@@ -149,7 +173,37 @@ class GeoSplatter(nn.Module):
         images = splat_views(g.means, g.scales, g.quats, g.opacities, attrs.kd, attrs.ks, attrs.normals, list(inputs),
                              exposures=self.exposure_params.exp(), envmap=envmap, fg_lut=self.fg_lut,
                              min_roughness=self.min_roughness, max_metallic=self.max_metallic, n_streams=self.n_streams)
+        regularization = regularization + self._smoothness(gsplat, attrs, list(inputs), gt_outputs)
         return images, g.means.shape[0], regularization + light_reg * self.light_weight
+
+    def _smoothness(self, gsplat: GSplatter, attrs: RenderableAttrs, cameras, gt_outputs) -> Tensor:
+        """geosplat.py:881-922: image-space smoothness of kd / ks / normals, rendered as plain colours (render_rgb)."""
+        reg = torch.zeros((), device=self.device)
+        B = len(cameras)
+        passes = []
+        if self.smooth_type in ("grad", "tv") and self.kd_grad_weight > 0:
+            passes.append((attrs.kd, self.kd_grad_weight, self.smooth_type))
+        if self.smooth_type in ("grad", "tv") and self.ks_grad_weight > 0:
+            passes.append((torch.cat((torch.zeros_like(attrs.ks[..., :1]), attrs.ks), dim=-1), self.ks_grad_weight,
+                           self.smooth_type))
+        if self.normal_grad_weight > 0:
+            passes.append((attrs.normals * 0.5 + 0.5, self.normal_grad_weight, "grad"))
+        if not passes:
+            return reg
+        gsplat.training = self.training
+        gt_rgb = None
+        if any(kind == "grad" for _, _, kind in passes):
+            if gt_outputs is None:
+                raise ValueError("the edge-aware smoothness terms need gt_outputs")
+            bg = self.get_background_color().to(self.device)
+            gt_rgb = [gt[..., 3:] * gt[..., :3] + bg * (1 - gt[..., 3:]) for gt in gt_outputs]     # RGBAImages.blend
+        for i, camera in enumerate(cameras):
+            for colors, weight, kind in passes:
+                gsplat.gaussians.replace_(colors=colors)
+                rendered = gsplat.render_rgb(camera)
+                term = _edge_aware(rendered, gt_rgb[i]) if kind == "grad" else _tv(rendered)
+                reg = reg + term * weight / B
+        return reg
 
     def training_loss(self, inputs: Sequence[PinholeCamera], gt_rgba: Sequence[Tensor], *, use_mask_loss: bool = True
                       ) -> Tuple[Tensor, dict]:

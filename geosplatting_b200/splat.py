@@ -63,6 +63,7 @@ class GSplatter:
     block_width: int = 16
     background_color: str = "random"
     rasterize_mode: str = "classic"
+    training: bool = True
 
     def begin_render(self, inputs) -> Projected:
         """Geometry half of `render_rgba`: activations, projection and the intersection count (the colours are not
@@ -88,6 +89,34 @@ class GSplatter:
         """-> [H,W,4] (linear RGB + alpha), differentiable w.r.t. the Gaussians (gsplat.py:284-358: `rasterization`
         with packed=True, tile 16, near 0.01, far 1e10, render_mode 'RGB', sh_degree None, dense gradients)."""
         return self.finish_render(self.begin_render(inputs))
+
+    def get_background_color(self) -> Tensor:
+        """gsplat.py:100-107."""
+        if self.background_color == "black":
+            return torch.zeros(3)
+        if self.background_color == "white":
+            return torch.ones(3)
+        if self.training:
+            return torch.rand(3)
+        return torch.tensor([0.1490, 0.1647, 0.2157])
+
+    def render_rgb(self, inputs) -> Tensor:
+        """-> [H,W,3]: the colours composited over `get_background_color()` (gsplat.py:187-282; the blend is the
+        reference's `render + (1 - alpha) * background`, done on the image, not inside the rasterizer)."""
+        st = self.begin_render(inputs)
+        g = self.gaussians
+        render, alpha, _ = rasterization_end(st, torch.sigmoid(g.opacities).squeeze(-1), g.colors, render_mode="RGB",
+                                             tile_size=self.block_width)
+        background = self.get_background_color().to(render.device)
+        return (render[..., :3] + (1 - alpha) * background).squeeze(0)
+
+    def render_depth(self, inputs) -> Tensor:
+        """-> [H,W,2]: expected depth (accumulated depth / alpha) and alpha (gsplat.py:112-186, render_mode 'ED')."""
+        st = self.begin_render(inputs)
+        g = self.gaussians
+        render, alpha, _ = rasterization_end(st, torch.sigmoid(g.opacities).squeeze(-1), g.colors.detach(),
+                                             render_mode="ED", tile_size=self.block_width)
+        return torch.cat((render, alpha), dim=-1).squeeze(0)
 
 
 @dataclass

@@ -98,3 +98,38 @@ def test_a_few_adam_steps_reduce_the_loss():
     assert all(h == h for h in history)
     assert sum(history[-5:]) / 5 < 0.9 * sum(history[:5]) / 5, history
     assert float(m.exposure_params) > 0 and float(m.cubemap.mean()) > 0.4
+
+
+@pytest.mark.parametrize("smooth_type", ["tv", "grad"])
+def test_image_space_smoothness_terms(smooth_type):
+    """smooth_type 'tv' / 'grad' and the normal term (geosplat.py:881-922) render kd / ks / normals as plain colours
+    through GSplatter.render_rgb: the terms add to the regularisation and reach the kd field and the geometry."""
+    m = make_model(0.55, 4)
+    m.smooth_type = smooth_type
+    cams = scenes.orbit_cameras(2, 64, 64, seed=6)
+    gt = [torch.rand(64, 64, 4, device=DEV) for _ in cams]
+    _, _, reg0 = m.render_report(cams, gt_outputs=gt)
+    m.kd_grad_weight, m.ks_grad_weight, m.normal_grad_weight = 0.03, 0.001, 0.5
+    _, _, reg = m.render_report(cams, gt_outputs=gt)
+    assert float(reg.detach()) > float(reg0.detach())
+    grads = torch.autograd.grad(reg, [next(m.field.kd_enc.parameters()), m.sdf_params])
+    assert all(bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0 for g in grads)
+
+
+def test_gsplatter_render_rgb_and_depth():
+    """GSplatter.render_rgb (gsplat.py:187-282) = render_rgba blended over the background; render_depth (:112-186)
+    = expected depth + alpha, inside the scene's depth range where covered."""
+    m = make_model(0.55, 5)
+    cam = scenes.orbit_cameras(1, 64, 64, seed=7)[0]
+    _, gsplat, attrs, _, _ = m.get_gsplat("face")
+    gsplat.gaussians.replace_(colors=attrs.kd.detach())
+    gsplat.training = False
+    rgba = gsplat.render_rgba(cam)
+    rgb = gsplat.render_rgb(cam)
+    bg = gsplat.get_background_color().to(DEV)
+    assert rgb.shape == (64, 64, 3) and float((rgb - (rgba[..., :3] + (1 - rgba[..., 3:]) * bg)).abs().max()) <= 1e-6
+    d = gsplat.render_depth(cam)
+    assert d.shape == (64, 64, 2) and float((d[..., 1] - rgba[..., 3]).abs().max()) <= 1e-6
+    covered = d[..., 1] > 0.99
+    dist = float(torch.tensor(cam.position).norm())
+    assert bool(covered.any()) and float(d[..., 0][covered].min()) > dist - 0.7 and float(d[..., 0][covered].max()) < dist + 0.1
