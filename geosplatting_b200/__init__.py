@@ -11,6 +11,7 @@ reference's interfaces for this path:
     mgadapter.MGAdapter / compute_vertex_normals
     encoding.HashEncoding / MLP, field.GaussianField   <- the kd / ks / z fields and their glue (geosplat.py:482-674)
     flexicubes.FlexiCubes                    <- FlexiCubes.dual_marching_cubes / compute_entropy (_flexicubes.py:368-802)
+    model.GeoSplatter                        <- GeoSplatter stage 1 (geosplat.py:676-927) + GeoSplatTrainer.step's loss
     loss.view_loss(...)                      <- the per-view loss of GeoSplatTrainer.step (geosplat_trainer.py:171-180)
     parallel.shard_views / GradientBucket    <- view sharding + one all-reduce per batch (new: the reference is single-GPU)
 
