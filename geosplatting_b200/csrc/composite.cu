@@ -47,9 +47,13 @@ struct Rec {
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef GSB_NO_INLINE_PTX   // host compilation of this file by tests/emu
+    return exp2f(x);
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 // Half extents of {d : 0.5 d^T C d <= tau}, tau = ln(255 * opac): the only region where alpha >= 1/255.
@@ -366,9 +370,13 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
+#ifdef GSB_NO_INLINE_PTX
+    return 1.0f / x;
+#else
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 // Backward.  The per-Gaussian gradient is a sum over pixels, the transmittance recurrence runs over Gaussians: the

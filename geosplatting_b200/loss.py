@@ -19,6 +19,7 @@ import torch
 from torch import Tensor
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 
 class _ViewLoss(torch.autograd.Function):
@@ -57,8 +58,7 @@ def view_loss(rgba: Tensor, gt_rgba: Tensor, train_bg_color: Optional[Tensor] = 
     gt_rgba [H,W,4]: ground truth in LINEAR rgb + mask (`gt_rgba.srgb2rgb()`); train_bg_color [H,W,3] (default:
     torch.rand_like, as the reference draws it).  Differentiable w.r.t. `rgba`.  -> scalar loss
     (with return_terms: also the three raw sums: SSIM map, |img1 - img2|, (mask - alpha)^2)."""
-    if not rgba.is_cuda:
-        raise RuntimeError("geosplatting_b200.view_loss needs CUDA tensors; there is no CPU path")
+    _require_cuda(rgba, "view_loss")
     assert rgba.shape[-1] == 4 and gt_rgba.shape == rgba.shape and rgba.dim() == 3
     if train_bg_color is None:
         train_bg_color = torch.rand_like(rgba[..., :3])

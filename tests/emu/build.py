@@ -13,27 +13,73 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "geosplatting_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
-_LAUNCH = re.compile(r"(\w+(?:<[\w, ]+>)?)<<<(.+?), (\d+), 0, (?:\(cudaStream_t\)stream|st)>>>\(")
+_DYN_SMEM = re.compile(r"extern __shared__ (\w+) (\w+)\[\];")
 
 
-def build(*names: str) -> C.CDLL:
-    """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu.so (rebuilt when a source is newer)."""
+def _split_top_level(text: str):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def _rewrite(text: str, name: str) -> str:
+    """`kernel<...><<<grid, block, smem, stream>>>(` -> `gsb_emu::launch(grid, block, smem, [](auto... a) { kernel<...>(a...); })(`
+    and `extern __shared__ T x[];` -> a pointer into the emulator's dynamic shared memory."""
+    out, pos = "", 0
+    while True:
+        i = text.find("<<<", pos)
+        if i < 0:
+            break
+        j = text.index(">>>", i)
+        assert text[j + 3] == "(", f"{name}.cu: launch without an argument list"
+        # kernel name (with optional template arguments) right before <<<
+        k = i
+        if text[k - 1] == ">":
+            depth = 0
+            while True:
+                k -= 1
+                depth += {">": 1, "<": -1}.get(text[k], 0)
+                if depth == 0:
+                    break
+        while text[k - 1].isalnum() or text[k - 1] == "_":
+            k -= 1
+        kernel = text[k:i]
+        cfg = _split_top_level(text[i + 3:j])
+        assert len(cfg) == 4, f"{name}.cu: launch configuration {cfg}"
+        out += text[pos:k] + f"gsb_emu::launch({cfg[0]}, {cfg[1]}, {cfg[2]}, [](auto... a) {{ {kernel}(a...); }})"
+        pos = j + 3
+    out += text[pos:]
+    return _DYN_SMEM.sub(r"\1 *\2 = static_cast<\1 *>(gsb_emu::dyn_smem());", out)
+
+
+def build(*names: str, simt: bool = False) -> C.CDLL:
+    """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu[_simt].so (rebuilt when a source is newer).
+    simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h)."""
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
-    lib = os.path.join(OUT, "lib" + "_".join(names) + "_emu.so")
+    tag = "_simt" if simt else ""
+    lib = os.path.join(OUT, "lib" + "_".join(names) + f"_emu{tag}.so")
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \
         [os.path.join(d, f) for d, _, fs in os.walk(HERE) if "_build" not in d for f in fs if f.endswith((".h", ".cuh"))]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         cpps = []
         for n, src in zip(names, srcs):
-            text = open(src).read()
-            text, k = _LAUNCH.subn(r"gsb_emu::launch(\2, \3, [](auto... a) { \1(a...); })(", text)
-            assert k > 0 and "<<<" not in text, f"{n}.cu: a launch site the emulation rewrite does not understand"
-            cpps.append(os.path.join(OUT, n + "_emu.cpp"))
+            cpps.append(os.path.join(OUT, f"{n}_emu{tag}.cpp"))
             with open(cpps[-1], "w") as f:
-                f.write(text)
+                f.write(_rewrite(open(src).read(), n))
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", HERE, "-I", CSRC,
-                               "-o", lib, *cpps, "-x", "c++", os.path.join(CSRC, "error.cu")])
+                               *(["-DGSB_EMU_SIMT"] if simt else []), "-o", lib, *cpps, "-x", "c++",
+                               os.path.join(CSRC, "error.cu")])
     so = C.CDLL(lib)
     so.gsb_last_error.restype = C.c_char_p
     return so

@@ -1,16 +1,25 @@
-// TEST INFRASTRUCTURE ONLY.  A stand-in for <cuda_runtime.h> that lets g++ compile the simple streaming kernels of
-// geosplatting_b200/csrc (those without shared memory or warp intrinsics) for the host, so that the "-m 'not gpu'" suite
-// can execute the REAL kernel source -- index arithmetic and gradient formulas included -- against the golden fixtures
-// in this GPU-less container.  tests/emu/build.py rewrites `kernel<<<grid, block, 0, stream>>>(args)` into
-// gsb_emu::launch(grid, block, ...)(args), which runs every thread of every block one after another.  Nothing in the
-// product imports, links or ships this; the shipped library is built by nvcc for sm_100a only.
+// TEST INFRASTRUCTURE ONLY.  A stand-in for <cuda_runtime.h> that lets g++ compile the kernel files of
+// geosplatting_b200/csrc for the host, so that the "-m 'not gpu'" suite can execute the REAL kernel source -- index
+// arithmetic and gradient formulas included -- against the golden fixtures in this GPU-less container.
+// tests/emu/build.py rewrites `kernel<<<grid, block, smem, stream>>>(args)` into gsb_emu::launch(grid, block, smem, ...)
+// (args).  Two execution modes:
+//   sequential (default): every thread of every block runs to completion, one after another -- for kernels without
+//       shared memory or warp collectives.  GSB_HOST_EMULATION is defined and the few warp reductions of such kernels
+//       route around themselves (atomics);
+//   SIMT (-DGSB_EMU_SIMT, simt.h): the threads of a block are fibers that rendezvous at __syncthreads and the *_sync
+//       warp primitives; shared memory is real.  The kernels compile their true code paths (GSB_HOST_EMULATION is NOT
+//       defined); only inline PTX is replaced (GSB_NO_INLINE_PTX).
+// Nothing in the product imports, links or ships this; the shipped library is built by nvcc for sm_100a only.
 #pragma once
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
+#define GSB_NO_INLINE_PTX 1
+#ifndef GSB_EMU_SIMT
 #define GSB_HOST_EMULATION 1
+#endif
 #define __global__
 #define __device__
 #define __host__
@@ -18,8 +27,11 @@
 #define __restrict__
 #define __launch_bounds__(...)
 
-struct gsb_emu_dim3 { unsigned x, y, z; };
-static thread_local gsb_emu_dim3 blockIdx, blockDim, threadIdx, gridDim;
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+static dim3 blockIdx, blockDim, threadIdx, gridDim;
 
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
@@ -57,8 +69,6 @@ static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 static inline float min(float a, float b) { return fminf(a, b); }
 static inline float max(float a, float b) { return fmaxf(a, b); }
-// warp intrinsics have no sequential meaning: kernels route around them under GSB_HOST_EMULATION; reaching one is a bug
-template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { abort(); }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
 
@@ -85,20 +95,29 @@ static inline float4 atomicAdd(float4 *p, float4 v) {   // sm_90+ vector reducti
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
+#ifdef GSB_EMU_SIMT
+#define __shared__ static
+#include "simt.h"
+#else
+// warp intrinsics have no sequential meaning: kernels route around them under GSB_HOST_EMULATION; reaching one is a bug
+template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { abort(); }
+
 namespace gsb_emu {
 template <class F> struct Launcher {
-    int grid, block;
+    dim3 grid, block;
     F f;
     template <class... A> void operator()(A... a) const {
-        gridDim = {(unsigned)grid, 1, 1};
-        blockDim = {(unsigned)block, 1, 1};
-        for (int b = 0; b < grid; ++b)
-            for (int t = 0; t < block; ++t) {
-                blockIdx = {(unsigned)b, 0, 0};
-                threadIdx = {(unsigned)t, 0, 0};
-                f(a...);
-            }
+        gridDim = grid;
+        blockDim = block;
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx)
+                for (unsigned t = 0; t < block.x; ++t) {
+                    blockIdx = dim3(bx, by, 0);
+                    threadIdx = dim3(t, 0, 0);
+                    f(a...);
+                }
     }
 };
-template <class F> static inline Launcher<F> launch(int grid, int block, F f) { return Launcher<F>{grid, block, f}; }
+template <class F> static inline Launcher<F> launch(dim3 grid, dim3 block, size_t, F f) { return Launcher<F>{grid, block, f}; }
 }  // namespace gsb_emu
+#endif

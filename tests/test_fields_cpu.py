@@ -42,3 +42,14 @@ def test_mgadapter_kernel_source_on_host_against_oracle(host_mgadapter):
 def test_mgadapter_degenerate_faces_and_tonemap_on_host(host_mgadapter):
     GM.test_flat_normals_and_degenerate_faces()
     GM.test_tonemap_against_reference_fixture()
+
+
+def test_warp_reductions_under_simt(monkeypatch):
+    """SIMT mode of tests/emu (threads of a block as fibers): the segmented 16-lane butterfly that sums d/dx of the hash
+    encoding over its levels and the block reduction of the exposure gradient run as written."""
+    route(monkeypatch, emu.build("hashgrid", simt=True), E)
+    monkeypatch.setattr(GE, "DEV", "cpu")
+    GE.test_fields_match_reference_code("ks", [32, 32, 2], "none")
+    route(monkeypatch, emu.build("mgadapter", simt=True), M)
+    monkeypatch.setattr(GM, "DEV", "cpu")
+    GM.test_tonemap_against_reference_fixture()

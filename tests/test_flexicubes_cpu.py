@@ -88,3 +88,11 @@ def test_tiny_random_grids_against_oracle(host_kernels, res, seed):
     assert a[0].shape == b[0].shape and np.array_equal(a[0], b[0])
     for x, y in zip(a[1:], b[1:]):
         assert x.shape == y.shape and np.abs(x - y).max(initial=0.0) <= 1e-4 * max(1.0, np.abs(y).max(initial=0.0))
+
+
+def test_warp_reduction_of_the_entropy_pass_under_simt(monkeypatch):
+    """The same fixture with the block's threads as fibers (tests/emu SIMT mode): the warp-shuffle reduction of the
+    entropy forward, compiled out in the sequential mode above, runs as written."""
+    route(monkeypatch, emu.build("flexicubes", simt=True), FC)
+    fc_cases.check_smooth_fixture("cpu")
+    fc_cases.check_rough_fixture("cpu")

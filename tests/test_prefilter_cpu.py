@@ -1,0 +1,70 @@
+"""The split-sum prefilter kernels (csrc/prefilter.cu: cone bounds, GGX-weighted gather with direction tables and
+warp-cooperative loads, diffuse irradiance through dynamic shared memory, the 2x2 mip chain and its non-transpose
+backward) without a GPU: the real kernel source under the SIMT mode of tests/emu, called through the C ABI, against
+the C oracle (which tests/test_prefilter_gpu.py pins on the reference's own compiled plugin on the GPU box).
+Acceptance as in the GPU suite: bounds within one texel, rgb / wsum 1e-3, wsum 5e-3, gradients 2e-3 of the max."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prefilter as P
+from oracle import shade as S
+from tests.emu import build as emu
+from tests.test_prefilter_gpu import _close, _close_spec, _cubemap
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu.build("prefilter", simt=True)
+
+
+@pytest.mark.parametrize("R,rough,tables", [(16, 1.0, True), (32, 0.5, True), (32, 0.29, False), (64, 0.185, True)])
+def test_specular_prefilter_on_the_host(lib, R, rough, tables):
+    ct = P.ndf_cutoff_costheta(rough)
+    c = _cubemap(R, 3 + R).numpy()
+    i32, f32 = C.c_int32, C.c_float
+    bounds = np.zeros((6, R, R, 24), np.float32)
+    assert lib.gsb_specular_bounds(i32(R), f32(ct), _p(bounds), None) == 0
+    b_orc = P.specular_bounds(R, ct)
+    assert np.abs(bounds - b_orc).max() <= 1
+    ws = None
+    if tables:                      # the direction-table kernels; a NULL workspace selects the table-free kernel
+        nb = C.c_size_t(0)
+        assert lib.gsb_specular_workspace_bytes(i32(R), C.byref(nb)) == 0
+        ws = np.zeros(nb.value + 256, np.uint8)
+    out = np.zeros((6, R, R, 4), np.float32)
+    assert lib.gsb_specular_cubemap_fwd(i32(R), _p(c), _p(bounds), f32(rough), f32(ct), i32(0), _p(out), _p(ws),
+                                        None) == 0, lib.gsb_last_error()
+    _close_spec(out, P.specular_fwd(c, b_orc, rough, ct), "spec fwd")
+    g = torch.randn(6, R, R, 4, generator=torch.Generator().manual_seed(5)).numpy()
+    gin = np.zeros((6, R, R, 3), np.float32)
+    assert lib.gsb_specular_cubemap_bwd(i32(R), _p(bounds), _p(g), None, f32(rough), f32(ct), _p(gin), _p(ws),
+                                        None) == 0, lib.gsb_last_error()
+    _close(gin, P.specular_bwd(b_orc, g, rough, ct), 2e-3, "spec bwd")
+
+
+def test_diffuse_irradiance_and_mip_chain_on_the_host(lib):
+    R = 16
+    c = _cubemap(R, 9).numpy()
+    i32 = C.c_int32
+    out = np.zeros_like(c)
+    assert lib.gsb_diffuse_cubemap_fwd(i32(R), _p(c), _p(out), i32(3), None) == 0
+    _close(out, P.diffuse_fwd(c), 1e-4, "diffuse fwd")
+    g = torch.randn(6, R, R, 3, generator=torch.Generator().manual_seed(6)).numpy()
+    gin = np.zeros_like(g)
+    assert lib.gsb_diffuse_cubemap_bwd(i32(R), _p(g), i32(3), _p(gin), None) == 0
+    _close(gin, P.diffuse_bwd(g), 1e-4, "diffuse bwd")
+    fine = _cubemap(32, 4)
+    down = np.zeros((6, 16, 16, 3), np.float32)
+    assert lib.gsb_cubemap_mip_fwd(i32(16), _p(fine.numpy()), i32(3), _p(down), i32(3), None) == 0
+    _close(down, S.cubemap_mip_fwd(fine), 1e-6, "mip fwd")
+    cot = torch.randn(6, 16, 16, 3, generator=torch.Generator().manual_seed(8))
+    gfine = np.zeros((6, 32, 32, 3), np.float32)
+    assert lib.gsb_cubemap_mip_bwd(i32(16), _p(cot.numpy()), _p(gfine), None) == 0
+    _close(gfine, S.cubemap_mip_bwd(cot), 1e-5, "mip bwd")
