@@ -64,10 +64,13 @@ def _rewrite(text: str, name: str) -> str:
 
 def build(*names: str, simt: bool = False) -> C.CDLL:
     """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu[_simt].so (rebuilt when a source is newer).
-    simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h)."""
+    simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h).
+    GSB_EMU_SANITIZE=1 in the environment builds the sequential libraries with AddressSanitizer + UBSan (the process
+    must run with libasan preloaded: tests/test_kernels_asan_cpu.py does that in a subprocess)."""
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
-    tag = "_simt" if simt else ""
+    sanitize = bool(os.environ.get("GSB_EMU_SANITIZE")) and not simt    # ASan does not follow ucontext fibers unannotated
+    tag = ("_simt" if simt else "") + ("_asan" if sanitize else "")
     lib = os.path.join(OUT, "lib" + "_".join(names) + f"_emu{tag}.so")
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \
         [os.path.join(d, f) for d, _, fs in os.walk(HERE) if "_build" not in d for f in fs if f.endswith((".h", ".cuh"))]
@@ -78,7 +81,9 @@ def build(*names: str, simt: bool = False) -> C.CDLL:
             with open(cpps[-1], "w") as f:
                 f.write(_rewrite(open(src).read(), n))
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", HERE, "-I", CSRC,
-                               *(["-DGSB_EMU_SIMT"] if simt else []), "-o", lib, *cpps, "-x", "c++",
+                               *(["-DGSB_EMU_SIMT"] if simt else []),
+                               *(["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if sanitize else []),
+                               "-o", lib, *cpps, "-x", "c++",
                                os.path.join(CSRC, "error.cu")])
     so = C.CDLL(lib)
     so.gsb_last_error.restype = C.c_char_p
