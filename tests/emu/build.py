@@ -65,11 +65,11 @@ def _rewrite(text: str, name: str) -> str:
 def build(*names: str, simt: bool = False) -> C.CDLL:
     """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu[_simt].so (rebuilt when a source is newer).
     simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h).
-    GSB_EMU_SANITIZE=1 in the environment builds the sequential libraries with AddressSanitizer + UBSan (the process
+    GSB_EMU_SANITIZE=1 in the environment builds the libraries with AddressSanitizer + UBSan (the process
     must run with libasan preloaded: tests/test_kernels_asan_cpu.py does that in a subprocess)."""
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
-    sanitize = bool(os.environ.get("GSB_EMU_SANITIZE")) and not simt    # ASan does not follow ucontext fibers unannotated
+    sanitize = bool(os.environ.get("GSB_EMU_SANITIZE"))      # simt.h tells ASan about its fiber switches
     tag = ("_simt" if simt else "") + ("_asan" if sanitize else "")
     lib = os.path.join(OUT, "lib" + "_".join(names) + f"_emu{tag}.so")
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \

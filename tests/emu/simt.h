@@ -15,6 +15,11 @@
 #include <functional>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define GSB_EMU_ASAN 1
+#endif
+
 namespace gsb_emu {
 
 constexpr size_t FIBER_STACK = 256 * 1024;
@@ -40,6 +45,11 @@ struct Block {
     ucontext_t sched;
     std::function<void()> body;
     dim3 block_dim;
+    // AddressSanitizer has to be told about every stack switch (fake-stack handles per fiber, the scheduler's bounds)
+    std::vector<void *> fake;
+    void *sched_fake = nullptr;
+    const void *sched_bottom = nullptr;
+    size_t sched_size = 0;
 };
 
 static Block *g_block = nullptr;
@@ -50,17 +60,30 @@ static inline void *dyn_smem() { return g_dyn_smem.data(); }
 
 static inline void yield() {
     Block *b = g_block;
-    swapcontext(&b->ctx[b->cur], &b->sched);
+    const int t = b->cur;
+#ifdef GSB_EMU_ASAN
+    __sanitizer_start_switch_fiber(&b->fake[t], b->sched_bottom, b->sched_size);
+#endif
+    swapcontext(&b->ctx[t], &b->sched);
+#ifdef GSB_EMU_ASAN
+    __sanitizer_finish_switch_fiber(b->fake[t], &b->sched_bottom, &b->sched_size);
+#endif
 }
 
 static void fiber_main() {
     Block *b = g_block;
+#ifdef GSB_EMU_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &b->sched_bottom, &b->sched_size);
+#endif
     b->body();
     const int t = b->cur;
     b->done[t] = 1;
     b->live--;
     b->warps[t >> 5].alive &= ~(1u << (t & 31));
     b->progress++;
+#ifdef GSB_EMU_ASAN
+    __sanitizer_start_switch_fiber(nullptr, b->sched_bottom, b->sched_size);   // nullptr: this fiber's fake stack dies
+#endif
     swapcontext(&b->ctx[t], &b->sched);   // never resumed
 }
 
@@ -75,6 +98,7 @@ static inline void run_block(Block &b) {
     const int n = b.n;
     while ((int)g_stacks.size() < n) g_stacks.push_back((char *)malloc(FIBER_STACK));
     b.ctx.resize(n);
+    b.fake.assign(n, nullptr);
     b.done.assign(n, 0);
     b.warps.assign((n + 31) / 32, Warp());
     b.live = n;
@@ -94,7 +118,13 @@ static inline void run_block(Block &b) {
             if (b.done[t]) continue;
             b.cur = t;
             set_thread_index(b, t);
+#ifdef GSB_EMU_ASAN
+            __sanitizer_start_switch_fiber(&b.sched_fake, g_stacks[t], FIBER_STACK);
+#endif
             swapcontext(&b.sched, &b.ctx[t]);
+#ifdef GSB_EMU_ASAN
+            __sanitizer_finish_switch_fiber(b.sched_fake, nullptr, nullptr);
+#endif
         }
         if (b.progress == before) {
             if (++idle_rounds > 2) {

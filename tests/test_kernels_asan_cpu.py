@@ -1,7 +1,8 @@
-"""AddressSanitizer + UBSan over kernel source compiled for the host (tests/emu sequential mode, GSB_EMU_SANITIZE=1): the
-projection, tile-emission and binning kernels' global-memory accesses are bounds-checked against the buffers the parity
-tests hand them, in a subprocess with libasan preloaded.  scripts/memcheck_host.sh runs the same over every sequential
-emulation test (log in profiles/r01_host_asan.log); a negative control shows the checker sees a kernel's stray write."""
+"""AddressSanitizer + UBSan over kernel source compiled for the host (tests/emu, GSB_EMU_SANITIZE=1): the projection,
+tile-emission and binning kernels' global-memory accesses are bounds-checked against the buffers the parity tests hand
+them, in a subprocess with libasan preloaded.  scripts/memcheck_host.sh runs the same over EVERY emulation test, SIMT
+mode included (8 minutes; log in profiles/r01_host_asan.log); a negative control shows the checker sees a kernel's
+stray write."""
 import os
 import subprocess
 import sys
