@@ -111,10 +111,26 @@ static inline void run_block(Block &b) {
         makecontext(&b.ctx[t], fiber_main, 0);
         b.warps[t >> 5].alive |= 1u << (t & 31);
     }
+    // Resume order inside a round: any order must give the same results for code whose only inter-thread ordering comes
+    // from barriers and warp collectives.  GSB_EMU_ORDER=reverse | random[:seed] turns the scheduler into a race fuzzer
+    // (tests/test_simt_order_cpu.py): a missing __syncwarp / __syncthreads shows up as a result that depends on it.
+    static const char *order_env = getenv("GSB_EMU_ORDER");
+    static unsigned long long rng = order_env && !strncmp(order_env, "random", 6)
+                                        ? (strlen(order_env) > 7 ? strtoull(order_env + 7, nullptr, 10) : 1ull) * 2654435761ull + 1
+                                        : 0ull;
+    const bool reverse = order_env && !strcmp(order_env, "reverse");
+    std::vector<int> order(n);
+    for (int t = 0; t < n; ++t) order[t] = reverse ? n - 1 - t : t;
     int idle_rounds = 0;
     while (b.live > 0) {
         const unsigned long before = b.progress;
-        for (int t = 0; t < n; ++t) {
+        if (rng)
+            for (int i = n - 1; i > 0; --i) {   // Fisher-Yates with an xorshift generator, a new permutation every round
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                std::swap(order[i], order[rng % (unsigned long long)(i + 1)]);
+            }
+        for (int k = 0; k < n; ++k) {
+            const int t = order[k];
             if (b.done[t]) continue;
             b.cur = t;
             set_thread_index(b, t);
