@@ -62,6 +62,11 @@ def _rewrite(text: str, name: str) -> str:
     return _DYN_SMEM.sub(r"\1 *\2 = static_cast<\1 *>(gsb_emu::dyn_smem());", out)
 
 
+def all_kernel_files():
+    """Every .cu of the library (error.cu is always linked in)."""
+    return sorted(f[:-3] for f in os.listdir(CSRC) if f.endswith(".cu") and f != "error.cu")
+
+
 def build(*names: str, simt: bool = False) -> C.CDLL:
     """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu[_simt].so (rebuilt when a source is newer).
     simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h).
@@ -71,7 +76,8 @@ def build(*names: str, simt: bool = False) -> C.CDLL:
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
     sanitize = bool(os.environ.get("GSB_EMU_SANITIZE"))      # simt.h tells ASan about its fiber switches
     tag = ("_simt" if simt else "") + ("_asan" if sanitize else "")
-    lib = os.path.join(OUT, "lib" + "_".join(names) + f"_emu{tag}.so")
+    stem = "_".join(names) if len(names) <= 3 else f"all{len(names)}"
+    lib = os.path.join(OUT, f"lib{stem}_emu{tag}.so")
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \
         [os.path.join(d, f) for d, _, fs in os.walk(HERE) if "_build" not in d for f in fs if f.endswith((".h", ".cuh"))]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):

@@ -81,6 +81,8 @@ static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+typedef void *cudaEvent_t;
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 
 template <class T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 static inline float2 atomicAdd(float2 *p, float2 v) {   // red.global.add.v2.f32
