@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the whole-training-step probe of BASELINE config 3 (model.GeoSplatter + loss + Adam)")
     ap.add_argument("--fc-res", type=int, default=0,
                     help="with --full-step: the mesh comes from FlexiCubes on an R^3 SDF grid every step (8f rank 3)")
     return ap.parse_args()
@@ -538,6 +540,68 @@ def run_b200(a):
     return out, rank, world
 
 
+def train_step_probe(R=140, n=5):
+    """BASELINE configs[2] ("1M Gaussians + FlexiCubes MGAdaptor, 800x800, full train step") through the reference-facing
+    model: FlexiCubes mesh + regularisers on an R^3 SDF grid -> vertex normals + MGAdaptor -> kd / ks / z hash-grid
+    fields (jitter regularisers on) -> split-sum prefilter of a 6 x 512^2 cube map -> 8 views 800 x 800 -> per-view
+    SSIM / L1 / mask loss -> backward to all eight parameter groups -> Adam.  CUDA events over n steps after 3 warm-up
+    steps.  A reported extra, outside the timed region of the headline metric (same code as scripts/bench_train_step.py)."""
+    import torch
+
+    from geosplatting_b200 import _lib, scenes
+    from geosplatting_b200.model import GeoSplatter
+    from geosplatting_b200.shade import synthetic_fg_lut
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    m = GeoSplatter(resolution=R, light_resolution=512, scale=0.9, fg_lut=synthetic_fg_lut(torch.device("cpu"))).to(dev)
+    gv = m.geometric_repr.vertices.to(dev)
+    with torch.no_grad():
+        m.sdf_params.copy_(gv.norm(dim=-1, keepdim=True) - 0.6 + 0.06 * torch.sin(5.0 * gv[:, :1]) * torch.cos(4.0 * gv[:, 1:2]))
+        m.cubemap.copy_(torch.exp(torch.randn_like(m.cubemap)).clamp_min(1e-2))
+    m.train()
+    m.sdf_weight, m.light_weight = 0.2, 2e-3
+    m.kd_regualr_perturb_std = m.ks_regualr_perturb_std = 0.01
+    m.kd_grad_weight, m.ks_grad_weight = 0.03, 0.001
+    m.cubemap.register_hook(lambda g: g * 64)
+    cams = scenes.orbit_cameras(8, 800, 800, seed=1)
+    gen = torch.Generator().manual_seed(1)
+    gt = []
+    for _ in cams:
+        img = torch.rand(800, 800, 4, generator=gen)
+        img[..., 3] = (img[..., 3] > 0.5).float()
+        gt.append(img.to(dev))
+    opt = torch.optim.Adam([
+        {"params": [m.sdf_params, m.deform_params, m.weight_params], "lr": 1e-3},
+        {"params": list(m.field.parameters()), "lr": 1e-2},
+        {"params": [m.cubemap], "lr": 1e-2}, {"params": [m.exposure_params], "lr": 5e-3}], eps=1e-15)
+    stats = {}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss, metrics = m.training_loss(cams, gt)
+        loss.backward()
+        opt.step()
+        stats.update(gaussians=int(metrics["#gaussians"]), loss=round(float(metrics["loss"]), 5))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.CallStats.reset()
+    s.record()
+    for _ in range(n):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / n
+    launches = _lib.CallStats.launches() // n
+    _lib.CallStats.reset()
+    return {"what": "whole stage-1 training step of BASELINE config 3: model.GeoSplatter.training_loss (FlexiCubes, fields, "
+                    "prefilter, 8 views 800x800, per-view loss) + backward + Adam", "flexicubes_resolution": R, **stats,
+            "ms_per_step": round(ms, 3), "views_per_s": round(8 / (ms / 1e3), 2), "steps_timed": n,
+            "gpu_launches_per_step": launches, "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+
+
 def stats_last_view(params, cam, W, H):
     """(M, Nv) of one view, read back outside the timed region."""
     import torch
@@ -645,6 +709,11 @@ def main():
         print(json.dumps(out))
         return
     out, rank, world = run_b200(a)
+    if rank == 0 and world == 1 and not a.no_train_step:
+        try:
+            out["train_step"] = train_step_probe()
+        except Exception as exc:      # the probe is an extra: it must never cost the headline line
+            out["train_step"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             cb = run_oracle(a, steps=2, warmup=1, budget_s=25.0)
