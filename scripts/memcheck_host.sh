@@ -8,5 +8,6 @@ cd "$(dirname "$0")/.."
 ASAN=$(gcc -print-file-name=libasan.so)
 GSB_EMU_SANITIZE=1 LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
   python -m pytest tests/test_project_cpu.py tests/test_flexicubes_cpu.py tests/test_shade_cpu.py tests/test_fields_cpu.py \
-  tests/test_composite_cpu.py tests/test_loss_cpu.py tests/test_prefilter_cpu.py \
+  tests/test_composite_cpu.py tests/test_loss_cpu.py tests/test_prefilter_cpu.py tests/test_view_driver_cpu.py \
+  tests/test_edge_cases_cpu.py \
   -q -p no:cacheprovider "$@" 2>&1 | tee profiles/r01_host_asan.log | tail -5
