@@ -131,3 +131,45 @@ def test_one_view_forward_and_backward_through_the_native_driver(lib, mode, W, H
             assert float(np.abs(a).max()) == 0, name
             continue
         assert float(np.abs(a - b).max()) <= 2e-3 * scale, (name, float(np.abs(a - b).max()), scale)
+
+
+@pytest.mark.parametrize("N,behind", [(50, True), (0, False)])
+def test_driver_with_nothing_to_draw(lib, N, behind):
+    """Every Gaussian culled (M = 0) and the empty scene (N = 0): the three calls succeed, the image is transparent black,
+    no gradient is produced, nothing is read out of bounds (scripts/memcheck_host.sh runs this under ASan)."""
+    W, H, R0, L, Rb = 40, 24, 16, 3, 8
+    sg = scenes.surface_gaussians(max(N, 1), seed=1)
+    f = lambda t: np.ascontiguousarray(t.numpy()[:N], np.float32)   # noqa: E731
+    means, quats, scales, nrm, kd, ks = (f(sg[k]) for k in ("means", "quats", "scales", "normals", "kd", "ks"))
+    cam = scenes.orbit_cameras(1, W, H, seed=3)[0]
+    if behind:
+        means = means + 100 * np.asarray(cam.position, np.float32)
+    lg = np.zeros(N, np.float32)
+    texels = C.c_int64(0)
+    assert lib.gsb_envstack_texels(C.c_int32(R0), C.c_int32(L), C.c_int32(Rb), C.byref(texels)) == 0
+    T = texels.value
+    stack = np.random.default_rng(0).random((T, 4)).astype(np.float32)
+    cfg = _lib.GsbViewConfig(N, W, H, 256, R0, L, Rb, 0.1, 1.0, 0.08, 0.5, 0, 1)
+    gc = make_camera(cam.view_matrix, cam.intrinsic_matrix, W, H, antialiased=True)
+    cp = (C.c_float * 3)(*[float(x) for x in cam.position])
+    sizes = (C.c_size_t * 5)()
+    assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
+    keep1, tmp1 = np.zeros(sizes[0] + 256, np.uint8), np.zeros(sizes[1] + 256, np.uint8)
+    total = np.full(1, -7, np.int64)
+    lut, ex = synthetic_fg_lut(), np.ones(1, np.float32)
+    assert lib.gsb_view_prepare(C.byref(cfg), C.byref(gc), cp, _p(means), _p(quats), _p(scales), _p(nrm), _p(kd), _p(ks),
+                                _p(lut), _p(stack), _p(keep1), _p(tmp1), _p(total), None) == 0, lib.gsb_last_error()
+    assert int(total[0]) == 0
+    assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
+    keep2, tmp2 = np.zeros(sizes[2] + 256, np.uint8), np.zeros(sizes[3] + 256, np.uint8)
+    out = np.full((H, W, 4), 9, np.float32)
+    assert lib.gsb_view_finish(C.byref(cfg), C.byref(gc), C.c_int64(0), _p(lg), _p(ex), _p(keep1), _p(tmp1), _p(keep2),
+                               _p(tmp2), _p(out), None) == 0, lib.gsb_last_error()
+    assert np.all(out == 0)
+    tmp3 = np.zeros(sizes[4] + 256, np.uint8)
+    g = [np.zeros(s, np.float32) for s in ((N, 3), (N, 4), (N, 3), N, (N, 3), (N, 3), (N, 2), (T, 4), 1)]
+    v_out = np.random.default_rng(1).random((H, W, 4)).astype(np.float32)
+    assert lib.gsb_view_backward(C.byref(cfg), C.byref(gc), cp, C.c_int64(0), _p(means), _p(quats), _p(scales), _p(lg),
+                                 _p(nrm), _p(kd), _p(ks), _p(lut), _p(stack), _p(ex), _p(keep1), _p(keep2), _p(tmp3),
+                                 _p(v_out), *[_p(x) for x in g], None, None, None) == 0, lib.gsb_last_error()
+    assert all(float(np.abs(x).max()) == 0 for x in g if x.size)
