@@ -537,6 +537,48 @@ def run_b200(a):
         }
         if full:
             out["full_step"] = full
+    # ---- extra: the e2e of a TRAINING view as the reference's trainer drives the path:
+    #      the Gaussians stay on the device, the host supplies a view's ground-truth image (pinned, H2D inside the timed
+    #      region) and reads back the batch's loss scalar.  Guarded: it can never cost the headline line.
+    if world == 1 and out is not None and not a.no_e2e:
+        try:
+            from geosplatting_b200.loss import view_loss
+            n_b = max(2, min(6, a.steps // B))
+            gt_host = [torch.rand(H, W, 4, generator=gen).pin_memory() for _ in range(B)]
+            copy_stream = torch.cuda.Stream(dev)
+
+            def train_batch():
+                cs = [cams[j % len(cams)] for j in range(B)]
+                with torch.cuda.stream(copy_stream):
+                    gts = [g.to(dev, non_blocking=True) for g in gt_host]
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+                imgs = splat_views(params["means"], params["scales"], params["quats"], params["opacities"], params["kd"],
+                                   params["ks"], params["normals"], cs, exposures=exposure, envmap=env, fg_lut=lut,
+                                   min_roughness=0.1, max_metallic=1.0, n_streams=a.streams)
+                torch.cuda.current_stream(dev).wait_event(done)
+                loss = sum(view_loss(i_, g_) for i_, g_ in zip(imgs, gts)) / B
+                torch.autograd.grad(loss, grad_inputs)
+                return float(loss)                          # the D2H read of the batch's result
+
+            for _ in range(2):
+                train_batch()
+            barrier()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(n_b):
+                last = train_batch()
+            e_.record()
+            barrier()
+            ms_b = s_.elapsed_time(e_) / n_b
+            out["e2e_training_view"] = {
+                "value": round(B * world / (ms_b / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": H * W * 4 * 4,
+                "d2h_bytes_per_step": 4.0 / B, "batches_timed": n_b, "loss": round(last, 5),
+                "what": "per view: ground-truth image (pinned host) -> device, splat fwd, per-view SSIM/L1/mask loss, "
+                        "backward to the per-Gaussian state, env texels and exposure; per batch of 8: the loss scalar "
+                        "-> host.  Gaussian state resident on the device, as in the reference's trainer"}
+        except Exception as exc:
+            out["e2e_training_view"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     return out, rank, world
 
 
