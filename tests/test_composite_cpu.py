@@ -91,3 +91,31 @@ def test_empty_lists_and_one_pixel_image(lib):
     render, alphas, _, _ = _composite(lib, 1, 1, means2d, conics, colors, opac, flatten_ids, offsets)
     o_render, o_alphas, _ = R.composite_fwd(means2d, conics, colors, opac, offsets, flatten_ids, 1, 1)
     assert np.abs(render - o_render).max() <= 1e-4 and np.abs(alphas - o_alphas).max() <= 1e-4
+
+
+@pytest.mark.parametrize("CH", [1, 4, 16])
+def test_wide_channel_composite_on_the_host(lib, CH):
+    """depth-only (1), RGB+ED (4) and the D = 14 G-buffer padded to 16 channels through the same
+    kernels -- channels beyond the third are read from `colors` through the list entry, not from the packed record."""
+    cam, means2d, conics, _, opac, flatten_ids, offsets = _inputs(1200, (56, 40), seed=21, scale_lo=0.01, scale_hi=0.1)
+    W, H = cam.width, cam.height
+    rng = np.random.default_rng(CH)
+    colors = rng.random((means2d.shape[0], CH)).astype(np.float32)
+    bg = rng.random(CH).astype(np.float32)
+    render, alphas, last_ids, ws = _composite(lib, W, H, means2d, conics, colors, opac, flatten_ids, offsets, bg)
+    o_render, o_alphas, o_last = R.composite_fwd(means2d, conics, colors, opac, offsets, flatten_ids, W, H, background=bg)
+    ok = ~R.composite_fragile(means2d, conics, opac, offsets, flatten_ids, W, H)
+    assert np.array_equal(last_ids[ok], o_last[ok]) and np.abs(render - o_render)[ok].max() <= 1e-4
+    v_render = (rng.standard_normal(render.shape) * ok[..., None]).astype(np.float32)
+    v_alphas = (rng.standard_normal(alphas.shape) * ok).astype(np.float32)
+    N, M = means2d.shape[0], flatten_ids.shape[0]
+    v_means2d, v_conics = np.zeros((N, 2), np.float32), np.zeros((N, 3), np.float32)
+    v_colors, v_opac = np.zeros((N, CH), np.float32), np.zeros(N, np.float32)
+    rc = lib.gsb_composite_bwd(C.c_int32(W), C.c_int32(H), C.c_int32(CH), C.c_int64(N), _p(colors), _p(bg), _p(offsets),
+                               C.c_int64(M), _p(alphas), _p(last_ids), _p(v_render), _p(v_alphas), _p(v_means2d),
+                               _p(v_conics), _p(v_colors), _p(v_opac), _p(ws), None)
+    assert rc == 0, lib.gsb_last_error()
+    o = R.composite_bwd(means2d, conics, colors, opac, offsets, flatten_ids, W, H, o_alphas, o_last, v_render, v_alphas,
+                        background=bg)
+    for a, b, name in zip((v_means2d, v_conics, v_colors, v_opac), o, ("means2d", "conics", "colors", "opacities")):
+        assert rel_l2(a, b) <= 2e-4, (name, rel_l2(a, b))
