@@ -39,7 +39,7 @@ def test_the_host_build_exports_the_whole_abi(lib):
     assert len(set(names)) >= 60 and all(hasattr(lib, n) for n in set(names))
 
 
-@pytest.mark.parametrize("mode,W,H", [("pbr", 96, 80), ("specular", 50, 37)])
+@pytest.mark.parametrize("mode,W,H", [("pbr", 96, 80), ("specular", 50, 37), ("diffuse", 33, 64)])
 def test_one_view_forward_and_backward_through_the_native_driver(lib, mode, W, H):
     N, R0, L, Rb = 2500, 32, 4, 8
     gen = torch.Generator().manual_seed(17)
