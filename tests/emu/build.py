@@ -67,15 +67,16 @@ def all_kernel_files():
     return sorted(f[:-3] for f in os.listdir(CSRC) if f.endswith(".cu") and f != "error.cu")
 
 
-def build(*names: str, simt: bool = False) -> C.CDLL:
+def build(*names: str, simt: bool = False, defines: tuple = ()) -> C.CDLL:
     """`names`.cu (compiled together) -> tests/emu/_build/lib<names>_emu[_simt].so (rebuilt when a source is newer).
     simt: run the threads of a block as fibers with real barriers, warp collectives and shared memory (simt.h).
+    defines: extra -D macros (the kernels' tuning constants, e.g. "GSB_FG=4").
     GSB_EMU_SANITIZE=1 in the environment builds the libraries with AddressSanitizer + UBSan (the process
     must run with libasan preloaded: tests/test_kernels_asan_cpu.py does that in a subprocess)."""
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(CSRC, n + ".cu") for n in names]
     sanitize = bool(os.environ.get("GSB_EMU_SANITIZE"))      # simt.h tells ASan about its fiber switches
-    tag = ("_simt" if simt else "") + ("_asan" if sanitize else "")
+    tag = ("_simt" if simt else "") + ("_asan" if sanitize else "") + "".join("_" + d.replace("=", "") for d in defines)
     stem = "_".join(names) if len(names) <= 3 else f"all{len(names)}"
     lib = os.path.join(OUT, f"lib{stem}_emu{tag}.so")
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [__file__] + \
@@ -87,7 +88,7 @@ def build(*names: str, simt: bool = False) -> C.CDLL:
             with open(cpps[-1], "w") as f:
                 f.write(_rewrite(open(src).read(), n))
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", HERE, "-I", CSRC,
-                               *(["-DGSB_EMU_SIMT"] if simt else []),
+                               *(["-DGSB_EMU_SIMT"] if simt else []), *[f"-D{d}" for d in defines],
                                *(["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if sanitize else []),
                                "-o", lib, *cpps, "-x", "c++",
                                os.path.join(CSRC, "error.cu")])

@@ -119,3 +119,28 @@ def test_wide_channel_composite_on_the_host(lib, CH):
                         background=bg)
     for a, b, name in zip((v_means2d, v_conics, v_colors, v_opac), o, ("means2d", "conics", "colors", "opacities")):
         assert rel_l2(a, b) <= 2e-4, (name, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("defines", [("GSB_WPB=4", "GSB_FG=4", "GSB_BG=4", "GSB_WPB_B=1"),
+                                     ("GSB_WPB=1", "GSB_FG=16", "GSB_BG=16", "GSB_WPB_B=4")])
+def test_tuning_constants_do_not_change_results(defines):
+    """The compile-time knobs scripts/tune_composite.sh sweeps on the GPU (warps per CTA, entries evaluated together in
+    the forward groups and in the backward's phase A): every setting is the same function."""
+    lib = emu.build("composite", simt=True, defines=defines)
+    cam, means2d, conics, colors, opac, flatten_ids, offsets = _inputs(900, (48, 40), seed=31, scale_lo=0.01, scale_hi=0.1)
+    W, H = cam.width, cam.height
+    render, alphas, last_ids, ws = _composite(lib, W, H, means2d, conics, colors, opac, flatten_ids, offsets)
+    o_render, o_alphas, o_last = R.composite_fwd(means2d, conics, colors, opac, offsets, flatten_ids, W, H)
+    ok = ~R.composite_fragile(means2d, conics, opac, offsets, flatten_ids, W, H)
+    assert np.array_equal(last_ids[ok], o_last[ok]) and np.abs(render - o_render)[ok].max() <= 1e-4
+    rng = np.random.default_rng(5)
+    v_render = (rng.standard_normal(render.shape) * ok[..., None]).astype(np.float32)
+    v_alphas = (rng.standard_normal(alphas.shape) * ok).astype(np.float32)
+    N, M = means2d.shape[0], flatten_ids.shape[0]
+    g = [np.zeros(s, np.float32) for s in ((N, 2), (N, 3), (N, 3), N)]
+    assert lib.gsb_composite_bwd(C.c_int32(W), C.c_int32(H), C.c_int32(3), C.c_int64(N), _p(colors), None, _p(offsets),
+                                 C.c_int64(M), _p(alphas), _p(last_ids), _p(v_render), _p(v_alphas), *[_p(x) for x in g],
+                                 _p(ws), None) == 0, lib.gsb_last_error()
+    o = R.composite_bwd(means2d, conics, colors, opac, offsets, flatten_ids, W, H, o_alphas, o_last, v_render, v_alphas)
+    for a, b in zip(g, o):
+        assert rel_l2(a, b) <= 2e-4
