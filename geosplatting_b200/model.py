@@ -105,6 +105,22 @@ class GeoSplatter(nn.Module):
     def save_memory(self) -> bool:
         return self.last_num_gaussians > self.gaussian_limits_soft and self.training
 
+    def parameter_groups(self) -> dict:
+        """The eight groups GeoSplatTrainer.setup builds one Adam optimiser for (geosplat_trainer.py:84-142; the first
+        five are what `as_module(field_name=...)` exposes, geosplat.py:929-942)."""
+        return {"deforms": [self.deform_params], "sdfs": [self.sdf_params], "weights": [self.weight_params],
+                "light": [self.cubemap], "exposure": [self.exposure_params],
+                "kd": list(self.field.kd_enc.parameters()), "ks": list(self.field.ks_enc.parameters()),
+                "z": list(self.field.z_enc.parameters())}
+
+    @torch.no_grad()
+    def export_model(self, path) -> None:
+        """geosplat.py:838-854: the attribute dictionary the reference's relighting tools load."""
+        torch.save({"geom_scale": self.scale, "resolution": self.resolution, "min_roughness": self.min_roughness,
+                    "max_metallic": self.max_metallic, "exposure": self.exposure_params, "cubemap": self.cubemap,
+                    "deforms": self.deform_params, "weights": self.weight_params, "sdfs": self.sdf_params,
+                    "ks_enc": self.field.ks_enc.state_dict(), "initial_guess": self.initial_guess_bias}, path)
+
     def get_geometry(self) -> Tuple[TriangleMesh, Tensor]:
         """geosplat.py:751-769."""
         if self.geometric_repr.device != self.device:
