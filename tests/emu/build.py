@@ -78,7 +78,7 @@ def build(*names: str, simt: bool = False, defines: tuple = ()) -> C.CDLL:
         import pytest
         pytest.skip("g++ not available: the kernel source cannot be compiled for the host")
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(CSRC, n + ".cu") for n in names]
+    srcs = [os.path.join(HERE if n == "selftest" else CSRC, n + ".cu") for n in names]     # selftest.cu lives here
     sanitize = bool(os.environ.get("GSB_EMU_SANITIZE"))      # simt.h tells ASan about its fiber switches
     tag = ("_simt" if simt else "") + ("_asan" if sanitize else "") + "".join("_" + d.replace("=", "") for d in defines)
     stem = "_".join(names) if len(names) <= 3 else f"all{len(names)}"

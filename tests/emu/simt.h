@@ -229,7 +229,14 @@ template <class T> static inline T shfl(unsigned mask, T v, int src_lane) {
     unsigned part;
     // every lane must leave the rendezvous with its partner's operand of THIS rendezvous: read before returning
     Warp &w = warp_rendezvous(mask, to_bits(v), &part);
-    if (src_lane < 0 || src_lane > 31 || !((part >> src_lane) & 1u)) return v;
+    if (src_lane < 0 || src_lane > 31) return v;          // out of range: the lane keeps its own value (defined)
+    if (!((part >> src_lane) & 1u)) {
+        // reading a lane that is not part of the collective (exited, or outside the mask) is undefined in CUDA
+        fprintf(stderr, "gsb_emu: lane %d of block (%u,%u) shuffles from lane %d, which is not a participant "
+                "(mask %08x, participants %08x): undefined behaviour on the GPU\n", lane_id(), blockIdx.x, blockIdx.y,
+                src_lane, mask, part);
+        abort();
+    }
     return from_bits<T>(w.res[lane_id()][src_lane]);
 }
 
