@@ -38,7 +38,7 @@ def _composite(lib, W, H, means2d, conics, colors, opac, flatten_ids, offsets, b
     N, M, CH = means2d.shape[0], flatten_ids.shape[0], colors.shape[1]
     nb = C.c_size_t(0)
     assert lib.gsb_composite_workspace_bytes(C.c_int64(N), C.c_int64(M), C.c_int32(W), C.c_int32(H), C.byref(nb)) == 0
-    ws = np.zeros(nb.value + 256, np.uint8)
+    ws = np.full(nb.value + 256, 0xFF, np.uint8)
     render, alphas = np.zeros((H, W, CH), np.float32), np.zeros((H, W), np.float32)
     last_ids = np.zeros((H, W), np.int32)
     rc = lib.gsb_composite_fwd(C.c_int32(W), C.c_int32(H), C.c_int32(CH), C.c_int64(N), _p(means2d), _p(conics),

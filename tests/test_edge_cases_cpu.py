@@ -42,19 +42,19 @@ def _raster(lib, g, cam, antialiased=True):
     order, cum, total = np.zeros(max(N, 1), np.int32), np.zeros(max(N, 1), np.int64), np.zeros(1, np.int64)
     if N:
         assert lib.gsb_bin2_workspace_bytes(i32(N), i64(0), C.byref(nb)) == 0
-        ws = np.zeros(nb.value + 256, np.uint8)
+        ws = np.full(nb.value + 256, 0xFF, np.uint8)
         assert lib.gsb_bin2_count(i32(N), _p(depths), _p(tpg), _p(order), _p(cum), _p(total), _p(ws), sz(ws.size),
                                   None) == 0
         M = int(total[0])
     flat, off = np.zeros(M, np.int32), np.zeros(tw * th, np.int32)
     if M:
         assert lib.gsb_bin2_workspace_bytes(i32(0), i64(M), C.byref(nb)) == 0
-        ws = np.zeros(nb.value + 256, np.uint8)
+        ws = np.full(nb.value + 256, 0xFF, np.uint8)
         assert lib.gsb_bin2_sort(i32(N), i64(M), _p(means2d), _p(radii), _p(order), _p(cum), C.byref(gc), _p(flat),
                                  _p(off), _p(ws), sz(ws.size), None) == 0, lib.gsb_last_error()
     opac = (g["opacities"] * (comps if antialiased else 1.0)).astype(np.float32)
     assert lib.gsb_composite_workspace_bytes(i64(N), i64(M), i32(W), i32(H), C.byref(nb)) == 0
-    ws = np.zeros(nb.value + 256, np.uint8)
+    ws = np.full(nb.value + 256, 0xFF, np.uint8)
     render, alphas = np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.float32)
     last = np.zeros((H, W), np.int32)
     assert lib.gsb_composite_fwd(i32(W), i32(H), i32(3), i64(N), _p(means2d), _p(conics), _p(g["colors"]), _p(opac),

@@ -37,7 +37,7 @@ def test_specular_prefilter_on_the_host(lib, R, rough, tables):
     if tables:                      # the direction-table kernels; a NULL workspace selects the table-free kernel
         nb = C.c_size_t(0)
         assert lib.gsb_specular_workspace_bytes(i32(R), C.byref(nb)) == 0
-        ws = np.zeros(nb.value + 256, np.uint8)
+        ws = np.full(nb.value + 256, 0xFF, np.uint8)
     out = np.zeros((6, R, R, 4), np.float32)
     assert lib.gsb_specular_cubemap_fwd(i32(R), _p(c), _p(bounds), f32(rough), f32(ct), i32(0), _p(out), _p(ws),
                                         None) == 0, lib.gsb_last_error()

@@ -106,18 +106,18 @@ def _bin_both_ways(lib, gc, radii, means2d, depths, tpg):
     nb = sz(0)
     # two-stage
     assert lib.gsb_bin2_workspace_bytes(i32(N), i64(0), C.byref(nb)) == 0
-    ws = np.zeros(nb.value, np.uint8)
+    ws = np.full(nb.value, 0xFF, np.uint8)
     order, cum, total = np.zeros(N, np.int32), np.zeros(N, np.int64), np.zeros(1, np.int64)
     assert lib.gsb_bin2_count(i32(N), _p(depths), _p(tpg), _p(order), _p(cum), _p(total), _p(ws), sz(ws.size), None) == 0
     M = int(total[0])
     assert lib.gsb_bin2_workspace_bytes(i32(0), i64(M), C.byref(nb)) == 0
-    ws = np.zeros(nb.value, np.uint8)
+    ws = np.full(nb.value, 0xFF, np.uint8)
     flat2, off2 = np.zeros(M, np.int32), np.zeros(tw * th, np.int32)
     assert lib.gsb_bin2_sort(i32(N), i64(M), _p(means2d), _p(radii), _p(order), _p(cum), C.byref(gc), _p(flat2), _p(off2),
                              _p(ws), sz(ws.size), None) == 0, lib.gsb_last_error()
     # stage split
     assert lib.gsb_bin_workspace_bytes(i32(N), i64(M), C.byref(nb)) == 0
-    ws = np.zeros(nb.value, np.uint8)
+    ws = np.full(nb.value, 0xFF, np.uint8)
     cum1 = np.zeros(N, np.int64)
     assert lib.gsb_isect_scan(i32(N), _p(tpg), _p(cum1), _p(ws), sz(ws.size), None) == 0
     assert lib.gsb_isect_total(i32(N), _p(cum1), _p(total), None) == 0 and int(total[0]) == M

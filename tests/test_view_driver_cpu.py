@@ -93,7 +93,7 @@ def test_one_view_forward_and_backward_through_the_native_driver(lib, mode, W, H
     cam_pos = (C.c_float * 3)(*[float(x) for x in cam.position])
     sizes = (C.c_size_t * 5)()
     assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
-    keep1, tmp1 = np.zeros(sizes[0] + 256, np.uint8), np.zeros(sizes[1] + 256, np.uint8)
+    keep1, tmp1 = np.full(sizes[0] + 256, 0xFF, np.uint8), np.full(sizes[1] + 256, 0xFF, np.uint8)
     total = np.zeros(1, np.int64)
     lutn, ex = f(lut), f(exposure)
     assert lib.gsb_view_prepare(C.byref(cfg), C.byref(gc), cam_pos, _p(means), _p(quats), _p(scales), _p(nrm), _p(kd),
@@ -102,7 +102,7 @@ def test_one_view_forward_and_backward_through_the_native_driver(lib, mode, W, H
     M = int(total[0])
     assert M == o_info["flatten_ids"].shape[0]                       # same number of (tile, Gaussian) intersections
     assert lib.gsb_view_bytes(C.addressof(cfg), M, C.addressof(sizes)) == 0
-    keep2, tmp2 = np.zeros(sizes[2] + 256, np.uint8), np.zeros(sizes[3] + 256, np.uint8)
+    keep2, tmp2 = np.full(sizes[2] + 256, 0xFF, np.uint8), np.full(sizes[3] + 256, 0xFF, np.uint8)
     out = np.zeros((H, W, 4), np.float32)
     assert lib.gsb_view_finish(C.byref(cfg), C.byref(gc), i64(M), _p(lg), _p(ex), _p(keep1), _p(tmp1), _p(keep2),
                                _p(tmp2), _p(out), None) == 0, lib.gsb_last_error()
@@ -111,7 +111,7 @@ def test_one_view_forward_and_backward_through_the_native_driver(lib, mode, W, H
     diff = np.abs(out - o_img.detach().numpy())[ok].max(-1)
     assert np.quantile(diff, 0.999) <= 1e-4 and diff.max() <= 5e-4, (np.quantile(diff, 0.999), diff.max())
 
-    tmp3 = np.zeros(sizes[4] + 256, np.uint8)
+    tmp3 = np.full(sizes[4] + 256, 0xFF, np.uint8)
     g = {k: np.zeros(s, np.float32) for k, s in (("means", (N, 3)), ("quats", (N, 4)), ("scales", (N, 3)), ("logits", N),
                                                   ("normals", (N, 3)), ("kd", (N, 3)), ("ks", (N, 2)), ("env", (T, 4)),
                                                   ("exposure", 1))}
@@ -154,19 +154,19 @@ def test_driver_with_nothing_to_draw(lib, N, behind):
     cp = (C.c_float * 3)(*[float(x) for x in cam.position])
     sizes = (C.c_size_t * 5)()
     assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
-    keep1, tmp1 = np.zeros(sizes[0] + 256, np.uint8), np.zeros(sizes[1] + 256, np.uint8)
+    keep1, tmp1 = np.full(sizes[0] + 256, 0xFF, np.uint8), np.full(sizes[1] + 256, 0xFF, np.uint8)
     total = np.full(1, -7, np.int64)
     lut, ex = synthetic_fg_lut(), np.ones(1, np.float32)
     assert lib.gsb_view_prepare(C.byref(cfg), C.byref(gc), cp, _p(means), _p(quats), _p(scales), _p(nrm), _p(kd), _p(ks),
                                 _p(lut), _p(stack), _p(keep1), _p(tmp1), _p(total), None) == 0, lib.gsb_last_error()
     assert int(total[0]) == 0
     assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
-    keep2, tmp2 = np.zeros(sizes[2] + 256, np.uint8), np.zeros(sizes[3] + 256, np.uint8)
+    keep2, tmp2 = np.full(sizes[2] + 256, 0xFF, np.uint8), np.full(sizes[3] + 256, 0xFF, np.uint8)
     out = np.full((H, W, 4), 9, np.float32)
     assert lib.gsb_view_finish(C.byref(cfg), C.byref(gc), C.c_int64(0), _p(lg), _p(ex), _p(keep1), _p(tmp1), _p(keep2),
                                _p(tmp2), _p(out), None) == 0, lib.gsb_last_error()
     assert np.all(out == 0)
-    tmp3 = np.zeros(sizes[4] + 256, np.uint8)
+    tmp3 = np.full(sizes[4] + 256, 0xFF, np.uint8)
     g = [np.zeros(s, np.float32) for s in ((N, 3), (N, 4), (N, 3), N, (N, 3), (N, 3), (N, 2), (T, 4), 1)]
     v_out = np.random.default_rng(1).random((H, W, 4)).astype(np.float32)
     assert lib.gsb_view_backward(C.byref(cfg), C.byref(gc), cp, C.c_int64(0), _p(means), _p(quats), _p(scales), _p(lg),
