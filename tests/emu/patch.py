@@ -2,6 +2,8 @@
 `_lib.load` to a host-compiled kernel library for the duration of one test (pytest's monkeypatch undoes it)."""
 import ctypes as C
 
+import torch
+
 from geosplatting_b200 import _lib
 
 
@@ -12,8 +14,25 @@ def host_ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _poisoned_empty(real_empty):
+    """torch.empty that hands out NaN / -1 / 0xFF instead of whatever the allocator held (usually fresh zero pages on
+    the CPU): a kernel that reads a buffer the host module allocated with torch.empty before writing it shows up."""
+    def empty(*args, **kwargs):
+        t = real_empty(*args, **kwargs)
+        if t.numel():
+            if t.is_floating_point():
+                t.fill_(float("nan"))
+            elif t.dtype == torch.bool:
+                t.fill_(True)
+            else:
+                t.fill_(255 if t.dtype == torch.uint8 else -1)
+        return t
+    return empty
+
+
 def route(monkeypatch, so, *modules):
     monkeypatch.setattr(_lib, "load", lambda: so)
+    monkeypatch.setattr(torch, "empty", _poisoned_empty(torch.empty))
     for m in modules:
         monkeypatch.setattr(m, "ptr", host_ptr)
         monkeypatch.setattr(m, "stream_ptr", lambda dev: None)
