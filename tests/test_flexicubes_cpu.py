@@ -96,3 +96,35 @@ def test_warp_reduction_of_the_entropy_pass_under_simt(monkeypatch):
     route(monkeypatch, emu.build("flexicubes", simt=True), FC)
     fc_cases.check_smooth_fixture("cpu")
     fc_cases.check_rough_fixture("cpu")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_sdf_with_exact_zeros_and_ties(host_kernels, seed):
+    """SDF quantised to {-1, -0.5, 0, 0.5, 1}: many vertices exactly on the surface (occupancy is `sdf < 0`, so zero counts
+    as outside), crossings that coincide with grid vertices, dual vertices at zero distance from a crossing (the norm's
+    subgradient), equal values on both sides of ambiguous faces -- same mesh and finite, matching gradients."""
+    import numpy as np
+    from oracle import flexicubes as OF
+    gen = torch.Generator().manual_seed(seed)
+    res = (5, 4, 6)
+    fc0 = FC.FlexiCubes.from_resolution(*res, random_sdf=False, scale=1.0)
+    sdf0 = (torch.randint(-2, 3, (fc0.vertices.shape[0], 1), generator=gen).float() * 0.5)
+    w0 = 0.4 * torch.randn(fc0.indices.shape[0], 21, generator=gen)
+    tbl = fc_cases.tables(fc_cases.load("ref_flexicubes.npz"))
+    got = {}
+    for which in ("ours", "oracle"):
+        sdf, w = sdf0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        if which == "ours":
+            fc = fc0.replace(sdf_values=sdf, alpha=w[:, :8], beta=w[:, 8:20], gamma=w[:, 20:])
+            mesh, l_dev = fc.dual_marching_cubes()
+            mv, mf, ent = mesh.vertices, mesh.indices, fc.compute_entropy()
+        else:
+            mv, mf, l_dev = OF.dual_marching_cubes(fc0.vertices, sdf, fc0.indices, res, w[:, :8], w[:, 8:20], w[:, 20:], tbl)
+            ent = OF.entropy(sdf, fc0.indices, tbl)
+        g = torch.autograd.grad(mv.square().sum() + l_dev.sum() + ent, [sdf, w])
+        got[which] = [x.detach().numpy() for x in (mf, mv, l_dev, ent, *g)]
+    a, b = got["ours"], got["oracle"]
+    assert np.array_equal(a[0], b[0]) and a[0].shape[0] > 0
+    for x, y in zip(a[1:], b[1:]):
+        assert np.isfinite(x).all() and np.isfinite(y).all()
+        assert np.abs(x - y).max(initial=0.0) <= 1e-4 * max(1.0, np.abs(y).max(initial=0.0))
