@@ -21,6 +21,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import GsbCamera, call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 
 TILE = 16
 _SUPPORTED_CH = (1, 2, 3, 4, 8, 16)
@@ -316,8 +317,7 @@ def _check_geometry(means, quats, scales, viewmats, Ks):
     assert scales.shape == (N, 3), scales.shape
     assert viewmats.dim() == 3 and viewmats.shape[1:] == (4, 4), viewmats.shape
     assert Ks.shape == (viewmats.shape[0], 3, 3), Ks.shape
-    if not means.is_cuda:
-        raise RuntimeError("geosplatting_b200.rasterization needs CUDA tensors; there is no CPU path")
+    _require_cuda(means, "rasterization")
 
 
 class Projected:

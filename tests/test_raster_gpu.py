@@ -142,7 +142,7 @@ def test_background_and_depth_modes():
     od, oa, _ = R.composite_fwd(o_info["means2d"], o_info["conics"], o_info["depths"][:, None], o_info["opacities"],
                                 o_info["isect_offsets"][0], o_info["flatten_ids"], 96, 96)
     ref = od[..., 0] / np.maximum(oa, 1e-10)
-    assert np.abs(ed[0, ..., 0].cpu().numpy() - ref)[ok].max() <= 1e-3
+    assert np.abs(ed[0, ..., 0].detach().cpu().numpy() - ref)[ok].max() <= 1e-3
 
 
 def test_idempotent_and_deterministic_forward():

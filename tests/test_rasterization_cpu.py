@@ -1,0 +1,69 @@
+"""The public operator `geosplatting_b200.rasterization` (gsplat.rasterization's signature; rfstudio/model/gsplat.py:334-355)
+without a GPU: the real Python host module (two-phase begin / end, workspace cache, packed `info` dictionary, autograd
+nodes) over the host build of the whole library (tests/emu SIMT mode), on the GPU suite's own test bodies
+(tests/test_raster_gpu.py) with the device switched.  The handful of CUDA-runtime objects the module touches (current
+stream, an event, the pinned slot M lands in) are replaced by inert stand-ins here; nothing else is patched."""
+import importlib
+
+import pytest
+import torch
+
+import tests.test_raster_gpu as G
+from tests.emu import build as emu
+from tests.emu.patch import route
+
+RZ = importlib.import_module("geosplatting_b200.rasterization")     # the module (the package exports the function)
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+@pytest.fixture()
+def host_raster(monkeypatch):
+    route(monkeypatch, emu.build(*emu.all_kernel_files(), simt=True), RZ)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(RZ, "_total_slot", lambda device: torch.zeros(1, dtype=torch.int64))
+    monkeypatch.setattr(RZ, "_workspaces", {})
+    monkeypatch.setattr(G, "DEV", "cpu")
+
+
+@pytest.mark.parametrize("mode", ["antialiased", "classic"])
+def test_config1_through_the_public_operator(host_raster, mode):
+    """BASELINE configs[0]: 10 k random Gaussians, one camera, 256 x 256 -- packed info bit-exact, image 1e-4 / 70 dB,
+    gradients 2e-4, through `rasterization()` itself."""
+    G.test_config1_10k_256(mode)
+
+
+def test_ragged_resolution_and_culling_through_the_public_operator(host_raster):
+    G.test_ragged_resolution_and_big_splats()
+    G.test_camera_inside_cloud_culls_and_clamps()
+
+
+def test_empty_scene_backgrounds_depth_modes_and_two_cameras(host_raster):
+    G.test_empty_scene_and_all_culled()
+    G.test_background_and_depth_modes()
+    G.test_two_cameras_in_one_call()
+
+
+def test_two_stage_binning_equals_single_sort_on_the_host(host_raster):
+    G.test_two_stage_binning_equals_single_sort()
