@@ -67,3 +67,13 @@ def test_empty_scene_backgrounds_depth_modes_and_two_cameras(host_raster):
 
 def test_two_stage_binning_equals_single_sort_on_the_host(host_raster):
     G.test_two_stage_binning_equals_single_sort()
+
+
+@pytest.mark.parametrize("D", [1, 4, 14])
+def test_wide_channel_features_through_the_public_operator(host_raster, D):
+    """SURVEY 8f rank 4 (D = 14 is the G-buffer of geosplat.py:276-295, padded to 16 channels inside the operator)."""
+    G.test_wide_channel_backward(D)
+
+
+def test_forward_is_deterministic_through_the_public_operator(host_raster):
+    G.test_idempotent_and_deterministic_forward()
