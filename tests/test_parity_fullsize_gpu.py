@@ -1,0 +1,95 @@
+"""Oracle parity AT THE BASELINE SIZES (not only size-independent properties): one training view of
+BASELINE.json configs[2] (1 002 528 MGAdaptor Gaussians, 800x800 -- the bench's headline workload) and of configs[1]
+(496 008 Gaussians, 800x800) through the product's batched path (fused.splat_views -> gsb_batch_* / gsb_view_* over
+the C ABI) against the composed CPU oracle (oracle/parity.py: torch shade -> C rasterizer -> tone map), on IDENTICAL
+Gaussians (the MGAdaptor kernel's output, downloaded) and the same env levels.
+
+Tolerances (north_star): tile lists `flatten_ids` / `isect_offsets` bit-identical; image 1e-4 per-pixel L-inf on the
+pixels whose discrete decisions are not within 2e-5 of flipping (< 0.1 % are, asserted); all ten gradient groups
+within 2e-3 of their largest entry and 1e-3 relative L2 (chained tolerances of tests/test_splat_gpu.py; the
+rasterizer alone is held to 2e-4 in tests/test_raster_gpu.py).  The oracle costs a few seconds per view."""
+import numpy as np
+import pytest
+import torch
+
+from geosplatting_b200 import rasterization, scenes, splitsum
+from geosplatting_b200.fused import splat_views
+from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
+from geosplatting_b200.shade import EnvStack, synthetic_fg_lut
+from oracle import parity as OP
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ORDER = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
+
+
+def device_view(g, env0: EnvStack, lut, cam, exposure, cot):
+    """The product path on one view: image, gradients in oracle/parity.py's group layout, tile lists."""
+    p = {k: g[k].to(DEV).requires_grad_(True) for k in ORDER}
+    leaf = env0.data.detach().clone().requires_grad_(True)
+    env = EnvStack(leaf, env0.R0, env0.L, env0.Rb, env0.min_roughness, env0.max_roughness)
+    ex = exposure.to(DEV).requires_grad_(True)
+    (img,) = splat_views(*[p[k] for k in ORDER], [cam], exposures=ex, envmap=env, fg_lut=lut.to(DEV),
+                         min_roughness=0.1, max_metallic=1.0)
+    gr = torch.autograd.grad(img, [p[k] for k in ORDER] + [leaf, ex], grad_outputs=cot.to(DEV))
+    lv = EnvStack(gr[7], env0.R0, env0.L, env0.Rb).level_views()
+    grads = {"means": gr[0], "scales": gr[1], "quats": gr[2], "logits": gr[3], "kd": gr[4], "ks": gr[5],
+             "normals": gr[6], "base": lv[-1][..., :3], "mips": [x[..., :3] for x in lv[:-1]], "exposure": gr[8]}
+    with torch.no_grad():
+        vm = torch.from_numpy(cam.view_matrix)[None].to(DEV)
+        K = torch.from_numpy(cam.intrinsic_matrix)[None].to(DEV)
+        _, _, info = rasterization(p["means"], p["quats"], p["scales"].exp(), torch.sigmoid(p["opacities"])[:, 0],
+                                   p["normals"], vm, K, cam.width, cam.height, rasterize_mode="antialiased")
+    return (img.detach().cpu().numpy(), grads, info["flatten_ids"].cpu().numpy(),
+            info["isect_offsets"].cpu().numpy())
+
+
+def scene(mesh_n: int, light_res: int = 512, seed: int = 0):
+    verts, faces = scenes.cube_sphere(mesh_n)
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        vd, fd = verts.to(DEV), faces.to(DEV)
+        sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+        cube = torch.exp(torch.randn(6, light_res, light_res, 3, generator=gen)).clamp_min(1e-2).to(DEV)
+        env0 = splitsum.as_envstack(cube)
+    N = sp.means.shape[0]
+    g = {"means": sp.means, "scales": sp.scales, "quats": sp.quats, "opacities": sp.opacities,
+         "kd": (torch.rand(N, 3, generator=gen) * 0.8 + 0.1), "ks": torch.rand(N, 2, generator=gen),
+         "normals": sp.colors}
+    g = {k: v.detach().cpu().contiguous() for k, v in g.items()}
+    lv = [x.detach().cpu() for x in env0.level_views()]
+    base, mips = lv[-1][..., :3].contiguous(), [x[..., :3].contiguous() for x in lv[:-1]]
+    return g, env0, base, mips
+
+
+def check_view(mesh_n, n_expected, cam_seed, cam_index=0):
+    g, env0, base, mips = scene(mesh_n)
+    assert g["means"].shape[0] == n_expected
+    cam = scenes.orbit_cameras(8, 800, 800, seed=cam_seed)[cam_index]
+    lut = synthetic_fg_lut(torch.device("cpu"))
+    exposure = torch.tensor([1.1])
+    cot = torch.randn(800, 800, 4, generator=torch.Generator().manual_seed(5))
+    o = OP.oracle_view(g, base, mips, lut, cam, exposure, cot)
+    img, grads, flat, offs = device_view(g, env0, lut, cam, exposure, o["cot"])
+    rep = OP.compare(o, img, flat, offs, grads)
+    print("parity", mesh_n, {k: v for k, v in rep.items() if k != "grads"},
+          {k: (round(v["rel_l2"], 7), round(v["linf_over_max"], 7)) for k, v in rep["grads"].items()})
+    assert rep["ids_equal"], "tile lists differ from the oracle's"
+    assert rep["fragile_frac"] < 1e-3, rep["fragile_frac"]
+    assert rep["linf"] <= 1e-4, rep["linf"]
+    assert rep["psnr_db_all_pixels"] >= 70.0
+    for k, v in rep["grads"].items():
+        assert v["linf_over_max"] <= 2e-3 and v["rel_l2"] <= 1e-3, (k, v)
+    return rep
+
+
+def test_config3_one_view_1m_gaussians_800_against_the_oracle():
+    """BASELINE.json configs[2] / the bench workload: N = 1 002 528, 800 x 800, M ~ 2.3 M."""
+    rep = check_view(118, 1_002_528, cam_seed=1)
+    assert 2_000_000 < rep["intersections"] < 2_600_000
+
+
+def test_config2_one_view_500k_gaussians_800_against_the_oracle():
+    """BASELINE.json configs[1]: ~500 k Gaussians (496 008), 800 x 800, shade + raster fwd+bwd."""
+    rep = check_view(83, 496_008, cam_seed=2, cam_index=3)
+    assert rep["intersections"] > 1_000_000
