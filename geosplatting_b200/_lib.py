@@ -60,15 +60,20 @@ def load() -> C.CDLL:
                 f"geosplatting_b200: {LIB_PATH} is missing. Build it with `python -c 'import "
                 "__graft_entry__ as g; g.build()'` (or `make -C geosplatting_b200/csrc`). "
                 "There is no CPU or PyTorch fallback for this path.")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.gsb_last_error.restype = C.c_char_p
-        # the per-view driver is called with raw integers (tensor.data_ptr()): declare the pointer widths
-        vp, i64 = C.c_void_p, C.c_int64
-        _lib.gsb_view_bytes.argtypes = [vp, i64, vp]
-        _lib.gsb_view_prepare.argtypes = [vp] * 15
-        _lib.gsb_view_finish.argtypes = [vp, vp, i64] + [vp] * 8
-        _lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 26
+        _lib = declare(C.CDLL(LIB_PATH))
     return _lib
+
+
+def declare(lib: C.CDLL) -> C.CDLL:
+    """Prototypes of the entry points that are called with raw integers (tensor.data_ptr()) rather than ctypes objects:
+    the pointer widths have to be declared."""
+    lib.gsb_last_error.restype = C.c_char_p
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.gsb_view_bytes.argtypes = [vp, i64, vp]
+    lib.gsb_view_prepare.argtypes = [vp] * 15
+    lib.gsb_view_finish.argtypes = [vp, vp, i64] + [vp] * 8
+    lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 26
+    return lib
 
 
 class CallStats:
@@ -116,6 +121,10 @@ def call(name: str, dev: torch.device, *args) -> None:
     """Invoke C-ABI entry point `name` on `dev`'s current stream; raise on a non-zero return code."""
     fn = getattr(load(), name)
     CallStats.counts[name] = CallStats.counts.get(name, 0) + 1
+    # tensors on a GPU that is not the current one: launch with that device current (streams and kernels are per device)
+    if dev is not None and dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return call(name, dev, *args)
     if CallStats.timing is True or (CallStats.timing and name in CallStats.timing):
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)

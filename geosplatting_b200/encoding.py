@@ -79,20 +79,32 @@ class MLP(nn.Module):
                 raise ValueError("MLP(layers=[-1, ...]) needs in_dim")
             layers[0] = in_dim
         self.layers, self.activation = layers, activation
-        self.weights = nn.ParameterList()
-        for i, o in zip(layers[:-1], layers[1:]):
-            w = torch.empty(o, i)
-            nn.init.kaiming_uniform_(w, nonlinearity="relu")              # mlp.py:99-100
-            self.weights.append(nn.Parameter(w))
+        # parameter names are the reference's (mlp.py:46-57: `nn_layers.<i>.weight`), so a state_dict of this module loads
+        # into the reference's MLP and back (geosplat.py:848 exports ks_enc.state_dict(); geosplat_mc.py:73 loads it)
+        self.nn_layers = nn.ModuleList(nn.Linear(i, o, bias=False) for i, o in zip(layers[:-1], layers[1:]))
+        for layer in self.nn_layers:
+            nn.init.kaiming_uniform_(layer.weight, nonlinearity="relu")   # mlp.py:99-100
+
+    @property
+    def weights(self) -> List[nn.Parameter]:
+        return [layer.weight for layer in self.nn_layers]
 
     def forward(self, x: Tensor) -> Tensor:
-        n = len(self.weights)
-        for i, w in enumerate(self.weights):
-            x = torch.nn.functional.linear(x, w)
+        n = len(self.nn_layers)
+        for i, layer in enumerate(self.nn_layers):
+            x = layer(x)
             if i < n - 1:
                 x = torch.relu(x)
         return {"none": lambda t: t, "sigmoid": torch.sigmoid, "relu": torch.relu, "tanh": torch.tanh,
                 "softplus": torch.nn.functional.softplus}[self.activation](x)
+
+
+class _Table(nn.Module):
+    """The reference's ParameterModule (rfstudio/nn/module.py:1478-1492): one parameter called `params`."""
+
+    def __init__(self, t: Tensor):
+        super().__init__()
+        self.params = nn.Parameter(t)
 
 
 class HashEncoding(nn.Module):
@@ -111,8 +123,14 @@ class HashEncoding(nn.Module):
         self.log2_hashmap_size, self.features_per_level, self.grad_scaling = log2_hashmap_size, features_per_level, grad_scaling
         self.hash_table_size = 2 ** log2_hashmap_size
         self.scalings = level_scalings(num_levels, min_res, max_res)
-        self.hash_table = nn.Parameter((torch.rand(self.hash_table_size * num_levels, features_per_level) * 2 - 1)
-                                       * hash_init_scale)                                   # encoding.py:144-147
+        # registered as `encoder.params`, the reference's key for either backend (encoding.py:144-148: ParameterModule;
+        # tcnn.Encoding.params)
+        self.encoder = _Table((torch.rand(self.hash_table_size * num_levels, features_per_level) * 2 - 1)
+                              * hash_init_scale)                                            # encoding.py:144-147
+
+    @property
+    def hash_table(self) -> nn.Parameter:
+        return self.encoder.params
 
     def encode(self, in_tensor: Tensor) -> Tensor:
         """pytorch_fwd (encoding.py:182-229): [..., 3] in [-1, 1] -> [..., num_levels * features_per_level]."""
@@ -128,6 +146,38 @@ class HashEncoding(nn.Module):
         `f*s + f.detach()(1-s)`) leave values unchanged and multiply the gradient that reaches the table by s while the
         one that reaches x stays as it is: that factor is applied inside the backward kernel."""
         return self.mlp(self.encode(in_tensor))
+
+
+class TcnnEncoding(nn.Module):
+    """Stand-in for `tinycudann.Encoding(n_input_dims=3, encoding_config={"otype": "HashGrid", ...})` as the reference
+    constructs and calls it (rfstudio/model/components/encoding.py:150-163, :235-236): one parameter `params`, called
+    with points in [0, 1]^3, returns [N, n_levels * n_features_per_level].
+
+    Semantics are those of the reference's own `backend='torch'` (hash, level resolutions, trilinear weights; fp32
+    storage and output), NOT tinycudann's (different level layout, fp16 tables): a tcnn checkpoint does not load."""
+
+    def __init__(self, n_input_dims: int, encoding_config: dict, seed: Optional[int] = None, dtype=None):
+        super().__init__()
+        c = dict(encoding_config)
+        if n_input_dims != 3 or c.get("otype", "HashGrid") != "HashGrid":
+            raise NotImplementedError("TcnnEncoding: only the 3-D HashGrid encoding of GeoSplatting's fields")
+        if str(c.get("interpolation", "Linear")).lower() != "linear":
+            raise NotImplementedError(f"interpolation {c.get('interpolation')!r} is not supported")
+        self.n_levels, self.n_features = int(c.get("n_levels", 16)), int(c.get("n_features_per_level", 2))
+        if self.n_features != 2:
+            raise NotImplementedError("TcnnEncoding: n_features_per_level must be 2")
+        self.log2_hashmap_size = int(c.get("log2_hashmap_size", 19))
+        base, growth = int(c.get("base_resolution", 16)), float(c.get("per_level_scale", 2.0))
+        self.scalings = [float(v) for v in torch.floor(base * growth ** torch.arange(self.n_levels))]
+        self.n_output_dims = self.n_levels * self.n_features
+        gen = None if seed is None else torch.Generator().manual_seed(seed)
+        self.params = nn.Parameter((torch.rand((2 ** self.log2_hashmap_size) * self.n_levels, self.n_features,
+                                               generator=gen) * 2 - 1) * 1e-3)
+
+    def forward(self, x01: Tensor) -> Tensor:
+        _require_cuda(x01, "TcnnEncoding")
+        assert x01.shape[-1] == 3
+        return _HashGrid.apply(x01.reshape(-1, 3) * 2.0 - 1.0, self.params, self.scalings, self.log2_hashmap_size, 1.0)
 
 
 def kd_field() -> HashEncoding:

@@ -20,15 +20,16 @@ At ~1.2 ms of device time per view the host would otherwise be the bottleneck (s
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, NamedTuple, Sequence
+from typing import List, NamedTuple, Optional, Sequence
 
 import torch
 from torch import Tensor
 
 from ._lib import GsbViewConfig, call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 from .rasterization import BinCount, _release_slot, _total_slot, bin_finish, make_camera
-from .scenes import PinholeCamera
-from .shade import MODES, EnvStack, shade_workspace
+from .scenes import PinholeCamera, to_pinhole
+from .shade import MODES, EnvStack, get_fg_lut, shade_workspace
 
 
 class ViewMeta(NamedTuple):
@@ -357,7 +358,7 @@ def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic,
 
 
 def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
-                normals: Tensor, cameras: Sequence[PinholeCamera], *, exposures, envmap: EnvStack, fg_lut: Tensor,
+                normals: Tensor, cameras, *, exposures, envmap, fg_lut: Optional[Tensor] = None,
                 min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
                 rasterize_mode: str = "antialiased", n_streams: int = 4, native: bool = True) -> List[Tensor]:
     """The per-view loop of GeoSplatter.render_report for a batch of cameras: list of [H,W,4] tone-mapped RGBA images,
@@ -366,10 +367,12 @@ def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits
     `exposures`: one tensor shared by all views or a sequence of one per view.  `n_streams` <= 1 keeps everything on
     the caller's stream.  `native`: sequence the kernels of a view in the library's per-view driver (three C-ABI calls
     per view, csrc/view.cu) rather than call by call from Python (what per-kernel instrumentation needs)."""
-    if not means.is_cuda:
-        raise RuntimeError("geosplatting_b200.splat_views needs CUDA tensors; there is no CPU path")
+    _require_cuda(means, "splat_views")
+    envmap = EnvStack.coerce(envmap)                 # the reference's TextureSplitSum is accepted as is
+    if fg_lut is None:
+        fg_lut = get_fg_lut(256, means.device)      # `_get_fg_lut(256, device)`: the reference's asset
     meta, lut = _meta_and_lut(envmap, fg_lut, min_roughness, max_metallic, mode, tone_type, rasterize_mode)
-    cameras = list(cameras)
+    cameras = to_pinhole(cameras)                    # PinholeCameras or the reference's `Cameras[B]`
     ex = [exposures] * len(cameras) if isinstance(exposures, Tensor) else list(exposures)
     assert len(ex) == len(cameras)
     if not cameras:
@@ -379,7 +382,7 @@ def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits
 
 
 def splat_view(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
-               normals: Tensor, camera: PinholeCamera, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
+               normals: Tensor, camera, *, exposure: Tensor, envmap, fg_lut: Optional[Tensor] = None,
                min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
                rasterize_mode: str = "antialiased", native: bool = True) -> Tensor:
     """[H,W,4] tone-mapped RGBA of one view on the caller's stream (a batch of one)."""

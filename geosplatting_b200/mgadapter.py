@@ -112,8 +112,14 @@ class MGSplats:
 class MGAdapter:
     """Same constants as the reference dataclass (geosplat.py:378-388); they are compiled into the kernel."""
 
-    def make(self, vertices: Tensor, faces: Tensor, vertex_normals: Optional[Tensor] = None, *,
+    def make(self, vertices, faces: Optional[Tensor] = None, vertex_normals: Optional[Tensor] = None, *,
              normal_interpolation: bool = True) -> Tuple[MGSplats, Tensor]:
+        """geosplat.py:426-431: `make(mesh, normal_interpolation=True)` with a mesh object (fields vertices [V,3],
+        indices [F,3], normals [V,3] -- rfstudio's TriangleMesh after compute_vertex_normals(fix=True)), or the three
+        tensors spelled out."""
+        if faces is None and hasattr(vertices, "vertices") and hasattr(vertices, "indices"):
+            mesh = vertices
+            vertices, faces, vertex_normals = mesh.vertices, mesh.indices, getattr(mesh, "normals", None)
         _require_cuda(vertices, "MGAdapter")
         if normal_interpolation and vertex_normals is None:
             raise ValueError("normal_interpolation=True needs vertex normals (mesh.compute_vertex_normals(fix=True))")

@@ -56,6 +56,32 @@ class PinholeCamera:
         return K
 
 
+def _f(x) -> float:
+    return float(x.item()) if hasattr(x, "item") else float(x)
+
+
+def to_pinhole(cameras) -> list:
+    """Any of the camera arguments the reference's operators take -> list of PinholeCamera.
+
+    Accepts a PinholeCamera, a sequence of them, or an object with the fields of rfstudio's `Cameras` tensor dataclass
+    (rfstudio/graphics/_cameras.py:33-52: c2w [..,3,4], fx, fy, cx, cy, width, height; batch shape () or (B,)), e.g. the
+    `inputs[i:i+1]` slices GeoSplatter.render_report passes to RenderableAttrs.splat (geosplat.py:869-879).  Reading the
+    scalars is a device->host copy when the tensors live on the GPU -- the reference does the same per view
+    (`camera.width.item()`, rfstudio/model/gsplat.py:295)."""
+    if isinstance(cameras, PinholeCamera):
+        return [cameras]
+    if hasattr(cameras, "c2w") and hasattr(cameras, "fx"):
+        c2w = cameras.c2w.detach().to("cpu", torch.float32).reshape(-1, 3, 4).numpy()
+        flat = {k: getattr(cameras, k).detach().reshape(-1).cpu() for k in ("fx", "fy", "cx", "cy", "width", "height")}
+        return [PinholeCamera(np.ascontiguousarray(c2w[i]), _f(flat["fx"][i]), _f(flat["fy"][i]), _f(flat["cx"][i]),
+                              _f(flat["cy"][i]), int(flat["width"][i]), int(flat["height"][i]))
+                for i in range(c2w.shape[0])]
+    out = []
+    for c in cameras:
+        out.extend(to_pinhole(c))
+    return out
+
+
 def look_at_camera(eye, width: int, height: int, fov: float = FOV, target=(0.0, 0.0, 0.0)) -> PinholeCamera:
     eye = np.asarray(eye, dtype=np.float64)
     target = np.asarray(target, dtype=np.float64)

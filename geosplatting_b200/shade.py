@@ -46,6 +46,22 @@ class EnvStack:
         data = _EnvPack.apply(mipmaps, base, int(num_mipmaps))
         return cls(data, mipmaps.shape[-1], int(num_mipmaps), base.shape[1], min_roughness, max_roughness)
 
+    @classmethod
+    def coerce(cls, envmap) -> "EnvStack":
+        """EnvStack as is; an object with the fields of rfstudio's `TextureSplitSum` (_texture.py:559-569: base, mipmaps,
+        num_mipmaps, min_roughness, max_roughness) is packed into the native layout (differentiable)."""
+        if isinstance(envmap, cls):
+            return envmap
+        if all(hasattr(envmap, k) for k in ("base", "mipmaps", "num_mipmaps")):
+            if getattr(envmap, "transform", None) is not None:
+                raise NotImplementedError("TextureSplitSum.transform is not used by stage 1 (geosplat.py:784)")
+            f = lambda v, d: d if v is None else (float(v.item()) if hasattr(v, "item") else float(v))   # noqa: E731
+            n = envmap.num_mipmaps
+            return cls.from_splitsum(envmap.base, envmap.mipmaps, int(n.item()) if hasattr(n, "item") else int(n),
+                                     f(getattr(envmap, "min_roughness", None), 0.08),
+                                     f(getattr(envmap, "max_roughness", None), 0.5))
+        raise TypeError(f"envmap: expected EnvStack or a TextureSplitSum-like object, got {type(envmap).__name__}")
+
     def level_views(self) -> List[Tensor]:
         """Per-level [6,R,R,4] views (spec levels, then base)."""
         out, o = [], 0
@@ -272,6 +288,41 @@ def load_fg_lut(path: str, device, resolution: int = 256) -> Tensor:
     if lut.size != resolution * resolution * 2:
         raise ValueError(f"{path}: expected {resolution * resolution * 2} floats, found {lut.size}")
     return torch.from_numpy(lut).to(device).view(resolution, resolution, 2)
+
+
+_default_luts: dict = {}
+
+
+def fg_lut_asset_path() -> Optional[str]:
+    """Where the DFG table lives: $GSB_FG_LUT, else the asset inside an importable `rfstudio` package
+    (rfstudio/assets/geometry/pbr/bsdf_256_256.bin, what shaders.py:22-26 reads)."""
+    env = os.environ.get("GSB_FG_LUT")
+    if env:
+        return env
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("rfstudio")
+        if spec is not None and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "assets", "geometry", "pbr", "bsdf_256_256.bin")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def get_fg_lut(resolution: int = 256, device="cuda") -> Tensor:
+    """`_get_fg_lut(resolution, device)` (rfstudio/graphics/shaders.py:22-26), cached per device: [R,R,2].  Raises when
+    the asset cannot be found -- there is no silent substitute for the reference's table."""
+    key = (resolution, str(device))
+    hit = _default_luts.get(key)
+    if hit is None:
+        path = fg_lut_asset_path()
+        if path is None:
+            raise RuntimeError("geosplatting_b200: no DFG table. Pass fg_lut=, or set GSB_FG_LUT to the reference's "
+                               "rfstudio/assets/geometry/pbr/bsdf_256_256.bin (or make `rfstudio` importable)")
+        hit = _default_luts[key] = load_fg_lut(path, device, resolution)
+    return hit
 
 
 def synthetic_fg_lut(device, resolution: int = 256) -> Tensor:

@@ -19,8 +19,8 @@ from torch import Tensor
 from .fused import splat_view
 from .mgadapter import tone_mapping_naive
 from .rasterization import Projected, rasterization_begin, rasterization_end
-from .scenes import PinholeCamera
-from .shade import EnvStack, shade
+from .scenes import PinholeCamera, to_pinhole
+from .shade import EnvStack, get_fg_lut, shade
 
 
 @dataclass
@@ -46,11 +46,14 @@ class Splats:
         return Splats(self.means[mask], self.scales[mask], self.quats[mask], self.colors[mask], self.opacities[mask])
 
 
-def _single_camera(cameras: Union[PinholeCamera, Sequence[PinholeCamera]]) -> PinholeCamera:
+def _single_camera(cameras) -> PinholeCamera:
+    """`Cameras[1]` of the reference (rfstudio Cameras with shape (1,), gsplat.py:293 / geosplat.py:66), a PinholeCamera or
+    a one-element sequence of either."""
     if isinstance(cameras, PinholeCamera):
         return cameras
-    assert len(cameras) == 1  # gsplat.py:293 / geosplat.py:66
-    return cameras[0]
+    cams = to_pinhole(cameras)
+    assert len(cams) == 1  # gsplat.py:293 / geosplat.py:66
+    return cams[0]
 
 
 @dataclass
@@ -130,16 +133,21 @@ class RenderableAttrs:
     kd_jitter: Optional[Tensor] = None
     ks_jitter: Optional[Tensor] = None
 
-    def splat(self, gsplat: GSplatter, cameras, *, exposure: Tensor, envmap: EnvStack, fg_lut: Tensor,
-              min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-              culling: bool = False, fused: bool = True) -> Tensor:
-        """geosplat.py:53-132.  `envmap` is this library's EnvStack (splitsum.as_envstack(cubemap) or
-        EnvStack.from_splitsum(TextureSplitSum fields)); `fg_lut` is `_get_fg_lut(256, device)`.
+    def splat(self, gsplat: GSplatter, cameras, *, exposure: Tensor, envmap, min_roughness: float, max_metallic: float,
+              mode: str = "pbr", tone_type: str = "naive", culling: bool = False, fg_lut: Optional[Tensor] = None,
+              fused: bool = True) -> Tensor:
+        """geosplat.py:53-65, same keyword arguments.  `cameras`: the reference's `Cameras[1]` (any object with its tensor
+        fields) or a PinholeCamera; `envmap`: the reference's `TextureSplitSum` (base / mipmaps / num_mipmaps ...) or this
+        library's EnvStack (splitsum.as_envstack(cubemap): no quad-tree pack per step); `fg_lut`: defaults to
+        `_get_fg_lut(256, device)`, i.e. the reference's asset (shade.get_fg_lut).
 
         With culling=False and tone_type 'naive' / 'none' (what GeoSplatter.render_report uses) the whole view is
         one autograd node over the C-ABI kernels (fused.splat_view); `fused=False`, culling or 'aces' take the
         stage-by-stage operators below -- same kernels, same results, more host work."""
         camera = _single_camera(cameras)
+        envmap = EnvStack.coerce(envmap)
+        if fg_lut is None:
+            fg_lut = get_fg_lut(256, self.kd.device)
         if fused and not culling and tone_type in ("naive", "none") and exposure.numel() == 1:
             if gsplat.sh_degree != 0:
                 raise NotImplementedError("geosplatting_b200.GSplatter: sh_degree must be 0 (GeoSplatter, geosplat.py:794)")

@@ -17,19 +17,24 @@ import torch
 from torch import Tensor
 
 from ._lib import call, f32c, ptr, stream_ptr
+from ._lib import require_cuda as _require_cuda
 from .shade import EnvStack
+
+
+def _bounds_device(index) -> torch.device:
+    """Device of a bounds table from the `device.index` the reference passes (_wrap.py:151; None = current device)."""
+    return torch.device("cuda", torch.cuda.current_device() if index is None else index)
 
 
 def _spec_workspace(R: int, dev) -> Tensor:
     n = C.c_size_t(0)
     call("gsb_specular_workspace_bytes", dev, C.c_int32(R), C.byref(n))
-    return torch.empty(n.value, dtype=torch.uint8, device=dev)
+    return torch.empty(n.value + 256, dtype=torch.uint8, device=dev)     # the library aligns its carve to 256 B
 
 
 def _check_cubemap(t: Tensor, channels: int, name: str) -> None:
     # same checks as CHECK_TENSOR in torch_bindings.cpp:27-31
-    if not t.is_cuda:
-        raise RuntimeError(f"{name} must be a CUDA tensor")
+    _require_cuda(t, f"render_utils: {name}")
     if t.dim() != 4 or t.shape[0] != 6 or t.shape[1] != t.shape[2] or t.shape[3] != channels:
         raise RuntimeError(f"{name} must have shape [6,R,R,{channels}], got {tuple(t.shape)}")
 
@@ -58,11 +63,9 @@ class render_utils:
 
     @staticmethod
     def specular_bounds(resolution: int, costheta_cutoff: float, index: int) -> Tensor:
-        dev = torch.device("cuda", index)
+        dev = _bounds_device(index)
         out = torch.zeros(6, resolution, resolution, 24, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            call("gsb_specular_bounds", dev, C.c_int32(resolution), C.c_float(costheta_cutoff), ptr(out),
-                 stream_ptr(dev))
+        call("gsb_specular_bounds", dev, C.c_int32(resolution), C.c_float(costheta_cutoff), ptr(out), stream_ptr(dev))
         return out
 
     @staticmethod
@@ -72,9 +75,9 @@ class render_utils:
         c, b = f32c(cubemap), f32c(bounds)
         R = c.shape[1]
         out = torch.empty(6, R, R, 4, dtype=torch.float32, device=c.device)
+        ws = _spec_workspace(R, c.device)
         call("gsb_specular_cubemap_fwd", c.device, C.c_int32(R), ptr(c), ptr(b), C.c_float(roughness),
-             C.c_float(costheta_cutoff), C.c_int32(0), ptr(out), ptr(_spec_workspace(R, c.device)),
-             stream_ptr(c.device))
+             C.c_float(costheta_cutoff), C.c_int32(0), ptr(out), ptr(ws), stream_ptr(c.device))
         return out
 
     @staticmethod
@@ -86,83 +89,82 @@ class render_utils:
         b, g = f32c(bounds), f32c(grad)
         R = g.shape[1]
         out = torch.empty(6, R, R, 3, dtype=torch.float32, device=g.device)
+        ws = _spec_workspace(R, g.device)
         call("gsb_specular_cubemap_bwd", g.device, C.c_int32(R), ptr(b), ptr(g), None, C.c_float(roughness),
-             C.c_float(costheta_cutoff), ptr(out), ptr(_spec_workspace(R, g.device)), stream_ptr(g.device))
+             C.c_float(costheta_cutoff), ptr(out), ptr(ws), stream_ptr(g.device))
         return out
 
 
-# ---- _wrap.py:82-157 ------------------------------------------------------------------------------------
-class _diffuse_cubemap_func(torch.autograd.Function):
+# ---- the two prefilter passes as differentiable operators (reference API: _splitsum/_wrap.py:95-103, :139-157) -------
+class _PrefilterPass(torch.autograd.Function):
+    """One node for either plugin pass.  `lobe` is None for the cosine (diffuse) pass, else (roughness, cos_cut, bounds);
+    the backward of both passes is a gather over the same footprint (csrc/prefilter.cu), which needs the cotangent only
+    (the passes are linear in the texels)."""
+
     @staticmethod
-    def forward(ctx, cubemap):
-        out = render_utils.diffuse_cubemap_fwd(cubemap)
+    def forward(ctx, cubemap: Tensor, lobe):
+        ctx.lobe = lobe
         ctx.save_for_backward(cubemap)
-        return out
+        if lobe is None:
+            return render_utils.diffuse_cubemap_fwd(cubemap)
+        roughness, cos_cut, bounds = lobe
+        return render_utils.specular_cubemap_fwd(cubemap, bounds, roughness, cos_cut)
 
     @staticmethod
-    def backward(ctx, dout):
-        cubemap, = ctx.saved_tensors
-        return render_utils.diffuse_cubemap_bwd(cubemap, dout.contiguous())
+    def backward(ctx, v_out: Tensor):
+        (cubemap,) = ctx.saved_tensors
+        v_out = v_out.contiguous()
+        if ctx.lobe is None:
+            return render_utils.diffuse_cubemap_bwd(cubemap, v_out), None
+        roughness, cos_cut, bounds = ctx.lobe
+        return render_utils.specular_cubemap_bwd(cubemap, bounds, v_out, roughness, cos_cut), None
 
 
-def diffuse_cubemap(cubemap: Tensor) -> Tensor:
-    assert cubemap.is_cuda
-    out = _diffuse_cubemap_func.apply(cubemap)
-    if torch.is_anomaly_enabled():
-        assert torch.all(torch.isfinite(out)), "Output of diffuse_cubemap contains inf or NaN"
+def _finite_under_anomaly_mode(out: Tensor, what: str) -> Tensor:
+    if torch.is_anomaly_enabled() and not bool(torch.isfinite(out).all()):
+        raise AssertionError(f"Output of {what} contains inf or NaN")
     return out
 
 
-class _specular_cubemap(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, cubemap, roughness, costheta_cutoff, bounds):
-        out = render_utils.specular_cubemap_fwd(cubemap, bounds, roughness, costheta_cutoff)
-        ctx.save_for_backward(cubemap, bounds)
-        ctx.roughness, ctx.theta_cutoff = roughness, costheta_cutoff
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        cubemap, bounds = ctx.saved_tensors
-        grad = render_utils.specular_cubemap_bwd(cubemap, bounds, dout.contiguous(), ctx.roughness, ctx.theta_cutoff)
-        return grad, None, None, None
+def diffuse_cubemap(cubemap: Tensor) -> Tensor:
+    """Cosine-weighted irradiance of a cube map [6,R,R,3] (same call as the reference's `diffuse_cubemap`)."""
+    _check_cubemap(cubemap, 3, "cubemap")
+    return _finite_under_anomaly_mode(_PrefilterPass.apply(cubemap, None), "diffuse_cubemap")
 
 
 _ndf_bounds_cache: Dict[Tuple[int, float, float, int], Tuple[float, Tensor]] = {}
 
 
-def ndf_cutoff_costheta(roughness: float, cutoff: float) -> float:
-    """_wrap.py:120-132: cos(theta) at which the cumulative GGX NDF (1e6 uniform angles) reaches `cutoff`."""
-    def ndf_ggx(alpha_sqr, costheta):
-        costheta = np.clip(costheta, 0.0, 1.0)
-        d = (costheta * alpha_sqr - costheta) * costheta + 1.0
-        return alpha_sqr / (d * d * np.pi)
+def ndf_cutoff_costheta(roughness: float, cutoff: float, n_samples: int = 1000000) -> float:
+    """cos(theta) below which the GGX lobe of `roughness` holds the fraction `cutoff` of its mass, on the reference's
+    grid of 1e6 uniform angles in [0, pi/2] (_wrap.py:120-132).  The table of bounds and the kernels' cone test depend
+    on this number bit for bit, so the density keeps the reference's float64 expression order."""
+    cos_t = np.cos(np.linspace(0.0, 0.5 * np.pi, n_samples))
+    a2 = roughness ** 4
+    c = np.clip(cos_t, 0.0, 1.0)
+    d = (c * a2 - c) * c + 1.0
+    mass = np.cumsum(a2 / (d * d * np.pi))
+    first = int(np.searchsorted(mass, mass[-1] * cutoff, side="left"))      # first index with mass >= cutoff * total
+    return float(cos_t[first])
 
-    n_samples = 1000000
-    costheta = np.cos(np.linspace(0, np.pi / 2.0, n_samples))
-    D = np.cumsum(ndf_ggx(roughness ** 4, costheta))
-    idx = np.argmax(D >= D[..., -1] * cutoff)
-    return float(costheta[idx])
 
-
-def ndf_bounds(res: int, roughness: float, cutoff: float, index: int) -> Tuple[float, Tensor]:
-    """(cos(theta_cutoff), bounds[6,res,res,24]); cached per (res, roughness, cutoff, device) like _wrap.py:133-154."""
+def ndf_bounds(res: int, roughness: float, cutoff: float, index) -> Tuple[float, Tensor]:
+    """(cos(theta_cutoff), bounds[6,res,res,24]), computed once per (res, roughness, cutoff, device)."""
     key = (res, roughness, cutoff, index)
-    if key not in _ndf_bounds_cache:
-        ct = ndf_cutoff_costheta(roughness, cutoff)
-        _ndf_bounds_cache[key] = (ct, render_utils.specular_bounds(res, ct, index))
-    return _ndf_bounds_cache[key]
+    hit = _ndf_bounds_cache.get(key)
+    if hit is None:
+        cos_cut = ndf_cutoff_costheta(roughness, cutoff)
+        hit = _ndf_bounds_cache[key] = (cos_cut, render_utils.specular_bounds(res, cos_cut, index))
+    return hit
 
 
 def specular_cubemap(cubemap: Tensor, roughness: float, cutoff: float = 0.99) -> Tensor:
-    assert cubemap.shape[0] == 6 and cubemap.shape[1] == cubemap.shape[2], \
-        "Bad shape for cubemap tensor: %s" % str(cubemap.shape)
-    assert cubemap.is_cuda
-    ct, bounds = ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device.index or 0)
-    out = _specular_cubemap.apply(cubemap, roughness, ct, bounds)
-    if torch.is_anomaly_enabled():
-        assert torch.all(torch.isfinite(out)), "Output of specular_cubemap contains inf or NaN"
-    return out[..., 0:3] / out[..., 3:]
+    """GGX-prefiltered cube map [6,R,R,3] for one roughness (same call as the reference's `specular_cubemap`): weighted
+    sum / weight sum of the plugin pass."""
+    _check_cubemap(cubemap, 3, "cubemap")
+    cos_cut, bounds = ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device.index)
+    acc = _finite_under_anomaly_mode(_PrefilterPass.apply(cubemap, (roughness, cos_cut, bounds)), "specular_cubemap")
+    return acc[..., :3] / acc[..., 3:]
 
 
 # ---- _texture.py:199-226 --------------------------------------------------------------------------------
@@ -255,7 +257,7 @@ class _PrefilterStack(torch.autograd.Function):
         cts = []
         for l in range(L):
             r = R0 >> l
-            ct, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
+            ct, bounds = ndf_bounds(r, rough[l], cutoff, dev.index)
             cts.append(ct)
             call("gsb_specular_cubemap_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(bounds), C.c_float(rough[l]),
                  C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), ptr(ws), st)
@@ -283,7 +285,7 @@ class _PrefilterStack(torch.autograd.Function):
         g_levels = []
         for l in range(L):
             r = R0 >> l
-            _, bounds = ndf_bounds(r, rough[l], cutoff, dev.index or 0)
+            _, bounds = ndf_bounds(r, rough[l], cutoff, dev.index)
             g = torch.empty(6, r, r, 3, dtype=torch.float32, device=dev)
             call("gsb_specular_cubemap_bwd", dev, C.c_int32(r), ptr(bounds), C.c_void_p(v.data_ptr() + offs[l] * 16),
                  C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), ptr(ws), st)
@@ -304,8 +306,7 @@ def as_envstack(cubemap: Tensor, *, cutoff: float = 0.99, min_resolution: int = 
                 max_roughness: float = 0.5) -> EnvStack:
     """Same result as as_splitsum, produced directly in the native env-stack layout (no quad-tree pack, no
     per-view unpack): the fast path GeoSplatter.get_envmap -> RenderableAttrs.splat uses."""
-    if not cubemap.is_cuda:
-        raise RuntimeError("geosplatting_b200.as_envstack needs CUDA tensors; there is no CPU path")
+    _require_cuda(cubemap, "as_envstack")
     data = _PrefilterStack.apply(cubemap, cutoff, min_resolution, min_roughness, max_roughness)
     R0 = cubemap.shape[1]
     L = 1
