@@ -160,6 +160,28 @@ def main():
          packed=packed.detach(), num_mipmaps=5,
          cam_pos=torch.from_numpy(cam.c2w[:, 3].copy()), **shade_out)
 
+    # ---- B2. the same shade block on the REFERENCE'S OWN FG LUT (shaders.py:22-26 loads the asset): pbr mode, its own
+    #          generator so that the fixtures above and below do not move
+    g2 = torch.Generator().manual_seed(11)
+    ns["_get_fg_lut"] = RS._get_fg_lut
+    N2 = 2000
+    sg2 = scenes.surface_gaussians(N2, seed=6)
+    leaves2 = [sg2["means"].clone().requires_grad_(True),
+               torch.nn.functional.normalize(sg2["normals"] + 0.3 * torch.randn(N2, 3, generator=g2), dim=-1).requires_grad_(True),
+               torch.rand(N2, 3, generator=g2).requires_grad_(True), torch.rand(N2, 2, generator=g2).requires_grad_(True)]
+    attrs2 = ns["RenderableAttrs"](kd=leaves2[2], ks=leaves2[3], normals=leaves2[1], occ=None, kd_jitter=None,
+                                   ks_jitter=None)
+    fake2 = _FakeGSplatter(leaves2[0])
+    gauss2 = fake2.gaussians
+    attrs2.splat(fake2, cams, exposure=torch.ones(1), envmap=envmap, min_roughness=0.1, max_metallic=1.0, mode="pbr",
+                 tone_type="none")
+    cot2 = torch.randn(N2, 3, generator=g2)
+    gr2 = torch.autograd.grad((gauss2.colors * cot2).sum(), leaves2)
+    save("ref_shade_real_lut.npz", means=leaves2[0], normals=leaves2[1], kd=leaves2[2], ks=leaves2[3], colors=gauss2.colors,
+         cot=cot2, v_means=gr2[0], v_normals=gr2[1], v_kd=gr2[2], v_ks=gr2[3], base=base, packed=packed.detach(),
+         num_mipmaps=5, cam_pos=torch.from_numpy(cam.c2w[:, 3].copy()))
+    ns["_get_fg_lut"] = lambda resolution, device: lut.view(1, 256, 256, 2)
+
     # ---- C. tone mapping (geosplat.py:474-476)
     rgba = (torch.rand(32, 32, 4, generator=g) * 1.6).requires_grad_(True)
     exposure = torch.tensor([1.3], requires_grad=True)
@@ -210,6 +232,9 @@ def main():
     full = np.frombuffer(raw, dtype=np.float32).reshape(256, 256, 2)
     save("ref_fg_lut_sub.npz", sha256=hashlib.sha256(raw).hexdigest(), sub=full[::8, ::8].copy(),
          corners=np.stack([full[0, 0], full[0, 255], full[255, 0], full[255, 255]]))
+    # the whole table (a published split-sum DFG table, 512 KB of data, no code): the GPU box has no reference tree,
+    # and the shade kernels must be exercised on the reference's bytes, not only on a synthetic table
+    save("ref_fg_lut.npz", lut=full, sha256=hashlib.sha256(raw).hexdigest())
 
     # ---- H. HashEncoding (torch backend) + MLP: the fields that produce kd / ks / z (SURVEY section 8f rank 1;
     #         rfstudio/model/components/encoding.py:124-241, rfstudio/nn/mlp.py:125-145, configs geosplat.py:485-518).

@@ -235,3 +235,28 @@ def test_flexicubes_oracle_rough_sdf_with_inverted_cases():
     v_sdf, v_w = torch.autograd.grad((mv * torch.from_numpy(g["cot_vertices"])).sum() + l_dev.mean(), [sdf, weights])
     assert np.abs(v_sdf.numpy() - g["v_sdf"]).max() <= 1e-4 * np.abs(g["v_sdf"]).max()
     assert np.abs(v_w.numpy() - g["v_weights"]).max() <= 1e-4 * np.abs(g["v_weights"]).max()
+
+
+def test_fg_lut_asset_loader_reads_the_reference_bytes(tmp_path):
+    """`shade.load_fg_lut` on the reference's asset = the committed copy of the table = the
+    sha256 / subsample / corner values recorded from /root/reference (ref_fg_lut_sub.npz)."""
+    import hashlib
+    import os
+
+    from geosplatting_b200.shade import load_fg_lut
+    full, sub = load("ref_fg_lut.npz"), load("ref_fg_lut_sub.npz")
+    lut = full["lut"]
+    assert lut.shape == (256, 256, 2) and lut.dtype == np.float32
+    assert hashlib.sha256(np.ascontiguousarray(lut).tobytes()).hexdigest() == str(sub["sha256"])
+    assert np.array_equal(lut[::8, ::8], sub["sub"])
+    assert np.array_equal(np.stack([lut[0, 0], lut[0, 255], lut[255, 0], lut[255, 255]]), sub["corners"])
+    assert abs(lut[0, 0, 0] - 0.00973) < 1e-4 and abs(lut[0, 0, 1] - 0.99025) < 1e-4      # SURVEY 8c
+    p = tmp_path / "lut.bin"
+    p.write_bytes(np.ascontiguousarray(lut).tobytes())
+    assert np.array_equal(load_fg_lut(str(p), "cpu").numpy(), lut)
+    (tmp_path / "short.bin").write_bytes(b"\0" * 100)
+    with pytest.raises(ValueError):
+        load_fg_lut(str(tmp_path / "short.bin"), "cpu")
+    asset = "/root/reference/rfstudio/assets/geometry/pbr/bsdf_256_256.bin"
+    if os.path.exists(asset):                     # this container only: the GPU box has no reference tree
+        assert np.array_equal(load_fg_lut(asset, "cpu").numpy(), lut)

@@ -54,7 +54,10 @@ def _check(g, cam, mode, check_grads=True, seed=1, grad_rel_l2=2e-4, grad_linf=1
     # --- floating point
     assert linf(info["conics"].detach().cpu().numpy(), o_info["conics"]) <= 1e-6 * max(1.0, np.abs(o_info["conics"]).max())
     ok = ~frag
-    assert ok.mean() > 0.98, f"too many fragile pixels: {1 - ok.mean():.4f}"
+    # fewer than 0.1 % of the pixels have a discrete decision within 2e-5 of flipping
+    print(f"[parity] {mode} {W}x{H}: fragile pixels {int(frag.sum())} of {frag.size} ({frag.mean():.5%}), "
+          f"L-inf on the others {np.abs(render - o_render)[ok].max():.2e}")
+    assert ok.mean() > 0.999, f"too many fragile pixels: {1 - ok.mean():.5f}"
     assert np.abs(render - o_render)[ok].max() <= 1e-4
     assert np.abs(alpha - o_alpha)[ok].max() <= 1e-4
     assert np.abs(render - o_render)[frag].max(initial=0) <= 1.0  # a flipped decision moves a pixel by < 1 colour unit
@@ -142,7 +145,7 @@ def test_background_and_depth_modes():
     od, oa, _ = R.composite_fwd(o_info["means2d"], o_info["conics"], o_info["depths"][:, None], o_info["opacities"],
                                 o_info["isect_offsets"][0], o_info["flatten_ids"], 96, 96)
     ref = od[..., 0] / np.maximum(oa, 1e-10)
-    assert np.abs(ed[0, ..., 0].detach().cpu().numpy() - ref)[ok].max() <= 1e-3
+    assert np.abs(ed[0, ..., 0].detach().cpu().numpy() - ref)[ok].max() <= 1e-4     # north_star's 1e-4, depths ~2
 
 
 def test_idempotent_and_deterministic_forward():

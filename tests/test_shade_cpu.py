@@ -33,6 +33,10 @@ def test_shade_kernel_source_on_host_reference_fixture(host_kernels, mode):
     G.test_shade_against_reference_fixture(mode)
 
 
+def test_shade_on_the_reference_fg_lut_on_host(host_kernels, tmp_path):
+    G.test_shade_on_the_reference_fg_lut_against_reference_fixture(tmp_path)
+
+
 def test_splitsum_sample_on_host_reference_fixture(host_kernels):
     G.test_splitsum_sample_against_reference_fixture()
 

@@ -50,6 +50,32 @@ def test_shade_against_reference_fixture(mode):
         _close(grads[5].reshape(-1), dense, 2e-4, "packed")
 
 
+def test_shade_on_the_reference_fg_lut_against_reference_fixture(tmp_path):
+    """the reference's own DFG table (rfstudio/assets/geometry/pbr/bsdf_256_256.bin, loaded by
+    shaders.py:22-26) reaches the shade kernel through shade.load_fg_lut, and the result is the one the reference's own
+    RenderableAttrs.splat code computed with `_get_fg_lut` (scripts/make_golden.py section B2)."""
+    import hashlib
+    from geosplatting_b200.shade import load_fg_lut
+    lut_fix = load("ref_fg_lut.npz")
+    raw = np.ascontiguousarray(lut_fix["lut"]).tobytes()
+    assert hashlib.sha256(raw).hexdigest() == str(lut_fix["sha256"]) == str(load("ref_fg_lut_sub.npz")["sha256"])
+    path = tmp_path / "bsdf_256_256.bin"
+    path.write_bytes(raw)
+    lut = load_fg_lut(str(path), DEV)
+    assert lut.shape == (256, 256, 2) and np.array_equal(lut.cpu().numpy(), lut_fix["lut"])
+    g = load("ref_shade_real_lut.npz")
+    t = lambda k: torch.tensor(g[k], device=DEV, requires_grad=True)   # noqa: E731
+    means, normals, kd, ks = t("means"), t("normals"), t("kd"), t("ks")
+    env = EnvStack.from_splitsum(torch.tensor(g["base"], device=DEV), torch.tensor(g["packed"], device=DEV),
+                                 int(g["num_mipmaps"]))
+    colors = shade(means, normals, kd, ks, g["cam_pos"].tolist(), env, lut, min_roughness=0.1, max_metallic=1.0,
+                   mode="pbr")
+    _close(colors, g["colors"], 1e-5, "colors")
+    grads = torch.autograd.grad((colors * torch.tensor(g["cot"], device=DEV)).sum(), [means, normals, kd, ks])
+    for nm, gr in zip(("means", "normals", "kd", "ks"), grads):
+        _close(gr, g[f"v_{nm}"], 2e-4, nm)
+
+
 def test_splitsum_sample_against_reference_fixture():
     g = load("ref_splitsum.npz")
     env = EnvStack.from_splitsum(torch.tensor(g["base"], device=DEV), torch.tensor(g["merged"], device=DEV), 3)
