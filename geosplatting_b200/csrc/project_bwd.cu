@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     float4 q4 = reinterpret_cast<const float4 *>(quats)[i];
     float q[4] = {q4.x, q4.y, q4.z, q4.w};
     float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
-    if (radii[i] > 0 && gsb_project_one(m, q, s, cam, o)) {
+    if (radii[i] > 0 && gsb_project_one<false>(m, q, s, cam, o)) {   // the forward's cull verdict is final
         const float fx = cam.fx, fy = cam.fy;
         float a = o.conic[0], b = o.conic[1], c = o.conic[2];
         float va = v_conics[3 * i], vb = 0.5f * v_conics[3 * i + 1], vc = v_conics[3 * i + 2];

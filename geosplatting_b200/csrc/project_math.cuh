@@ -35,6 +35,10 @@ __device__ __forceinline__ void gsb_quat_to_rot(const float *q, float *R, float 
 }
 
 // Returns false when the Gaussian is culled.  Operation order is part of the parity contract.
+// DECIDE = false (the backward): the forward's verdict (radii > 0) is final -- the recomputation runs in a translation
+// unit compiled WITH fma contraction, so a borderline near-plane / radius-clip / screen-edge predicate could disagree
+// with the forward's and silently drop a gradient; only the division guard (det > 0) is kept.
+template <bool DECIDE = true>
 __device__ __forceinline__ bool gsb_project_one(const float *mean, const float *quat, const float *scale,
                                                 const CamK &cam, ProjOut &o) {
     const float *Rcw = cam.r;
@@ -42,7 +46,7 @@ __device__ __forceinline__ bool gsb_project_one(const float *mean, const float *
     for (int i = 0; i < 3; ++i)
         o.pc[i] = ((Rcw[i * 3 + 0] * mean[0] + Rcw[i * 3 + 1] * mean[1]) + Rcw[i * 3 + 2] * mean[2]) + cam.t[i];
     float x = o.pc[0], y = o.pc[1], z = o.pc[2];
-    if (z < cam.near_plane || z > cam.far_plane) return false;
+    if (DECIDE && (z < cam.near_plane || z > cam.far_plane)) return false;
 
     float inv_norm;
     gsb_quat_to_rot(quat, o.R, inv_norm);
@@ -106,9 +110,9 @@ __device__ __forceinline__ bool gsb_project_one(const float *mean, const float *
     float b = 0.5f * (c00 + c11);
     float v1 = b + sqrtf(fmaxf(GSB_RADIUS_DET_FLOOR, b * b - det));
     float rad = ceilf(3.0f * sqrtf(v1));
-    if (rad <= cam.radius_clip) return false;
-    if (o.mean2d[0] + rad <= 0.0f || o.mean2d[0] - rad >= Wf || o.mean2d[1] + rad <= 0.0f ||
-        o.mean2d[1] - rad >= Hf)
+    if (DECIDE && rad <= cam.radius_clip) return false;
+    if (DECIDE && (o.mean2d[0] + rad <= 0.0f || o.mean2d[0] - rad >= Wf || o.mean2d[1] + rad <= 0.0f ||
+        o.mean2d[1] - rad >= Hf))
         return false;
     o.radius = rad;
     return true;

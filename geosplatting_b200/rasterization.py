@@ -297,6 +297,21 @@ class _LazyInfo(dict):
     def keys(self):
         return list(dict.keys(self)) + [k for k in self._lazy if not dict.__contains__(self, k)]
 
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
 
 def _pad_channels(colors: Tensor) -> Tuple[Tensor, int]:
     D = colors.shape[-1]
@@ -371,6 +386,8 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
         bg = None
         if backgrounds is not None:
             bg = backgrounds[c]
+            if render_mode in ("D", "ED"):
+                bg = bg.new_zeros(1)            # gsplat 1.4.0: depth-only modes composite over a zero background
             if render_mode in ("RGB+D", "RGB+ED"):
                 bg = torch.cat((bg, bg.new_zeros(1)))
         feats_p, D = _pad_channels(feats)
@@ -407,6 +424,25 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
     def gather(idx):
         return lambda: torch.cat([per_cam[c][idx][g] for c, g in enumerate(packed()[2])])
 
+    def means2d_packed():
+        """gsplat's densification idiom reads `info['means2d'].grad` after `retain_grad()` (rfstudio/model/gsplat.py:
+        175-181, :264-270).  The packed tensor is gathered lazily, off the path to the image, so the screen-space gradient
+        is delivered by hooks on the projected means: after backward, `.grad` of the returned tensor holds it."""
+        gids = packed()[2]
+        out = torch.cat([per_cam[c][0].detach()[g] for c, g in enumerate(gids)])
+        if any(pc[0].requires_grad for pc in per_cam):
+            out.requires_grad_(True)
+            base = 0
+            for c, g in enumerate(gids):
+                def deliver(grad, g=g, lo=base, hi=base + g.shape[0]):
+                    if out.grad is None:
+                        out.grad = torch.zeros_like(out)
+                    out.grad[lo:hi] += grad[g]
+                if per_cam[c][0].requires_grad:
+                    per_cam[c][0].register_hook(deliver)
+                base += g.shape[0]
+        return out
+
     def flat_packed():
         out, base = [], 0
         for c, g in enumerate(packed()[2]):
@@ -433,7 +469,7 @@ def rasterization_end(st: Projected, opacities: Tensor, colors: Tensor, *, backg
     lazy = dict(
         camera_ids=lambda: packed()[0],
         gaussian_ids=lambda: packed()[1],
-        radii=gather(4), means2d=gather(0), depths=gather(1), conics=gather(2),
+        radii=gather(4), means2d=means2d_packed, depths=gather(1), conics=gather(2),
         opacities=gather(6), tiles_per_gauss=gather(5),
         compensations=(gather(3) if aa else (lambda: None)),
         isect_ids=isect_ids_all, flatten_ids=flat_packed, isect_offsets=offsets_all,

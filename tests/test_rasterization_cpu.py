@@ -77,3 +77,8 @@ def test_wide_channel_features_through_the_public_operator(host_raster, D):
 
 def test_forward_is_deterministic_through_the_public_operator(host_raster):
     G.test_idempotent_and_deterministic_forward()
+
+
+def test_info_idioms_and_depth_backgrounds_through_the_public_operator(host_raster):
+    G.test_info_means2d_retain_grad_idiom_and_dict_protocol()
+    G.test_depth_modes_ignore_the_colour_background()
