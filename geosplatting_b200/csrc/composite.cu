@@ -1,17 +1,21 @@
 // Alpha compositing forward / backward.
 //
-// Work decomposition (B200): the unit of work is one WARP owning an 8x4 pixel sub-rectangle of a 16x16 tile
-// (8 units per tile, ~20k units for 800x800).  Three kernels:
-//   pack_records    : per Gaussian, one 48-byte record {x, y, hx, hy | conic a,b,c, opacity | r, g, b, -} where
-//                     (hx, hy) is the axis-aligned half extent of the region in which alpha >= 1/255;
+// Work decomposition (B200): the unit of work is one WARP owning a 4x4 pixel sub-rectangle of a 16x16 tile (16 units per
+// tile, ~40k units for 800x800), and the warp evaluates TWO list entries per step: lanes 0-15 hold the 16 pixels for
+// the even entry of a pair, lanes 16-31 the same 16 pixels for the odd entry.  GeoSplatting's Gaussians are ~5 px wide:
+// with 8x4 units (round 1) 87 % of the (entry, pixel) evaluations failed the alpha test; 4x4 units evaluate 1.5x fewer
+// pairs, and pairing the entries keeps all 32 lanes busy.  Three kernels:
+//   pack_records    : per Gaussian, one 48-byte record {x, y, hx, hy | qa, qb, qc, log2(opacity) | r, g, b, opacity}
+//                     where (hx, hy) is the axis-aligned half extent of the region in which alpha >= 1/255 and
+//                     (qa, qb, qc) = -log2(e) * (a/2, b, c/2) of the conic, so that alpha = 2^(qa dx^2 + qb dx dy +
+//                     qc dy^2 + log2(opacity)) costs 5 FMA + one ex2 per pixel;
 //   build_sublists  : per (tile, sub-rectangle), the tile's depth-sorted list filtered to the records whose
 //                     extent overlaps the sub-rectangle (order preserved, ballot + popc compaction);
 //   composite fwd/bwd: each warp walks ITS sub-list only, 32 records at a time staged in a private shared-memory
 //                     slab with register prefetch of the next 32 -- no block-level barrier anywhere, per-warp
-//                     early termination, and the hardware block scheduler balances ~20k small units.
-// GeoSplatting's Gaussians are a few pixels wide, so a sub-list holds ~1/3 of its tile's list.  Filtering never
-// changes results: a filtered pair is exactly one the reference kernel would `continue` on (alpha < 1/255 at
-// every pixel centre of the sub-rectangle), and `last_ids` still indexes the 16x16 tile list.
+//                     early termination, and the hardware block scheduler balances ~40k small units.
+// Filtering never changes results: a filtered pair is exactly one the reference kernel would `continue` on (alpha <
+// 1/255 at every pixel centre of the sub-rectangle), and `last_ids` still indexes the 16x16 tile list.
 // Backward: same units and sub-lists; pixel-parallel recurrence and Gaussian-parallel gradient accumulation are
 // separated by a transpose through shared memory (see composite_bwd_kernel), one atomic per value per (Gaussian, warp).
 //
@@ -20,13 +24,15 @@
 #include "gsb_common.cuh"
 
 #define LOG2E 1.4426950408889634f
+#define LOG2_ALPHA_MIN (-7.994353436858858f)   // log2(1/255)
 
 namespace {
 
-constexpr int SUB_W = 8, SUB_H = 4;                       // pixel footprint of one warp
-constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 8 sub-rectangles per tile
+constexpr int SUB_W = 4, SUB_H = 4;                            // pixel footprint of one warp
+constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 16 sub-rectangles per tile
+constexpr int PIX = SUB_W * SUB_H;                             // 16 pixels, held twice per warp
 #ifndef GSB_WPB
-#define GSB_WPB 2
+#define GSB_WPB 4
 #endif
 #ifndef GSB_FG
 #define GSB_FG 8
@@ -35,15 +41,17 @@ constexpr int SUBS = (GSB_TILE / SUB_W) * (GSB_TILE / SUB_H);  // 8 sub-rectangl
 #define GSB_BG 8
 #endif
 #ifndef GSB_WPB_B
-#define GSB_WPB_B 2
+#define GSB_WPB_B 4
 #endif
 constexpr int WPB = GSB_WPB;                              // warps (units) per CTA in the composite kernels
-constexpr int FG = GSB_FG;                                // entries evaluated together in the forward
+constexpr int FS = GSB_FG / 2;                            // pair-steps evaluated together in the forward
+static_assert(GSB_FG >= 2 && GSB_FG % 2 == 0 && 32 % GSB_FG == 0, "GSB_FG: even divisor of 32");
+static_assert(GSB_BG >= 2 && GSB_BG % 2 == 0 && 32 % GSB_BG == 0, "GSB_BG: even divisor of 32");
 
 struct Rec {
     float4 k;  // x, y, hx, hy
-    float4 q;  // conic a, b, c, opacity
-    float4 c;  // r, g, b, unused
+    float4 q;  // -log2e * (a/2, b, c/2), log2(opacity)
+    float4 c;  // r, g, b, opacity
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -52,6 +60,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+#ifdef GSB_NO_INLINE_PTX
+    return 1.0f / x;
+#else
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 #endif
 }
@@ -67,6 +85,11 @@ __device__ __forceinline__ float2 alpha_extent(float ca, float cb, float cc, flo
     if (!(det > 0.f)) return make_float2(1e30f, 1e30f);  // degenerate conic: never cull
     float hx = sqrtf(tau2 * cc / det), hy = sqrtf(tau2 * ca / det);
     return make_float2(hx * 1.0005f + 0.02f, hy * 1.0005f + 0.02f);
+}
+
+// log2 of alpha before the 0.999 clamp at offset (dx, dy) from the centre; 5 FMA-class instructions
+__device__ __forceinline__ float log2_alpha(const float4 q, float dx, float dy) {
+    return fmaf(q.z * dy, dy, fmaf(fmaf(q.y, dy, q.x * dx), dx, q.w));
 }
 
 template <int CH>
@@ -85,33 +108,36 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
     float2 ext = alpha_extent(ca, cb, cc, op);
     Rec r;
     r.k = make_float4(xy.x, xy.y, ext.x, ext.y);
-    r.q = make_float4(ca, cb, cc, op);
+    // op <= 0 (or NaN): log2 -> -inf / NaN, every comparison in the kernels fails, the record contributes nowhere
+    r.q = make_float4(-0.5f * LOG2E * ca, -LOG2E * cb, -0.5f * LOG2E * cc, log2f(op));
     float c3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < (CH < 3 ? CH : 3); ++k) c3[k] = colors[(size_t)g * CH + k];
-    r.c = make_float4(c3[0], c3[1], c3[2], 0.f);
+    r.c = make_float4(c3[0], c3[1], c3[2], op);
     rec[g] = r;
 }
 
 // One CTA (8 warps) per tile walks the tile's depth-sorted list ONCE, 256 entries per step, and appends every entry
 // to the sub-lists of the sub-rectangles its extent overlaps, order preserved (per sub-rectangle: ballot + popc
-// inside a warp, an 8 x 8 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
+// inside a warp, an 8 x 16 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
 // (list entry -> record is a dependent gather).  Sub-list w of tile t lives at entries[SUBS * start_t + w * len_t ...]
 // (worst-case capacity, no global prefix sum needed).
 constexpr int BUILD_THREADS = 256;
 
-__global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_w, int n_tiles, int M,
+__global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_w, int n_tiles, int M_host,
+                                                                        const int64_t *__restrict__ m_dev,
                                                                         const int32_t *__restrict__ offsets,
                                                                         const int32_t *__restrict__ flatten_ids,
                                                                         const Rec *__restrict__ rec,
                                                                         int2 *__restrict__ entries,
                                                                         int32_t *__restrict__ counts) {
-    static_assert(SUBS == 8 && BUILD_THREADS == 256, "build_sublists: 8 warps x 8 sub-rectangles");
+    static_assert(SUBS == 16 && BUILD_THREADS == 256, "build_sublists: 8 warps x 16 sub-rectangles");
     __shared__ int s_cnt[2][8][SUBS];   // [parity][warp][sub-rectangle] hits of this step
     __shared__ int s_pre[2][8][SUBS];   // exclusive prefix over warps
     __shared__ int s_base[2][SUBS];     // sub-list length before this step
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = m_dev ? (int)*m_dev : M_host;
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int len = end - start;
@@ -120,6 +146,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
         return;
     }
     const int tx = tile % tile_w, ty = tile / tile_w;
+    // centre of sub-rectangle column / row 0; columns and rows are SUB_W / SUB_H apart
     const float x0 = (float)(tx * GSB_TILE) + 0.5f * SUB_W, y0 = (float)(ty * GSB_TILE) + 0.5f * SUB_H;
     const float rhx = 0.5f * (SUB_W - 1), rhy = 0.5f * (SUB_H - 1);
     int2 *const out = entries + (size_t)SUBS * start;
@@ -136,20 +163,25 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
         const int gid2 = (p2 < end) ? flatten_ids[p2] : -1;
         const float4 k1 = (gid1 >= 0) ? __ldg(&rec[gid1].k) : miss;
 
-        unsigned hits = 0u;          // bit w: this entry overlaps sub-rectangle w
+        // 4 column tests x 4 row tests -> 16-bit overlap mask (bit w = row * 4 + column)
+        unsigned colm = 0u, rowm = 0u;
+#pragma unroll
+        for (int c = 0; c < GSB_TILE / SUB_W; ++c)
+            if (fabsf(k0.x - (x0 + (float)(c * SUB_W))) <= k0.z + rhx) colm |= 1u << c;
+#pragma unroll
+        for (int r = 0; r < GSB_TILE / SUB_H; ++r)
+            if (fabsf(k0.y - (y0 + (float)(r * SUB_H))) <= k0.w + rhy) rowm |= 0xFu << (4 * r);
+        const unsigned hits = (colm * 0x1111u) & rowm;
         int my_pre[SUBS];            // hits of lower lanes of my warp
 #pragma unroll
         for (int w = 0; w < SUBS; ++w) {
-            const float rcx = x0 + (float)((w & 1) * SUB_W), rcy = y0 + (float)((w >> 1) * SUB_H);
-            const bool hit = (fabsf(k0.x - rcx) <= k0.z + rhx) && (fabsf(k0.y - rcy) <= k0.w + rhy);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const unsigned m = __ballot_sync(0xffffffffu, (hits >> w) & 1u);
             my_pre[w] = __popc(m & ((1u << lane) - 1u));
-            if (hit) hits |= 1u << w;
             if (lane == w) s_cnt[par][warp][w] = __popc(m);
         }
         __syncthreads();
         if (tid < 8 * SUBS) {
-            const int wp = tid >> 3, w = tid & 7;
+            const int wp = tid >> 4, w = tid & (SUBS - 1);
             int pre = 0, tot = 0;
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
@@ -173,14 +205,14 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
     if (tid < SUBS) counts[tile * SUBS + tid] = s_base[par][tid];
 }
 
-// Longest-processing-time-first order of the TILES (their 8 units stay adjacent in launch order so that they
+// Longest-processing-time-first order of the TILES (their 16 units stay adjacent in launch order so that they
 // share the tile's records in L1/L2): single-CTA counting sort on the mean per-unit work (4096 buckets of width 4,
 // heaviest first; order inside a bucket is irrelevant).  `n_units` here is the number of tiles.
 __device__ __forceinline__ int tile_work(const int32_t *__restrict__ counts, int tile) {
     int s = 0;
 #pragma unroll
     for (int k = 0; k < SUBS; ++k) s += counts[tile * SUBS + k];
-    return s >> 3;  // mean sub-list length of the tile's 8 units
+    return s / SUBS;  // mean sub-list length of the tile's units
 }
 
 __global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int32_t *__restrict__ counts,
@@ -231,27 +263,37 @@ struct Unit {
     float px, py;
 };
 
+// lane -> (entry parity h = lane >> 4, pixel p = lane & 15) of the 4x4 unit
 __device__ __forceinline__ Unit make_unit(int unit, int lane, int tile_w, int W, int H) {
     Unit u;
     u.tile = unit / SUBS;
     u.w = unit % SUBS;
+    const int p = lane & (PIX - 1);
     const int tx = u.tile % tile_w, ty = u.tile / tile_w;
-    u.j = tx * GSB_TILE + (u.w & 1) * SUB_W + (lane & 7);
-    u.i = ty * GSB_TILE + (u.w >> 1) * SUB_H + (lane >> 3);
+    u.j = tx * GSB_TILE + (u.w & 3) * SUB_W + (p & 3);
+    u.i = ty * GSB_TILE + (u.w >> 2) * SUB_H + (p >> 2);
     u.inside = (u.i < H && u.j < W);
     u.px = (float)u.j + 0.5f;
     u.py = (float)u.i + 0.5f;
     return u;
 }
 
+__device__ __forceinline__ Rec null_record() {
+    Rec r;
+    r.k = make_float4(0.f, 0.f, -1e30f, -1e30f);
+    r.q = make_float4(0.f, 0.f, 0.f, -1e30f);     // log2(alpha) = -1e30: fails the alpha test at every pixel
+    r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB)
 composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
-                     const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
-                     const int32_t *__restrict__ counts, const int32_t *__restrict__ order,
-                     int32_t *__restrict__ work, float *__restrict__ render, float *__restrict__ alphas,
-                     int32_t *__restrict__ last_ids) {
+                     const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
+                     const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
+                     const int32_t *__restrict__ order, int32_t *__restrict__ work, float *__restrict__ render,
+                     float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
     __shared__ Rec s_rec[WPB][32];
     __shared__ int2 s_ent[WPB][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -259,22 +301,24 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     if (slot >= n_units) return;
     const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);   // heaviest tiles are scheduled first (LPT)
     const Unit u = make_unit(unit, lane, tile_w, W, H);
+    const bool hi = lane >= PIX;       // this lane evaluates the ODD entry of every pair
     bool done = !u.inside;
 
+    const int M = m_dev ? (int)*m_dev : M_host;
     const int start = offsets[u.tile];
     const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
     const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
     const int n = counts[unit];
 
-    float T = 1.0f;
-    float acc[CH];
+    float T = 1.0f;       // transmittance in front of the current pair (identical in both half-warps)
+    float acc[CH];        // this half-warp's share of the colour sum
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-    int last_k = -1;   // sub-list index of the pixel's last contributor
+    int last_k = -1;      // sub-list index of the last contributor among this half-warp's entries
 
     // prefetch chunk 0
     int2 e = make_int2(0, 0);
-    Rec r;
+    Rec r = null_record();
     int processed = n;
     if (lane < n) { e = list[lane]; r = rec[e.y]; }
     for (int base = 0; base < n; base += 32) {
@@ -283,38 +327,76 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         s_rec[wib][lane] = r;
         __syncwarp();
         const int nb = base + 32;
-        if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }   // next chunk in flight during the loop
+        r = null_record();                                             // rows past the end of the list never contribute
+        if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }     // next chunk in flight during the loop
         const int cnt = min(32, n - base);
-        // Groups of FG entries.  The FG alpha evaluations are independent (ILP for a warp that runs alone: the longest
-        // sub-list of a view is this kernel's critical path); the transmittance chain is one multiply per entry.
-        // alpha == 0 stands for "does not contribute" and makes every update the identity, so the common case has no
-        // branch.  Only a group in which some pixel reaches the T <= 1e-4 stop replays the exact per-entry logic.
+        // Groups of FS pair-steps.  The alpha evaluations are independent (ILP for a warp that runs alone: the longest
+        // sub-list of a view is this kernel's critical path); alpha == 0 stands for "does not contribute" and makes
+        // every update the identity, so the common case has no branch.  The state is saved before a group; only a
+        // group in which some pixel reaches the T <= 1e-4 stop is rolled back and replayed with the exact per-entry
+        // logic (T only decreases, so the group's end value decides).
         bool all_done = false;
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += FG) {
-            float a[FG];
+        for (int t0 = 0; t0 < cnt; t0 += 2 * FS) {
+            float a[FS], ao[FS];
 #pragma unroll
-            for (int jj = 0; jj < FG; ++jj) {
-                const int t = min(t0 + jj, 31);
+            for (int s = 0; s < FS; ++s) {
+                const int t = t0 + 2 * s + (hi ? 1 : 0);
                 const float4 kk = s_rec[wib][t].k;
                 const float4 q = s_rec[wib][t].q;
-                const float dx = kk.x - u.px, dy = kk.y - u.py;
-                const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
-                const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * ex2_approx(-LOG2E * sigma));
-                a[jj] = (done || sigma < 0.f || alpha < GSB_ALPHA_MIN || t0 + jj >= cnt) ? 0.f : alpha;
+                const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
+                const float alpha = fminf(GSB_ALPHA_CLAMP, ex2_approx(l2a));
+                // sigma < 0 <=> log2(alpha) > log2(opacity); alpha < 1/255 <=> log2(alpha) < log2(1/255)
+                a[s] = (done || !(l2a <= q.w) || l2a < LOG2_ALPHA_MIN) ? 0.f : alpha;
             }
-            float Tend = T;
 #pragma unroll
-            for (int jj = 0; jj < FG; ++jj) Tend *= 1.0f - a[jj];
-            // T only decreases, so a pixel trips the stop inside this group iff the group's end value is below it
-            if (!__any_sync(0xffffffffu, Tend <= GSB_T_STOP)) {
+            for (int s = 0; s < FS; ++s) ao[s] = __shfl_xor_sync(0xffffffffu, a[s], PIX);
+            const float T_saved = T;
+            const int last_saved = last_k;
+            float acc_saved[CH];
 #pragma unroll
-                for (int jj = 0; jj < FG; ++jj) {
-                    const float alpha = a[jj];
-                    const int t = min(t0 + jj, 31);
-                    const float vis = alpha * T;
-                    T *= 1.0f - alpha;
-                    if (alpha > 0.f) {   // predicated: a non-contributing Gaussian's colour is never read into the sum
+            for (int k = 0; k < CH; ++k) acc_saved[k] = acc[k];
+#pragma unroll
+            for (int s = 0; s < FS; ++s) {
+                const int t = t0 + 2 * s + (hi ? 1 : 0);
+                const float a_even = hi ? ao[s] : a[s], a_odd = hi ? a[s] : ao[s];
+                const float T1 = T * (1.0f - a_even);          // behind the even entry
+                const float vis = a[s] * (hi ? T1 : T);
+                T = T1 * (1.0f - a_odd);
+                if (a[s] > 0.f) {   // predicated: a non-contributing Gaussian's colour is never read into the sum
+                    const float4 c = s_rec[wib][t].c;
+                    acc[0] += c.x * vis;
+                    if (CH > 1) acc[1] += c.y * vis;
+                    if (CH > 2) acc[2] += c.z * vis;
+                    if (CH > 3) {
+                        const int g = s_ent[wib][t].y;
+#pragma unroll
+                        for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+                    }
+                    last_k = base + t;
+                }
+            }
+            if (!__any_sync(0xffffffffu, T <= GSB_T_STOP)) continue;
+            // ---- roll back and replay this group entry by entry (both half-warps run the same recurrence)
+            T = T_saved;
+            last_k = last_saved;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) acc[k] = acc_saved[k];
+#pragma unroll
+            for (int s = 0; s < FS; ++s) {
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {                  // o = 0: the even entry of the pair, then the odd one
+                    const bool mine = (o == 1) == hi;
+                    const float alpha = mine ? a[s] : ao[s];
+                    if (done || alpha == 0.f) continue;
+                    const float next_T = T * (1.0f - alpha);
+                    if (next_T <= GSB_T_STOP) {   // this entry is excluded
+                        done = true;
+                        continue;
+                    }
+                    if (mine) {
+                        const int t = t0 + 2 * s + o;
+                        const float vis = alpha * T;
                         const float4 c = s_rec[wib][t].c;
                         acc[0] += c.x * vis;
                         if (CH > 1) acc[1] += c.y * vis;
@@ -326,40 +408,21 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                         }
                         last_k = base + t;
                     }
+                    T = next_T;
                 }
-                continue;
-            }
-#pragma unroll
-            for (int jj = 0; jj < FG; ++jj) {
-                const float alpha = a[jj];
-                if (done || alpha == 0.f) continue;
-                const int t = t0 + jj;
-                const float next_T = T * (1.0f - alpha);
-                if (next_T <= GSB_T_STOP) {   // this entry is excluded
-                    done = true;
-                    continue;
-                }
-                const float vis = alpha * T;
-                const float4 c = s_rec[wib][t].c;
-                acc[0] += c.x * vis;
-                if (CH > 1) acc[1] += c.y * vis;
-                if (CH > 2) acc[2] += c.z * vis;
-                if (CH > 3) {
-                    const int g = s_ent[wib][t].y;
-#pragma unroll
-                    for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
-                }
-                last_k = base + t;
-                T = next_T;
             }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
         if (all_done) { processed = min(n, base + 32); break; }
     }
-    int cur_idx = 0;
-    if (last_k >= 0) cur_idx = list[last_k].x;
+    // the two half-warps hold the even / odd entries' shares of the same 16 pixels
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], PIX);
+    last_k = max(last_k, __shfl_xor_sync(0xffffffffu, last_k, PIX));
     if (lane == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
-    if (u.inside) {
+    if (u.inside && !hi) {
+        int cur_idx = 0;
+        if (last_k >= 0) cur_idx = list[last_k].x;
         const size_t pix = (size_t)u.i * W + u.j;
         alphas[pix] = 1.0f - T;
 #pragma unroll
@@ -369,56 +432,52 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     }
 }
 
-__device__ __forceinline__ float rcp_approx(float x) {
-#ifdef GSB_NO_INLINE_PTX
-    return 1.0f / x;
-#else
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#endif
-}
-
 // Backward.  The per-Gaussian gradient is a sum over pixels, the transmittance recurrence runs over Gaussians: the
 // kernel does each along the axis where it is register-local and TRANSPOSES through shared memory in between, so no
-// warp shuffle and no cross-lane reduction is left.  Per chunk of 32 sub-list entries (walked back to front):
-//   phase A (lane = pixel)   : evaluate the 32 entries, run the T / suffix-colour recurrence, and store per (entry,
-//                              pixel) the three scalars the gradient needs -- vis = exp(-sigma) (0 if the pair does not
-//                              contribute), T before the Gaussian, E = (suffix . v_out - T_final (v_alpha - bg . v_out))
-//                              / (1 - alpha) -- into 32 x 33 slabs (row = entry, conflict-free both ways);
-//   phase B (lane = Gaussian): read its row, accumulate the 9 gradient values over the 32 pixels in registers, one
+// cross-lane reduction is left.  Per chunk of 32 sub-list entries (walked back to front, two entries per step):
+//   phase A (lane = (entry parity, pixel)): evaluate the pair, run the T / suffix-colour recurrence of both entries
+//                              (each half-warp gets the other entry's alpha and colour . v_out by one shuffle each),
+//                              and store per (entry, pixel) the three scalars the gradient needs -- A = opacity *
+//                              exp(-sigma) (0 if the pair does not contribute), T before the Gaussian, E = (suffix .
+//                              v_out - T_final (v_alpha - bg . v_out)) / (1 - alpha) -- into 32 x 16 slabs whose columns
+//                              are rotated by row / 2 (conflict-free for both access patterns, no padding);
+//   phase B (lane = Gaussian): read its row, accumulate the gradient moments over the 16 pixels in registers, one
 //                              atomic per value per (Gaussian, warp) -- only for Gaussians that touched a pixel.
 // v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
 // (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
-constexpr int BSTRIDE = 33;
-constexpr int BG = GSB_BG;   // entries evaluated together in phase A
-constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (15 KB of shared memory per warp)
+constexpr int BS = GSB_BG / 2;     // pair-steps evaluated together in phase A
+constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (8 KB of shared memory per warp)
+
+__device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + (row >> 1)) & (PIX - 1)); }
 
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB_B)
 composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
-                     const int32_t *__restrict__ offsets, int n_tiles, int M, const int2 *__restrict__ entries,
-                     const int32_t *__restrict__ counts, const int32_t *__restrict__ order,
-                     const float *__restrict__ alphas,
+                     const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
+                     const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
+                     const int32_t *__restrict__ order, const float *__restrict__ alphas,
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                      float *__restrict__ v_colors, float *__restrict__ v_opacities) {
     constexpr int C3 = CH < 3 ? CH : 3;                 // channels carried in the packed record
     constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
-    __shared__ float s_vis[WPB_B][32 * BSTRIDE];
-    __shared__ float s_T[WPB_B][32 * BSTRIDE];
-    __shared__ float s_E[WPB_B][32 * BSTRIDE];
+    __shared__ float s_A[WPB_B][32 * PIX];
+    __shared__ float s_T[WPB_B][32 * PIX];
+    __shared__ float s_E[WPB_B][32 * PIX];
     __shared__ Rec s_rec[WPB_B][32];
     __shared__ int2 s_ent[WPB_B][32];
-    __shared__ float4 s_vo[WPB_B][32][NV4];
+    __shared__ float4 s_vo[WPB_B][PIX][NV4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB_B + wib;
     if (slot >= n_units) return;
     const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);
     const Unit u = make_unit(unit, lane, tile_w, W, H);
+    const bool hi = lane >= PIX;
+    const int p = lane & (PIX - 1);
     const size_t pix = u.inside ? (size_t)u.i * W + u.j : 0;
 
+    const int M = m_dev ? (int)*m_dev : M_host;
     const int start = offsets[u.tile];
     const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
     const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
@@ -434,39 +493,39 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     }
     const float c0 = T_final * ((u.inside ? v_alphas[pix] : 0.f) - bg_dot);
     const int bin_final = u.inside ? last_ids[pix] : -1;
-    {
+    if (!hi) {
         float vo4[NV4 * 4];
 #pragma unroll
         for (int k = 0; k < NV4 * 4; ++k) vo4[k] = (k < CH) ? v_out[k] : 0.f;
 #pragma unroll
         for (int k = 0; k < NV4; ++k)
-            s_vo[wib][lane][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
+            s_vo[wib][p][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
     }
     int wmax = bin_final;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    for (int o = 8; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
 
     // Entries are sorted by tile-list position: drop the tail that lies behind every pixel's last contributor
     // (binary search for the first position > wmax).
     {
-        int lo = 0, hi = n;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (list[mid].x <= wmax) lo = mid + 1; else hi = mid;
+        int lo = 0, hi_ = n;
+        while (lo < hi_) {
+            int mid = (lo + hi_) >> 1;
+            if (list[mid].x <= wmax) lo = mid + 1; else hi_ = mid;
         }
         n = lo;
     }
     if (n == 0) return;
 
-    float *const my_vis = s_vis[wib], *const my_T = s_T[wib], *const my_E = s_E[wib];
-    const float bx = (float)(u.j - (lane & 7)) + 0.5f, by = (float)(u.i - (lane >> 3)) + 0.5f;  // pixel (0,0) of the unit
+    float *const my_A = s_A[wib], *const my_T = s_T[wib], *const my_E = s_E[wib];
+    const float bx = (float)(u.j - (p & 3)) + 0.5f, by = (float)(u.i - (p >> 2)) + 0.5f;  // pixel (0,0) of the unit
     float T = T_final;
     float B = 0.f;    // suffix colour behind the current Gaussian, dotted with v_out
 
-    // walk back to front: chunk c covers sub-list indices [top - 32, top), slab row t holds index top - 1 - t
+    // walk back to front: chunk c covers sub-list indices [top - 32, top), slab row t holds index top - 1 - t; the pair
+    // of step s is rows (2s, 2s + 1): the low half-warp owns the nearer-to-the-back row 2s, which comes first
     int2 e = make_int2(0, 0);
-    Rec r;
-    r.k = r.q = r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    Rec r = null_record();
     if (n - 1 - lane >= 0) { e = list[n - 1 - lane]; r = rec[e.y]; }
     for (int top = n; top > 0; top -= 32) {
         __syncwarp();
@@ -474,30 +533,28 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         s_rec[wib][lane] = r;
         __syncwarp();
         const int nt = top - 32;
+        r = null_record();
         if (nt - 1 - lane >= 0) { e = list[nt - 1 - lane]; r = rec[e.y]; }
         const int cnt = min(32, top);
 
-        // ---- phase A: lane = pixel -------------------------------------------------------------------------
-        unsigned touched = 0u;   // bit t: entry t contributes to at least one pixel of the unit
+        // ---- phase A: lane = (entry parity, pixel) -------------------------------------------------------------
+        unsigned touched = 0u;   // bit t: row t contributes to at least one pixel of the unit
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += BG) {
-            // independent per entry: alpha, 1 / (1 - alpha), colour . v_out  (ILP for a warp that runs alone)
-            float visg[BG], alg[BG], rag[BG], wg[BG];
+        for (int t0 = 0; t0 < cnt; t0 += 2 * BS) {
+            // independent per pair: alpha, colour . v_out  (ILP for a warp that runs alone)
+            float Ag[BS], al[BS], wg[BS];
 #pragma unroll
-            for (int jj = 0; jj < BG; ++jj) {
-                const int t = min(t0 + jj, 31);
+            for (int s = 0; s < BS; ++s) {
+                const int t = t0 + 2 * s + (hi ? 1 : 0);
                 const float4 kk = s_rec[wib][t].k;
                 const float4 q = s_rec[wib][t].q;
                 const float4 c = s_rec[wib][t].c;
                 const int2 en = s_ent[wib][t];
-                const float dx = kk.x - u.px, dy = kk.y - u.py;
-                const float sigma = 0.5f * (q.x * dx * dx + q.z * dy * dy) + q.y * dx * dy;
-                const float vis = ex2_approx(-LOG2E * sigma);
-                const float alpha = fminf(GSB_ALPHA_CLAMP, q.w * vis);
-                const bool valid = (t0 + jj < cnt) && (en.x <= bin_final) && !(sigma < 0.f || alpha < GSB_ALPHA_MIN);
-                visg[jj] = valid ? vis : 0.f;
-                alg[jj] = valid ? alpha : 0.f;
-                rag[jj] = rcp_approx(1.0f - alg[jj]);
+                const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
+                const float araw = ex2_approx(l2a);
+                const bool valid = (en.x <= bin_final) && (l2a <= q.w) && !(l2a < LOG2_ALPHA_MIN);
+                Ag[s] = valid ? araw : 0.f;
+                al[s] = fminf(GSB_ALPHA_CLAMP, Ag[s]);
                 float w = c.x * v_out[0];
                 if (C3 > 1) w += c.y * v_out[1];
                 if (C3 > 2) w += c.z * v_out[2];
@@ -505,18 +562,31 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 #pragma unroll
                     for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)en.y * CH + k) * v_out[k];
                 }
-                wg[jj] = w;
-                if (__any_sync(0xffffffffu, valid)) touched |= 1u << t;
+                wg[s] = w;
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                touched |= ((m & 0xFFFFu) ? 1u : 0u) << (t0 + 2 * s);
+                touched |= ((m >> 16) ? 1u : 0u) << (t0 + 2 * s + 1);
             }
             // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch
 #pragma unroll
-            for (int jj = 0; jj < BG; ++jj) {
-                const int t = min(t0 + jj, 31);
-                T *= rag[jj];
-                my_vis[t * BSTRIDE + lane] = visg[jj];
-                my_T[t * BSTRIDE + lane] = T;
-                my_E[t * BSTRIDE + lane] = rag[jj] * (B - c0);
-                B += wg[jj] * (alg[jj] * T);
+            for (int s = 0; s < BS; ++s) {
+                const int t = t0 + 2 * s + (hi ? 1 : 0);
+                const float al_o = __shfl_xor_sync(0xffffffffu, al[s], PIX);
+                const float w_o = __shfl_xor_sync(0xffffffffu, wg[s], PIX);
+                const float a0 = hi ? al_o : al[s], a1 = hi ? al[s] : al_o;      // rows 2s (first), 2s + 1
+                const float w0 = hi ? w_o : wg[s], w1 = hi ? wg[s] : w_o;
+                const float r0 = rcp_approx(1.0f - a0), r1 = rcp_approx(1.0f - a1);
+                const float T0 = T * r0;                     // transmittance in front of row 2s
+                const float E0 = r0 * (B - c0);
+                const float B1 = B + w0 * (a0 * T0);
+                const float T1 = T0 * r1;
+                const float E1 = r1 * (B1 - c0);
+                B = B1 + w1 * (a1 * T1);
+                T = T1;
+                const int at = slab_at(t, p);
+                my_A[at] = Ag[s];
+                my_T[at] = hi ? T1 : T0;
+                my_E[at] = hi ? E1 : E0;
             }
         }
         __syncwarp();
@@ -540,20 +610,20 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
             float g_col[CH];
 #pragma unroll
             for (int k = 0; k < CH; ++k) g_col[k] = 0.f;
-            float sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, g_op = 0.f;
-            const float *row_vis = my_vis + lane * BSTRIDE, *row_T = my_T + lane * BSTRIDE,
-                        *row_E = my_E + lane * BSTRIDE;
+            float s0 = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f;   // moments of v_sigma
+            const int rot = lane >> 1;
+            const float *row_A = my_A + lane * PIX, *row_T = my_T + lane * PIX, *row_E = my_E + lane * PIX;
 #pragma unroll 8
-            for (int p = 0; p < 32; ++p) {
-                const float vis = row_vis[p], Tp = row_T[p], Ep = row_E[p];
+            for (int pp = 0; pp < PIX; ++pp) {
+                const int at = (pp + rot) & (PIX - 1);
+                const float A = row_A[at], Tp = row_T[at], Ep = row_E[at];
                 float vo[NV4 * 4];
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
-                    const float4 v4 = s_vo[wib][p][k];
+                    const float4 v4 = s_vo[wib][pp][k];
                     vo[4 * k] = v4.x; vo[4 * k + 1] = v4.y; vo[4 * k + 2] = v4.z; vo[4 * k + 3] = v4.w;
                 }
-                const float ov = q.w * vis;
-                const float fac = fminf(GSB_ALPHA_CLAMP, ov) * Tp;
+                const float fac = fminf(GSB_ALPHA_CLAMP, A) * Tp;
                 float w = 0.f;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
@@ -561,11 +631,11 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                     g_col[k] += fac * vo[k];
                 }
                 float v_alpha = Tp * w - Ep;
-                v_alpha = (ov <= GSB_ALPHA_CLAMP) ? v_alpha : 0.f;   // clamped alpha passes no gradient to sigma / opacity
-                g_op += vis * v_alpha;
-                const float v_sigma = -ov * v_alpha;
-                const float dx = kk.x - (bx + (float)(p & 7)), dy = kk.y - (by + (float)(p >> 3));   // exact pixel centre
+                v_alpha = (A <= GSB_ALPHA_CLAMP) ? v_alpha : 0.f;   // clamped alpha passes no gradient to sigma / opacity
+                const float v_sigma = -A * v_alpha;                 // d alpha / d sigma = -alpha
+                const float dx = kk.x - (bx + (float)(pp & 3)), dy = kk.y - (by + (float)(pp >> 2));   // exact pixel centre
                 const float t1 = v_sigma * dx, t2 = v_sigma * dy;
+                s0 += v_sigma;
                 sxx += t1 * dx;
                 sxy += t1 * dy;
                 syy += t2 * dy;
@@ -578,9 +648,12 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                 atomicAdd(v_conics + 3 * (size_t)g, 0.5f * sxx);
                 atomicAdd(v_conics + 3 * (size_t)g + 1, sxy);
                 atomicAdd(v_conics + 3 * (size_t)g + 2, 0.5f * syy);
-                atomicAdd(v_means2d + 2 * (size_t)g, q.x * sx + q.y * sy);
-                atomicAdd(v_means2d + 2 * (size_t)g + 1, q.y * sx + q.z * sy);
-                atomicAdd(v_opacities + g, g_op);
+                // conic back from the folded coefficients: a = qa / (-log2e / 2), b = qb / (-log2e), c = qc / (-log2e / 2)
+                const float ca = q.x * (-2.0f / LOG2E), cb = q.y * (-1.0f / LOG2E), cc = q.z * (-2.0f / LOG2E);
+                atomicAdd(v_means2d + 2 * (size_t)g, ca * sx + cb * sy);
+                atomicAdd(v_means2d + 2 * (size_t)g + 1, cb * sx + cc * sy);
+                // d alpha / d opacity = exp(-sigma) = A / opacity, and sum A v_alpha = -s0
+                atomicAdd(v_opacities + g, -s0 / c.w);
             }
         }
     }
@@ -618,8 +691,8 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
 template <int CH>
 int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conics, const float *colors,
                const float *opacities, int opacity_is_logit, const float *comps, const float *background,
-               const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render, float *alphas,
-               int32_t *last_ids, void *ws, cudaStream_t st) {
+               const int32_t *offsets, const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render,
+               float *alphas, int32_t *last_ids, void *ws, cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
@@ -627,26 +700,27 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
                                                                     conics, colors, opacities, opacity_is_logit,
                                                                     comps, w.rec);
-    build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, offsets, flatten_ids, w.rec,
+    build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, m_dev, offsets, flatten_ids, w.rec,
                                                              w.entries, w.counts);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order,
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
         w.work, render, alphas, last_ids);
     return 0;
 }
 
 template <int CH>
 int launch_bwd(int W, int H, int64_t N, const float *colors, const float *background, const int32_t *offsets,
-               int64_t M, const float *alphas, const int32_t *last_ids, const float *v_render, const float *v_alphas,
-               float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, void *ws, cudaStream_t st) {
+               int64_t M, const int64_t *m_dev, const float *alphas, const int32_t *last_ids, const float *v_render,
+               const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, void *ws,
+               cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.work, w.order);   // order by the forward's measured work
     composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB_B), 32 * WPB_B, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, w.entries, w.counts, w.order, alphas,
-        last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
+        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
+        alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
 }
 
@@ -674,13 +748,13 @@ GSB_API int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, i
     return GSB_OK;
 }
 
-GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
-                              const float *conics, const float *colors, const float *opacities,
-                              int32_t opacity_is_logit, const float *comps, const float *background,
-                              const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render,
-                              float *alphas, int32_t *last_ids, void *workspace, size_t workspace_bytes_,
-                              void *stream) {
-    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 268435455LL);
+// `M` is the CAPACITY of the tile lists when `m_dev` (the device-resident intersection count) is given, else the count.
+int gsb_composite_fwd_impl(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
+                           const float *conics, const float *colors, const float *opacities, int32_t opacity_is_logit,
+                           const float *comps, const float *background, const int32_t *offsets,
+                           const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render, float *alphas,
+                           int32_t *last_ids, void *workspace, size_t workspace_bytes_, void *stream) {
+    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 134217727LL);
     GSB_CHECK_ARG(offsets && render && alphas && last_ids && workspace);
     GSB_CHECK_ARG(M == 0 || (means2d && conics && colors && opacities && flatten_ids));
     int tw = (width + GSB_TILE - 1) / GSB_TILE, th = (height + GSB_TILE - 1) / GSB_TILE;
@@ -690,7 +764,7 @@ GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, i
     }
     int rc = 0;
     GSB_DISPATCH_CH(channels, (rc = launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities,
-                                                    opacity_is_logit, comps, background, offsets, flatten_ids, M,
+                                                    opacity_is_logit, comps, background, offsets, flatten_ids, M, m_dev,
                                                     render, alphas, last_ids, workspace, (cudaStream_t)stream)));
     if (rc != 0) {
         gsb_set_error("gsb_composite_fwd: internal sort scratch too small");
@@ -700,18 +774,38 @@ GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, i
     return GSB_OK;
 }
 
+int gsb_composite_bwd_impl(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
+                           const float *background, const int32_t *offsets, int64_t M, const int64_t *m_dev,
+                           const float *alphas, const int32_t *last_ids, const float *v_render, const float *v_alphas,
+                           float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                           const void *workspace, void *stream) {
+    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 134217727LL);
+    GSB_CHECK_ARG(offsets && alphas && last_ids && v_render && v_alphas && workspace);
+    if (M == 0) return GSB_OK;
+    GSB_CHECK_ARG(colors && v_means2d && v_conics && v_colors && v_opacities);
+    GSB_DISPATCH_CH(channels, (launch_bwd<C_>(width, height, N, colors, background, offsets, M, m_dev, alphas, last_ids,
+                                               v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities,
+                                               const_cast<void *>(workspace), (cudaStream_t)stream)));
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
+                              const float *conics, const float *colors, const float *opacities,
+                              int32_t opacity_is_logit, const float *comps, const float *background,
+                              const int32_t *offsets, const int32_t *flatten_ids, int64_t M, float *render,
+                              float *alphas, int32_t *last_ids, void *workspace, size_t workspace_bytes_,
+                              void *stream) {
+    return gsb_composite_fwd_impl(width, height, channels, N, means2d, conics, colors, opacities, opacity_is_logit, comps,
+                                  background, offsets, flatten_ids, M, nullptr, render, alphas, last_ids, workspace,
+                                  workspace_bytes_, stream);
+}
+
 GSB_API int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
                               const float *background, const int32_t *offsets, int64_t M, const float *alphas,
                               const int32_t *last_ids, const float *v_render, const float *v_alphas,
                               float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                               const void *workspace, void *stream) {
-    GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 268435455LL);
-    GSB_CHECK_ARG(offsets && alphas && last_ids && v_render && v_alphas && workspace);
-    if (M == 0) return GSB_OK;
-    GSB_CHECK_ARG(colors && v_means2d && v_conics && v_colors && v_opacities);
-    GSB_DISPATCH_CH(channels, (launch_bwd<C_>(width, height, N, colors, background, offsets, M, alphas, last_ids,
-                                               v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities,
-                                               const_cast<void *>(workspace), (cudaStream_t)stream)));
-    GSB_CHECK_LAUNCH();
-    return GSB_OK;
+    return gsb_composite_bwd_impl(width, height, channels, N, colors, background, offsets, M, nullptr, alphas, last_ids,
+                                  v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities, workspace, stream);
 }
