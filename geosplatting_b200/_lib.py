@@ -73,6 +73,12 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.gsb_view_prepare.argtypes = [vp] * 15
     lib.gsb_view_finish.argtypes = [vp, vp, i64] + [vp] * 8
     lib.gsb_view_backward.argtypes = [vp, vp, vp, i64] + [vp] * 26
+    i32 = C.c_int32
+    lib.gsb_batch_bytes.argtypes = [vp, i32, i32, i64, vp]
+    lib.gsb_batch_grad_floats.argtypes = [vp, i32, i64, vp]
+    lib.gsb_batch_forward.argtypes = [vp, i32, vp, vp] + [vp] * 10 + [i32, vp, vp, i64, vp, vp, vp, i32, vp]
+    lib.gsb_batch_backward.argtypes = ([vp, i32, vp, vp] + [vp] * 10 + [i32, vp, vp, i64, vp, i64, vp, C.c_float, vp,
+                                       i32, vp, vp])
     return lib
 
 
@@ -93,6 +99,10 @@ class CallStats:
                # the native per-view driver: prepare = project + iota + total + shade; finish = emit + offsets + pack +
                # build + order + composite + tone map; backward = tone map + order + composite + project + shade + sum
                "gsb_view_bytes": 0, "gsb_view_prepare": 4, "gsb_view_finish": 7, "gsb_view_backward": 6,
+               # the batch driver: per view forward = prepare (project, iota, total, publish, shade) + finish (emit,
+               # offsets, pack, build, order, composite, tone map); per view backward = 6; + 1 gradient sum per batch
+               "gsb_batch_bytes": 0, "gsb_batch_grad_floats": 0, "gsb_batch_forward": 0, "gsb_batch_backward": 1,
+               "batch_view_forward": 12, "batch_view_backward": 6,
                # FlexiCubes: surface = classify (+ cub select); topology = resolve, class flags, numbering, edge keys,
                # edge flags, edge assignment (+ cub sort and two scans)
                "gsb_fc_workspace_bytes": 0, "gsb_fc_surface": 1, "gsb_fc_topology": 6, "gsb_fc_entropy_fwd": 2}

@@ -247,3 +247,78 @@ extern "C" __attribute__((visibility("default"))) int gsb_bin2_sort(int32_t N, i
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
+
+// ---- speculative capacity: nothing on the host waits for M --------------------------------------------------------
+// The batch driver (view.cu: gsb_batch_*) sizes the M-dependent arrays from a capacity `cap` the caller chose (e.g. the
+// count of this camera's previous visit + a margin) and keeps M on the device: m_eff = min(M, cap) is what every later
+// kernel reads, the raw M goes to `total_out` (pinned host memory) for the caller to check and adapt the capacity.
+
+int gsb_isect_tiles_ordered_cap(int32_t N, const float *means2d, const int32_t *radii, const int32_t *order,
+                                const int64_t *cum_ordered, const gsb_camera *cam, int64_t cap, uint32_t *tile_keys,
+                                int32_t *gauss_ids, void *stream);
+
+__global__ void publish_total_kernel(int N, const int64_t *__restrict__ cum_ordered, int64_t cap, int64_t *m_eff,
+                                     volatile int64_t *total_out) {
+    const int64_t m = N > 0 ? cum_ordered[N - 1] : 0;
+    *m_eff = m < cap ? m : cap;
+    if (total_out) {
+        *total_out = m;
+        __threadfence_system();
+    }
+}
+
+int gsb_bin2_publish(int32_t N, const int64_t *cum_ordered, int64_t cap, int64_t *m_eff, int64_t *total_out, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && cap >= 0 && m_eff != nullptr && (N == 0 || cum_ordered != nullptr));
+    publish_total_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(N, cum_ordered, cap, m_eff, total_out);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+// Sorted keys past m_eff are the 0xFFFFFFFF fill: they compare above every tile id in the sorted bit range.
+__global__ void __launch_bounds__(256) tile_offsets_cap_kernel(int64_t cap, const int64_t *__restrict__ m_eff,
+                                                                const uint32_t *__restrict__ tile_keys, int n_tiles,
+                                                                int32_t *__restrict__ offsets) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t M = *m_eff;
+    if (i >= M || i >= cap) return;
+    int cur = (int)tile_keys[i];
+    int prev = (i == 0) ? -1 : (int)tile_keys[i - 1];
+    for (int id = prev + 1; id <= cur; ++id) offsets[id] = (int32_t)i;
+    if (i == M - 1)
+        for (int id = cur + 1; id < n_tiles; ++id) offsets[id] = (int32_t)M;
+}
+
+// gsb_bin2_sort with a capacity instead of the count: emission (guarded), stable sort of `cap` pairs by tile id -- the
+// unused tail is filled with all-ones keys and sorts behind every tile --, per-tile offsets from the device-side count.
+int gsb_bin2_sort_cap(int32_t N, int64_t cap, const int64_t *m_eff, const float *means2d, const int32_t *radii,
+                      const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam, int32_t *flatten_ids,
+                      int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && cap >= 0 && cam != nullptr && offsets != nullptr && m_eff != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tile_w = (cam->width + GSB_TILE - 1) / GSB_TILE, tile_h = (cam->height + GSB_TILE - 1) / GSB_TILE;
+    const int n_tiles = tile_w * tile_h;
+    GSB_CHECK_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)n_tiles, st));   // stays when M == 0
+    if (cap == 0 || N == 0) return GSB_OK;
+    GSB_CHECK_ARG(means2d && radii && order && cum_ordered && flatten_ids && workspace);
+    size_t need = 0;
+    GSB_CHECK_ARG(gsb_bin2_workspace_bytes(0, cap, &need) == GSB_OK);
+    if (need > workspace_bytes) {
+        gsb_set_error("gsb_bin2_sort_cap: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GSB_ENOMEM;
+    }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)cap);
+    uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)cap);
+    int32_t *gids = reinterpret_cast<int32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)cap);
+    void *temp = p;
+    GSB_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(uint32_t) * (size_t)cap, st));
+    GSB_CHECK_CUDA(cudaMemsetAsync(gids, 0, sizeof(int32_t) * (size_t)cap, st));
+    int rc = gsb_isect_tiles_ordered_cap(N, means2d, radii, order, cum_ordered, cam, cap, keys, gids, stream);
+    if (rc != GSB_OK) return rc;
+    size_t tb = tile_sort_temp_bytes(cap);
+    GSB_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_sorted, gids, flatten_ids, cap, 0,
+                                                   gsb_tile_bits(n_tiles), st));
+    tile_offsets_cap_kernel<<<gsb_div_up(cap, 256), 256, 0, st>>>(cap, m_eff, keys_sorted, n_tiles, offsets);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}

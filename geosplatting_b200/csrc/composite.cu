@@ -43,10 +43,11 @@ constexpr int PIX = SUB_W * SUB_H;                             // 16 pixels, hel
 #ifndef GSB_WPB_B
 #define GSB_WPB_B 4
 #endif
-constexpr int WPB = GSB_WPB;                              // warps (units) per CTA in the composite kernels
-constexpr int FS = GSB_FG / 2;                            // pair-steps evaluated together in the forward
-static_assert(GSB_FG >= 2 && GSB_FG % 2 == 0 && 32 % GSB_FG == 0, "GSB_FG: even divisor of 32");
-static_assert(GSB_BG >= 2 && GSB_BG % 2 == 0 && 32 % GSB_BG == 0, "GSB_BG: even divisor of 32");
+constexpr int WPB = GSB_WPB;                              // warps (pairs of units) per CTA in the composite kernels
+constexpr int FSZ = GSB_FG;                               // entries evaluated together in the forward
+constexpr int BSZ = GSB_BG;                               // entries evaluated together in the backward's phase A
+static_assert(GSB_FG >= 1 && 16 % GSB_FG == 0, "GSB_FG: divisor of 16");
+static_assert(GSB_BG >= 1 && 16 % GSB_BG == 0, "GSB_BG: divisor of 16");
 
 struct Rec {
     float4 k;  // x, y, hx, hy
@@ -257,17 +258,24 @@ __global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int3
     }
 }
 
+// A warp owns TWO horizontally adjacent 4x4 units of a tile (an 8x4 pixel region) and walks BOTH sub-lists at once:
+// lanes 0-15 are the pixels of unit 2k with its list, lanes 16-31 the pixels of unit 2k+1 with its own list.  The two
+// half-warps never exchange data inside the loops (no shuffles, identical code on different lists); the warp runs as
+// long as the longer list, and neighbouring units' lists differ by a few percent.
+constexpr int UPW = 2;                 // units per warp
+constexpr int CHUNK = 32 / UPW;        // list entries staged per unit and step (shared-memory rows 2 * i + half)
+
 struct Unit {
     int tile, w, i, j;
     bool inside;
     float px, py;
 };
 
-// lane -> (entry parity h = lane >> 4, pixel p = lane & 15) of the 4x4 unit
-__device__ __forceinline__ Unit make_unit(int unit, int lane, int tile_w, int W, int H) {
+// lane -> (half h = lane >> 4 selects the unit, pixel p = lane & 15)
+__device__ __forceinline__ Unit make_unit(int pair, int lane, int tile, int tile_w, int W, int H) {
     Unit u;
-    u.tile = unit / SUBS;
-    u.w = unit % SUBS;
+    u.tile = tile;
+    u.w = pair * UPW + (lane >> 4);
     const int p = lane & (PIX - 1);
     const int tx = u.tile % tile_w, ty = u.tile / tile_w;
     u.j = tx * GSB_TILE + (u.w & 3) * SUB_W + (p & 3);
@@ -286,141 +294,135 @@ __device__ __forceinline__ Rec null_record() {
     return r;
 }
 
+constexpr float FAR_AWAY = 1e15f;   // pixel coordinate of a lane that must not contribute any more: log2(alpha) = -inf
+
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB)
-composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
+composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
                      const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
                      const int32_t *__restrict__ order, int32_t *__restrict__ work, float *__restrict__ render,
                      float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
+    constexpr int PAIRS = SUBS / UPW;
     __shared__ Rec s_rec[WPB][32];
-    __shared__ int2 s_ent[WPB][32];
+    __shared__ int s_gid[WPB][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB + wib;
-    if (slot >= n_units) return;
-    const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);   // heaviest tiles are scheduled first (LPT)
-    const Unit u = make_unit(unit, lane, tile_w, W, H);
-    const bool hi = lane >= PIX;       // this lane evaluates the ODD entry of every pair
+    if (slot >= n_pairs) return;
+    const int tile = order[slot / PAIRS];          // heaviest tiles are scheduled first (LPT)
+    const int half = lane >> 4;
+    const Unit u = make_unit(slot % PAIRS, lane, tile, tile_w, W, H);
+    const int unit = tile * SUBS + u.w;
     bool done = !u.inside;
+    float px = done ? FAR_AWAY : u.px;             // a finished pixel moves out of every Gaussian's reach
+    const float py = u.py;
 
     const int M = m_dev ? (int)*m_dev : M_host;
-    const int start = offsets[u.tile];
-    const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
+    const int start = offsets[tile];
+    const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
-    const int n = counts[unit];
+    const int n = counts[unit];                                           // this half-warp's list
+    const int n_max = max(n, __shfl_xor_sync(0xffffffffu, n, 16));        // the warp walks the longer one
 
-    float T = 1.0f;       // transmittance in front of the current pair (identical in both half-warps)
-    float acc[CH];        // this half-warp's share of the colour sum
+    float T = 1.0f;
+    float acc[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-    int last_k = -1;      // sub-list index of the last contributor among this half-warp's entries
+    int last_k = -1;   // sub-list index of the pixel's last contributor
 
-    // prefetch chunk 0
+    // prefetch chunk 0: lane (half, i) fetches entry i of its unit's list into shared-memory row 2 * i + half
+    const int li = lane & (CHUNK - 1);
+    const int my_row = 2 * li + half;
+    const Rec *const rows = &s_rec[wib][half];     // rows of my unit: rows[2 * s]
+    const int *const gids = &s_gid[wib][half];
     int2 e = make_int2(0, 0);
     Rec r = null_record();
     int processed = n;
-    if (lane < n) { e = list[lane]; r = rec[e.y]; }
-    for (int base = 0; base < n; base += 32) {
+    if (li < n) { e = list[li]; r = rec[e.y]; }
+    for (int base = 0; base < n_max; base += CHUNK) {
         __syncwarp();
-        s_ent[wib][lane] = e;
-        s_rec[wib][lane] = r;
+        s_gid[wib][my_row] = e.y;
+        s_rec[wib][my_row] = r;
         __syncwarp();
-        const int nb = base + 32;
-        r = null_record();                                             // rows past the end of the list never contribute
-        if (nb + lane < n) { e = list[nb + lane]; r = rec[e.y]; }     // next chunk in flight during the loop
-        const int cnt = min(32, n - base);
-        // Groups of FS pair-steps.  The alpha evaluations are independent (ILP for a warp that runs alone: the longest
+        const int nb = base + CHUNK;
+        r = null_record();                                            // rows past the end of a list never contribute
+        if (nb + li < n) { e = list[nb + li]; r = rec[e.y]; }       // next chunk in flight during the loop
+        // Groups of FS entries.  The alpha evaluations are independent (ILP for a warp that runs alone: the longest
         // sub-list of a view is this kernel's critical path); alpha == 0 stands for "does not contribute" and makes
-        // every update the identity, so the common case has no branch.  The state is saved before a group; only a
-        // group in which some pixel reaches the T <= 1e-4 stop is rolled back and replayed with the exact per-entry
-        // logic (T only decreases, so the group's end value decides).
+        // every update the identity, so the common case has no branch.  The state is saved before a group; only a group
+        // in which some pixel reaches the T <= 1e-4 stop is rolled back and replayed with the exact per-entry logic
+        // (T only decreases, so the group's end value decides).
         bool all_done = false;
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += 2 * FS) {
-            float a[FS], ao[FS];
+        for (int t0 = 0; t0 < CHUNK; t0 += FSZ) {
+            float a[FSZ];
 #pragma unroll
-            for (int s = 0; s < FS; ++s) {
-                const int t = t0 + 2 * s + (hi ? 1 : 0);
-                const float4 kk = s_rec[wib][t].k;
-                const float4 q = s_rec[wib][t].q;
-                const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
+            for (int s = 0; s < FSZ; ++s) {
+                const float4 kk = rows[2 * (t0 + s)].k;
+                const float4 q = rows[2 * (t0 + s)].q;
+                const float l2a = log2_alpha(q, kk.x - px, kk.y - py);
                 const float alpha = fminf(GSB_ALPHA_CLAMP, ex2_approx(l2a));
                 // sigma < 0 <=> log2(alpha) > log2(opacity); alpha < 1/255 <=> log2(alpha) < log2(1/255)
-                a[s] = (done || !(l2a <= q.w) || l2a < LOG2_ALPHA_MIN) ? 0.f : alpha;
+                a[s] = (l2a <= q.w && l2a >= LOG2_ALPHA_MIN) ? alpha : 0.f;
             }
-#pragma unroll
-            for (int s = 0; s < FS; ++s) ao[s] = __shfl_xor_sync(0xffffffffu, a[s], PIX);
             const float T_saved = T;
             const int last_saved = last_k;
             float acc_saved[CH];
 #pragma unroll
             for (int k = 0; k < CH; ++k) acc_saved[k] = acc[k];
 #pragma unroll
-            for (int s = 0; s < FS; ++s) {
-                const int t = t0 + 2 * s + (hi ? 1 : 0);
-                const float a_even = hi ? ao[s] : a[s], a_odd = hi ? a[s] : ao[s];
-                const float T1 = T * (1.0f - a_even);          // behind the even entry
-                const float vis = a[s] * (hi ? T1 : T);
-                T = T1 * (1.0f - a_odd);
-                if (a[s] > 0.f) {   // predicated: a non-contributing Gaussian's colour is never read into the sum
-                    const float4 c = s_rec[wib][t].c;
-                    acc[0] += c.x * vis;
-                    if (CH > 1) acc[1] += c.y * vis;
-                    if (CH > 2) acc[2] += c.z * vis;
-                    if (CH > 3) {
-                        const int g = s_ent[wib][t].y;
+            for (int s = 0; s < FSZ; ++s) {
+                const float vis = a[s] * T;
+                T = T * (1.0f - a[s]);
+                const float4 c = rows[2 * (t0 + s)].c;      // finite by contract: alpha == 0 makes the products vanish
+                acc[0] = fmaf(c.x, vis, acc[0]);
+                if (CH > 1) acc[1] = fmaf(c.y, vis, acc[1]);
+                if (CH > 2) acc[2] = fmaf(c.z, vis, acc[2]);
+                if (CH > 3) {
+                    if (a[s] > 0.f) {
+                        const int g = gids[2 * (t0 + s)];
 #pragma unroll
                         for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
                     }
-                    last_k = base + t;
                 }
+                last_k = a[s] > 0.f ? base + t0 + s : last_k;
             }
             if (!__any_sync(0xffffffffu, T <= GSB_T_STOP)) continue;
-            // ---- roll back and replay this group entry by entry (both half-warps run the same recurrence)
+            // ---- roll back and replay this group entry by entry
             T = T_saved;
             last_k = last_saved;
 #pragma unroll
             for (int k = 0; k < CH; ++k) acc[k] = acc_saved[k];
 #pragma unroll
-            for (int s = 0; s < FS; ++s) {
-#pragma unroll
-                for (int o = 0; o < 2; ++o) {                  // o = 0: the even entry of the pair, then the odd one
-                    const bool mine = (o == 1) == hi;
-                    const float alpha = mine ? a[s] : ao[s];
-                    if (done || alpha == 0.f) continue;
-                    const float next_T = T * (1.0f - alpha);
-                    if (next_T <= GSB_T_STOP) {   // this entry is excluded
-                        done = true;
-                        continue;
-                    }
-                    if (mine) {
-                        const int t = t0 + 2 * s + o;
-                        const float vis = alpha * T;
-                        const float4 c = s_rec[wib][t].c;
-                        acc[0] += c.x * vis;
-                        if (CH > 1) acc[1] += c.y * vis;
-                        if (CH > 2) acc[2] += c.z * vis;
-                        if (CH > 3) {
-                            const int g = s_ent[wib][t].y;
-#pragma unroll
-                            for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
-                        }
-                        last_k = base + t;
-                    }
-                    T = next_T;
+            for (int s = 0; s < FSZ; ++s) {
+                const float alpha = a[s];
+                if (done || alpha == 0.f) continue;
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= GSB_T_STOP) {   // this entry is excluded
+                    done = true;
+                    px = FAR_AWAY;
+                    continue;
                 }
+                const float vis = alpha * T;
+                const float4 c = rows[2 * (t0 + s)].c;
+                acc[0] += c.x * vis;
+                if (CH > 1) acc[1] += c.y * vis;
+                if (CH > 2) acc[2] += c.z * vis;
+                if (CH > 3) {
+                    const int g = gids[2 * (t0 + s)];
+#pragma unroll
+                    for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
+                }
+                last_k = base + t0 + s;
+                T = next_T;
             }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
-        if (all_done) { processed = min(n, base + 32); break; }
+        if (all_done) { processed = min(n, base + CHUNK); break; }
     }
-    // the two half-warps hold the even / odd entries' shares of the same 16 pixels
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], PIX);
-    last_k = max(last_k, __shfl_xor_sync(0xffffffffu, last_k, PIX));
-    if (lane == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
-    if (u.inside && !hi) {
+    if (li == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
+    if (u.inside) {
         int cur_idx = 0;
         if (last_k >= 0) cur_idx = list[last_k].x;
         const size_t pix = (size_t)u.i * W + u.j;
@@ -434,25 +436,24 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
 
 // Backward.  The per-Gaussian gradient is a sum over pixels, the transmittance recurrence runs over Gaussians: the
 // kernel does each along the axis where it is register-local and TRANSPOSES through shared memory in between, so no
-// cross-lane reduction is left.  Per chunk of 32 sub-list entries (walked back to front, two entries per step):
-//   phase A (lane = (entry parity, pixel)): evaluate the pair, run the T / suffix-colour recurrence of both entries
-//                              (each half-warp gets the other entry's alpha and colour . v_out by one shuffle each),
-//                              and store per (entry, pixel) the three scalars the gradient needs -- A = opacity *
-//                              exp(-sigma) (0 if the pair does not contribute), T before the Gaussian, E = (suffix .
-//                              v_out - T_final (v_alpha - bg . v_out)) / (1 - alpha) -- into 32 x 16 slabs whose columns
-//                              are rotated by row / 2 (conflict-free for both access patterns, no padding);
+// cross-lane reduction is left.  Per step, 16 entries of each of the warp's two sub-lists (walked back to front):
+//   phase A (lane = (unit, pixel)): evaluate the unit's 16 entries, run the T / suffix-colour recurrence, and store
+//                              per (entry, pixel) the three scalars the gradient needs -- A = opacity * exp(-sigma)
+//                              (0 if the pair does not contribute), T before the Gaussian, E = (suffix . v_out -
+//                              T_final (v_alpha - bg . v_out)) / (1 - alpha) -- into a 32 x 16 slab whose columns are
+//                              rotated by row / 2 (conflict-free for both access patterns, no padding);
 //   phase B (lane = Gaussian): read its row, accumulate the gradient moments over the 16 pixels in registers, one
-//                              atomic per value per (Gaussian, warp) -- only for Gaussians that touched a pixel.
+//                              atomic per value per (Gaussian, unit) -- only for Gaussians that touched a pixel.
 // v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
 // (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
-constexpr int BS = GSB_BG / 2;     // pair-steps evaluated together in phase A
 constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (8 KB of shared memory per warp)
+constexpr int SLAB = 32 * PIX;     // floats per slab
 
 __device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + (row >> 1)) & (PIX - 1)); }
 
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB_B)
-composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restrict__ rec,
+composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
                      const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
@@ -460,26 +461,25 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                      float *__restrict__ v_colors, float *__restrict__ v_opacities) {
+    constexpr int PAIRS = SUBS / UPW;
     constexpr int C3 = CH < 3 ? CH : 3;                 // channels carried in the packed record
     constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
-    __shared__ float s_A[WPB_B][32 * PIX];
-    __shared__ float s_T[WPB_B][32 * PIX];
-    __shared__ float s_E[WPB_B][32 * PIX];
+    __shared__ float s_slab[WPB_B][3 * SLAB];           // A | T | E
     __shared__ Rec s_rec[WPB_B][32];
     __shared__ int2 s_ent[WPB_B][32];
-    __shared__ float4 s_vo[WPB_B][PIX][NV4];
+    __shared__ float4 s_vo[WPB_B][UPW][PIX][NV4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB_B + wib;
-    if (slot >= n_units) return;
-    const int unit = order[slot / SUBS] * SUBS + (slot % SUBS);
-    const Unit u = make_unit(unit, lane, tile_w, W, H);
-    const bool hi = lane >= PIX;
-    const int p = lane & (PIX - 1);
+    if (slot >= n_pairs) return;
+    const int tile = order[slot / PAIRS];
+    const int half = lane >> 4, p = lane & (PIX - 1);
+    const Unit u = make_unit(slot % PAIRS, lane, tile, tile_w, W, H);
+    const int unit = tile * SUBS + u.w;
     const size_t pix = u.inside ? (size_t)u.i * W + u.j : 0;
 
     const int M = m_dev ? (int)*m_dev : M_host;
-    const int start = offsets[u.tile];
-    const int end = (u.tile == n_tiles - 1) ? M : offsets[u.tile + 1];
+    const int start = offsets[tile];
+    const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
     int n = counts[unit];
 
@@ -493,15 +493,15 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
     }
     const float c0 = T_final * ((u.inside ? v_alphas[pix] : 0.f) - bg_dot);
     const int bin_final = u.inside ? last_ids[pix] : -1;
-    if (!hi) {
+    {
         float vo4[NV4 * 4];
 #pragma unroll
         for (int k = 0; k < NV4 * 4; ++k) vo4[k] = (k < CH) ? v_out[k] : 0.f;
 #pragma unroll
         for (int k = 0; k < NV4; ++k)
-            s_vo[wib][p][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
+            s_vo[wib][half][p][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
     }
-    int wmax = bin_final;
+    int wmax = bin_final;     // per unit: maximum over its 16 pixels
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
 
@@ -515,46 +515,53 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
         }
         n = lo;
     }
-    if (n == 0) return;
+    const int n_max = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+    if (n_max == 0) return;
 
-    float *const my_A = s_A[wib], *const my_T = s_T[wib], *const my_E = s_E[wib];
-    const float bx = (float)(u.j - (p & 3)) + 0.5f, by = (float)(u.i - (p >> 2)) + 0.5f;  // pixel (0,0) of the unit
+    float *const my_A = s_slab[wib];
+    const float bx = (float)(u.j - (p & 3)) + 0.5f, by = (float)(u.i - (p >> 2)) + 0.5f;  // pixel (0,0) of my unit
+    const float bx_other = __shfl_xor_sync(0xffffffffu, bx, 16);
     float T = T_final;
     float B = 0.f;    // suffix colour behind the current Gaussian, dotted with v_out
 
-    // walk back to front: chunk c covers sub-list indices [top - 32, top), slab row t holds index top - 1 - t; the pair
-    // of step s is rows (2s, 2s + 1): the low half-warp owns the nearer-to-the-back row 2s, which comes first
-    int2 e = make_int2(0, 0);
+    // walk back to front: per unit, step c covers sub-list indices [top - 16, top); lane (half, i) stages index
+    // top - 1 - i into shared-memory row 2 * i + half
+    const int li = lane & (CHUNK - 1);
+    const int my_row = 2 * li + half;
+    const Rec *const rows = &s_rec[wib][half];
+    const int2 *const ents = &s_ent[wib][half];
+    int2 e = make_int2(0x7fffffff, 0);            // position beyond every last_id: a null row is never valid
     Rec r = null_record();
-    if (n - 1 - lane >= 0) { e = list[n - 1 - lane]; r = rec[e.y]; }
-    for (int top = n; top > 0; top -= 32) {
+    if (n - 1 - li >= 0) { e = list[n - 1 - li]; r = rec[e.y]; }
+    for (int top = n, walked = 0; walked < n_max; top -= CHUNK, walked += CHUNK) {
         __syncwarp();
-        s_ent[wib][lane] = e;
-        s_rec[wib][lane] = r;
+        s_ent[wib][my_row] = e;
+        s_rec[wib][my_row] = r;
         __syncwarp();
-        const int nt = top - 32;
+        const int nt = top - CHUNK;
+        e = make_int2(0x7fffffff, 0);
         r = null_record();
-        if (nt - 1 - lane >= 0) { e = list[nt - 1 - lane]; r = rec[e.y]; }
-        const int cnt = min(32, top);
+        if (nt - 1 - li >= 0) { e = list[nt - 1 - li]; r = rec[e.y]; }
 
-        // ---- phase A: lane = (entry parity, pixel) -------------------------------------------------------------
-        unsigned touched = 0u;   // bit t: row t contributes to at least one pixel of the unit
+        // ---- phase A: lane = (unit, pixel) --------------------------------------------------------------------
+        unsigned mine_mask = 0u;   // bit t: shared-memory row t (one of my unit's) contributes to my pixel
 #pragma unroll 1
-        for (int t0 = 0; t0 < cnt; t0 += 2 * BS) {
-            // independent per pair: alpha, colour . v_out  (ILP for a warp that runs alone)
-            float Ag[BS], al[BS], wg[BS];
+        for (int t0 = 0; t0 < CHUNK; t0 += BSZ) {
+            // independent per entry: alpha, 1 / (1 - alpha), colour . v_out  (ILP for a warp that runs alone)
+            float Ag[BSZ], al[BSZ], rag[BSZ], wg[BSZ];
 #pragma unroll
-            for (int s = 0; s < BS; ++s) {
-                const int t = t0 + 2 * s + (hi ? 1 : 0);
-                const float4 kk = s_rec[wib][t].k;
-                const float4 q = s_rec[wib][t].q;
-                const float4 c = s_rec[wib][t].c;
-                const int2 en = s_ent[wib][t];
+            for (int s = 0; s < BSZ; ++s) {
+                const int t = 2 * (t0 + s);
+                const float4 kk = rows[t].k;
+                const float4 q = rows[t].q;
+                const float4 c = rows[t].c;
+                const int2 en = ents[t];
                 const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
                 const float araw = ex2_approx(l2a);
-                const bool valid = (en.x <= bin_final) && (l2a <= q.w) && !(l2a < LOG2_ALPHA_MIN);
+                const bool valid = (en.x <= bin_final) && (l2a <= q.w) && (l2a >= LOG2_ALPHA_MIN);
                 Ag[s] = valid ? araw : 0.f;
                 al[s] = fminf(GSB_ALPHA_CLAMP, Ag[s]);
+                rag[s] = rcp_approx(1.0f - al[s]);
                 float w = c.x * v_out[0];
                 if (C3 > 1) w += c.y * v_out[1];
                 if (C3 > 2) w += c.z * v_out[2];
@@ -563,41 +570,31 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                     for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)en.y * CH + k) * v_out[k];
                 }
                 wg[s] = w;
-                const unsigned m = __ballot_sync(0xffffffffu, valid);
-                touched |= ((m & 0xFFFFu) ? 1u : 0u) << (t0 + 2 * s);
-                touched |= ((m >> 16) ? 1u : 0u) << (t0 + 2 * s + 1);
+                mine_mask |= valid ? (1u << (t + half)) : 0u;
             }
             // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch
 #pragma unroll
-            for (int s = 0; s < BS; ++s) {
-                const int t = t0 + 2 * s + (hi ? 1 : 0);
-                const float al_o = __shfl_xor_sync(0xffffffffu, al[s], PIX);
-                const float w_o = __shfl_xor_sync(0xffffffffu, wg[s], PIX);
-                const float a0 = hi ? al_o : al[s], a1 = hi ? al[s] : al_o;      // rows 2s (first), 2s + 1
-                const float w0 = hi ? w_o : wg[s], w1 = hi ? wg[s] : w_o;
-                const float r0 = rcp_approx(1.0f - a0), r1 = rcp_approx(1.0f - a1);
-                const float T0 = T * r0;                     // transmittance in front of row 2s
-                const float E0 = r0 * (B - c0);
-                const float B1 = B + w0 * (a0 * T0);
-                const float T1 = T0 * r1;
-                const float E1 = r1 * (B1 - c0);
-                B = B1 + w1 * (a1 * T1);
-                T = T1;
-                const int at = slab_at(t, p);
+            for (int s = 0; s < BSZ; ++s) {
+                const int at = slab_at(2 * (t0 + s) + half, p);
+                T *= rag[s];
                 my_A[at] = Ag[s];
-                my_T[at] = hi ? T1 : T0;
-                my_E[at] = hi ? E1 : E0;
+                my_A[at + SLAB] = T;
+                my_A[at + 2 * SLAB] = rag[s] * (B - c0);
+                B += wg[s] * (al[s] * T);
             }
         }
+        const unsigned touched = __reduce_or_sync(0xffffffffu, mine_mask);   // also orders phase A's stores before phase B
         __syncwarp();
         if (touched == 0u) continue;
 
-        // ---- phase B: lane = Gaussian (slab row `lane`) ------------------------------------------------------
+        // ---- phase B: lane = Gaussian (shared-memory row `lane`: entry lane / 2 of unit lane % 2) -------------
         {
             const float4 kk = s_rec[wib][lane].k;
             const float4 q = s_rec[wib][lane].q;
             const float4 c = s_rec[wib][lane].c;
             const int g = s_ent[wib][lane].y;
+            const int hb = lane & 1;                                   // the unit this row belongs to
+            const float ox = (hb == half) ? bx : bx_other;             // pixel (0,0) of that unit (same row of pixels)
             float col[CH];
             col[0] = c.x;
             if (CH > 1) col[1] = c.y;
@@ -612,15 +609,15 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
             for (int k = 0; k < CH; ++k) g_col[k] = 0.f;
             float s0 = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f;   // moments of v_sigma
             const int rot = lane >> 1;
-            const float *row_A = my_A + lane * PIX, *row_T = my_T + lane * PIX, *row_E = my_E + lane * PIX;
+            const float *row_A = my_A + lane * PIX;
 #pragma unroll 8
             for (int pp = 0; pp < PIX; ++pp) {
                 const int at = (pp + rot) & (PIX - 1);
-                const float A = row_A[at], Tp = row_T[at], Ep = row_E[at];
+                const float A = row_A[at], Tp = row_A[at + SLAB], Ep = row_A[at + 2 * SLAB];
                 float vo[NV4 * 4];
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
-                    const float4 v4 = s_vo[wib][pp][k];
+                    const float4 v4 = s_vo[wib][hb][pp][k];
                     vo[4 * k] = v4.x; vo[4 * k + 1] = v4.y; vo[4 * k + 2] = v4.z; vo[4 * k + 3] = v4.w;
                 }
                 const float fac = fminf(GSB_ALPHA_CLAMP, A) * Tp;
@@ -633,7 +630,7 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_units, const Rec *__restric
                 float v_alpha = Tp * w - Ep;
                 v_alpha = (A <= GSB_ALPHA_CLAMP) ? v_alpha : 0.f;   // clamped alpha passes no gradient to sigma / opacity
                 const float v_sigma = -A * v_alpha;                 // d alpha / d sigma = -alpha
-                const float dx = kk.x - (bx + (float)(pp & 3)), dy = kk.y - (by + (float)(pp >> 2));   // exact pixel centre
+                const float dx = kk.x - (ox + (float)(pp & 3)), dy = kk.y - (by + (float)(pp >> 2));   // exact pixel centre
                 const float t1 = v_sigma * dx, t2 = v_sigma * dy;
                 s0 += v_sigma;
                 sxx += t1 * dx;
@@ -703,8 +700,8 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
     build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, m_dev, offsets, flatten_ids, w.rec,
                                                              w.entries, w.counts);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
-    composite_fwd_kernel<CH><<<gsb_div_up(n_units, WPB), 32 * WPB, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
+    composite_fwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB), 32 * WPB, 0, st>>>(
+        W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
         w.work, render, alphas, last_ids);
     return 0;
 }
@@ -718,8 +715,8 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.work, w.order);   // order by the forward's measured work
-    composite_bwd_kernel<CH><<<gsb_div_up(n_units, WPB_B), 32 * WPB_B, 0, st>>>(
-        W, H, tw, n_units, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
+    composite_bwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB_B), 32 * WPB_B, 0, st>>>(
+        W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
         alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
 }

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) isect_tiles_ordered_kernel(int N, const f
                                                                    const int32_t *__restrict__ radii,
                                                                    const int32_t *__restrict__ order,
                                                                    const int64_t *__restrict__ cum_ordered, CamK cam,
-                                                                   uint32_t *__restrict__ tile_keys,
+                                                                   int64_t cap, uint32_t *__restrict__ tile_keys,
                                                                    int32_t *__restrict__ gauss_ids) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -91,23 +91,32 @@ __global__ void __launch_bounds__(256) isect_tiles_ordered_kernel(int N, const f
     int64_t pos = (i == 0) ? 0 : cum_ordered[i - 1];
     for (int y = y0; y < y1; ++y)
         for (int x = x0; x < x1; ++x) {
-            tile_keys[pos] = (uint32_t)(y * cam.tile_w + x);
-            gauss_ids[pos] = g;
+            if (pos < cap) {      // speculative capacity (gsb_batch_*): the farthest intersections are dropped, never written out of bounds
+                tile_keys[pos] = (uint32_t)(y * cam.tile_w + x);
+                gauss_ids[pos] = g;
+            }
             ++pos;
         }
 }
 
-extern "C" __attribute__((visibility("default"))) int gsb_isect_tiles_ordered(int32_t N, const float *means2d, const int32_t *radii,
-                                       const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam,
-                                       uint32_t *tile_keys, int32_t *gauss_ids, void *stream) {
+// `cap`: capacity of tile_keys / gauss_ids (entries at positions >= cap are dropped).
+int gsb_isect_tiles_ordered_cap(int32_t N, const float *means2d, const int32_t *radii, const int32_t *order,
+                                const int64_t *cum_ordered, const gsb_camera *cam, int64_t cap, uint32_t *tile_keys,
+                                int32_t *gauss_ids, void *stream) {
     GSB_CHECK_ARG(N >= 0 && cam != nullptr);
     if (N == 0) return GSB_OK;
     GSB_CHECK_ARG(means2d && radii && order && cum_ordered && tile_keys && gauss_ids);
     CamK k = gsb_make_cam(cam);
     isect_tiles_ordered_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        N, reinterpret_cast<const float2 *>(means2d), radii, order, cum_ordered, k, tile_keys, gauss_ids);
+        N, reinterpret_cast<const float2 *>(means2d), radii, order, cum_ordered, k, cap, tile_keys, gauss_ids);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gsb_isect_tiles_ordered(int32_t N, const float *means2d, const int32_t *radii,
+                                       const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam,
+                                       uint32_t *tile_keys, int32_t *gauss_ids, void *stream) {
+    return gsb_isect_tiles_ordered_cap(N, means2d, radii, order, cum_ordered, cam, INT64_MAX, tile_keys, gauss_ids, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int gsb_project_fwd(int32_t N, const float *means, const float *quats, const float *scales,

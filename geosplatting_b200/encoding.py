@@ -31,8 +31,14 @@ def level_scalings(num_levels: int, min_res: int, max_res: int) -> List[float]:
 
 class _HashGrid(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x: Tensor, table: Tensor, scalings, log2_T: int, table_grad_scale: float):
+    def forward(ctx, x: Tensor, table: Tensor, scalings, log2_T: int, table_grad_scale: float,
+                straight_through: bool = False):
         x_c, table_c = f32c(x), f32c(table)
+        if straight_through and table_grad_scale != 1.0:
+            # encoding.py:232-233 evaluates the grid at x * (1/s) + x.detach() * (1 - 1/s): the same point up to an ulp,
+            # and an ulp decides the cell when x sits on a cell boundary of some level -- take the reference's point
+            inv = 1.0 / table_grad_scale
+            x_c = x_c * inv + x_c * (1.0 - inv)
         dev = x_c.device
         N, L, F = x_c.shape[0], len(scalings), table_c.shape[1]
         feats = torch.empty(N, L * F, dtype=torch.float32, device=dev)
@@ -52,10 +58,24 @@ class _HashGrid(torch.autograd.Function):
         v_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
         v_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         if v_table is None and v_x is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         call("gsb_hashgrid_bwd", dev, C.c_int64(N), ptr(x), ptr(table), C.c_int32(L), C.c_int32(F), C.c_int32(log2_T), sc,
              ptr(f32c(v_feats)), C.c_float(gscale), ptr(v_table), ptr(v_x), stream_ptr(dev))
-        return v_x, v_table, None, None, None
+        return v_x, v_table, None, None, None, None
+
+
+class _ReferenceRounding(torch.autograd.Function):
+    """encoding.py:239-240 hands the MLP `feats * s + feats.detach() * (1 - s)`: the features up to an fp32 rounding, and a
+    rounding decides which side of a ReLU kink a hidden unit is on.  Same values here; the gradient factor s lives in the
+    hash-grid backward kernel, so this node passes gradients through unchanged."""
+
+    @staticmethod
+    def forward(ctx, feats: Tensor, s: float):
+        return feats * s + feats * (1.0 - s)
+
+    @staticmethod
+    def backward(ctx, v):
+        return v, None
 
 
 class MLP(nn.Module):
@@ -132,20 +152,24 @@ class HashEncoding(nn.Module):
     def hash_table(self) -> nn.Parameter:
         return self.encoder.params
 
-    def encode(self, in_tensor: Tensor) -> Tensor:
-        """pytorch_fwd (encoding.py:182-229): [..., 3] in [-1, 1] -> [..., num_levels * features_per_level]."""
+    def encode(self, in_tensor: Tensor, straight_through: bool = False) -> Tensor:
+        """pytorch_fwd (encoding.py:182-229): [..., 3] in [-1, 1] -> [..., num_levels * features_per_level].
+        `straight_through`: evaluate at the point `__call__` (encoding.py:231-233) hands to pytorch_fwd."""
         _require_cuda(in_tensor, "HashEncoding")
         assert in_tensor.shape[-1] == 3
         flat = in_tensor.reshape(-1, 3)
         feats = _HashGrid.apply(flat, self.hash_table, self.scalings, self.log2_hashmap_size,
-                                1.0 if self.grad_scaling is None else float(self.grad_scaling))
+                                1.0 if self.grad_scaling is None else float(self.grad_scaling), straight_through)
         return feats.view(*in_tensor.shape[:-1], self.num_levels * self.features_per_level)
 
     def forward(self, in_tensor: Tensor) -> Tensor:
         """encoding.py:231-241.  The two straight-through expressions of the reference (`x/s + x.detach()(1-1/s)`,
         `f*s + f.detach()(1-s)`) leave values unchanged and multiply the gradient that reaches the table by s while the
         one that reaches x stays as it is: that factor is applied inside the backward kernel."""
-        return self.mlp(self.encode(in_tensor))
+        feats = self.encode(in_tensor, straight_through=True)
+        if self.grad_scaling is not None:
+            feats = _ReferenceRounding.apply(feats, float(self.grad_scaling))
+        return self.mlp(feats)
 
 
 class TcnnEncoding(nn.Module):

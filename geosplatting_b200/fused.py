@@ -25,7 +25,7 @@ from typing import List, NamedTuple, Optional, Sequence
 import torch
 from torch import Tensor
 
-from ._lib import GsbViewConfig, call, f32c, ptr, stream_ptr
+from ._lib import CallStats, GsbCamera, GsbViewConfig, call, f32c, ptr, stream_ptr
 from ._lib import require_cuda as _require_cuda
 from .rasterization import BinCount, _release_slot, _total_slot, bin_finish, make_camera
 from .scenes import PinholeCamera, to_pinhole
@@ -255,6 +255,155 @@ def _view_backward(sh: _Shared, v: _View, v_out: Tensor, g: _Grads, v_exp: Tenso
          ptr(g.kd), ptr(g.ks), ptr(g.env), ptr(sws), C.c_size_t(sws.numel()), C.c_int32(1), st)
 
 
+# ---- batch driver: ONE C-ABI call per batch each way, nothing waits for a view's intersection count (csrc/view.cu) -----
+_caps: dict = {}          # (device, N, W, H) -> capacity of the tile lists (intersections per view)
+_pinned_pool: list = []   # recycled pinned int64 buffers the device publishes the raw counts to
+CAP_MARGIN = 1.25
+CAP_QUANTUM = 1 << 16
+
+
+def _round_cap(m: int) -> int:
+    return max(CAP_QUANTUM, (int(m * CAP_MARGIN) + CAP_QUANTUM - 1) // CAP_QUANTUM * CAP_QUANTUM)
+
+
+def _pinned_counts(n: int) -> Tensor:
+    for i, t in enumerate(_pinned_pool):
+        if t.numel() >= n:
+            return _pinned_pool.pop(i)
+    return torch.empty(max(n, 64), dtype=torch.int64).pin_memory()
+
+
+class CapacityExceeded(RuntimeError):
+    """A view produced more tile intersections than the batch's arenas were carved for (the farthest ones were
+    dropped).  The capacity has been raised: run the step again."""
+
+
+class _Batch:
+    """State of one batch between forward and backward."""
+    __slots__ = ("cfg", "cams", "cam_pos", "n", "streams", "stream_ptrs", "cap", "keep", "totals", "event", "ex_all",
+                 "ex_stride", "key", "checked")
+
+
+def _batch_arrays(sh: _Shared, cameras, side):
+    n = len(cameras)
+    cams = (GsbCamera * n)()
+    pos = (C.c_float * (3 * n))()
+    for i, c in enumerate(cameras):
+        cam, p = _camera_struct(c, sh.meta.antialiased)
+        C.memmove(C.addressof(cams) + i * C.sizeof(GsbCamera), C.addressof(cam), C.sizeof(GsbCamera))
+        pos[3 * i], pos[3 * i + 1], pos[3 * i + 2] = p[0], p[1], p[2]
+    main = torch.cuda.current_stream(sh.dev)
+    streams = list(side) if side else [main]
+    ptrs = (C.c_void_p * len(streams))(*[st.cuda_stream for st in streams])
+    return cams, pos, streams, ptrs, main
+
+
+def _exposure_array(exposures, dev):
+    """(device float array, stride): stride 0 when every view shares one exposure tensor."""
+    first = exposures[0]
+    if all(e is first for e in exposures) and first.numel() == 1:
+        return f32c(first).reshape(1), 0
+    return torch.cat([f32c(e).reshape(1) for e in exposures]), 1
+
+
+def _batch_forward(sh: _Shared, cameras, exposures, side) -> tuple:
+    dev, N, n = sh.dev, sh.N, len(cameras)
+    b = _Batch()
+    b.n = n
+    b.cams, b.cam_pos, b.streams, b.stream_ptrs, main = _batch_arrays(sh, cameras, side)
+    W, H = b.cams[0].width, b.cams[0].height
+    b.cfg = _view_config(sh, b.cams[0])
+    b.ex_all, b.ex_stride = _exposure_array(exposures, dev)
+    b.key = (dev.index if dev.index is not None else torch.cuda.current_device(), N, W, H)
+    ns = len(b.streams)
+    out = torch.empty(n, H, W, 4, dtype=torch.float32, device=dev)
+    probing = b.key not in _caps
+    cap = _caps.get(b.key) or _round_cap(4 * N + 4 * ((W + 15) // 16) * ((H + 15) // 16))
+    while True:
+        sizes = (C.c_size_t * 2)()
+        call("gsb_batch_bytes", dev, C.addressof(b.cfg), n, ns, cap, C.addressof(sizes))
+        b.keep, scratch = _u8(sizes[0], dev), _u8(sizes[1], dev)
+        b.totals = _pinned_counts(n)
+        call("gsb_batch_forward", dev, C.addressof(b.cfg), n, C.addressof(b.cams), C.addressof(b.cam_pos),
+             sh.means.data_ptr(), sh.quats.data_ptr(), sh.scales.data_ptr(), sh.logits.data_ptr(), sh.normals.data_ptr(),
+             sh.kd.data_ptr(), sh.ks.data_ptr(), sh.lut.data_ptr(), sh.env.data_ptr(), b.ex_all.data_ptr(), b.ex_stride,
+             b.keep.data_ptr(), scratch.data_ptr(), cap, b.totals.data_ptr(), out.data_ptr(), C.addressof(b.stream_ptrs),
+             ns, main.cuda_stream)
+        CallStats.counts["batch_view_forward"] = CallStats.counts.get("batch_view_forward", 0) + n
+        b.cap = cap
+        b.event = torch.cuda.Event()
+        b.event.record(main)
+        b.checked = False
+        if not probing:
+            return b, out
+        # first batch of this (scene size, resolution): the capacity was a guess -- wait once, size it from the counts
+        b.event.synchronize()
+        m_max = int(b.totals[:n].max())
+        _caps[b.key] = _round_cap(m_max)
+        if m_max <= cap:
+            b.checked = True
+            _pinned_pool.append(b.totals)
+            b.totals = None
+            return b, out
+        cap = _caps[b.key]
+
+
+def _batch_check(b: _Batch) -> None:
+    """Before the backward touches the saved state: did every view fit its capacity?  (The forward has long finished
+    when autograd gets here; the wait is a formality.)"""
+    if b.checked:
+        return
+    b.event.synchronize()
+    m_max = int(b.totals[:b.n].max())
+    _pinned_pool.append(b.totals)
+    b.totals, b.checked = None, True
+    if _round_cap(m_max) > _caps.get(b.key, 0):
+        _caps[b.key] = _round_cap(m_max)                     # the scene grew: follow it
+    if m_max > b.cap:
+        raise CapacityExceeded(f"a view of this batch has {m_max} tile intersections, the batch was carved for {b.cap}; "
+                               "the capacity has been raised -- run the step again")
+
+
+def _batch_backward(sh: _Shared, b: _Batch, v_outs, T: int):
+    dev, N, n = sh.dev, sh.N, b.n
+    _batch_check(b)
+    main = torch.cuda.current_stream(dev)
+    ns = len(b.streams)
+    nf = C.c_int64(0)
+    call("gsb_batch_grad_floats", dev, C.addressof(b.cfg), n, T, C.byref(nf))
+    used = min(ns, n)
+    bufs = torch.zeros(used, nf.value, dtype=torch.float32, device=dev)
+    sizes = (C.c_size_t * 2)()
+    call("gsb_batch_bytes", dev, C.addressof(b.cfg), n, ns, b.cap, C.addressof(sizes))
+    scratch = _u8(sizes[1], dev)
+    keepalive = [None if v is None else f32c(v) for v in v_outs]
+    vptrs = (C.c_void_p * n)(*[None if v is None else v.data_ptr() for v in keepalive])
+    gptrs = (C.c_void_p * ns)(*[bufs[min(i, used - 1)].data_ptr() for i in range(ns)])
+    probes = None
+    if PROBES is not None:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n)]
+        for e in evs:
+            e.record(main)            # materialises the cudaEvent_t; the driver re-records it around the stage
+        probes = (C.c_void_p * (2 * n))(*[e.cuda_event for e in evs])
+        PROBES.extend((evs[2 * i], evs[2 * i + 1]) for i in range(n) if keepalive[i] is not None)
+    call("gsb_batch_backward", dev, C.addressof(b.cfg), n, C.addressof(b.cams), C.addressof(b.cam_pos),
+         sh.means.data_ptr(), sh.quats.data_ptr(), sh.scales.data_ptr(), sh.logits.data_ptr(), sh.normals.data_ptr(),
+         sh.kd.data_ptr(), sh.ks.data_ptr(), sh.lut.data_ptr(), sh.env.data_ptr(), b.ex_all.data_ptr(), b.ex_stride,
+         b.keep.data_ptr(), scratch.data_ptr(), b.cap, C.addressof(vptrs), T, C.addressof(gptrs), C.c_float(1.0),
+         C.addressof(b.stream_ptrs), ns, None if probes is None else C.addressof(probes), main.cuda_stream)
+    CallStats.counts["batch_view_backward"] = CallStats.counts.get("batch_view_backward", 0) + sum(
+        v is not None for v in keepalive)
+    flat = bufs[0]
+    g = _Grads.__new__(_Grads)
+    g.flat = flat
+    o = 0
+    for name, k in (("env", 4 * T), ("quats", 4 * N), ("ks", 2 * N), ("means", 3 * N), ("scales", 3 * N),
+                    ("logits", N), ("normals", 3 * N), ("kd", 3 * N)):
+        setattr(g, name, flat[o:o + k])
+        o += k
+    return g, flat[o:o + n]
+
+
 class _SplatBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, log_scales, quats, logits, kd, ks, normals, env_data, lut, meta, cameras, n_streams,
@@ -268,18 +417,25 @@ class _SplatBatch(torch.autograd.Function):
         sh.scales = f32c(log_scales).exp()                    # rfstudio/model/gsplat.py:337, once per batch
         main = torch.cuda.current_stream(dev)
         side = _streams(dev, n_streams) if n_streams > 1 and len(cameras) > 1 else []
+        n = len(cameras)
+        ctx.batch = None
+        if native == "batch" and len({(c.width, c.height) for c in cameras}) == 1:
+            ctx.batch, out = _batch_forward(sh, cameras, exposures, side)
+            ctx.sh, ctx.views, ctx.side, ctx.native = sh, None, side, native
+            ctx.save_for_backward(sh.means, sh.quats, sh.logits, sh.kd, sh.ks, sh.normals, sh.env)
+            ctx.shapes = (tuple(logits.shape), [tuple(e.shape) for e in exposures], env_data.shape[0])
+            return tuple(out[i] for i in range(n))
         # what outlives the side streams' work (the images here, the gradient buffers in the backward) is allocated
         # on the CALLER's stream before the side streams wait for it: the caching allocator then recycles it in plain
         # stream order, with no record_stream() events that would delay reuse and grow the pool
         outs = [torch.empty(c.height, c.width, 4, dtype=torch.float32, device=dev) for c in cameras]
         for s in side:
             s.wait_stream(main)
-        where = [side[i % len(side)] if side else main for i in range(len(cameras))]
+        where = [side[i % len(side)] if side else main for i in range(n)]
         # Software pipeline over the views: one view per stream is prepared up front; after view i is finished (the
         # only point where the host waits, for M_i), view i + n_streams is prepared on the same stream.  The host never
         # waits on an idle device, and at any time the streams are in different phases, so the big compositing
         # kernels of one view share the SMs with the small sort / scan kernels of its neighbours.
-        n = len(cameras)
         views, cfgs = [None] * n, {}
 
         def prep(i):
@@ -311,6 +467,16 @@ class _SplatBatch(torch.autograd.Function):
         _ = ctx.saved_tensors                                  # raises if an input was modified in place since the forward
         logits_shape, exposure_shapes, T = ctx.shapes
         dev, N = sh.dev, sh.N
+        if ctx.batch is not None:
+            if all(v is None for v in v_outs):
+                return (None,) * (13 + len(v_outs))
+            total, v_exp = _batch_backward(sh, ctx.batch, v_outs, T)
+            total.scales.mul_(sh.scales.reshape(-1))           # d exp(s) / d s
+            return (total.means.view(N, 3), total.scales.view(N, 3), total.quats.view(N, 4),
+                    total.logits.view(logits_shape), total.kd.view(N, 3), total.ks.view(N, 2), total.normals.view(N, 3),
+                    total.env.view(T, 4), None, None, None, None, None,
+                    *[None if v is None else v_exp[i].reshape(shp)
+                      for i, (v, shp) in enumerate(zip(v_outs, exposure_shapes))])
         main = torch.cuda.current_stream(dev)
         v_exps = []
         # one zero-filled gradient buffer per stream in use, every view on that stream adds into it (allocated on the
@@ -360,13 +526,16 @@ def _meta_and_lut(envmap: EnvStack, fg_lut: Tensor, min_roughness, max_metallic,
 def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
                 normals: Tensor, cameras, *, exposures, envmap, fg_lut: Optional[Tensor] = None,
                 min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-                rasterize_mode: str = "antialiased", n_streams: int = 4, native: bool = True) -> List[Tensor]:
+                rasterize_mode: str = "antialiased", n_streams: int = 4, native="batch") -> List[Tensor]:
     """The per-view loop of GeoSplatter.render_report for a batch of cameras: list of [H,W,4] tone-mapped RGBA images,
     ready on the caller's stream, differentiable w.r.t. every tensor argument and `envmap.data`.
 
     `exposures`: one tensor shared by all views or a sequence of one per view.  `n_streams` <= 1 keeps everything on
-    the caller's stream.  `native`: sequence the kernels of a view in the library's per-view driver (three C-ABI calls
-    per view, csrc/view.cu) rather than call by call from Python (what per-kernel instrumentation needs)."""
+    the caller's stream.  `native`: "batch" (default) = the whole batch is ONE C-ABI call each way (gsb_batch_forward /
+    gsb_batch_backward, csrc/view.cu): nothing on the host waits for a view's intersection count, the tile lists are
+    carved for a capacity learned from the first batch (+25 %) and an overflow raises CapacityExceeded in the backward;
+    True = three C-ABI calls per view with exact sizes (the host waits for each count, views software-pipelined over the
+    streams); False = every kernel group called from Python (what per-kernel instrumentation needs)."""
     _require_cuda(means, "splat_views")
     envmap = EnvStack.coerce(envmap)                 # the reference's TextureSplitSum is accepted as is
     if fg_lut is None:
@@ -378,13 +547,13 @@ def splat_views(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits
     if not cameras:
         return []
     return list(_SplatBatch.apply(means, log_scales, quats, opacity_logits, kd, ks, normals, envmap.data, lut, meta,
-                                  cameras, int(n_streams), bool(native), *ex))
+                                  cameras, int(n_streams), native if native == "batch" else bool(native), *ex))
 
 
 def splat_view(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_logits: Tensor, kd: Tensor, ks: Tensor,
                normals: Tensor, camera, *, exposure: Tensor, envmap, fg_lut: Optional[Tensor] = None,
                min_roughness: float, max_metallic: float, mode: str = "pbr", tone_type: str = "naive",
-               rasterize_mode: str = "antialiased", native: bool = True) -> Tensor:
+               rasterize_mode: str = "antialiased", native="batch") -> Tensor:
     """[H,W,4] tone-mapped RGBA of one view on the caller's stream (a batch of one)."""
     return splat_views(means, log_scales, quats, opacity_logits, kd, ks, normals, [camera], exposures=exposure,
                        envmap=envmap, fg_lut=fg_lut, min_roughness=min_roughness, max_metallic=max_metallic, mode=mode,

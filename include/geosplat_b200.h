@@ -417,6 +417,39 @@ int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const f
 /* probe_start / probe_stop: optional caller-owned cudaEvent_t (NULL to skip) recorded on `stream` right before and
  * after the compositing backward, the dominant stage, so that a benchmark can time it inside a running batch. */
 
+/* -------------------------------------------------------------------------------------------
+ * Batch driver: every view of a training batch in ONE call each way -- the per-view loop of
+ * GeoSplatter.render_report (rfstudio/model/geosplat.py:869-879: `for i in range(batch_size): attrs.splat(...)`) and
+ * its backward.  No host wait on any view's intersection count: the M-sized arrays are carved for the capacity
+ * `m_cap`, the count stays on the device, the raw counts are published to `totals_out[n_views]` (pinned host memory;
+ * M > m_cap means the farthest intersections of that view were dropped -- grow m_cap and redo the batch).
+ *   keep / scratch: gsb_batch_bytes -> {keep, scratch}; keep lives forward..backward, scratch inside either call.
+ *   cams[n_views], cam_pos_host[n_views][3]: host arrays.  exposures: device, element v at exposures[v * stride].
+ *   out: [n_views][H][W][4]; v_outs_host[n_views]: host array of device pointers to the [H][W][4] cotangents (NULL =
+ *   this view has none).  streams[n_streams <= 4]: the views are spread round-robin over them;
+ *   main_stream is forked into them and joined again (results are ready on main_stream).
+ *   grad_bufs[n_streams]: zero-filled buffers of gsb_batch_grad_floats floats each, layout
+ *     [ env 4T | quats 4N | ks 2N | means 3N | scales(linear) 3N | logits N | normals 3N | kd 3N | exposure n_views ];
+ *     the sum over streams times grad_scale ends up in grad_bufs[0].
+ *   probe_events: optional
+ *   cudaEvent_t[2 * n_views] recorded around each view's compositing backward.
+ * ------------------------------------------------------------------------------------------- */
+int gsb_batch_bytes(const gsb_view_config *cfg, int32_t n_views, int32_t n_streams, int64_t m_cap, size_t *bytes2_host);
+int gsb_batch_grad_floats(const gsb_view_config *cfg, int32_t n_views, int64_t env_texels, int64_t *floats_host);
+int gsb_batch_forward(const gsb_view_config *cfg, int32_t n_views, const gsb_camera *cams, const float *cam_pos_host,
+                      const float *means, const float *quats, const float *scales, const float *opacity_logits,
+                      const float *normals, const float *kd, const float *ks, const float *fg_lut,
+                      const float *env_stack, const float *exposures, int32_t exposure_stride, void *keep,
+                      void *scratch, int64_t m_cap, int64_t *totals_out, float *out, void *const *streams,
+                      int32_t n_streams, void *main_stream);
+int gsb_batch_backward(const gsb_view_config *cfg, int32_t n_views, const gsb_camera *cams, const float *cam_pos_host,
+                       const float *means, const float *quats, const float *scales, const float *opacity_logits,
+                       const float *normals, const float *kd, const float *ks, const float *fg_lut,
+                       const float *env_stack, const float *exposures, int32_t exposure_stride, const void *keep,
+                       void *scratch, int64_t m_cap, const float *const *v_outs_host,
+                       int64_t env_texels, float *const *grad_bufs, float grad_scale, void *const *streams,
+                       int32_t n_streams, void *probe_events, void *main_stream);
+
 #ifdef __cplusplus
 }
 #endif

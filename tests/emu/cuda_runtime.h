@@ -83,6 +83,11 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 typedef void *cudaEvent_t;
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+// the host build is one stream in program order: events and cross-stream waits are no-ops
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 
 template <class T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 static inline float2 atomicAdd(float2 *p, float2 v) {   // red.global.add.v2.f32

@@ -291,6 +291,24 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {      // REDUX.OR (sm_80+)
+    unsigned part;
+    gsb_emu::Warp &w = gsb_emu::warp_rendezvous(mask, (unsigned long long)v, &part);
+    const int me = gsb_emu::lane_id();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((part >> l) & 1u) r |= (unsigned)w.res[me][l];
+    return r;
+}
+static inline int __reduce_max_sync(unsigned mask, int v) {               // REDUX.MAX.S32
+    unsigned part;
+    gsb_emu::Warp &w = gsb_emu::warp_rendezvous(mask, (unsigned long long)(unsigned)v, &part);
+    const int me = gsb_emu::lane_id();
+    int r = v;
+    for (int l = 0; l < 32; ++l)
+        if ((part >> l) & 1u) { const int x = (int)(unsigned)w.res[me][l]; r = x > r ? x : r; }
+    return r;
+}
 static inline int __all_sync(unsigned mask, int pred) {
     unsigned part;
     gsb_emu::Warp &w = gsb_emu::warp_rendezvous(mask, pred ? 1ull : 0ull, &part);

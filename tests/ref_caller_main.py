@@ -90,6 +90,7 @@ def route_library_to_host():
     rz._total_slot = lambda device: torch.zeros(1, dtype=torch.int64)
     fu = importlib.import_module("geosplatting_b200.fused")
     fu._total_slot = rz._total_slot
+    fu._pinned_counts = lambda n: torch.zeros(max(n, 64), dtype=torch.int64)     # pinned memory needs a CUDA runtime
     importlib.import_module("geosplatting_b200.splitsum")._bounds_device = lambda index: torch.device("cpu")
     return gb
 

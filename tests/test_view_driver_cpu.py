@@ -173,3 +173,121 @@ def test_driver_with_nothing_to_draw(lib, N, behind):
                                  _p(nrm), _p(kd), _p(ks), _p(lut), _p(stack), _p(ex), _p(keep1), _p(keep2), _p(tmp3),
                                  _p(v_out), *[_p(x) for x in g], None, None, None) == 0, lib.gsb_last_error()
     assert all(float(np.abs(x).max()) == 0 for x in g if x.size)
+
+
+def _batch_inputs(N=1800, W=72, H=56, n_views=3):
+    R0, L, Rb = 32, 4, 8
+    gen = torch.Generator().manual_seed(23)
+    sg = scenes.surface_gaussians(N, seed=6)
+    normals = torch.nn.functional.normalize(sg["normals"] + 0.2 * torch.randn(N, 3, generator=gen), dim=-1)
+    logits = torch.logit(sg["opacities"].clamp(0.02, 0.98))
+    base, mips = _random_env(R0, L, Rb, seed=9)
+    f = lambda t: np.ascontiguousarray(t.detach().numpy(), np.float32)   # noqa: E731
+    arrs = dict(means=f(sg["means"]), quats=f(sg["quats"]), scales=f(sg["scales"]), logits=f(logits), normals=f(normals),
+                kd=f(sg["kd"]), ks=f(sg["ks"]), lut=f(torch.from_numpy(synthetic_fg_lut())))
+    cams = scenes.orbit_cameras(n_views, W, H, seed=11)
+    return arrs, cams, (R0, L, Rb), base, mips
+
+
+def test_batch_driver_equals_the_per_view_driver(lib):
+    """gsb_batch_forward / gsb_batch_backward (one call per batch, capacity-sized tile lists, device-resident counts,
+    views round-robin over 'streams', per-stream gradient buffers summed at the end) against three per-view calls with
+    exact sizes: identical images, gradients equal to the order of additions; the raw counts are published; an
+    undersized capacity is reported, not a crash."""
+    _lib.declare(lib)
+    N, W, H, n = 1800, 72, 56, 3
+    a, cams, (R0, L, Rb), base, mips = _batch_inputs(N, W, H, n)
+    i32, i64 = C.c_int32, C.c_int64
+    texels = i64(0)
+    assert lib.gsb_envstack_texels(i32(R0), i32(L), i32(Rb), C.byref(texels)) == 0
+    T = texels.value
+    stack = np.zeros((T, 4), np.float32)
+    packed = np.ascontiguousarray(OT.merge_mipmaps(mips).numpy(), np.float32)
+    assert lib.gsb_envstack_pack(i32(R0), i32(L), i32(Rb), _p(packed), _p(np.ascontiguousarray(base.numpy())), _p(stack),
+                                 None) == 0
+    cfg = _lib.GsbViewConfig(N, W, H, 256, R0, L, Rb, 0.1, 1.0, 0.08, 0.5, 0, 1)
+    gcs = (_lib.GsbCamera * n)()
+    pos = (C.c_float * (3 * n))()
+    for i, c in enumerate(cams):
+        g = make_camera(c.view_matrix, c.intrinsic_matrix, W, H, antialiased=True)
+        C.memmove(C.addressof(gcs) + i * C.sizeof(_lib.GsbCamera), C.addressof(g), C.sizeof(_lib.GsbCamera))
+        pos[3 * i:3 * i + 3] = [float(x) for x in c.position]
+    ex = np.array([1.0, 1.2, 0.9], np.float32)
+    rng = np.random.default_rng(3)
+    v_out = rng.standard_normal((n, H, W, 4)).astype(np.float32)
+
+    # ---- per view, exact sizes
+    ref_imgs, ref_M = [], []
+    ref_g = {k: np.zeros(s, np.float32) for k, s in (("means", (N, 3)), ("quats", (N, 4)), ("scales", (N, 3)),
+                                                      ("logits", N), ("normals", (N, 3)), ("kd", (N, 3)), ("ks", (N, 2)),
+                                                      ("env", (T, 4)))}
+    ref_ex = np.zeros(n, np.float32)
+    for v in range(n):
+        sizes = (C.c_size_t * 5)()
+        assert lib.gsb_view_bytes(C.addressof(cfg), 0, C.addressof(sizes)) == 0
+        keep1, tmp1 = np.full(sizes[0] + 256, 0xFF, np.uint8), np.full(sizes[1] + 256, 0xFF, np.uint8)
+        total = np.zeros(1, np.int64)
+        cp = (C.c_float * 3)(*pos[3 * v:3 * v + 3])
+        assert lib.gsb_view_prepare(C.addressof(cfg), C.addressof(gcs[v]), C.addressof(cp), _p(a["means"]), _p(a["quats"]), _p(a["scales"]),
+                                    _p(a["normals"]), _p(a["kd"]), _p(a["ks"]), _p(a["lut"]), _p(stack), _p(keep1),
+                                    _p(tmp1), _p(total), None) == 0, lib.gsb_last_error()
+        M = int(total[0])
+        ref_M.append(M)
+        assert lib.gsb_view_bytes(C.addressof(cfg), M, C.addressof(sizes)) == 0
+        keep2, tmp2 = np.full(sizes[2] + 256, 0xFF, np.uint8), np.full(sizes[3] + 256, 0xFF, np.uint8)
+        out = np.zeros((H, W, 4), np.float32)
+        assert lib.gsb_view_finish(C.addressof(cfg), C.addressof(gcs[v]), M, _p(a["logits"]), _p(ex[v:v + 1]), _p(keep1), _p(tmp1),
+                                   _p(keep2), _p(tmp2), _p(out), None) == 0, lib.gsb_last_error()
+        ref_imgs.append(out)
+        tmp3 = np.full(sizes[4] + 256, 0xFF, np.uint8)
+        assert lib.gsb_view_backward(C.addressof(cfg), C.addressof(gcs[v]), C.addressof(cp), M, _p(a["means"]), _p(a["quats"]),
+                                     _p(a["scales"]), _p(a["logits"]), _p(a["normals"]), _p(a["kd"]), _p(a["ks"]),
+                                     _p(a["lut"]), _p(stack), _p(ex[v:v + 1]), _p(keep1), _p(keep2), _p(tmp3), _p(v_out[v]),
+                                     _p(ref_g["means"]), _p(ref_g["quats"]), _p(ref_g["scales"]), _p(ref_g["logits"]),
+                                     _p(ref_g["normals"]), _p(ref_g["kd"]), _p(ref_g["ks"]), _p(ref_g["env"]),
+                                     _p(ref_ex[v:v + 1]), None, None, None) == 0, lib.gsb_last_error()
+
+    # ---- the batch driver, two 'streams', capacity 30 % above the largest count
+    def run_batch(cap, ns=2):
+        sizes = (C.c_size_t * 2)()
+        assert lib.gsb_batch_bytes(C.addressof(cfg), n, ns, cap, C.addressof(sizes)) == 0
+        keep, scratch = np.full(sizes[0] + 256, 0xFF, np.uint8), np.full(sizes[1] + 256, 0xFF, np.uint8)
+        totals = np.full(n, -1, np.int64)
+        out = np.zeros((n, H, W, 4), np.float32)
+        streams = (C.c_void_p * ns)()
+        assert lib.gsb_batch_forward(C.addressof(cfg), n, C.addressof(gcs), C.addressof(pos), _p(a["means"]), _p(a["quats"]), _p(a["scales"]),
+                                     _p(a["logits"]), _p(a["normals"]), _p(a["kd"]), _p(a["ks"]), _p(a["lut"]), _p(stack),
+                                     _p(ex), 1, _p(keep), _p(scratch), cap, _p(totals), _p(out), C.addressof(streams), ns,
+                                     None) == 0, lib.gsb_last_error()
+        return keep, scratch, totals, out, streams
+
+    cap = int(max(ref_M) * 1.3)
+    keep, scratch, totals, out, streams = run_batch(cap)
+    assert totals.tolist() == ref_M                                   # raw counts published
+    for v in range(n):
+        assert np.array_equal(out[v], ref_imgs[v]), v                 # same kernels, same lists -> same bits
+    nf = i64(0)
+    assert lib.gsb_batch_grad_floats(C.addressof(cfg), n, T, C.byref(nf)) == 0
+    bufs = np.zeros((2, nf.value), np.float32)
+    gptrs = (C.c_void_p * 2)(bufs[0].ctypes.data, bufs[1].ctypes.data)
+    vptrs = (C.c_void_p * n)(*[v_out[v].ctypes.data for v in range(n)])
+    scratch[:] = 0xFF
+    assert lib.gsb_batch_backward(C.addressof(cfg), n, C.addressof(gcs), C.addressof(pos), _p(a["means"]), _p(a["quats"]), _p(a["scales"]),
+                                  _p(a["logits"]), _p(a["normals"]), _p(a["kd"]), _p(a["ks"]), _p(a["lut"]), _p(stack), _p(ex),
+                                  1, _p(keep), _p(scratch), cap, C.addressof(vptrs), T, C.addressof(gptrs), C.c_float(0.5), C.addressof(streams), 2,
+                                  None, None) == 0, lib.gsb_last_error()
+    flat, o = bufs[0], 0
+    for name, k in (("env", 4 * T), ("quats", 4 * N), ("ks", 2 * N), ("means", 3 * N), ("scales", 3 * N), ("logits", N),
+                    ("normals", 3 * N), ("kd", 3 * N)):
+        got, want = flat[o:o + k], 0.5 * ref_g[name].reshape(-1)      # grad_scale = 0.5
+        o += k
+        scale = float(np.abs(want).max())
+        assert float(np.abs(got - want).max()) <= 1e-5 * max(scale, 1e-20), (name, float(np.abs(got - want).max()), scale)
+    assert np.allclose(flat[o:o + n], 0.5 * ref_ex, rtol=1e-5, atol=1e-7)
+
+    # ---- an undersized capacity: counts still published (so the host can grow it), memory stays in bounds (ASan run),
+    #      the image loses only the farthest intersections
+    small = int(min(ref_M) * 0.8)
+    _, _, totals2, out2, _ = run_batch(small)
+    assert totals2.tolist() == ref_M and all(t > small for t in totals2.tolist())
+    assert np.isfinite(out2).all() and float(np.abs(out2 - np.stack(ref_imgs)).mean()) < 0.05
