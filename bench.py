@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a batch are spread over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 2 / 4 / 5")
     ap.add_argument("--full-step", action="store_true", help="also time a full train step (a1-a12, B=8 views)")
     ap.add_argument("--no-train-step", action="store_true",
                     help="skip the whole-training-step probe of BASELINE config 3 (model.GeoSplatter + loss + Adam)")
@@ -150,7 +151,7 @@ def run_b200(a):
 
     from geosplatting_b200 import _lib, scenes, splitsum
     from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
-    from geosplatting_b200.parallel import GradientBucket, shard_views
+    from geosplatting_b200.parallel import FlatAllReduce, shard_views
     from geosplatting_b200.shade import EnvStack, synthetic_fg_lut
     from geosplatting_b200.splat import GSplatter, RenderableAttrs, Splats
 
@@ -193,8 +194,11 @@ def run_b200(a):
         return attrs.splat(gs, [cam], exposure=ex, envmap=env_, fg_lut=lut, min_roughness=0.1, max_metallic=1.0)
 
     grad_inputs = [params[k] for k in PARAM_NAMES] + [env_data, exposure]
-    bucket = GradientBucket([t.shape for t in grad_inputs], dev) if world > 1 else None
     B = max(1, a.views)                     # the reference's batch: 8 views per step of the trainer
+    # the trainer's loss is the mean over the views of the (global) batch: that 1 / (views x ranks) rides in the image
+    # cotangent, so the summed gradients need no scaling pass
+    v_img_batch = v_img / float(B * world) if world > 1 else v_img
+    pending = {"work": None, "nbytes": 0}
 
     def run_views(i0, n):
         """n consecutive views (steps) the way GeoSplatter.render_report + the trainer run a batch: all forwards,
@@ -204,10 +208,14 @@ def run_b200(a):
         imgs = splat_views(params["means"], params["scales"], params["quats"], params["opacities"], params["kd"],
                            params["ks"], params["normals"], cs, exposures=exposure, envmap=env, fg_lut=lut,
                            min_roughness=0.1, max_metallic=1.0, n_streams=a.streams)
-        grads = torch.autograd.grad(imgs, grad_inputs, grad_outputs=[v_img] * n)
+        grads = torch.autograd.grad(imgs, grad_inputs, grad_outputs=[v_img_batch] * n)
         if world > 1:
-            bucket.pack(list(grads))           # waits for the previous collective, then one fused copy
-            bucket.all_reduce(average_over=n * world, async_op=True)   # overlaps the next batch
+            if pending["work"] is not None:
+                pending["work"].wait()         # the previous batch's collective
+            # ONE all-reduce, in place on the flat buffer the batched backward wrote (no pack); asynchronous, it
+            # overlaps the next batch
+            pending["work"] = FlatAllReduce(list(grads), async_op=True)
+            pending["nbytes"] = pending["work"].nbytes
         return imgs, grads
 
     batch_marks = []
@@ -216,14 +224,16 @@ def run_b200(a):
         i = 0
         while i < k:
             n = min(B, k - i)
+            if marks is not None:
+                f0 = torch.cuda.Event(enable_timing=True); f0.record()
             flush.zero_()                      # L2 flush between batches (a view's own working set is ~4x L2)
             if marks is not None:
-                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+                e0 = torch.cuda.Event(enable_timing=True); e0.record()   # also closes the flush's own window (f0, e0)
                 h0 = time.perf_counter()
             run_views(i, n)
             if marks is not None:
                 e1 = torch.cuda.Event(enable_timing=True); e1.record()
-                marks.append((n, e0, e1, time.perf_counter() - h0))
+                marks.append((n, e0, e1, time.perf_counter() - h0, f0))
             i += n
 
     def step(i):
@@ -244,9 +254,13 @@ def run_b200(a):
     # inputs cached; on top of that a 256 MB write flushes L2 between batches.
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     n_warm = max(a.warmup, 2 * B)           # at least two full batches: the allocator must have seen a batch's peak
+    def wait_collective():
+        if pending["work"] is not None:
+            pending["work"].wait()
+            pending["work"] = None
+
     run_steps(n_warm)
-    if bucket is not None:
-        bucket.wait()
+    wait_collective()
     barrier()
 
     # ---- timed region: EXACTLY K steps (views), device-timed ----------------------------------------------------
@@ -255,8 +269,7 @@ def run_b200(a):
         sampler.start()
     gc.collect()
     run_steps(B)                               # the sampler's start-up left the GPU idle for 0.3 s: clocks back up
-    if bucket is not None:
-        bucket.wait()
+    wait_collective()
     _lib.CallStats.reset(timing=False)         # launch counters only ...
     import geosplatting_b200.fused as fused_mod
     fused_mod.PROBES = []                      # ... plus one event pair per view around the compositing backward
@@ -269,8 +282,7 @@ def run_b200(a):
     gc.disable()
     t_begin.record()
     run_steps(a.steps, batch_marks)
-    if bucket is not None:
-        bucket.wait()                          # the last collective completes inside the timed region
+    wait_collective()                          # the last collective completes inside the timed region
     t_end.record()
     barrier()
     gc.enable()
@@ -278,20 +290,18 @@ def run_b200(a):
     batches = {"views": [m[0] for m in batch_marks], "device_ms": [round(m[1].elapsed_time(m[2]), 3) for m in batch_marks],
                "host_enqueue_ms": [round(m[3] * 1e3, 3) for m in batch_marks],
                "cuda_mallocs_in_region": torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0}
+    batches["l2_flush_ms_in_region"] = None
     launches = _lib.CallStats.launches()
     probes, fused_mod.PROBES = fused_mod.PROBES, None
     live_ms = [a_.elapsed_time(b_) for a_, b_ in probes]
     live_bwd_ms = sum(live_ms) / max(1, len(live_ms))
     clocks = sampler.stop() if rank == 0 else None
-    # the L2-flush writes are not part of a step: measure them once, outside, and take them off the region
-    n_flush = (a.steps + B - 1) // B
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(n_flush):
-        flush.zero_()
-    f1.record()
+    # the L2-flush writes are not part of a step: each one runs alone on the caller's stream between two batches (the
+    # previous batch has been joined, the next not yet forked) inside its own event window, which is taken off the region
     torch.cuda.synchronize()
-    total_ms = t_begin.elapsed_time(t_end) - f0.elapsed_time(f1)
+    flush_ms = sum(m[4].elapsed_time(m[1]) for m in batch_marks)
+    total_ms = t_begin.elapsed_time(t_end) - flush_ms
+    batches["l2_flush_ms_in_region"] = round(flush_ms, 3)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -530,13 +540,31 @@ def run_b200(a):
                        "batch": f"{B} views forwarded, then back-propagated together, spread over {a.streams} CUDA streams",
                        "l2": "per-view working set ~400 MB (inputs 110 MB) vs 126 MB L2; 256 MB flush write between batches",
                        "parallelism": f"views sharded over {world} rank(s)" +
-                                      (f", 1 NCCL all-reduce of {bucket.nbytes} B per {B} views" if bucket else "")},
+                                      (f", 1 NCCL all-reduce of {pending['nbytes']} B per {B} views, in place on the backward's flat "
+                                       f"gradient buffer" if world > 1 else "")},
             "sequential_ms_per_view": round(seq_ms / a.steps, 4), "batches": batches,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
             "wall_s_timed_region": round(wall, 3), "impl": "b200",
         }
         if full:
             out["full_step"] = full
+    # ---- parity of the headline configuration: the view the CPU baseline leg times, compared with the CUDA path's result
+    if world == 1 and out is not None and not a.no_cpu_baseline:
+        try:
+            out["parity"] = parity_block(host, env0, lut, cams[0], dev, a.streams)
+        except Exception as exc:
+            out["parity"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    # ---- the other BASELINE.json configurations, short device-timed runs (N = 1: configs 2, 4, 5 on one GPU; N > 1: the
+    #      strong-scaling form of config 4 and the 64-view batch of config 5 sharded over the ranks)
+    if out is not None or world > 1:
+        extra = None
+        if not a.no_configs:
+            try:
+                extra = other_configs(a, rank, world, dev)
+            except Exception as exc:
+                extra = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if out is not None:
+            out["configs"] = extra
     # ---- extra: the e2e of a TRAINING view as the reference's trainer drives the path:
     #      the Gaussians stay on the device, the host supplies a view's ground-truth image (pinned, H2D inside the timed
     #      region) and reads back the batch's loss scalar.  Guarded: it can never cost the headline line.
@@ -582,6 +610,145 @@ def run_b200(a):
     return out, rank, world
 
 
+def parity_block(host, env0, lut, cam, dev, n_streams):
+    """One view of the bench workload through the product path (fused.splat_views -> the batch driver) against the
+    composed CPU oracle on identical inputs (oracle/parity.py): image L-inf on the non-fragile pixels, fragile fraction,
+    identity of the tile lists, and the relative L2 error of every gradient group."""
+    import time as _t
+
+    import torch
+
+    from geosplatting_b200.fused import splat_views
+    from geosplatting_b200.rasterization import rasterization
+    from geosplatting_b200.shade import EnvStack
+    from oracle import parity as OP
+    t0 = _t.perf_counter()
+    g = {k: v.detach().cpu() for k, v in host.items()}
+    lv = [x.detach().cpu() for x in env0.level_views()]
+    base, mips = lv[-1][..., :3].contiguous(), [x[..., :3].contiguous() for x in lv[:-1]]
+    exposure = torch.tensor([1.0])
+    cot = torch.randn(cam.height, cam.width, 4, generator=torch.Generator().manual_seed(7))
+    o = OP.oracle_view(g, base, mips, lut.detach().cpu(), cam, exposure, cot)
+    order = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
+    p = {k: g[k].to(dev).requires_grad_(True) for k in order}
+    leaf = env0.data.detach().clone().requires_grad_(True)
+    env = EnvStack(leaf, env0.R0, env0.L, env0.Rb, env0.min_roughness, env0.max_roughness)
+    ex = exposure.to(dev).requires_grad_(True)
+    (img,) = splat_views(*[p[k] for k in order], [cam], exposures=ex, envmap=env, fg_lut=lut, min_roughness=0.1,
+                         max_metallic=1.0, n_streams=n_streams)
+    gr = torch.autograd.grad(img, [p[k] for k in order] + [leaf, ex], grad_outputs=o["cot"].to(dev))
+    lvg = EnvStack(gr[7], env0.R0, env0.L, env0.Rb).level_views()
+    grads = {"means": gr[0], "scales": gr[1], "quats": gr[2], "logits": gr[3], "kd": gr[4], "ks": gr[5], "normals": gr[6],
+             "base": lvg[-1][..., :3], "mips": [x[..., :3] for x in lvg[:-1]], "exposure": gr[8]}
+    with torch.no_grad():
+        vm = torch.from_numpy(cam.view_matrix)[None].to(dev)
+        K = torch.from_numpy(cam.intrinsic_matrix)[None].to(dev)
+        _, _, info = rasterization(p["means"], p["quats"], p["scales"].exp(), torch.sigmoid(p["opacities"])[:, 0],
+                                   p["normals"], vm, K, cam.width, cam.height, rasterize_mode="antialiased")
+    rep = OP.compare(o, img.detach().cpu().numpy(), info["flatten_ids"].cpu().numpy(), info["isect_offsets"].cpu().numpy(),
+                     grads)
+    return {"view": "camera 0 of the timed workload, identical Gaussians / env levels on both sides",
+            "linf": rep["linf"], "linf_tolerance": 1e-4, "fragile_frac": rep["fragile_frac"],
+            "fragile_pixels": rep["fragile_pixels"], "psnr_db_all_pixels": rep["psnr_db_all_pixels"],
+            "ids_equal": rep["ids_equal"], "intersections": rep["intersections"],
+            "grad_rel_l2": {k: round(v["rel_l2"], 8) for k, v in rep["grads"].items()},
+            "oracle_seconds": {k: round(v, 3) for k, v in o["seconds"].items()},
+            "seconds": round(_t.perf_counter() - t0, 2)}
+
+
+def other_configs(a, rank, world, dev):
+    """Device-timed views/s of the BASELINE.json configurations the headline does not cover, same protocol (batches of
+    views through fused.splat_views + one backward, L2 flushed between batches, CUDA events, max over ranks):
+      N = 1 : config 2 (~0.5 M Gaussians, 800^2), config 4 (~2 M, 800^2), config 5 (~5 M, 1600^2), 8 views each;
+      N > 1 : config 4 as STRONG scaling (the trainer's 8 views in total, 8 / N per rank, one all-reduce) and config 5 with
+              its 64-view batch sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from geosplatting_b200 import scenes, splitsum
+    from geosplatting_b200.fused import splat_views
+    from geosplatting_b200.mgadapter import MGAdapter, compute_vertex_normals
+    from geosplatting_b200.parallel import FlatAllReduce, shard_views
+    from geosplatting_b200.shade import EnvStack, synthetic_fg_lut
+    lut = synthetic_fg_lut(dev)
+    gen = torch.Generator().manual_seed(0)
+    cube = torch.exp(torch.randn(6, a.light_res, a.light_res, 3, generator=gen)).clamp_min(1e-2).to(dev)
+    with torch.no_grad():
+        env0 = splitsum.as_envstack(cube)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    order = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
+
+    def run(mesh_n, res, global_views, n_batches):
+        verts, faces = scenes.cube_sphere(mesh_n)
+        with torch.no_grad():
+            vd, fd = verts.to(dev), faces.to(dev)
+            sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+        N = sp.means.shape[0]
+        g = torch.Generator().manual_seed(1)
+        p = {"means": sp.means, "scales": sp.scales, "quats": sp.quats, "opacities": sp.opacities,
+             "kd": (torch.rand(N, 3, generator=g) * 0.8 + 0.1).to(dev), "ks": torch.rand(N, 2, generator=g).to(dev),
+             "normals": sp.colors}
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        leaf = env0.data.detach().clone().requires_grad_(True)
+        env = EnvStack(leaf, env0.R0, env0.L, env0.Rb, env0.min_roughness, env0.max_roughness)
+        ex = torch.ones(1, device=dev, requires_grad=True)
+        cams = shard_views(scenes.orbit_cameras(global_views, res, res, seed=1), rank, world)
+        cot = torch.randn(res, res, 4, generator=g).to(dev) / float(global_views)
+        inputs = [p[k] for k in order] + [leaf, ex]
+        pend = [None]
+
+        def batch():
+            imgs = splat_views(*[p[k] for k in order], cams, exposures=ex, envmap=env, fg_lut=lut, min_roughness=0.1,
+                               max_metallic=1.0, n_streams=a.streams)
+            grads = torch.autograd.grad(imgs, inputs, grad_outputs=[cot] * len(cams))
+            if world > 1:
+                if pend[0] is not None:
+                    pend[0].wait()
+                pend[0] = FlatAllReduce(list(grads), async_op=True)
+
+        for _ in range(2):
+            batch()
+        if pend[0] is not None:
+            pend[0].wait()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(n_batches):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            batch()
+            if pend[0] is not None:
+                pend[0].wait()                 # strong scaling: the step ends when the summed gradients are there
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        t = torch.tensor([ms / n_batches], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_batch = float(t.item())
+        del p, leaf, env, sp
+        torch.cuda.empty_cache()
+        return {"gaussians": N, "resolution": [res, res], "views_global": global_views, "views_per_rank": len(cams),
+                "ms_per_batch": round(ms_batch, 3), "views_per_s": round(global_views / (ms_batch / 1e3), 2),
+                "batches_timed": n_batches}
+
+    out = {}
+    if world == 1:
+        out["config2_500k_800"] = run(83, 800, 8, 4)
+        out["config4_2M_800"] = run(167, 800, 8, 3)
+        out["config5_5M_1600"] = run(264, 1600, 8, 2)
+    else:
+        r = run(167, 800, 8, 4)
+        r["scaling"] = "strong: the trainer's batch of 8 views in total, one all-reduce per batch inside the timed window"
+        out["config4_2M_800_strong"] = r
+        r = run(264, 1600, 64, 2)
+        r["scaling"] = "the 64-view batch of config 5 sharded over the ranks"
+        out["config5_5M_1600_64views"] = r
+    return out
+
+
 def train_step_probe(R=140, n=5):
     """BASELINE configs[2] ("1M Gaussians + FlexiCubes MGAdaptor, 800x800, full train step") through the reference-facing
     model: FlexiCubes mesh + regularisers on an R^3 SDF grid -> vertex normals + MGAdaptor -> kd / ks / z hash-grid
@@ -615,7 +782,7 @@ def train_step_probe(R=140, n=5):
     opt = torch.optim.Adam([
         {"params": [m.sdf_params, m.deform_params, m.weight_params], "lr": 1e-3},
         {"params": list(m.field.parameters()), "lr": 1e-2},
-        {"params": [m.cubemap], "lr": 1e-2}, {"params": [m.exposure_params], "lr": 5e-3}], eps=1e-15)
+        {"params": [m.cubemap], "lr": 1e-2}, {"params": [m.exposure_params], "lr": 5e-3}], eps=1e-15, fused=True)
     stats = {}
 
     def step():

@@ -38,10 +38,16 @@ constexpr int PIX = SUB_W * SUB_H;                             // 16 pixels, hel
 #define GSB_FG 8
 #endif
 #ifndef GSB_BG
-#define GSB_BG 8
+#define GSB_BG 16
 #endif
 #ifndef GSB_WPB_B
 #define GSB_WPB_B 4
+#endif
+#ifndef GSB_MINB      // minimum resident CTAs per SM asked of ptxas (register cap) for the forward / backward kernels
+#define GSB_MINB 1
+#endif
+#ifndef GSB_MINB_B
+#define GSB_MINB_B 1
 #endif
 constexpr int WPB = GSB_WPB;                              // warps (pairs of units) per CTA in the composite kernels
 constexpr int FSZ = GSB_FG;                               // entries evaluated together in the forward
@@ -297,7 +303,7 @@ __device__ __forceinline__ Rec null_record() {
 constexpr float FAR_AWAY = 1e15f;   // pixel coordinate of a lane that must not contribute any more: log2(alpha) = -inf
 
 template <int CH>
-__global__ void __launch_bounds__(32 * WPB)
+__global__ void __launch_bounds__(32 * WPB, GSB_MINB)
 composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
@@ -305,8 +311,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                      const int32_t *__restrict__ order, int32_t *__restrict__ work, float *__restrict__ render,
                      float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
     constexpr int PAIRS = SUBS / UPW;
-    __shared__ Rec s_rec[WPB][32];
-    __shared__ int s_gid[WPB][32];
+    __shared__ Rec s_rec[WPB][32];     // k.z / k.w carry the entry's tile-list position / Gaussian id (bit patterns)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB + wib;
     if (slot >= n_pairs) return;
@@ -335,19 +340,24 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     const int li = lane & (CHUNK - 1);
     const int my_row = 2 * li + half;
     const Rec *const rows = &s_rec[wib][half];     // rows of my unit: rows[2 * s]
-    const int *const gids = &s_gid[wib][half];
-    int2 e = make_int2(0, 0);
+    // Software pipeline of the dependent gather (list entry -> record): while chunk c is evaluated, the records of
+    // chunk c + 1 and the list entries of chunk c + 2 are in flight, so neither latency is on the warp's critical path.
+    int2 e = make_int2(0, 0), e_next = make_int2(0, 0);
     Rec r = null_record();
     int processed = n;
     if (li < n) { e = list[li]; r = rec[e.y]; }
+    if (CHUNK + li < n) e_next = list[CHUNK + li];
     for (int base = 0; base < n_max; base += CHUNK) {
         __syncwarp();
-        s_gid[wib][my_row] = e.y;
+        r.k.z = __int_as_float(e.x);
+        r.k.w = __int_as_float(e.y);
         s_rec[wib][my_row] = r;
         __syncwarp();
         const int nb = base + CHUNK;
+        e = e_next;
         r = null_record();                                            // rows past the end of a list never contribute
-        if (nb + li < n) { e = list[nb + li]; r = rec[e.y]; }       // next chunk in flight during the loop
+        if (nb + li < n) r = rec[e.y];                                // records of the next chunk
+        if (nb + CHUNK + li < n) e_next = list[nb + CHUNK + li];     // list entries of the chunk after it
         // Groups of FS entries.  The alpha evaluations are independent (ILP for a warp that runs alone: the longest
         // sub-list of a view is this kernel's critical path); alpha == 0 stands for "does not contribute" and makes
         // every update the identity, so the common case has no branch.  The state is saved before a group; only a group
@@ -381,7 +391,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                 if (CH > 2) acc[2] = fmaf(c.z, vis, acc[2]);
                 if (CH > 3) {
                     if (a[s] > 0.f) {
-                        const int g = gids[2 * (t0 + s)];
+                        const int g = __float_as_int(rows[2 * (t0 + s)].k.w);
 #pragma unroll
                         for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
                     }
@@ -410,7 +420,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                 if (CH > 1) acc[1] += c.y * vis;
                 if (CH > 2) acc[2] += c.z * vis;
                 if (CH > 3) {
-                    const int g = gids[2 * (t0 + s)];
+                    const int g = __float_as_int(rows[2 * (t0 + s)].k.w);
 #pragma unroll
                     for (int k = 3; k < CH; ++k) acc[k] += __ldg(colors + (size_t)g * CH + k) * vis;
                 }
@@ -440,19 +450,21 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
 //   phase A (lane = (unit, pixel)): evaluate the unit's 16 entries, run the T / suffix-colour recurrence, and store
 //                              per (entry, pixel) the three scalars the gradient needs -- A = opacity * exp(-sigma)
 //                              (0 if the pair does not contribute), T before the Gaussian, E = (suffix . v_out -
-//                              T_final (v_alpha - bg . v_out)) / (1 - alpha) -- into a 32 x 16 slab whose columns are
-//                              rotated by row / 2 (conflict-free for both access patterns, no padding);
+//                              T_final (v_alpha - bg . v_out)) / (1 - alpha) -- as one float4 into a 32 x 16 slab whose
+//                              columns are rotated by the row (conflict-free for both access patterns, no padding);
 //   phase B (lane = Gaussian): read its row, accumulate the gradient moments over the 16 pixels in registers, one
 //                              atomic per value per (Gaussian, unit) -- only for Gaussians that touched a pixel.
 // v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
 // (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
-constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (8 KB of shared memory per warp)
-constexpr int SLAB = 32 * PIX;     // floats per slab
+constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (10 KB of shared memory per warp)
 
-__device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + (row >> 1)) & (PIX - 1)); }
+// slab[row][column] of float4 {A, T, E, -}; the column of pixel p in row r is (p + r) mod 16: every 16-byte access of a
+// quarter-warp then hits eight distinct bank groups both when the lanes are pixels of one row (phase A) and when they
+// are rows at one pixel (phase B)
+__device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + row) & (PIX - 1)); }
 
 template <int CH>
-__global__ void __launch_bounds__(32 * WPB_B)
+__global__ void __launch_bounds__(32 * WPB_B, GSB_MINB_B)
 composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
@@ -464,9 +476,8 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     constexpr int PAIRS = SUBS / UPW;
     constexpr int C3 = CH < 3 ? CH : 3;                 // channels carried in the packed record
     constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
-    __shared__ float s_slab[WPB_B][3 * SLAB];           // A | T | E
-    __shared__ Rec s_rec[WPB_B][32];
-    __shared__ int2 s_ent[WPB_B][32];
+    __shared__ float4 s_slab[WPB_B][32 * PIX];          // {A, T, E, -} per (row, pixel)
+    __shared__ Rec s_rec[WPB_B][32];                    // k.z / k.w carry the entry's tile-list position / Gaussian id
     __shared__ float4 s_vo[WPB_B][UPW][PIX][NV4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB_B + wib;
@@ -518,7 +529,7 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     const int n_max = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
     if (n_max == 0) return;
 
-    float *const my_A = s_slab[wib];
+    float4 *const slab = s_slab[wib];
     const float bx = (float)(u.j - (p & 3)) + 0.5f, by = (float)(u.i - (p >> 2)) + 0.5f;  // pixel (0,0) of my unit
     const float bx_other = __shfl_xor_sync(0xffffffffu, bx, 16);
     float T = T_final;
@@ -529,19 +540,24 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     const int li = lane & (CHUNK - 1);
     const int my_row = 2 * li + half;
     const Rec *const rows = &s_rec[wib][half];
-    const int2 *const ents = &s_ent[wib][half];
-    int2 e = make_int2(0x7fffffff, 0);            // position beyond every last_id: a null row is never valid
+    // same software pipeline as the forward: records one step ahead, list entries two steps ahead
+    const int2 none = make_int2(0x7fffffff, 0);   // position beyond every last_id: a null row is never valid
+    int2 e = none, e_next = none;
     Rec r = null_record();
     if (n - 1 - li >= 0) { e = list[n - 1 - li]; r = rec[e.y]; }
+    if (n - CHUNK - 1 - li >= 0) e_next = list[n - CHUNK - 1 - li];
     for (int top = n, walked = 0; walked < n_max; top -= CHUNK, walked += CHUNK) {
         __syncwarp();
-        s_ent[wib][my_row] = e;
+        r.k.z = __int_as_float(e.x);
+        r.k.w = __int_as_float(e.y);
         s_rec[wib][my_row] = r;
         __syncwarp();
         const int nt = top - CHUNK;
-        e = make_int2(0x7fffffff, 0);
+        e = e_next;
+        e_next = none;
         r = null_record();
-        if (nt - 1 - li >= 0) { e = list[nt - 1 - li]; r = rec[e.y]; }
+        if (nt - 1 - li >= 0) r = rec[e.y];
+        if (nt - CHUNK - 1 - li >= 0) e_next = list[nt - CHUNK - 1 - li];
 
         // ---- phase A: lane = (unit, pixel) --------------------------------------------------------------------
         unsigned mine_mask = 0u;   // bit t: shared-memory row t (one of my unit's) contributes to my pixel
@@ -555,10 +571,9 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                 const float4 kk = rows[t].k;
                 const float4 q = rows[t].q;
                 const float4 c = rows[t].c;
-                const int2 en = ents[t];
                 const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
                 const float araw = ex2_approx(l2a);
-                const bool valid = (en.x <= bin_final) && (l2a <= q.w) && (l2a >= LOG2_ALPHA_MIN);
+                const bool valid = (__float_as_int(kk.z) <= bin_final) && (l2a <= q.w) && (l2a >= LOG2_ALPHA_MIN);
                 Ag[s] = valid ? araw : 0.f;
                 al[s] = fminf(GSB_ALPHA_CLAMP, Ag[s]);
                 rag[s] = rcp_approx(1.0f - al[s]);
@@ -567,7 +582,7 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                 if (C3 > 2) w += c.z * v_out[2];
                 if (CH > 3) {
 #pragma unroll
-                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)en.y * CH + k) * v_out[k];
+                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)__float_as_int(kk.w) * CH + k) * v_out[k];
                 }
                 wg[s] = w;
                 mine_mask |= valid ? (1u << (t + half)) : 0u;
@@ -575,11 +590,8 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
             // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch
 #pragma unroll
             for (int s = 0; s < BSZ; ++s) {
-                const int at = slab_at(2 * (t0 + s) + half, p);
                 T *= rag[s];
-                my_A[at] = Ag[s];
-                my_A[at + SLAB] = T;
-                my_A[at + 2 * SLAB] = rag[s] * (B - c0);
+                slab[slab_at(2 * (t0 + s) + half, p)] = make_float4(Ag[s], T, rag[s] * (B - c0), 0.f);
                 B += wg[s] * (al[s] * T);
             }
         }
@@ -592,7 +604,7 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
             const float4 kk = s_rec[wib][lane].k;
             const float4 q = s_rec[wib][lane].q;
             const float4 c = s_rec[wib][lane].c;
-            const int g = s_ent[wib][lane].y;
+            const int g = __float_as_int(kk.w);
             const int hb = lane & 1;                                   // the unit this row belongs to
             const float ox = (hb == half) ? bx : bx_other;             // pixel (0,0) of that unit (same row of pixels)
             float col[CH];
@@ -608,12 +620,11 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
 #pragma unroll
             for (int k = 0; k < CH; ++k) g_col[k] = 0.f;
             float s0 = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f;   // moments of v_sigma
-            const int rot = lane >> 1;
-            const float *row_A = my_A + lane * PIX;
+            const float4 *row = slab + lane * PIX;
 #pragma unroll 8
             for (int pp = 0; pp < PIX; ++pp) {
-                const int at = (pp + rot) & (PIX - 1);
-                const float A = row_A[at], Tp = row_A[at + SLAB], Ep = row_A[at + 2 * SLAB];
+                const float4 ate = row[(pp + lane) & (PIX - 1)];
+                const float A = ate.x, Tp = ate.y, Ep = ate.z;
                 float vo[NV4 * 4];
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {

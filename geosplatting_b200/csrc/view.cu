@@ -228,7 +228,7 @@ GSB_API int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam,
  * Arenas (gsb_batch_bytes): keep    = n_views x (keep1 | keep2(m_cap))            forward -> backward
  *                           scratch = n_streams x max(tmp1 | tmp2(m_cap), tmp3)    inside either call
  * Gradient buffers (one per stream, zero-filled by the caller, summed into buffer 0 by gsb_batch_backward):
- *   [ env 4T | quats 4N | ks 2N | means 3N | scales 3N | logits N | normals 3N | kd 3N | exposure n_views ]
+ *   [ env 4T | quats 4N | ks 2N | means 3N | scales 3N | logits N | normals 3N | kd 3N | exposure n_views | 1 spare ]
  * (v_scales is w.r.t. the LINEAR scales; `grad_scale` multiplies the summed result, e.g. 1 / (views x ranks)).
  * ================================================================================================================== */
 namespace {
@@ -245,17 +245,21 @@ int batch_sizes(const gsb_view_config *c, int64_t m_cap, BatchSizes &b) {
     return GSB_OK;
 }
 
-__global__ void __launch_bounds__(256) grad_sum_kernel(int n_bufs, float *__restrict__ dst, const float *__restrict__ b1,
-                                                       const float *__restrict__ b2, const float *__restrict__ b3,
-                                                       int64_t n4, float scale) {
+constexpr int MAX_STREAMS = 8;
+struct GradBufs { float *p[MAX_STREAMS]; };
+
+__global__ void __launch_bounds__(256) grad_sum_kernel(int n_bufs, GradBufs b, int64_t n4, float scale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    float4 a = reinterpret_cast<float4 *>(dst)[i];
-    if (n_bufs > 1) { const float4 v = reinterpret_cast<const float4 *>(b1)[i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-    if (n_bufs > 2) { const float4 v = reinterpret_cast<const float4 *>(b2)[i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-    if (n_bufs > 3) { const float4 v = reinterpret_cast<const float4 *>(b3)[i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    float4 a = reinterpret_cast<float4 *>(b.p[0])[i];
+#pragma unroll
+    for (int k = 1; k < MAX_STREAMS; ++k)
+        if (k < n_bufs) {
+            const float4 v = reinterpret_cast<const float4 *>(b.p[k])[i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
     a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-    reinterpret_cast<float4 *>(dst)[i] = a;
+    reinterpret_cast<float4 *>(b.p[0])[i] = a;
 }
 
 // fork: every side stream waits for what `main` has queued so far; join: `main` waits for every side stream
@@ -284,7 +288,7 @@ int fork_join(cudaStream_t main, void *const *streams, int n, bool fork) {
 GSB_API int gsb_batch_bytes(const gsb_view_config *cfg, int32_t n_views, int32_t n_streams, int64_t m_cap,
                             size_t *bytes2_host) {
     VIEW_CHECK_CFG(cfg);
-    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= 4 && m_cap >= 0 && bytes2_host != nullptr);
+    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= MAX_STREAMS && m_cap >= 0 && bytes2_host != nullptr);
     BatchSizes b;
     VIEW_TRY(batch_sizes(cfg, m_cap, b));
     bytes2_host[0] = b.keep_view * (size_t)n_views + 256;
@@ -295,7 +299,7 @@ GSB_API int gsb_batch_bytes(const gsb_view_config *cfg, int32_t n_views, int32_t
 GSB_API int gsb_batch_grad_floats(const gsb_view_config *cfg, int32_t n_views, int64_t env_texels, int64_t *floats_host) {
     VIEW_CHECK_CFG(cfg);
     GSB_CHECK_ARG(n_views >= 0 && env_texels >= 0 && floats_host != nullptr);
-    const int64_t n = 4 * env_texels + 19 * (int64_t)cfg->N + n_views;
+    const int64_t n = 4 * env_texels + 19 * (int64_t)cfg->N + n_views + 1;   // + 1: room for the caller's sum over views
     *floats_host = (n + 3) & ~(int64_t)3;      // whole float4s
     return GSB_OK;
 }
@@ -307,7 +311,7 @@ GSB_API int gsb_batch_forward(const gsb_view_config *cfg, int32_t n_views, const
                               int32_t exposure_stride, void *keep, void *scratch, int64_t m_cap, int64_t *totals_out,
                               float *out, void *const *streams, int32_t n_streams, void *main_stream) {
     VIEW_CHECK_CFG(cfg);
-    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= 4 && m_cap >= 0);
+    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= MAX_STREAMS && m_cap >= 0);
     if (n_views == 0) return GSB_OK;
     GSB_CHECK_ARG(cams && cam_pos_host && exposures && keep && scratch && out && streams);
     BatchSizes b;
@@ -360,7 +364,7 @@ GSB_API int gsb_batch_backward(const gsb_view_config *cfg, int32_t n_views, cons
                                float *const *grad_bufs, float grad_scale, void *const *streams, int32_t n_streams,
                                void *probe_events, void *main_stream) {
     VIEW_CHECK_CFG(cfg);
-    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= 4 && m_cap >= 0 && env_texels >= 0);
+    GSB_CHECK_ARG(n_views >= 0 && n_streams >= 1 && n_streams <= MAX_STREAMS && m_cap >= 0 && env_texels >= 0);
     if (n_views == 0) return GSB_OK;
     GSB_CHECK_ARG(cams && cam_pos_host && exposures && keep && scratch && v_outs_host && grad_bufs && streams);
     BatchSizes b;
@@ -409,9 +413,9 @@ GSB_API int gsb_batch_backward(const gsb_view_config *cfg, int32_t n_views, cons
     VIEW_TRY(fork_join((cudaStream_t)main_stream, streams, n_streams, false));
     if (used > 1 || grad_scale != 1.0f) {
         const int64_t n4 = n_floats / 4;
-        grad_sum_kernel<<<gsb_div_up(n4, 256), 256, 0, (cudaStream_t)main_stream>>>(
-            used, grad_bufs[0], used > 1 ? grad_bufs[1] : nullptr, used > 2 ? grad_bufs[2] : nullptr,
-            used > 3 ? grad_bufs[3] : nullptr, n4, grad_scale);
+        GradBufs gb;
+        for (int k = 0; k < MAX_STREAMS; ++k) gb.p[k] = k < used ? grad_bufs[k] : nullptr;
+        grad_sum_kernel<<<gsb_div_up(n4, 256), 256, 0, (cudaStream_t)main_stream>>>(used, gb, n4, grad_scale);
         GSB_CHECK_LAUNCH();
     }
     return GSB_OK;

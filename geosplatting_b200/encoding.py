@@ -78,6 +78,46 @@ class _ReferenceRounding(torch.autograd.Function):
         return v, None
 
 
+_ACT = {"none": 0, "sigmoid": 1}
+
+
+def fused_mlp_supported(layers: Sequence[int], activation: str) -> bool:
+    """The shapes of GeoSplatting's fields (geosplat.py:485-518): 32 -> 32 [-> 32] -> {1..4}, `none` / `sigmoid`."""
+    return (len(layers) in (3, 4) and all(w == 32 for w in layers[:-1]) and 1 <= layers[-1] <= 4
+            and activation in _ACT)
+
+
+class _FusedMLP(torch.autograd.Function):
+    """All layers, ReLUs and the output activation in one kernel each way (csrc/mlp.cu)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, activation: str, ref_round_scale: float, *weights: Tensor):
+        x_c = f32c(x).reshape(-1, 32)
+        ws = [f32c(w) for w in weights]
+        dev = x_c.device
+        N, dout, nh = x_c.shape[0], ws[-1].shape[0], len(ws) - 1
+        y = torch.empty(N, dout, dtype=torch.float32, device=dev)
+        call("gsb_mlp_fwd", dev, C.c_int64(N), ptr(x_c), ptr(ws[0]), ptr(ws[1]) if nh == 2 else None, ptr(ws[-1]),
+             C.c_int32(nh), C.c_int32(dout), C.c_int32(_ACT[activation]), C.c_float(ref_round_scale), ptr(y),
+             stream_ptr(dev))
+        ctx.save_for_backward(x_c, *ws)
+        ctx.misc = (activation, float(ref_round_scale), x.shape)
+        return y.view(*x.shape[:-1], dout)
+
+    @staticmethod
+    def backward(ctx, v_y: Tensor):
+        x_c, *ws = ctx.saved_tensors
+        activation, rr, x_shape = ctx.misc
+        dev = x_c.device
+        N, dout, nh = x_c.shape[0], ws[-1].shape[0], len(ws) - 1
+        v_x = torch.empty_like(x_c) if ctx.needs_input_grad[0] else None
+        v_ws = [torch.empty_like(w) for w in ws]
+        call("gsb_mlp_bwd", dev, C.c_int64(N), ptr(x_c), ptr(ws[0]), ptr(ws[1]) if nh == 2 else None, ptr(ws[-1]),
+             C.c_int32(nh), C.c_int32(dout), C.c_int32(_ACT[activation]), C.c_float(rr), ptr(f32c(v_y).reshape(N, dout)),
+             ptr(v_x), ptr(v_ws[0]), ptr(v_ws[1]) if nh == 2 else None, ptr(v_ws[-1]), stream_ptr(dev))
+        return (None if v_x is None else v_x.view(x_shape), None, None, *v_ws)
+
+
 class MLP(nn.Module):
     """rfstudio/nn/mlp.py: `layers` [in, hidden..., out] (in may be -1 = inferred), ReLU between layers, `activation`
     after the last, kaiming-uniform weights, no bias."""
@@ -109,7 +149,14 @@ class MLP(nn.Module):
     def weights(self) -> List[nn.Parameter]:
         return [layer.weight for layer in self.nn_layers]
 
-    def forward(self, x: Tensor) -> Tensor:
+    def forward(self, x: Tensor, ref_round_scale: float = 0.0) -> Tensor:
+        """`ref_round_scale` s != 0: the input is taken as x * s + x * (1 - s), the value (up to an fp32 rounding the
+        same as x) that HashEncoding.__call__ hands the MLP (encoding.py:239-240)."""
+        if fused_mlp_supported(self.layers, self.activation) and x.shape[-1] == 32 and not x.device.type == "meta":
+            _require_cuda(x, "MLP")
+            return _FusedMLP.apply(x, self.activation, float(ref_round_scale), *self.weights)
+        if ref_round_scale:
+            x = _ReferenceRounding.apply(x, float(ref_round_scale))
         n = len(self.nn_layers)
         for i, layer in enumerate(self.nn_layers):
             x = layer(x)
@@ -167,9 +214,7 @@ class HashEncoding(nn.Module):
         `f*s + f.detach()(1-s)`) leave values unchanged and multiply the gradient that reaches the table by s while the
         one that reaches x stays as it is: that factor is applied inside the backward kernel."""
         feats = self.encode(in_tensor, straight_through=True)
-        if self.grad_scaling is not None:
-            feats = _ReferenceRounding.apply(feats, float(self.grad_scaling))
-        return self.mlp(feats)
+        return self.mlp(feats, ref_round_scale=0.0 if self.grad_scaling is None else float(self.grad_scaling))
 
 
 class TcnnEncoding(nn.Module):

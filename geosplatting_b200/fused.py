@@ -349,8 +349,7 @@ def _batch_forward(sh: _Shared, cameras, exposures, side) -> tuple:
 
 
 def _batch_check(b: _Batch) -> None:
-    """Before the backward touches the saved state: did every view fit its capacity?  (The forward has long finished
-    when autograd gets here; the wait is a formality.)"""
+    """Did every view of the forward fit its capacity?  (The forward has long finished when autograd gets here.)"""
     if b.checked:
         return
     b.event.synchronize()
@@ -366,7 +365,6 @@ def _batch_check(b: _Batch) -> None:
 
 def _batch_backward(sh: _Shared, b: _Batch, v_outs, T: int):
     dev, N, n = sh.dev, sh.N, b.n
-    _batch_check(b)
     main = torch.cuda.current_stream(dev)
     ns = len(b.streams)
     nf = C.c_int64(0)
@@ -393,6 +391,9 @@ def _batch_backward(sh: _Shared, b: _Batch, v_outs, T: int):
          C.addressof(b.stream_ptrs), ns, None if probes is None else C.addressof(probes), main.cuda_stream)
     CallStats.counts["batch_view_backward"] = CallStats.counts.get("batch_view_backward", 0) + sum(
         v is not None for v in keepalive)
+    # the kernels are memory-safe under an overflow (they read min(M, capacity)); checking AFTER the backward has been
+    # enqueued keeps the device busy while the host looks at the forward's counts -- and no gradient leaves if it failed
+    _batch_check(b)
     flat = bufs[0]
     g = _Grads.__new__(_Grads)
     g.flat = flat
@@ -401,7 +402,7 @@ def _batch_backward(sh: _Shared, b: _Batch, v_outs, T: int):
                     ("logits", N), ("normals", 3 * N), ("kd", 3 * N)):
         setattr(g, name, flat[o:o + k])
         o += k
-    return g, flat[o:o + n]
+    return g, flat[o:o + n + 1]       # per-view exposure gradients + the spare slot
 
 
 class _SplatBatch(torch.autograd.Function):
@@ -472,11 +473,18 @@ class _SplatBatch(torch.autograd.Function):
                 return (None,) * (13 + len(v_outs))
             total, v_exp = _batch_backward(sh, ctx.batch, v_outs, T)
             total.scales.mul_(sh.scales.reshape(-1))           # d exp(s) / d s
+            n = len(v_outs)
+            if ctx.batch.ex_stride == 0:
+                # one exposure tensor shared by every view: its gradient is the sum over the views, kept INSIDE the flat
+                # buffer (spare slot) so that a data-parallel caller all-reduces one contiguous buffer and nothing else
+                torch.sum(v_exp[:n], dim=0, keepdim=True, out=v_exp[n:n + 1])
+                ex_grads = [v_exp[n:n + 1].reshape(exposure_shapes[0])] + [None] * (n - 1)
+            else:
+                ex_grads = [None if v is None else v_exp[i].reshape(shp)
+                            for i, (v, shp) in enumerate(zip(v_outs, exposure_shapes))]
             return (total.means.view(N, 3), total.scales.view(N, 3), total.quats.view(N, 4),
                     total.logits.view(logits_shape), total.kd.view(N, 3), total.ks.view(N, 2), total.normals.view(N, 3),
-                    total.env.view(T, 4), None, None, None, None, None,
-                    *[None if v is None else v_exp[i].reshape(shp)
-                      for i, (v, shp) in enumerate(zip(v_outs, exposure_shapes))])
+                    total.env.view(T, 4), None, None, None, None, None, *ex_grads)
         main = torch.cuda.current_stream(dev)
         v_exps = []
         # one zero-filled gradient buffer per stream in use, every view on that stream adds into it (allocated on the

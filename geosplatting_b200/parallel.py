@@ -84,6 +84,55 @@ class GradientBucket:
         return self.views
 
 
+def common_flat(tensors: Sequence[Optional[Tensor]]) -> Optional[Tensor]:
+    """The contiguous 1-D tensor that covers every gradient when they are all views of ONE buffer (the batched backward of
+    fused.splat_views writes them into a single flat buffer: [env | quats | ks | means | scales | logits | normals | kd |
+    exposure]), else None.  Bytes between the views (alignment padding, per-view slots) are covered too."""
+    ts = [t for t in tensors if t is not None]
+    if not ts:
+        return None
+    st = ts[0].untyped_storage()
+    for t in ts:
+        if t.untyped_storage().data_ptr() != st.data_ptr() or not t.is_contiguous() or t.dtype != ts[0].dtype:
+            return None
+    lo = min(t.storage_offset() for t in ts)
+    hi = max(t.storage_offset() + t.numel() for t in ts)
+    return torch.empty(0, dtype=ts[0].dtype, device=ts[0].device).set_(st, lo, (hi - lo,))
+
+
+class FlatAllReduce:
+    """ONE sum all-reduce of a batch's gradients IN PLACE, without packing: `tensors` are what torch.autograd.grad
+    returned for fused.splat_views.  Falls back to a packed bucket when the gradients do not share a buffer."""
+
+    def __init__(self, tensors: Sequence[Optional[Tensor]], group=None, async_op: bool = False):
+        self.flat = common_flat(tensors)
+        self.packed = self.flat is None
+        self._work = None
+        self._bucket = None
+        if self.packed:
+            ts = [t for t in tensors if t is not None]
+            self._bucket = GradientBucket([t.shape for t in ts], ts[0].device, ts[0].dtype)
+            self._bucket.pack(ts)
+            self.flat = self._bucket.flat
+            self._targets = ts
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            self._work = work if async_op else None
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def wait(self) -> None:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self.packed and self._bucket is not None:
+            for t, v in zip(self._targets, self._bucket.views):
+                t.copy_(v)
+            self._bucket = None
+
+
 def allreduce_gradients(tensors: Sequence[Optional[Tensor]], bucket: Optional[GradientBucket] = None, group=None,
                         average_over: Optional[int] = None) -> List[Tensor]:
     """Sum `tensors` across ranks with a single collective; returns views into the bucket."""

@@ -418,6 +418,20 @@ int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const f
  * after the compositing backward, the dominant stage, so that a benchmark can time it inside a running batch. */
 
 /* -------------------------------------------------------------------------------------------
+ * The fields' MLPs, fused: replaces rfstudio/nn/mlp.py:125-145 (nn.Linear + F.relu per layer,
+ * activation after the last) for the shapes of rfstudio/model/geosplat.py:485-518: x[N,32] -> 32 [-> 32] -> dout <= 4,
+ * no bias.  Weights are nn.Linear's [out,in] row-major.  n_hidden: 1 or 2 (w1 NULL for 1).  activation: 0 none,
+ * 1 sigmoid.  ref_round_scale s != 0: the input is taken as x*s + x*(1-s) in fp32 (two roundings), the value
+ * rfstudio/model/components/encoding.py:239-240 hands the MLP.  gsb_mlp_bwd recomputes the forward and writes v_x[N,32]
+ * (NULL to skip), v_w0[32,32], v_w1[32,32], v_wout[dout,32] (zero-filled by the call).
+ * ------------------------------------------------------------------------------------------- */
+int gsb_mlp_fwd(int64_t N, const float *x, const float *w0, const float *w1, const float *wout, int32_t n_hidden,
+                int32_t dout, int32_t activation, float ref_round_scale, float *y, void *stream);
+int gsb_mlp_bwd(int64_t N, const float *x, const float *w0, const float *w1, const float *wout, int32_t n_hidden,
+                int32_t dout, int32_t activation, float ref_round_scale, const float *v_y, float *v_x, float *v_w0,
+                float *v_w1, float *v_wout, void *stream);
+
+/* -------------------------------------------------------------------------------------------
  * Batch driver: every view of a training batch in ONE call each way -- the per-view loop of
  * GeoSplatter.render_report (rfstudio/model/geosplat.py:869-879: `for i in range(batch_size): attrs.splat(...)`) and
  * its backward.  No host wait on any view's intersection count: the M-sized arrays are carved for the capacity
@@ -426,10 +440,11 @@ int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const f
  *   keep / scratch: gsb_batch_bytes -> {keep, scratch}; keep lives forward..backward, scratch inside either call.
  *   cams[n_views], cam_pos_host[n_views][3]: host arrays.  exposures: device, element v at exposures[v * stride].
  *   out: [n_views][H][W][4]; v_outs_host[n_views]: host array of device pointers to the [H][W][4] cotangents (NULL =
- *   this view has none).  streams[n_streams <= 4]: the views are spread round-robin over them;
+ *   this view has none).  streams[n_streams <= 8]: the views are spread round-robin over them;
  *   main_stream is forked into them and joined again (results are ready on main_stream).
  *   grad_bufs[n_streams]: zero-filled buffers of gsb_batch_grad_floats floats each, layout
- *     [ env 4T | quats 4N | ks 2N | means 3N | scales(linear) 3N | logits N | normals 3N | kd 3N | exposure n_views ];
+ *     [ env 4T | quats 4N | ks 2N | means 3N | scales(linear) 3N | logits N | normals 3N | kd 3N | exposure n_views |
+ *       1 spare float (the caller's sum over views) ];
  *     the sum over streams times grad_scale ends up in grad_bufs[0].
  *   probe_events: optional
  *   cudaEvent_t[2 * n_views] recorded around each view's compositing backward.

@@ -37,7 +37,7 @@ for _ in cams:
 opt = torch.optim.Adam([
     {"params": [m.sdf_params, m.deform_params, m.weight_params], "lr": 1e-3},
     {"params": list(m.field.parameters()), "lr": 1e-2},
-    {"params": [m.cubemap], "lr": 1e-2}, {"params": [m.exposure_params], "lr": 5e-3}], eps=1e-15)
+    {"params": [m.cubemap], "lr": 1e-2}, {"params": [m.exposure_params], "lr": 5e-3}], eps=1e-15, fused=True)
 stats = {}
 
 

@@ -25,6 +25,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
+#define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 
 struct dim3 {
