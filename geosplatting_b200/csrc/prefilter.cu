@@ -85,40 +85,85 @@ __global__ void __launch_bounds__(256) diffuse_kernel(int R, const float *__rest
     o[0] = acc.x * post; o[1] = acc.y * post; o[2] = acc.z * post;
 }
 
-// ---- specular bounds (cubemap.cu:181-244): AABB on every face of the texels inside the cone ----------------
+// ---- specular bounds: on every face, the texel AABB of the cone { L : L . V >= cos(theta_c) } ---------------------------
+// Output contract of the plugin's `specular_bounds` (torch_bindings.cpp:168-191): bounds[6,R,R,24] = per source face
+// (xmin, xmax, ymin, ymax) as floats, (R-1, 0, R-1, 0) when the cone misses the face.  The plugin finds them by testing
+// every texel of every face against every output texel (O(R^4), 137 ms per level at 512^2 on a B200, ~0.8 s before the
+// first training step).  Here the box is found from the geometry, one thread per (output texel, face):
+//   * on face s a direction is q(fx, fy) = A + fx U + fy W (unnormalised), so L . V >= c reads
+//         k(fx, fy) = a + u fx + w fy >= c sqrt(1 + fx^2 + fy^2),   a = A.V, u = U.V, w = W.V:
+//     a face whose axis is further than theta_c + acos(1/sqrt 3) from V cannot be touched (most are not);
+//   * for one texel row (fy fixed) that is a quadratic inequality in fx: its solution set clipped to [-1, 1] is the
+//     row's candidate column interval, solved in double precision for a cone widened by 2e-6;
+//   * the interval's ends are then moved to the first / last texel that passes the EXACT fp32 test the gather kernels
+//     evaluate (texel_dir + dot3 >= cutoff), so the box is the bounding box of exactly the texels those kernels accept.
+// O(R) quadratics + a handful of exact tests per touched face instead of O(R^2) exact tests per face.
+__device__ __forceinline__ bool in_cone(int x, int y, int s, float N, float3 V, float cutoff) {
+    return dot3(texel_dir(x, y, s, N), V) >= cutoff;
+}
+
 __global__ void __launch_bounds__(128) specular_bounds_kernel(int R, float cutoff, float *__restrict__ bounds) {
     int id = blockIdx.x * blockDim.x + threadIdx.x;  // (texel, face)
     if (id >= 36 * R * R) return;
-    int s = id % 6, o = id / 6;
-    int pz = o / (R * R), py = (o / R) % R, px = o % R;
-    const float invN = (float)R;  // texel_dir takes N
-    float3 V = texel_dir(px, py, pz, invN);
-    const int TS = 16;
-    int min_x = R - 1, max_x = 0, min_y = R - 1, max_y = 0;
-    int nt = (R + TS - 1) / TS;
-    for (int tx = 0; tx < nt; ++tx)
-        for (int ty = 0; ty < nt; ++ty) {
-            int tsx = tx * TS, tsy = ty * TS;
-            int tex = min((tx + 1) * TS, R), tey = min((ty + 1) * TS, R);
-            float3 L0 = texel_dir(tsx, tsy, s, invN), L1 = texel_dir(tex, tsy, s, invN);
-            float3 L2 = texel_dir(tsx, tey, s, invN), L3 = texel_dir(tex, tey, s, invN);
-            float minx = fminf(fminf(L0.x, L1.x), fminf(L2.x, L3.x)), maxx = fmaxf(fmaxf(L0.x, L1.x), fmaxf(L2.x, L3.x));
-            float miny = fminf(fminf(L0.y, L1.y), fminf(L2.y, L3.y)), maxy = fmaxf(fmaxf(L0.y, L1.y), fmaxf(L2.y, L3.y));
-            float minz = fminf(fminf(L0.z, L1.z), fminf(L2.z, L3.z)), maxz = fmaxf(fmaxf(L0.z, L1.z), fmaxf(L2.z, L3.z));
-            float maxdp = fmaxf(minx * V.x, maxx * V.x) + fmaxf(miny * V.y, maxy * V.y) + fmaxf(minz * V.z, maxz * V.z);
-            if (maxdp >= cutoff) {
-                for (int y = tsy; y < tey; ++y)
-                    for (int x = tsx; x < tex; ++x) {
-                        float3 L = texel_dir(x, y, s, invN);
-                        if (dot3(L, V) >= cutoff) {
-                            min_x = min(min_x, x); max_x = max(max_x, x);
-                            min_y = min(min_y, y); max_y = max(max_y, y);
-                        }
-                    }
+    const int s = id % 6, o = id / 6;
+    const int pz = o / (R * R), py = (o / R) % R, px = o % R;
+    const float N = (float)R;
+    const float3 V = texel_dir(px, py, pz, N);
+    int min_x = R - 1, max_x = 0, min_y = R - 1, max_y = 0;     // the empty box
+
+    // frame of face s: q(fx, fy) = A + fx U + fy W
+    float ax, ay, az, bx, by, bz, cx, cy, cz;
+    gsb_face_point(s, 0.f, 0.f, ax, ay, az);
+    gsb_face_point(s, 1.f, 0.f, bx, by, bz);
+    gsb_face_point(s, 0.f, 1.f, cx, cy, cz);
+    const double a = (double)ax * V.x + (double)ay * V.y + (double)az * V.z;
+    const double u = (double)(bx - ax) * V.x + (double)(by - ay) * V.y + (double)(bz - az) * V.z;
+    const double w = (double)(cx - ax) * V.x + (double)(cy - ay) * V.y + (double)(cz - az) * V.z;
+    const double c = fmax((double)cutoff - 2e-6, -1.0);        // slightly wider cone: candidates, not the verdict
+    // quick reject: every direction of a face is within acos(1/sqrt 3) of its axis A
+    const double theta = acos(fmin(fmax(c, -1.0), 1.0));
+    const bool reachable = theta + 0.9553166181245093 >= 3.141592653589793 ||
+                           a >= cos(theta + 0.9553166181245093) - 1e-9;
+    if (reachable) {
+        const double alpha = u * u - c * c;
+        for (int y = 0; y < R; ++y) {
+            const double fy = 2.0 * ((y + 0.5) / (double)R) - 1.0;
+            const double k0 = a + w * fy, g = 1.0 + fy * fy;
+            // { fx : (k0 + u fx)^2 >= c^2 (g + fx^2), k0 + u fx >= 0 } for c >= 0; for c < 0 the second condition drops
+            // and the complement of the mirrored cone is wanted -- the plugin's levels never get there (cutoff > 0)
+            double lo = -1.0, hi = 1.0;
+            if (c > 0.0) {
+                const double beta = u * k0, gamma = k0 * k0 - c * c * g;
+                const double disc = beta * beta - alpha * gamma;
+                if (fabs(alpha) < 1e-14) {                       // linear: 2 beta fx + gamma >= 0, with k0 + u fx >= 0
+                    if (fabs(beta) < 1e-300) { if (gamma < 0.0 || k0 < 0.0) continue; }
+                    else if (beta > 0.0) lo = fmax(lo, -gamma / (2.0 * beta));
+                    else hi = fmin(hi, -gamma / (2.0 * beta));
+                } else {
+                    if (disc < 0.0) continue;                     // (alpha > 0 always has real roots)
+                    const double sq = sqrt(disc);
+                    double r1 = (-beta - sq) / alpha, r2 = (-beta + sq) / alpha;
+                    if (r1 > r2) { const double t = r1; r1 = r2; r2 = t; }
+                    if (alpha < 0.0) {                            // between the roots, on the side where k0 + u fx >= 0
+                        if (k0 + u * 0.5 * (r1 + r2) < 0.0) continue;
+                        lo = fmax(lo, r1); hi = fmin(hi, r2);
+                    } else if (u > 0.0) lo = fmax(lo, r2);        // outside the roots: the ray on which k0 + u fx >= 0
+                    else hi = fmin(hi, r1);
+                }
+                if (lo > hi) continue;
             }
+            // candidate columns (one texel of slack each side), then the exact fp32 test decides the ends
+            int xl = max(0, (int)floor((lo + 1.0) * 0.5 * R - 0.5) - 1);
+            int xr = min(R - 1, (int)ceil((hi + 1.0) * 0.5 * R - 0.5) + 1);
+            while (xl <= xr && !in_cone(xl, y, s, N, V, cutoff)) ++xl;
+            if (xl > xr) continue;
+            while (!in_cone(xr, y, s, N, V, cutoff)) --xr;
+            min_x = min(min_x, xl); max_x = max(max_x, xr);
+            min_y = min(min_y, y); max_y = max(max_y, y);
         }
-    float4 *b = reinterpret_cast<float4 *>(bounds) + (size_t)o * 6 + s;
-    *b = make_float4((float)min_x, (float)max_x, (float)min_y, (float)max_y);
+    }
+    float4 *bptr = reinterpret_cast<float4 *>(bounds) + (size_t)o * 6 + s;
+    *bptr = make_float4((float)min_x, (float)max_x, (float)min_y, (float)max_y);
 }
 
 __device__ __forceinline__ float ndf_ggx(float alphaSqr, float cosTheta) {

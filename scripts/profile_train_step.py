@@ -64,7 +64,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
 
-OURS = ("composite", "sublists", "lpt_order", "pack_records", "shade", "project", "tonemap", "isect", "iota", "tile_offsets",
+OURS = ("mlp_fwd", "mlp_bwd", "composite", "sublists", "lpt_order", "pack_records", "shade", "project", "tonemap", "isect", "iota", "tile_offsets",
         "publish_total", "grad_sum", "specular", "diffuse", "cubemap", "dir_table", "prep_source", "hashgrid", "mgadapter",
         "vertex_normals", "fc_", "loss_", "envstack", "texture")
 groups = {"library kernels": {}, "cub / radix sort": {}, "torch elementwise / reduce / index": {}, "cuBLAS / GEMM": {},
@@ -85,7 +85,8 @@ for ev in prof.events():
         g = "cuBLAS / GEMM"
     else:
         g = "torch elementwise / reduce / index"
-    short = name.split("(")[0][-70:]
+    clean = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
+    short = clean.split("(")[0].split("<")[0][-70:] or clean[:70]
     c, t = groups[g].get(short, (0, 0.0))
     groups[g][short] = (c + 1, t + dur)
     tr = ev.time_range

@@ -68,3 +68,42 @@ def test_diffuse_irradiance_and_mip_chain_on_the_host(lib):
     gfine = np.zeros((6, 32, 32, 3), np.float32)
     assert lib.gsb_cubemap_mip_bwd(i32(16), _p(cot.numpy()), _p(gfine), None) == 0
     _close(gfine, S.cubemap_mip_bwd(cot), 1e-5, "mip bwd")
+
+
+def _dirs_fp32(R):
+    """texel_dir of csrc/prefilter.cu in numpy float32, operation for operation: [6,R,R,3]."""
+    f = np.float32
+    idx = np.arange(R, dtype=np.float32)
+    g = f(2.0) * ((idx + f(0.5)) / f(R)) - f(1.0)
+    gx, gy = np.meshgrid(g, g)                     # [y, x]
+    one = np.ones_like(gx)
+    faces = [(one, -gy, -gx), (-one, -gy, gx), (gx, one, gy), (gx, -one, -gy), (gx, -gy, one), (-gx, -gy, -one)]
+    out = np.empty((6, R, R, 3), np.float32)
+    for s, (px, py, pz) in enumerate(faces):
+        l = np.sqrt(px * px + py * py + pz * pz)
+        out[s] = np.stack([px / l, py / l, pz / l], -1)
+    return out
+
+
+@pytest.mark.parametrize("R,rough", [(16, 1.0), (16, 0.5), (32, 0.29), (32, 0.08), (64, 0.185), (64, 0.08)])
+def test_bounds_are_the_exact_box_of_the_fp32_cone_test(lib, R, rough):
+    """The geometric bounds search (a quadratic per texel row + exact tests at the ends) against the definition: the
+    bounding box, on every face, of the texels that pass the fp32 test `texel_dir . V >= cutoff` the gather kernels
+    evaluate -- every entry identical, empty faces included."""
+    ct = np.float32(P.ndf_cutoff_costheta(rough))
+    bounds = np.zeros((6, R, R, 24), np.float32)
+    assert lib.gsb_specular_bounds(C.c_int32(R), C.c_float(ct), _p(bounds), None) == 0
+    d = _dirs_fp32(R)
+    flat = d.reshape(-1, 3)
+    rng = np.random.default_rng(R)
+    picks = rng.choice(6 * R * R, size=min(6 * R * R, 400), replace=False)
+    for t in picks:
+        V = flat[t]
+        dots = (d[..., 0] * V[0] + d[..., 1] * V[1]) + d[..., 2] * V[2]      # dot3: left to right
+        inside = dots >= ct
+        want = np.empty(24, np.float32)
+        for s in range(6):
+            ys, xs = np.nonzero(inside[s])
+            want[4 * s:4 * s + 4] = (xs.min(), xs.max(), ys.min(), ys.max()) if xs.size else (R - 1, 0, R - 1, 0)
+        got = bounds.reshape(-1, 24)[t]
+        assert np.array_equal(got, want), (t, got, want)
