@@ -93,7 +93,8 @@ class CallStats:
 
     KERNELS = {"gsb_isect_scan": 0, "gsb_sort_pairs": 0, "gsb_bin_workspace_bytes": 0, "gsb_envstack_texels": 0,
                "gsb_composite_workspace_bytes": 0, "gsb_specular_workspace_bytes": 0, "gsb_specular_cubemap_fwd": 3,
-               "gsb_specular_cubemap_bwd": 3, "gsb_composite_fwd": 4, "gsb_composite_bwd": 2, "gsb_shade_bwd": 2,
+               "gsb_specular_cubemap_bwd": 3, "gsb_specular_plan_count": 2, "gsb_specular_plan_fill": 2,
+               "gsb_specular_plan_fwd": 3, "gsb_specular_plan_bwd": 3, "gsb_composite_fwd": 4, "gsb_composite_bwd": 2, "gsb_shade_bwd": 2,
                "gsb_shade_workspace_bytes": 0, "gsb_vertex_normals_fwd": 2, "gsb_vertex_normals_bwd": 2,
                "gsb_bin2_workspace_bytes": 0, "gsb_bin2_count": 2, "gsb_bin2_sort": 2,
                # the native per-view driver: prepare = project + iota + total + shade; finish = emit + offsets + pack +

@@ -10,6 +10,8 @@
 // float2, the 8 corner gathers hit the L2-resident table (2^18 entries x 16 levels x 8 B = 33.5 MB).  Algorithmic
 // bytes: 12 B in + 8 B/level out per point (+ 64 B/level of L2 gathers).  The backward scatters with one
 // red.global.add.v2.f32 per corner and writes d/dx once per point after a 16-lane segmented reduction.
+#include <stdlib.h>
+
 #include "gsb_common.cuh"
 
 namespace {
@@ -176,6 +178,115 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(long long total, int 
     }
 }
 
+// ---- level-major variants (L <= 32): a CTA = 32 consecutive points x L levels, WARP w = level w of those 32 points ----
+// The points arrive in mesh order (MGAdaptor emits Gaussians face by face), so the 32 points of a warp are neighbours in
+// space: at one level their cells coincide or touch, and the corner gathers of a warp fall into a few sectors instead of
+// 8 x 32 scattered ones (with a (point, level)-per-thread layout the lanes of a warp address 16 different level tables).
+// The [point][level] feature rows are transposed through shared memory so that global loads / stores stay coalesced.
+constexpr int TILE_P = 32;
+
+__global__ void __launch_bounds__(1024) hashgrid_fwd_lm_kernel(int64_t N, int L, int log2_T, Scalings sc,
+                                                                const float *__restrict__ x,
+                                                                const float2 *__restrict__ table,
+                                                                float2 *__restrict__ feats) {
+    __shared__ float2 s_out[TILE_P * (MAX_LEVELS + 1)];
+    const int l = threadIdx.x >> 5, p = threadIdx.x & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * TILE_P, n = n0 + p;
+    if (n < N) {
+        const Cell c = locate(x, (int)n, sc.s[l], (uint32_t)l << log2_T, (1u << log2_T) - 1u);
+        float2 f[8];
+        gather8(table, c, f);
+        const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.0f - ox, ry = 1.0f - oy, rz = 1.0f - oz;
+        float2 out;
+        {
+            const float f03 = f[0].x * ox + f[3].x * rx, f12 = f[1].x * ox + f[2].x * rx;
+            const float f56 = f[5].x * ox + f[6].x * rx, f47 = f[4].x * ox + f[7].x * rx;
+            out.x = (f03 * oy + f12 * ry) * oz + (f47 * oy + f56 * ry) * rz;
+        }
+        {
+            const float f03 = f[0].y * ox + f[3].y * rx, f12 = f[1].y * ox + f[2].y * rx;
+            const float f56 = f[5].y * ox + f[6].y * rx, f47 = f[4].y * ox + f[7].y * rx;
+            out.y = (f03 * oy + f12 * ry) * oz + (f47 * oy + f56 * ry) * rz;
+        }
+        s_out[p * (L + 1) + l] = out;
+    }
+    __syncthreads();
+    const int e = threadIdx.x, pp = e / L, ll = e % L;         // consecutive threads -> consecutive floats of the tile
+    if (n0 + pp < N) feats[(n0 + pp) * L + ll] = s_out[pp * (L + 1) + ll];
+}
+
+__global__ void __launch_bounds__(1024) hashgrid_bwd_lm_kernel(int64_t N, int L, int log2_T, Scalings sc,
+                                                                const float *__restrict__ x,
+                                                                const float2 *__restrict__ table,
+                                                                const float2 *__restrict__ v_feats,
+                                                                float table_grad_scale, float2 *__restrict__ v_table,
+                                                                float *__restrict__ v_x) {
+    __shared__ float2 s_v[TILE_P * (MAX_LEVELS + 1)];
+    __shared__ float s_g[3][MAX_LEVELS][TILE_P];
+    const int l = threadIdx.x >> 5, p = threadIdx.x & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * TILE_P, n = n0 + p;
+    {
+        const int e = threadIdx.x, pp = e / L, ll = e % L;
+        if (n0 + pp < N) s_v[pp * (L + 1) + ll] = v_feats[(n0 + pp) * L + ll];
+    }
+    __syncthreads();
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (n < N) {
+        const float scaling = sc.s[l];
+        const Cell c = locate(x, (int)n, scaling, (uint32_t)l << log2_T, (1u << log2_T) - 1u);
+        const float2 v = s_v[p * (L + 1) + l];
+        const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.0f - ox, ry = 1.0f - oy, rz = 1.0f - oz;
+        const float w[8] = {ox * oy * oz, ox * ry * oz, rx * ry * oz, rx * oy * oz,
+                            ox * oy * rz, ox * ry * rz, rx * ry * rz, rx * oy * rz};
+        if (v_table) {
+            if (c.paired) {   // one red.global.add.v4.f32 per aligned pair of entries
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t ic = c.idx[PAIR_C[k]];
+                    const float sc_ = w[PAIR_C[k]] * table_grad_scale, sf_ = w[PAIR_F[k]] * table_grad_scale;
+                    const float s0 = (ic & 1u) ? sf_ : sc_, s1 = (ic & 1u) ? sc_ : sf_;
+                    atomicAdd(reinterpret_cast<float4 *>(v_table) + (ic >> 1),
+                              make_float4(s0 * v.x, s0 * v.y, s1 * v.x, s1 * v.y));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float s_ = w[k] * table_grad_scale;
+                    atomicAdd(v_table + c.idx[k], make_float2(s_ * v.x, s_ * v.y));
+                }
+            }
+        }
+        if (v_x) {
+            float2 f[8];
+            gather8(table, c, f);
+            float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float a[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = ch ? f[k].y : f[k].x;
+                const float vv = ch ? v.y : v.x;
+                const float f03 = a[0] * ox + a[3] * rx, f12 = a[1] * ox + a[2] * rx;
+                const float f56 = a[5] * ox + a[6] * rx, f47 = a[4] * ox + a[7] * rx;
+                const float d03 = a[0] - a[3], d12 = a[1] - a[2], d56 = a[5] - a[6], d47 = a[4] - a[7];
+                d[0] += vv * ((d03 * oy + d12 * ry) * oz + (d47 * oy + d56 * ry) * rz);
+                d[1] += vv * ((f03 - f12) * oz + (f47 - f56) * rz);
+                d[2] += vv * ((f03 * oy + f12 * ry) - (f47 * oy + f56 * ry));
+            }
+            const float j = 0.5f * scaling;   // d offset / d x  (floor and ceil carry no gradient)
+            gx = d[0] * j; gy = d[1] * j; gz = d[2] * j;
+        }
+    }
+    if (!v_x) return;
+    s_g[0][l][p] = gx; s_g[1][l][p] = gy; s_g[2][l][p] = gz;
+    __syncthreads();
+    if (l == 0 && n < N) {                     // level 0's warp sums the levels of its 32 points, in level order
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int k = 0; k < L; ++k) { sx += s_g[0][k][p]; sy += s_g[1][k][p]; sz += s_g[2][k][p]; }
+        v_x[3 * n] = sx; v_x[3 * n + 1] = sy; v_x[3 * n + 2] = sz;
+    }
+}
+
 int check(int64_t N, int32_t L, int32_t F, int32_t log2_T, const float *scalings_host) {
     GSB_CHECK_ARG(N >= 0 && L >= 1 && L <= MAX_LEVELS && log2_T >= 1 && log2_T <= 24 && scalings_host != nullptr);
     if (F != 2) {
@@ -199,6 +310,14 @@ GSB_API int gsb_hashgrid_fwd(int64_t N, const float *x, const float *table, int3
     Scalings sc;
     for (int l = 0; l < L; ++l) sc.s[l] = scalings_host[l];
     const long long total = (long long)N * L;
+#ifndef GSB_HOST_EMULATION
+    if (L <= MAX_LEVELS && !getenv("GSB_HASHGRID_POINT_MAJOR")) {       // level-major warps (see hashgrid_fwd_lm_kernel)
+        hashgrid_fwd_lm_kernel<<<gsb_div_up(N, TILE_P), TILE_P * L, 0, (cudaStream_t)stream>>>(
+            N, L, log2_T, sc, x, reinterpret_cast<const float2 *>(table), reinterpret_cast<float2 *>(feats));
+        GSB_CHECK_LAUNCH();
+        return GSB_OK;
+    }
+#endif
     hashgrid_fwd_kernel<<<gsb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
         total, L, log2_T, sc, x, reinterpret_cast<const float2 *>(table), reinterpret_cast<float2 *>(feats));
     GSB_CHECK_LAUNCH();
@@ -215,6 +334,15 @@ GSB_API int gsb_hashgrid_bwd(int64_t N, const float *x, const float *table, int3
     Scalings sc;
     for (int l = 0; l < L; ++l) sc.s[l] = scalings_host[l];
     const long long total = (long long)N * L;
+#ifndef GSB_HOST_EMULATION
+    if (L <= MAX_LEVELS && !getenv("GSB_HASHGRID_POINT_MAJOR")) {
+        hashgrid_bwd_lm_kernel<<<gsb_div_up(N, TILE_P), TILE_P * L, 0, (cudaStream_t)stream>>>(
+            N, L, log2_T, sc, x, reinterpret_cast<const float2 *>(table), reinterpret_cast<const float2 *>(v_feats),
+            table_grad_scale, reinterpret_cast<float2 *>(v_table), v_x);
+        GSB_CHECK_LAUNCH();
+        return GSB_OK;
+    }
+#endif
 #ifdef GSB_HOST_EMULATION   // tests/emu runs the threads one after another: no warp to reduce over, d/dx through atomics
     const int segmented = 0;
 #else

@@ -272,33 +272,24 @@ __global__ void __launch_bounds__(256) prep_source_kernel(int R, const float *__
     }
 }
 
-// SPLIT == false: one launch dimension, a warp sums all six faces and writes the result.
-// SPLIT == true : gridDim.y = 6, a warp sums ONE face and adds into a zeroed float4 accumulator (small levels have
-//                 too few 8x4 patches to fill 148 SMs); specular_finalize_kernel then writes the result.
-template <bool BWD, bool SPLIT>
-__global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float4 *__restrict__ dirs,
-                                                               const float4 *__restrict__ pre,
-                                                               const float4 *__restrict__ bounds, float alphaSqr,
-                                                               float cutoff, int normalize, float *__restrict__ dst,
-                                                               float4 *__restrict__ accum) {
-    const int lane = threadIdx.x & 31;
-    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);           // 8x4 patches, (R/8) x (R/4) per face
-    const int ppf = (R / 8) * (R / 4);
-    if (patch >= 6 * ppf) return;
-    const int ts = patch / ppf, pr = patch % ppf;
-    const int tx = (pr % (R / 8)) * 8 + (lane & 7), ty = (pr / (R / 8)) * 4 + (lane >> 3);
-    const int t = (ts * R + ty) * R + tx;
-    const float4 Vd = __ldg(dirs + t);
-    const float3 V = make_float3(Vd.x, Vd.y, Vd.z);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float kscale = alphaSqr * (0.25f / 3.14159265358979323846f);
-    const float e_scale = 0.25f * (1.0f - alphaSqr);
-    const int s_begin = SPLIT ? blockIdx.y : 0, s_end = SPLIT ? blockIdx.y + 1 : 6;
+// The traversal shared by the on-the-fly gather, and by the two passes that BUILD a cached plan (below): a warp owns an
+// 8x4 patch of output texels and visits, face by face and row by row, the union of its lanes' cone spans; `vis.row(s, y,
+// xmin, xmax)` is called warp-uniformly for every non-empty union span.
+struct PatchGeom {
+    int t;            // this lane's output texel
+    float3 V;         // its direction
+    float area;
+};
+
+template <class Visitor>
+__device__ __forceinline__ void walk_cone_rows(int R, const float4 *__restrict__ bounds, float cutoff, const PatchGeom &g,
+                                               int s_begin, int s_end, Visitor &vis) {
+    const float3 V = g.V;
     // conservative copy of the cone test for the per-row spans below (the exact test on d decides membership)
     const float cs = cutoff * (1.0f - 1e-5f) - 1e-6f;
     const float halfR = 0.5f * (float)R, twoOverR = 2.0f / (float)R;
     for (int s = s_begin; s < s_end; ++s) {
-        const float4 b = __ldg(bounds + (size_t)t * 6 + s);
+        const float4 b = __ldg(bounds + (size_t)g.t * 6 + s);
         const int lxmin = (int)b.x, lxmax = (int)b.y, lymin = (int)b.z, lymax = (int)b.w;   // this lane's cone AABB
         int ymin = lymin, ymax = lymax;
         if (lxmin > lxmax) { ymin = 1 << 30; ymax = -1; }   // this lane's cone misses face s
@@ -307,6 +298,7 @@ __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float
             ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
             ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
         }
+        vis.face(s);
         if (ymax < ymin) continue;   // warp-uniform
         // face frame: p(gx, gy) = n + gx u + gy w, so p.V = a gx + (gy bw + cn)
         float nx, ny, nz, ux, uy, uz, wx, wy, wz;
@@ -352,33 +344,204 @@ __global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float
                 xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
             }
             if (xmax < xmin) continue;   // warp-uniform
-            const float4 *drow = dirs + ((size_t)s * R + y) * R;
-            const float4 *prow = pre + ((size_t)s * R + y) * R;
-            // branch-free body, 4 taps in flight: the loads are warp-broadcast L1 hits and the four weight
-            // evaluations are independent, which is what a latency-bound lone warp needs
-#pragma unroll 4
-            for (int x = xmin; x <= xmax; ++x) {
-                const float4 Ld = __ldg(drow + x);
-                const float4 P = __ldg(prow + x);
-                const float3 L = make_float3(Ld.x, Ld.y, Ld.z);
-                const float d = dot3(L, V);
-                // H bisects the unit vectors L and V, so 1 - (V.H)^2 = sin^2(theta/2) = |V - L|^2 / 4: exact
-                // differences of nearby unit vectors, no cancellation, no division.
-                const float ex = V.x - L.x, ey = V.y - L.y, ez = V.z - L.z;
-                const float e = ex * ex + ey * ey + ez * ez;
-                const float dd = fmaf(e, e_scale, alphaSqr);     // s2 + (1 - s2) * alphaSqr with s2 = e / 4
-                const float k = (d >= cutoff) ? d * __fdividef(kscale, dd * dd) : 0.f;
-                acc.x += P.x * k; acc.y += P.y * k; acc.z += P.z * k; acc.w += P.w * k;
-            }
+            vis.row(s, y, xmin, xmax);
         }
     }
+}
+
+__device__ __forceinline__ bool patch_geom(int R, const float4 *__restrict__ dirs, int patch, int lane, PatchGeom &g) {
+    const int ppf = (R / 8) * (R / 4);                                 // 8x4 patches, (R/8) x (R/4) per face
+    if (patch >= 6 * ppf) return false;
+    const int ts = patch / ppf, pr = patch % ppf;
+    const int tx = (pr % (R / 8)) * 8 + (lane & 7), ty = (pr / (R / 8)) * 4 + (lane >> 3);
+    g.t = (ts * R + ty) * R + tx;
+    const float4 Vd = __ldg(dirs + g.t);
+    g.V = make_float3(Vd.x, Vd.y, Vd.z);
+    g.area = Vd.w;
+    return true;
+}
+
+// GGX weight of one tap for this lane: k = max(L.V, 0) D_ggx(V.H) / 4 inside the cone, 0 outside.  H bisects the unit
+// vectors L and V, so 1 - (V.H)^2 = sin^2(theta/2) = |V - L|^2 / 4: exact differences of nearby unit vectors, no
+// cancellation, no division.
+__device__ __forceinline__ float tap_weight(const float4 Ld, const float3 V, float alphaSqr, float cutoff, float kscale,
+                                            float e_scale) {
+    const float3 L = make_float3(Ld.x, Ld.y, Ld.z);
+    const float d = dot3(L, V);
+    const float ex = V.x - L.x, ey = V.y - L.y, ez = V.z - L.z;
+    const float e = ex * ex + ey * ey + ez * ez;
+    const float dd = fmaf(e, e_scale, alphaSqr);     // s2 + (1 - s2) * alphaSqr with s2 = e / 4
+    return (d >= cutoff) ? d * __fdividef(kscale, dd * dd) : 0.f;
+}
+
+struct GatherVisitor {      // on-the-fly: weight evaluated at every tap
+    int R;
+    const float4 *dirs, *pre;
+    float3 V;
+    float alphaSqr, cutoff, kscale, e_scale;
+    float4 acc;
+    __device__ __forceinline__ void face(int) {}
+    __device__ __forceinline__ void row(int s, int y, int xmin, int xmax) {
+        const float4 *drow = dirs + ((size_t)s * R + y) * R;
+        const float4 *prow = pre + ((size_t)s * R + y) * R;
+        // branch-free body, 4 taps in flight: the loads are warp-broadcast L1 hits and the four weight
+        // evaluations are independent, which is what a latency-bound lone warp needs
+#pragma unroll 4
+        for (int x = xmin; x <= xmax; ++x) {
+            const float4 P = __ldg(prow + x);
+            const float k = tap_weight(__ldg(drow + x), V, alphaSqr, cutoff, kscale, e_scale);
+            acc.x += P.x * k; acc.y += P.y * k; acc.z += P.z * k; acc.w += P.w * k;
+        }
+    }
+};
+
+// SPLIT == false: one launch dimension, a warp sums all six faces and writes the result.
+// SPLIT == true : gridDim.y = 6, a warp sums ONE face and adds into a zeroed float4 accumulator (small levels have
+//                 too few 8x4 patches to fill 148 SMs); specular_finalize_kernel then writes the result.
+template <bool BWD, bool SPLIT>
+__global__ void __launch_bounds__(128) specular_gather_kernel(int R, const float4 *__restrict__ dirs,
+                                                               const float4 *__restrict__ pre,
+                                                               const float4 *__restrict__ bounds, float alphaSqr,
+                                                               float cutoff, int normalize, float *__restrict__ dst,
+                                                               float4 *__restrict__ accum) {
+    const int lane = threadIdx.x & 31;
+    PatchGeom g;
+    if (!patch_geom(R, dirs, blockIdx.x * 4 + (threadIdx.x >> 5), lane, g)) return;
+    GatherVisitor vis{R, dirs, pre, g.V, alphaSqr, cutoff, alphaSqr * (0.25f / 3.14159265358979323846f),
+                      0.25f * (1.0f - alphaSqr), make_float4(0.f, 0.f, 0.f, 0.f)};
+    walk_cone_rows(R, bounds, cutoff, g, SPLIT ? (int)blockIdx.y : 0, SPLIT ? (int)blockIdx.y + 1 : 6, vis);
+    const float4 acc = vis.acc;
+    const int t = g.t;
     if (SPLIT) {
         atomicAdd(accum + t, acc);
         return;
     }
     if (BWD) {
         float *o = dst + (size_t)t * 3;
-        o[0] = acc.x * Vd.w; o[1] = acc.y * Vd.w; o[2] = acc.z * Vd.w;
+        o[0] = acc.x * g.area; o[1] = acc.y * g.area; o[2] = acc.z * g.area;
+    } else {
+        float4 r = normalize ? make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w) : acc;
+        reinterpret_cast<float4 *>(dst)[t] = r;
+    }
+}
+
+// ---- cached plan: the GGX weights are a function of the geometry only ------------------------------------------------
+// The cube map changes every training step (it is a trainable parameter, geosplat.py:741-748); roughness, resolution and
+// cone do not.  A level's "plan" stores, once, per 8x4 patch the row segments of the union of its cones and per
+// (tap, lane) the weight k -- 32 consecutive floats per tap, so the per-step pass streams the weights with perfectly
+// coalesced 128-byte loads and does 4 FMAs per tap instead of evaluating a GGX lobe: ~5.5 GB of HBM for the six levels of
+// a 512^2 cube map (of 180), read once forward and once backward (the kernel k(V, L) is symmetric, so the backward
+// gathers with the same weights).  Built by the same traversal and the same weight expression as the on-the-fly
+// kernels, in the same tap order: the results are bit-identical to theirs.
+struct CountVisitor {
+    int segs, taps;
+    int2 *out;           // per (patch, face): {segments, taps}
+    int lane;
+    __device__ __forceinline__ void face(int s) {
+        if (s > 0 && lane == 0) out[s - 1] = make_int2(segs, taps);
+        if (s > 0) { segs = 0; taps = 0; }
+    }
+    __device__ __forceinline__ void row(int, int, int xmin, int xmax) { ++segs; taps += (xmax - xmin + 4) & ~3; }   // padded to whole float4 groups
+};
+
+__global__ void __launch_bounds__(128) specular_plan_count_kernel(int R, const float4 *__restrict__ dirs,
+                                                                   const float4 *__restrict__ bounds, float cutoff,
+                                                                   int2 *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);
+    PatchGeom g;
+    if (!patch_geom(R, dirs, patch, lane, g)) return;
+    CountVisitor vis{0, 0, counts + (size_t)patch * 6, lane};
+    walk_cone_rows(R, bounds, cutoff, g, 0, 6, vis);
+    if (lane == 0) counts[(size_t)patch * 6 + 5] = make_int2(vis.segs, vis.taps);
+}
+
+struct FillVisitor {
+    int R;
+    const float4 *dirs;
+    float3 V;
+    float alphaSqr, cutoff, kscale, e_scale;
+    const int *seg_start, *tap_start;    // exclusive prefix sums over (patch, face)
+    int4 *segs;
+    float *weights;
+    int lane, seg, tap;
+    size_t pf;                            // patch * 6
+    __device__ __forceinline__ void face(int s) { seg = seg_start[pf + s]; tap = tap_start[pf + s]; }
+    __device__ __forceinline__ void row(int s, int y, int xmin, int xmax) {
+        const int row0 = (s * R + y) * R;
+        if (lane == 0) segs[seg] = make_int4(row0 + xmin, xmax - xmin + 1, tap, 0);
+        ++seg;
+        // layout: groups of 4 consecutive taps, [group][lane][4] -- one 16-byte load per lane and group when streaming;
+        // every segment starts a new group and its tail is padded with zero weights
+        const float4 *drow = dirs + row0;
+        const int len = xmax - xmin + 1, padded = (len + 3) & ~3;
+        float4 *w4 = reinterpret_cast<float4 *>(weights) + (size_t)(tap >> 2) * 32 + lane;
+        for (int j = 0; j < padded; j += 4, w4 += 32) {
+            float k[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                k[i] = (j + i < len) ? tap_weight(__ldg(drow + xmin + j + i), V, alphaSqr, cutoff, kscale, e_scale) : 0.f;
+            *w4 = make_float4(k[0], k[1], k[2], k[3]);
+        }
+        tap += padded;
+    }
+};
+
+__global__ void __launch_bounds__(128) specular_plan_fill_kernel(int R, const float4 *__restrict__ dirs,
+                                                                  const float4 *__restrict__ bounds, float alphaSqr,
+                                                                  float cutoff, const int *__restrict__ seg_start,
+                                                                  const int *__restrict__ tap_start,
+                                                                  int4 *__restrict__ segs, float *__restrict__ weights) {
+    const int lane = threadIdx.x & 31;
+    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);
+    PatchGeom g;
+    if (!patch_geom(R, dirs, patch, lane, g)) return;
+    FillVisitor vis{R, dirs, g.V, alphaSqr, cutoff, alphaSqr * (0.25f / 3.14159265358979323846f),
+                    0.25f * (1.0f - alphaSqr), seg_start, tap_start, segs, weights, lane, 0, 0, (size_t)patch * 6};
+    walk_cone_rows(R, bounds, cutoff, g, 0, 6, vis);
+}
+
+// acc[t] += sum over the patch's taps of W[tap][lane] * pre[source texel]: same epilogues as the gather kernel
+template <bool BWD, bool SPLIT>
+__global__ void __launch_bounds__(128) specular_apply_kernel(int R, const float4 *__restrict__ dirs,
+                                                              const float4 *__restrict__ pre,
+                                                              const int *__restrict__ seg_start,
+                                                              const int4 *__restrict__ segs,
+                                                              const float *__restrict__ weights, int normalize,
+                                                              float *__restrict__ dst, float4 *__restrict__ accum) {
+    const int lane = threadIdx.x & 31;
+    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5);
+    PatchGeom g;
+    if (!patch_geom(R, dirs, patch, lane, g)) return;
+    const size_t pf = (size_t)patch * 6;
+    const int s0 = seg_start[pf + (SPLIT ? blockIdx.y : 0)], s1 = seg_start[pf + (SPLIT ? blockIdx.y + 1 : 6)];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int last = 6 * R * R - 1;
+    for (int i = s0; i < s1; ++i) {
+        const int4 sg = __ldg(segs + i);
+        const float4 *w4 = reinterpret_cast<const float4 *>(weights) + (size_t)(sg.z >> 2) * 32 + lane;
+        const int groups = (sg.y + 3) >> 2;
+        // 4 groups = 16 taps per iteration: four independent 16-byte weight loads per lane in flight (2 KB per warp)
+#pragma unroll 4
+        for (int gi = 0; gi < groups; ++gi) {
+            const float4 k = __ldcs(w4 + (size_t)gi * 32);     // streamed once per pass: do not keep it in L1 / L2
+            const int x = sg.x + 4 * gi;                        // the padded tail (zero weights) stays inside the buffer
+            const float4 P0 = __ldg(pre + x), P1 = __ldg(pre + min(x + 1, last));
+            const float4 P2 = __ldg(pre + min(x + 2, last)), P3 = __ldg(pre + min(x + 3, last));
+            acc.x += P0.x * k.x; acc.y += P0.y * k.x; acc.z += P0.z * k.x; acc.w += P0.w * k.x;
+            acc.x += P1.x * k.y; acc.y += P1.y * k.y; acc.z += P1.z * k.y; acc.w += P1.w * k.y;
+            acc.x += P2.x * k.z; acc.y += P2.y * k.z; acc.z += P2.z * k.z; acc.w += P2.w * k.z;
+            acc.x += P3.x * k.w; acc.y += P3.y * k.w; acc.z += P3.z * k.w; acc.w += P3.w * k.w;
+        }
+    }
+    const int t = g.t;
+    if (SPLIT) {
+        atomicAdd(accum + t, acc);
+        return;
+    }
+    if (BWD) {
+        float *o = dst + (size_t)t * 3;
+        o[0] = acc.x * g.area; o[1] = acc.y * g.area; o[2] = acc.z * g.area;
     } else {
         float4 r = normalize ? make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w) : acc;
         reinterpret_cast<float4 *>(dst)[t] = r;
@@ -533,6 +696,78 @@ GSB_API int gsb_specular_cubemap_bwd(int32_t R, const float *bounds, const float
     }
     GSB_CHECK_LAUNCH();
     return GSB_OK;
+}
+
+// ---- cached plan entry points -------------------------------------------------------------------------------------
+// Build: gsb_specular_plan_count -> counts[(6 R^2 / 32) * 6][2] = {segments, taps} per (8x4 patch, face); the caller
+// forms the exclusive prefix sums seg_start / tap_start (one more entry than counts) and allocates segs[n_segs][4] int32
+// and weights[n_taps * 32] floats; gsb_specular_plan_fill writes them.  Per step: gsb_specular_plan_fwd / _bwd.
+static bool plan_ok(int32_t R) { return R % 8 == 0 && R >= 8 && R <= 1024; }
+
+GSB_API int gsb_specular_plan_count(int32_t R, const float *bounds, float costheta_cutoff, int32_t *counts,
+                                    void *workspace, void *stream) {
+    GSB_CHECK_ARG(plan_ok(R) && bounds && counts && workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    float4 *dirs = ws_align(workspace);
+    const int total = 6 * R * R;
+    dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
+    specular_plan_count_kernel<<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+        R, dirs, reinterpret_cast<const float4 *>(bounds), costheta_cutoff, reinterpret_cast<int2 *>(counts));
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_specular_plan_fill(int32_t R, const float *bounds, float roughness, float costheta_cutoff,
+                                   const int32_t *seg_start, const int32_t *tap_start, int32_t *segs, float *weights,
+                                   void *workspace, void *stream) {
+    GSB_CHECK_ARG(plan_ok(R) && bounds && seg_start && tap_start && segs && weights && workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    float4 *dirs = ws_align(workspace);
+    const int total = 6 * R * R;
+    const float alpha = roughness * roughness;
+    dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
+    specular_plan_fill_kernel<<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+        R, dirs, reinterpret_cast<const float4 *>(bounds), alpha * alpha, costheta_cutoff, seg_start, tap_start,
+        reinterpret_cast<int4 *>(segs), weights);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+template <bool BWD>
+static int plan_apply(int32_t R, const float *src, int src_stride, const float *fwd_out, int mode, const int32_t *seg_start,
+                      const int32_t *segs, const float *weights, int normalize, float *dst, void *workspace,
+                      cudaStream_t st) {
+    float4 *dirs = ws_align(workspace), *pre = dirs + 6 * (size_t)R * R;
+    const int total = 6 * R * R;
+    dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
+    prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, src, src_stride, fwd_out, dirs, mode, pre);
+    if (R <= 64) {
+        float4 *accum = pre + 6 * (size_t)R * R;
+        GSB_CHECK_CUDA(cudaMemsetAsync(accum, 0, sizeof(float4) * total, st));
+        specular_apply_kernel<BWD, true><<<dim3(gsb_div_up(total / 32, 4), 6), 128, 0, st>>>(
+            R, dirs, pre, seg_start, reinterpret_cast<const int4 *>(segs), weights, normalize, dst, accum);
+        specular_finalize_kernel<BWD><<<gsb_div_up(total, 256), 256, 0, st>>>(R, accum, dirs, normalize, dst);
+    } else {
+        specular_apply_kernel<BWD, false><<<gsb_div_up(total / 32, 4), 128, 0, st>>>(
+            R, dirs, pre, seg_start, reinterpret_cast<const int4 *>(segs), weights, normalize, dst, nullptr);
+    }
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+GSB_API int gsb_specular_plan_fwd(int32_t R, const float *cubemap, const int32_t *seg_start, const int32_t *segs,
+                                  const float *weights, int32_t normalize, float *out, void *workspace, void *stream) {
+    GSB_CHECK_ARG(plan_ok(R) && cubemap && seg_start && segs && weights && out && workspace);
+    return plan_apply<false>(R, cubemap, 3, nullptr, 0, seg_start, segs, weights, normalize, out, workspace,
+                             (cudaStream_t)stream);
+}
+
+GSB_API int gsb_specular_plan_bwd(int32_t R, const int32_t *seg_start, const int32_t *segs, const float *weights,
+                                  const float *grad_out, const float *fwd_out, float *grad_in, void *workspace,
+                                  void *stream) {
+    GSB_CHECK_ARG(plan_ok(R) && seg_start && segs && weights && grad_out && grad_in && workspace);
+    return plan_apply<true>(R, grad_out, 4, fwd_out, fwd_out ? 2 : 1, seg_start, segs, weights, 0, grad_in, workspace,
+                            (cudaStream_t)stream);
 }
 
 GSB_API int gsb_cubemap_mip_fwd(int32_t R_out, const float *in, int32_t in_stride, float *out, int32_t out_stride,

@@ -167,6 +167,54 @@ def specular_cubemap(cubemap: Tensor, roughness: float, cutoff: float = 0.99) ->
     return acc[..., :3] / acc[..., 3:]
 
 
+# ---- cached plans: the GGX weights depend on (resolution, roughness, cone), not on the cube map ---------------------------
+class SpecularPlan:
+    """Per-level weight table of the specular prefilter (csrc/prefilter.cu, "cached plan"): built once per (resolution,
+    roughness, cutoff, device), then every training step streams it forward and backward instead of re-evaluating the
+    GGX lobe at every tap.  ~1-2.5 GB per level of a 512^2 cube map, 5.5 GB for the default chain -- sized for a 180 GB
+    part; `GSB_PREFILTER_PLAN_GB` (default 12) caps the total, levels past the cap keep the on-the-fly kernels."""
+
+    __slots__ = ("seg_start", "segs", "weights", "nbytes")
+
+
+_plans: Dict[Tuple[int, float, float, int], "SpecularPlan"] = {}
+_plan_bytes: Dict[int, int] = {}
+
+
+def specular_plan(res: int, roughness: float, cutoff: float, dev: torch.device):
+    """The cached plan of a level, or None (resolution not a multiple of 8, or the memory cap is reached)."""
+    import os
+    index = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else 0)
+    key = (res, roughness, cutoff, index)
+    if key in _plans:
+        return _plans[key]
+    plan = None
+    if res % 8 == 0 and 8 <= res <= 1024:
+        cos_cut, bounds = ndf_bounds(res, roughness, cutoff, dev.index)
+        ws = _spec_workspace(res, dev)
+        st = stream_ptr(dev)
+        n_pf = 6 * res * res // 32 * 6
+        counts = torch.empty(n_pf, 2, dtype=torch.int32, device=dev)
+        call("gsb_specular_plan_count", dev, C.c_int32(res), ptr(bounds), C.c_float(cos_cut), ptr(counts), ptr(ws), st)
+        zero = torch.zeros(1, 2, dtype=torch.int64, device=dev)
+        starts = torch.cat((zero, counts.to(torch.int64).cumsum(0)))            # [n_pf + 1, 2]
+        n_segs, n_taps = (int(v) for v in starts[-1].tolist())                  # one host read, once per level
+        nbytes = n_taps * 128 + n_segs * 16 + starts.numel() * 4
+        cap = float(os.environ.get("GSB_PREFILTER_PLAN_GB", "12")) * 2 ** 30
+        if n_taps * 32 < 2 ** 31 and _plan_bytes.get(index, 0) + nbytes <= cap:
+            plan = SpecularPlan()
+            plan.seg_start = starts[:, 0].to(torch.int32).contiguous()
+            tap_start = starts[:, 1].to(torch.int32).contiguous()
+            plan.segs = torch.empty(max(n_segs, 1), 4, dtype=torch.int32, device=dev)
+            plan.weights = torch.empty(max(n_taps, 1) * 32, dtype=torch.float32, device=dev)
+            call("gsb_specular_plan_fill", dev, C.c_int32(res), ptr(bounds), C.c_float(roughness), C.c_float(cos_cut),
+                 ptr(plan.seg_start), ptr(tap_start), ptr(plan.segs), ptr(plan.weights), ptr(ws), st)
+            plan.nbytes = nbytes
+            _plan_bytes[index] = _plan_bytes.get(index, 0) + nbytes
+    _plans[key] = plan
+    return plan
+
+
 # ---- _texture.py:199-226 --------------------------------------------------------------------------------
 class _CubeMapMip(torch.autograd.Function):
     @staticmethod
@@ -259,8 +307,13 @@ class _PrefilterStack(torch.autograd.Function):
             r = R0 >> l
             ct, bounds = ndf_bounds(r, rough[l], cutoff, dev.index)
             cts.append(ct)
-            call("gsb_specular_cubemap_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(bounds), C.c_float(rough[l]),
-                 C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), ptr(ws), st)
+            plan = specular_plan(r, rough[l], cutoff, dev)
+            if plan is not None:     # stream the cached weights instead of evaluating the lobe at every tap
+                call("gsb_specular_plan_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(plan.seg_start), ptr(plan.segs),
+                     ptr(plan.weights), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), ptr(ws), st)
+            else:
+                call("gsb_specular_cubemap_fwd", dev, C.c_int32(r), ptr(chain[l]), ptr(bounds), C.c_float(rough[l]),
+                     C.c_float(ct), C.c_int32(1), C.c_void_p(stack.data_ptr() + o * 16), ptr(ws), st)
             o += 6 * r * r
         stack[o:].zero_()
         call("gsb_diffuse_cubemap_fwd", dev, C.c_int32(Rb), ptr(chain[-1]), C.c_void_p(stack.data_ptr() + o * 16),
@@ -287,8 +340,15 @@ class _PrefilterStack(torch.autograd.Function):
             r = R0 >> l
             _, bounds = ndf_bounds(r, rough[l], cutoff, dev.index)
             g = torch.empty(6, r, r, 3, dtype=torch.float32, device=dev)
-            call("gsb_specular_cubemap_bwd", dev, C.c_int32(r), ptr(bounds), C.c_void_p(v.data_ptr() + offs[l] * 16),
-                 C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), ptr(ws), st)
+            plan = specular_plan(r, rough[l], cutoff, dev)
+            if plan is not None:
+                call("gsb_specular_plan_bwd", dev, C.c_int32(r), ptr(plan.seg_start), ptr(plan.segs), ptr(plan.weights),
+                     C.c_void_p(v.data_ptr() + offs[l] * 16), C.c_void_p(stack.data_ptr() + offs[l] * 16), ptr(g),
+                     ptr(ws), st)
+            else:
+                call("gsb_specular_cubemap_bwd", dev, C.c_int32(r), ptr(bounds), C.c_void_p(v.data_ptr() + offs[l] * 16),
+                     C.c_void_p(stack.data_ptr() + offs[l] * 16), C.c_float(rough[l]), C.c_float(cts[l]), ptr(g), ptr(ws),
+                     st)
             g_levels.append(g)
         gb = torch.empty(6, Rb, Rb, 3, dtype=torch.float32, device=dev)
         call("gsb_diffuse_cubemap_bwd", dev, C.c_int32(Rb), C.c_void_p(v.data_ptr() + o * 16), C.c_int32(4), ptr(gb), st)

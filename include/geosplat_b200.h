@@ -418,6 +418,27 @@ int gsb_view_backward(const gsb_view_config *cfg, const gsb_camera *cam, const f
  * after the compositing backward, the dominant stage, so that a benchmark can time it inside a running batch. */
 
 /* -------------------------------------------------------------------------------------------
+ * Cached specular prefilter ("plan"): the GGX weights of specular_cubemap_fwd / _bwd depend on the resolution, the
+ * roughness and the cone only -- not on the cube map, which is what changes every training step (it is a parameter:
+ * rfstudio/model/geosplat.py:741-748, :780-785).  A plan stores them once (32 floats per tap of every 8x4 patch of
+ * output texels, ~5.5 GB for the six levels of a 512^2 map) and the per-step passes stream them.
+ *   count : counts[(6 R^2 / 32) * 6][2] int32 = {row segments, taps} per (patch, face);
+ *   fill  : seg_start / tap_start = exclusive prefix sums of the counts (one more entry), segs[n_segs][4] int32,
+ *           weights[n_taps * 32] float;
+ *   fwd / bwd : same arguments and results as gsb_specular_cubemap_fwd / _bwd with the plan in place of `bounds`.
+ * R must be a multiple of 8, <= 1024.  workspace: gsb_specular_workspace_bytes(R).
+ * ------------------------------------------------------------------------------------------- */
+int gsb_specular_plan_count(int32_t R, const float *bounds, float costheta_cutoff, int32_t *counts, void *workspace,
+                            void *stream);
+int gsb_specular_plan_fill(int32_t R, const float *bounds, float roughness, float costheta_cutoff,
+                           const int32_t *seg_start, const int32_t *tap_start, int32_t *segs, float *weights,
+                           void *workspace, void *stream);
+int gsb_specular_plan_fwd(int32_t R, const float *cubemap, const int32_t *seg_start, const int32_t *segs,
+                          const float *weights, int32_t normalize, float *out, void *workspace, void *stream);
+int gsb_specular_plan_bwd(int32_t R, const int32_t *seg_start, const int32_t *segs, const float *weights,
+                          const float *grad_out, const float *fwd_out, float *grad_in, void *workspace, void *stream);
+
+/* -------------------------------------------------------------------------------------------
  * The fields' MLPs, fused: replaces rfstudio/nn/mlp.py:125-145 (nn.Linear + F.relu per layer,
  * activation after the last) for the shapes of rfstudio/model/geosplat.py:485-518: x[N,32] -> 32 [-> 32] -> dout <= 4,
  * no bias.  Weights are nn.Linear's [out,in] row-major.  n_hidden: 1 or 2 (w1 NULL for 1).  activation: 0 none,

@@ -102,6 +102,7 @@ static inline float4 atomicAdd(float4 *p, float4 v) {   // sm_90+ vector reducti
     return old;
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcs(const T *p) { return *p; }
 
 #ifdef GSB_EMU_SIMT
 #define __shared__ static

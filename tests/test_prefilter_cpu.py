@@ -107,3 +107,45 @@ def test_bounds_are_the_exact_box_of_the_fp32_cone_test(lib, R, rough):
             want[4 * s:4 * s + 4] = (xs.min(), xs.max(), ys.min(), ys.max()) if xs.size else (R - 1, 0, R - 1, 0)
         got = bounds.reshape(-1, 24)[t]
         assert np.array_equal(got, want), (t, got, want)
+
+
+@pytest.mark.parametrize("R,rough", [(16, 1.0), (32, 0.5), (64, 0.185), (64, 0.08)])
+def test_cached_plan_reproduces_the_on_the_fly_prefilter_bit_for_bit(lib, R, rough):
+    """gsb_specular_plan_count / _fill build the per-(tap, lane) weight table once; gsb_specular_plan_fwd / _bwd then
+    stream it.  Same traversal, same weight expression, same tap order as gsb_specular_cubemap_fwd / _bwd: the results
+    must be IDENTICAL (forward with and without normalisation, backward with and without the forward's weight sums)."""
+    ct = P.ndf_cutoff_costheta(rough)
+    c = _cubemap(R, 11 + R).numpy()
+    i32, f32 = C.c_int32, C.c_float
+    bounds = np.zeros((6, R, R, 24), np.float32)
+    assert lib.gsb_specular_bounds(i32(R), f32(ct), _p(bounds), None) == 0
+    nb = C.c_size_t(0)
+    assert lib.gsb_specular_workspace_bytes(i32(R), C.byref(nb)) == 0
+    ws = np.full(nb.value + 256, 0xFF, np.uint8)
+    n_pf = 6 * R * R // 32 * 6
+    counts = np.full((n_pf, 2), -1, np.int32)
+    assert lib.gsb_specular_plan_count(i32(R), _p(bounds), f32(ct), _p(counts), _p(ws), None) == 0, lib.gsb_last_error()
+    assert counts.min() >= 0 and counts[:, 1].sum() > 6 * R * R // 32
+    seg_start = np.concatenate([[0], np.cumsum(counts[:, 0])]).astype(np.int32)
+    tap_start = np.concatenate([[0], np.cumsum(counts[:, 1])]).astype(np.int32)
+    segs = np.full((int(seg_start[-1]), 4), -1, np.int32)
+    weights = np.full(int(tap_start[-1]) * 32, np.nan, np.float32)
+    assert lib.gsb_specular_plan_fill(i32(R), _p(bounds), f32(rough), f32(ct), _p(seg_start), _p(tap_start), _p(segs),
+                                      _p(weights), _p(ws), None) == 0, lib.gsb_last_error()
+    assert np.isfinite(weights).all() and (weights >= 0).all() and segs[:, :3].min() >= 0
+    assert int(((segs[:, 1] + 3) // 4 * 4).sum()) == int(tap_start[-1])          # segments padded to whole float4 groups
+    for normalize in (0, 1):
+        a, b = np.zeros((6, R, R, 4), np.float32), np.zeros((6, R, R, 4), np.float32)
+        assert lib.gsb_specular_cubemap_fwd(i32(R), _p(c), _p(bounds), f32(rough), f32(ct), i32(normalize), _p(a), _p(ws),
+                                            None) == 0
+        assert lib.gsb_specular_plan_fwd(i32(R), _p(c), _p(seg_start), _p(segs), _p(weights), i32(normalize), _p(b),
+                                         _p(ws), None) == 0, lib.gsb_last_error()
+        assert np.array_equal(a, b), normalize
+    g = torch.randn(6, R, R, 4, generator=torch.Generator().manual_seed(5)).numpy()
+    for fwd_out in (None, b):
+        ga, gb = np.zeros((6, R, R, 3), np.float32), np.zeros((6, R, R, 3), np.float32)
+        assert lib.gsb_specular_cubemap_bwd(i32(R), _p(bounds), _p(g), _p(fwd_out), f32(rough), f32(ct), _p(ga), _p(ws),
+                                            None) == 0
+        assert lib.gsb_specular_plan_bwd(i32(R), _p(seg_start), _p(segs), _p(weights), _p(g), _p(fwd_out), _p(gb), _p(ws),
+                                         None) == 0, lib.gsb_last_error()
+        assert np.array_equal(ga, gb)
