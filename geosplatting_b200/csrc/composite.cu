@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
                                                                         const int32_t *__restrict__ flatten_ids,
                                                                         const Rec *__restrict__ rec,
                                                                         int2 *__restrict__ entries,
-                                                                        int32_t *__restrict__ counts) {
+                                                                        int32_t *__restrict__ counts,
+                                                                        int32_t *__restrict__ tile_len,
+                                                                        int32_t *__restrict__ tile_work) {
     static_assert(SUBS == 16 && BUILD_THREADS == 256, "build_sublists: 8 warps x 16 sub-rectangles");
     __shared__ int s_cnt[2][8][SUBS];   // [parity][warp][sub-rectangle] hits of this step
     __shared__ int s_pre[2][8][SUBS];   // exclusive prefix over warps
@@ -148,8 +150,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int len = end - start;
+    if (tid == 0) tile_work[tile] = 0;            // the forward adds the entries its units actually walk
     if (len <= 0) {
         if (tid < SUBS) counts[tile * SUBS + tid] = 0;
+        if (tid == 0) tile_len[tile] = 0;
         return;
     }
     const int tx = tile % tile_w, ty = tile / tile_w;
@@ -210,16 +214,19 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
     // `par` now names the buffer the last step wrote its totals to
     __syncthreads();
     if (tid < SUBS) counts[tile * SUBS + tid] = s_base[par][tid];
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < SUBS; ++k) tot += s_base[par][k];
+        tile_len[tile] = tot;                        // the forward's scheduling key
+    }
 }
 
 // Longest-processing-time-first order of the TILES (their 16 units stay adjacent in launch order so that they
 // share the tile's records in L1/L2): single-CTA counting sort on the mean per-unit work (4096 buckets of width 4,
 // heaviest first; order inside a bucket is irrelevant).  `n_units` here is the number of tiles.
-__device__ __forceinline__ int tile_work(const int32_t *__restrict__ counts, int tile) {
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < SUBS; ++k) s += counts[tile * SUBS + k];
-    return s / SUBS;  // mean sub-list length of the tile's units
+__device__ __forceinline__ int tile_work(const int32_t *__restrict__ per_tile, int tile) {
+    return per_tile[tile] / SUBS;  // mean sub-list length of the tile's units
 }
 
 __global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int32_t *__restrict__ counts,
@@ -431,7 +438,7 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
         }
         if (all_done) { processed = min(n, base + CHUNK); break; }
     }
-    if (li == 0) work[unit] = processed;   // entries actually walked: the backward's work estimate
+    if (li == 0) atomicAdd(work + tile, processed);   // entries actually walked: the backward's scheduling key, per tile
     if (u.inside) {
         int cur_idx = 0;
         if (last_k >= 0) cur_idx = list[last_k].x;
@@ -669,7 +676,7 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
 
 struct Workspace {
     Rec *rec;
-    int32_t *counts, *work, *order;   // sub-list lengths, entries the forward walked (the backward's LPT key), tile order
+    int32_t *counts, *tile_len, *work, *order;   // sub-list lengths; per tile: listed / walked entries (LPT keys), tile order
     int2 *entries;
 };
 
@@ -677,7 +684,7 @@ struct Workspace {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t workspace_bytes(int64_t N, int64_t M, int n_tiles) {
-    return align256(sizeof(Rec) * (size_t)N) + 3 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
+    return align256(sizeof(Rec) * (size_t)N) + 4 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
            align256(sizeof(int2) * (size_t)SUBS * (size_t)M) +
            256;
 }
@@ -689,6 +696,7 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
     p += align256(sizeof(Rec) * (size_t)N);
     const size_t ub = align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
     w.counts = reinterpret_cast<int32_t *>(p); p += ub;
+    w.tile_len = reinterpret_cast<int32_t *>(p); p += ub;
     w.work = reinterpret_cast<int32_t *>(p); p += ub;
     w.order = reinterpret_cast<int32_t *>(p); p += ub;
     w.entries = reinterpret_cast<int2 *>(p);
@@ -709,8 +717,8 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
                                                                     conics, colors, opacities, opacity_is_logit,
                                                                     comps, w.rec);
     build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, m_dev, offsets, flatten_ids, w.rec,
-                                                             w.entries, w.counts);
-    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.counts, w.order);
+                                                             w.entries, w.counts, w.tile_len, w.work);
+    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.tile_len, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB), 32 * WPB, 0, st>>>(
         W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
         w.work, render, alphas, last_ids);

@@ -356,8 +356,9 @@ def _batch_check(b: _Batch) -> None:
     m_max = int(b.totals[:b.n].max())
     _pinned_pool.append(b.totals)
     b.totals, b.checked = None, True
-    if _round_cap(m_max) > _caps.get(b.key, 0):
-        _caps[b.key] = _round_cap(m_max)                     # the scene grew: follow it
+    if m_max * 1.08 > _caps.get(b.key, 0):
+        _caps[b.key] = _round_cap(m_max)                     # less than 8 % of headroom left: the scene grew, follow it
+                                                             # (a bump re-sizes the arenas -- keep it rare)
     if m_max > b.cap:
         raise CapacityExceeded(f"a view of this batch has {m_max} tile intersections, the batch was carved for {b.cap}; "
                                "the capacity has been raised -- run the step again")

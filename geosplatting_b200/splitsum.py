@@ -196,8 +196,9 @@ def specular_plan(res: int, roughness: float, cutoff: float, dev: torch.device):
         n_pf = 6 * res * res // 32 * 6
         counts = torch.empty(n_pf, 2, dtype=torch.int32, device=dev)
         call("gsb_specular_plan_count", dev, C.c_int32(res), ptr(bounds), C.c_float(cos_cut), ptr(counts), ptr(ws), st)
-        zero = torch.zeros(1, 2, dtype=torch.int64, device=dev)
-        starts = torch.cat((zero, counts.to(torch.int64).cumsum(0)))            # [n_pf + 1, 2]
+        zero = torch.zeros(2, 1, dtype=torch.int64, device=dev)
+        # scan along the contiguous axis (torch's scan over the outer axis of an [n, 2] tensor takes milliseconds)
+        starts = torch.cat((zero, counts.t().contiguous().to(torch.int64).cumsum(1)), dim=1).t()   # [n_pf + 1, 2]
         n_segs, n_taps = (int(v) for v in starts[-1].tolist())                  # one host read, once per level
         nbytes = n_taps * 128 + n_segs * 16 + starts.numel() * 4
         cap = float(os.environ.get("GSB_PREFILTER_PLAN_GB", "12")) * 2 ** 30

@@ -32,6 +32,16 @@ __device__ __forceinline__ float consume(const Rec *slab, int lane, float acc) {
     return acc;
 }
 
+__device__ __forceinline__ float consume_groups(const unsigned char (*groups)[256], int lane, float acc) {
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+        const Rec *r = reinterpret_cast<const Rec *>(&groups[t >> 2][0]) + (t & 3);
+        const float4 k = r->k, q = r->q;
+        acc = fmaf(k.x - (float)lane, q.x, fmaf(k.y, q.y, acc));
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(32 * WARPS) stage_lanes(const Rec *__restrict__ rec, const int *__restrict__ list,
                                                            int n_warps, float *__restrict__ out) {
     __shared__ Rec slab[WARPS][32];
@@ -58,7 +68,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __global__ void __launch_bounds__(32 * WARPS) stage_tma(const __grid_constant__ CUtensorMap tmap,
                                                          const int *__restrict__ list, int n_warps,
                                                          float *__restrict__ out, int *__restrict__ err) {
-    __shared__ __align__(128) Rec slab[WARPS][2][32];
+    // a gather4 lands 4 rows x 48 B = 192 B and needs a 128-byte aligned destination: every group of 4 rows gets 256 B
+    __shared__ __align__(128) unsigned char slab_raw[WARPS][2][8][256];
     __shared__ __align__(8) uint64_t bar[WARPS][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, w = blockIdx.x * WARPS + wib;
     if (lane == 0) {
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(32 * WARPS) stage_tma(const __grid_constant__ 
             const int4 rows = *reinterpret_cast<const int4 *>(my + base + 4 * lane);
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-                " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(&slab[wib][b][4 * lane])),
+                " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(&slab_raw[wib][b][lane][0])),
                 "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&bar[wib][b])), "r"(0), "r"(rows.x), "r"(rows.y),
                 "r"(rows.z), "r"(rows.w) : "memory");
         }
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(32 * WARPS) stage_tma(const __grid_constant__ 
                          : "=r"(done) : "r"(smem_u32(&bar[wib][b])), "r"(phase[b]) : "memory");
         if (!done) { if (lane == 0) atomicAdd(err, 1); return; }      // never hang the box
         phase[b] ^= 1;
-        acc = consume(slab[wib][b], lane, acc);
+        acc = consume_groups(slab_raw[wib][b], lane, acc);
         __syncwarp();                                                  // the slab is free for the next gather
     }
     out[(size_t)w * 32 + lane] = acc;
