@@ -292,6 +292,12 @@ def run_b200(a):
                "cuda_mallocs_in_region": torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0}
     batches["l2_flush_ms_in_region"] = None
     launches = _lib.CallStats.launches()
+    n_batches_timed = max(1, len(batch_marks))
+    batches["host_in_library_ms_per_batch"] = {k: round(v * 1e3 / n_batches_timed, 4)
+                                               for k, v in _lib.CallStats.host_s.items() if v * 1e3 / n_batches_timed > 0.005}
+    batches["note"] = ("host_enqueue_ms is wall time around a batch's forward + backward as the host sees it; it includes the "
+                       "backward's look at the forward's intersection counts (an event wait that ends when the device, one "
+                       "batch behind, finishes that forward) -- the time the host spends enqueueing is host_in_library_ms_per_batch")
     probes, fused_mod.PROBES = fused_mod.PROBES, None
     live_ms = [a_.elapsed_time(b_) for a_, b_ in probes]
     live_bwd_ms = sum(live_ms) / max(1, len(live_ms))
@@ -746,8 +752,45 @@ def other_configs(a, rank, world, dev):
                 "ms_per_batch": round(ms_batch, 3), "views_per_s": round(global_views / (ms_batch / 1e3), 2),
                 "batches_timed": n_batches}
 
+    def wide_channels(mesh_n, res):
+        """the D = 14 G-buffer splat of the later stages (geosplat.py:276-295) through the drop-in
+        `rasterization()` (padded to 16 channels), forward + backward per view, next to D = 3 through the same operator."""
+        from geosplatting_b200.rasterization import rasterization
+        verts, faces = scenes.cube_sphere(mesh_n)
+        with torch.no_grad():
+            vd, fd = verts.to(dev), faces.to(dev)
+            sp, _ = MGAdapter().make(vd, fd, compute_vertex_normals(vd, fd))
+        N = sp.means.shape[0]
+        cam = scenes.orbit_cameras(1, res, res, seed=1)[0]
+        vm = torch.from_numpy(cam.view_matrix)[None].to(dev)
+        K = torch.from_numpy(cam.intrinsic_matrix)[None].to(dev)
+        geo = [t.detach().clone().requires_grad_(True) for t in (sp.means, sp.quats)]
+        scales, opac = sp.scales.exp().detach(), torch.sigmoid(sp.opacities)[:, 0].detach()
+        res_ = {}
+        for D in (3, 14):
+            feats = torch.rand(N, D, device=dev, requires_grad=True)
+            cot = torch.randn(1, res, res, D, device=dev)
+
+            def one():
+                r, _, _ = rasterization(geo[0], geo[1], scales, opac, feats, vm, K, res, res, rasterize_mode="antialiased")
+                torch.autograd.grad(r, [feats] + geo, grad_outputs=cot)
+
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            res_[f"D{D}_ms_per_view"] = round(e0.elapsed_time(e1) / 5, 3)
+        res_.update(gaussians=N, resolution=[res, res], what="rasterization() fwd+bwd, one view at a time, staged operator")
+        return res_
+
     out = {}
     if world == 1:
+        out["wide_channel_raster_1M_800"] = wide_channels(118, 800)
         out["config2_500k_800"] = run(83, 800, 8, 4)
         out["config4_2M_800"] = run(167, 800, 8, 3)
         out["config5_5M_1600"] = run(264, 1600, 8, 2)

@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import time
 from typing import Optional
 
 import torch
@@ -110,12 +111,14 @@ class CallStats:
     timing = False        # False, True (every entry point) or a set of entry-point names
     counts: dict = {}
     events: dict = {}
+    host_s: dict = {}     # seconds the host spent INSIDE each entry point (enqueueing; none of them waits for the device)
 
     @classmethod
     def reset(cls, timing=False) -> None:
         cls.timing = timing
         cls.counts = {}
         cls.events = {}
+        cls.host_s = {}
 
     @classmethod
     def launches(cls) -> int:
@@ -144,7 +147,9 @@ def call(name: str, dev: torch.device, *args) -> None:
         b.record(torch.cuda.current_stream(dev))
         CallStats.events.setdefault(name, []).append((a, b))
     else:
+        t0 = time.perf_counter()
         rc = fn(*args)
+        CallStats.host_s[name] = CallStats.host_s.get(name, 0.0) + (time.perf_counter() - t0)
     check(rc, name)
 
 

@@ -124,12 +124,18 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
     rec[g] = r;
 }
 
-// One CTA (8 warps) per tile walks the tile's depth-sorted list ONCE, 256 entries per step, and appends every entry
+// One CTA (32 warps) per tile walks the tile's depth-sorted list ONCE, 1024 entries per step, and appends every entry
 // to the sub-lists of the sub-rectangles its extent overlaps, order preserved (per sub-rectangle: ballot + popc
-// inside a warp, an 8 x 16 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
+// inside a warp, a 32 x 16 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
 // (list entry -> record is a dependent gather).  Sub-list w of tile t lives at entries[SUBS * start_t + w * len_t ...]
-// (worst-case capacity, no global prefix sum needed).
-constexpr int BUILD_THREADS = 256;
+// (worst-case capacity, no global prefix sum needed).  The kernel's duration is the longest tile list's number of steps
+// times the latency of a step (two block barriers + the gather): 1024 entries per step keeps that at ~12 steps for the
+// 11.6 k-entry silhouette tiles of the bench scene (256 per step: 46 steps, 70 us).
+#ifndef GSB_BUILD_THREADS
+#define GSB_BUILD_THREADS 1024
+#endif
+constexpr int BUILD_THREADS = GSB_BUILD_THREADS;
+constexpr int BUILD_WARPS = BUILD_THREADS / 32;
 
 __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_w, int n_tiles, int M_host,
                                                                         const int64_t *__restrict__ m_dev,
@@ -140,9 +146,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
                                                                         int32_t *__restrict__ counts,
                                                                         int32_t *__restrict__ tile_len,
                                                                         int32_t *__restrict__ tile_work) {
-    static_assert(SUBS == 16 && BUILD_THREADS == 256, "build_sublists: 8 warps x 16 sub-rectangles");
-    __shared__ int s_cnt[2][8][SUBS];   // [parity][warp][sub-rectangle] hits of this step
-    __shared__ int s_pre[2][8][SUBS];   // exclusive prefix over warps
+    static_assert(SUBS == 16 && BUILD_THREADS % 32 == 0 && BUILD_WARPS * SUBS <= BUILD_THREADS, "build_sublists shape");
+    __shared__ int s_cnt[2][BUILD_WARPS][SUBS];   // [parity][warp][sub-rectangle] hits of this step
+    __shared__ int s_pre[2][BUILD_WARPS][SUBS];   // exclusive prefix over warps
     __shared__ int s_base[2][SUBS];     // sub-list length before this step
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,11 +197,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
             if (lane == w) s_cnt[par][warp][w] = __popc(m);
         }
         __syncthreads();
-        if (tid < 8 * SUBS) {
+        if (tid < BUILD_WARPS * SUBS) {
             const int wp = tid >> 4, w = tid & (SUBS - 1);
             int pre = 0, tot = 0;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
+            for (int v = 0; v < BUILD_WARPS; ++v) {
                 const int c = s_cnt[par][v][w];
                 pre += (v < wp) ? c : 0;
                 tot += c;
