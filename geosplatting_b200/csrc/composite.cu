@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
                                                                         int2 *__restrict__ entries,
                                                                         int32_t *__restrict__ counts,
                                                                         int32_t *__restrict__ tile_len,
-                                                                        int32_t *__restrict__ tile_work) {
+                                                                        int32_t *__restrict__ ctrl) {
     static_assert(SUBS == 16 && BUILD_THREADS % 32 == 0 && BUILD_WARPS * SUBS <= BUILD_THREADS, "build_sublists shape");
     __shared__ int s_cnt[2][BUILD_WARPS][SUBS];   // [parity][warp][sub-rectangle] hits of this step
     __shared__ int s_pre[2][BUILD_WARPS][SUBS];   // exclusive prefix over warps
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
     const int len = end - start;
-    if (tid == 0) tile_work[tile] = 0;            // the forward adds the entries its units actually walk
+    if (tile == 0 && tid < 4) ctrl[tid] = 0;      // job count, checkpoint count, job cursor (the forward fills them)
     if (len <= 0) {
         if (tid < SUBS) counts[tile * SUBS + tid] = 0;
         if (tid == 0) tile_len[tile] = 0;
@@ -284,6 +284,21 @@ __global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int3
 constexpr int UPW = 2;                 // units per warp
 constexpr int CHUNK = 32 / UPW;        // list entries staged per unit and step (shared-memory rows 2 * i + half)
 
+// Segments.  The backward walks a sub-list back to front, and the longest sub-list of a view (~2 500 entries at a
+// silhouette, 156 steps on one warp) used to be the kernel's critical path.  The forward therefore CHECKPOINTS its
+// per-pixel state {T, colour} every SEG entries of a sub-list longer than SEG, which makes every SEG-entry segment an
+// independent work item of the backward: T before the segment's last entry comes from the checkpoint behind it, the
+// colour accumulated behind it is (final - checkpoint).  Checkpoints exist for <= 3 channels (one float4 per pixel);
+// wider splats are walked whole.
+#ifndef GSB_SEG
+#define GSB_SEG 256
+#endif
+constexpr int SEG = GSB_SEG;
+static_assert(SEG >= CHUNK && SEG % CHUNK == 0, "GSB_SEG: multiple of 16");
+template <int CH> constexpr bool segmented() { return CH <= 3; }
+// control words in the workspace
+enum { CTRL_JOBS = 0, CTRL_CKPTS = 1, CTRL_CURSOR = 2 };
+
 struct Unit {
     int tile, w, i, j;
     bool inside;
@@ -321,9 +336,11 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
                      const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
-                     const int32_t *__restrict__ order, int32_t *__restrict__ work, float *__restrict__ render,
+                     const int32_t *__restrict__ order, int32_t *__restrict__ walk, int32_t *__restrict__ ckpt_base,
+                     int32_t *ctrl, int2 *__restrict__ jobs, float4 *__restrict__ ckpt, float *__restrict__ render,
                      float *__restrict__ alphas, int32_t *__restrict__ last_ids) {
     constexpr int PAIRS = SUBS / UPW;
+    constexpr bool SEGD = segmented<CH>();
     __shared__ Rec s_rec[WPB][32];     // k.z / k.w carry the entry's tile-list position / Gaussian id (bit patterns)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * WPB + wib;
@@ -350,27 +367,44 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     int last_k = -1;   // sub-list index of the pixel's last contributor
 
     // prefetch chunk 0: lane (half, i) fetches entry i of its unit's list into shared-memory row 2 * i + half
-    const int li = lane & (CHUNK - 1);
-    const int my_row = 2 * li + half;
+    // staging: lane l fills shared-memory row l = entry l / 2 of unit l % 2 of the step (48-byte rows at a 48-byte lane
+    // stride: conflict-free 16-byte stores), so a lane stages for the other half-warp's unit as often as for its own
+    const int li = lane >> 1;
+    const bool own = ((lane & 1) == half);
+    const int2 *const list_other = (const int2 *)__shfl_xor_sync(0xffffffffu, (unsigned long long)list, 16);
+    const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
+    const int2 *const slist = own ? list : list_other;
+    const int sn = own ? n : n_other;
     const Rec *const rows = &s_rec[wib][half];     // rows of my unit: rows[2 * s]
     // Software pipeline of the dependent gather (list entry -> record): while chunk c is evaluated, the records of
     // chunk c + 1 and the list entries of chunk c + 2 are in flight, so neither latency is on the warp's critical path.
     int2 e = make_int2(0, 0), e_next = make_int2(0, 0);
     Rec r = null_record();
-    int processed = n;
-    if (li < n) { e = list[li]; r = rec[e.y]; }
-    if (CHUNK + li < n) e_next = list[CHUNK + li];
+    int cb = -1;       // first checkpoint block of my unit (allocated when the walk passes entry SEG)
+    if (li < sn) { e = slist[li]; r = rec[e.y]; }
+    if (CHUNK + li < sn) e_next = slist[CHUNK + li];
     for (int base = 0; base < n_max; base += CHUNK) {
+        if (SEGD && base > 0 && base % SEG == 0) {
+            // state BEFORE entry `base` -> checkpoint base / SEG of my unit (slot 0 takes the final state, below)
+            if (base == SEG) {
+                int b = -1;
+                if ((lane & (PIX - 1)) == 0 && n > SEG) b = atomicAdd(ctrl + CTRL_CKPTS, (n + SEG - 1) / SEG);
+                cb = __shfl_sync(0xffffffffu, b, lane & 16);
+            }
+            if (cb >= 0 && base < n)
+                ckpt[((size_t)cb + base / SEG) * PIX + (lane & (PIX - 1))] =
+                    make_float4(T, acc[0], CH > 1 ? acc[CH > 1 ? 1 : 0] : 0.f, CH > 2 ? acc[CH > 2 ? 2 : 0] : 0.f);
+        }
         __syncwarp();
         r.k.z = __int_as_float(e.x);
         r.k.w = __int_as_float(e.y);
-        s_rec[wib][my_row] = r;
+        s_rec[wib][lane] = r;
         __syncwarp();
         const int nb = base + CHUNK;
         e = e_next;
         r = null_record();                                            // rows past the end of a list never contribute
-        if (nb + li < n) r = rec[e.y];                                // records of the next chunk
-        if (nb + CHUNK + li < n) e_next = list[nb + CHUNK + li];     // list entries of the chunk after it
+        if (nb + li < sn) r = rec[e.y];                                // records of the next chunk
+        if (nb + CHUNK + li < sn) e_next = slist[nb + CHUNK + li];    // list entries of the chunk after it
         // Groups of FS entries.  The alpha evaluations are independent (ILP for a warp that runs alone: the longest
         // sub-list of a view is this kernel's critical path); alpha == 0 stands for "does not contribute" and makes
         // every update the identity, so the common case has no branch.  The state is saved before a group; only a group
@@ -442,9 +476,27 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
             }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
-        if (all_done) { processed = min(n, base + CHUNK); break; }
+        if (all_done) break;
     }
-    if (li == 0) atomicAdd(work + tile, processed);   // entries actually walked: the backward's scheduling key, per tile
+    {
+        // what the backward has to walk: up to the unit's last contributor; one job per SEG entries of the longer list
+        int nb = last_k + 1;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+        const int nb_max = max(nb, __shfl_xor_sync(0xffffffffu, nb, 16));
+        if ((lane & (PIX - 1)) == 0) {
+            walk[unit] = nb;
+            ckpt_base[unit] = cb;
+        }
+        if (SEGD && cb >= 0)
+            ckpt[(size_t)cb * PIX + (lane & (PIX - 1))] =
+                make_float4(T, acc[0], CH > 1 ? acc[CH > 1 ? 1 : 0] : 0.f, CH > 2 ? acc[CH > 2 ? 2 : 0] : 0.f);
+        if (lane == 0 && nb_max > 0) {
+            const int nseg = SEGD ? (nb_max + SEG - 1) / SEG : 1;
+            const int jb = atomicAdd(ctrl + CTRL_JOBS, nseg);
+            for (int sgm = 0; sgm < nseg; ++sgm) jobs[jb + sgm] = make_int2(tile * PAIRS + slot % PAIRS, sgm);
+        }
+    }
     if (u.inside) {
         int cur_idx = 0;
         if (last_k >= 0) cur_idx = list[last_k].x;
@@ -461,51 +513,65 @@ composite_fwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
 // kernel does each along the axis where it is register-local and TRANSPOSES through shared memory in between, so no
 // cross-lane reduction is left.  Per step, 16 entries of each of the warp's two sub-lists (walked back to front):
 //   phase A (lane = (unit, pixel)): evaluate the unit's 16 entries, run the T / suffix-colour recurrence, and store
-//                              per (entry, pixel) the three scalars the gradient needs -- A = opacity * exp(-sigma)
-//                              (0 if the pair does not contribute), T before the Gaussian, E = (suffix . v_out -
-//                              T_final (v_alpha - bg . v_out)) / (1 - alpha) -- as one float4 into a 32 x 16 slab whose
-//                              columns are rotated by the row (conflict-free for both access patterns, no padding);
-//   phase B (lane = Gaussian): read its row, accumulate the gradient moments over the 16 pixels in registers, one
-//                              atomic per value per (Gaussian, unit) -- only for Gaussians that touched a pixel.
-// v_alpha = T (c . v_out) - E is the reference's expression ((c T - buffer / (1 - alpha)) . v_out + T_final / (1 - alpha)
-// (v_alpha_out - bg . v_out)) with the per-pixel constants folded into E.
-constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (10 KB of shared memory per warp)
+//                              per (entry, pixel) the two scalars the sums need -- alpha T (the weight of v_out in the
+//                              colour gradient) and v_sigma -- as one float2 into a 32 x 16 slab whose columns are
+//                              rotated by the row (conflict-free for both access patterns, no padding);
+//   phase B (lane = Gaussian): read its row, accumulate the colour gradient and the six moments of v_sigma over the 16
+//                              pixels in registers, one atomic per value per (Gaussian, unit) -- only for Gaussians
+//                              that touched a pixel.
+// The kernel is bound by the L1 / shared-memory data pipe (87 % busy with a float4 {A, T, E, -} slab; ncu, round 2):
+// what crosses the transpose is kept to 8 bytes per pair.
+constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (6 KB of shared memory per warp)
 
-// slab[row][column] of float4 {A, T, E, -}; the column of pixel p in row r is (p + r) mod 16: every 16-byte access of a
-// quarter-warp then hits eight distinct bank groups both when the lanes are pixels of one row (phase A) and when they
-// are rows at one pixel (phase B)
+// slab[row][column] of float2; the column of pixel p in row r is (p + r) mod 16: the 8-byte accesses of a half-warp then
+// cover all 32 banks both when the lanes are pixels of one row (phase A) and when they are rows at one pixel (phase B)
 __device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + row) & (PIX - 1)); }
 
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB_B, GSB_MINB_B)
-composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restrict__ rec,
+composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
                      const float *__restrict__ colors, const float *__restrict__ background,
                      const int32_t *__restrict__ offsets, int n_tiles, int M_host, const int64_t *__restrict__ m_dev,
-                     const int2 *__restrict__ entries, const int32_t *__restrict__ counts,
-                     const int32_t *__restrict__ order, const float *__restrict__ alphas,
+                     const int2 *__restrict__ entries, const int32_t *__restrict__ walk,
+                     const int32_t *__restrict__ ckpt_base, int32_t *ctrl, const int2 *__restrict__ jobs,
+                     const float4 *__restrict__ ckpt, const float *__restrict__ alphas,
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render,
                      const float *__restrict__ v_alphas, float *__restrict__ v_means2d, float *__restrict__ v_conics,
                      float *__restrict__ v_colors, float *__restrict__ v_opacities) {
     constexpr int PAIRS = SUBS / UPW;
     constexpr int C3 = CH < 3 ? CH : 3;                 // channels carried in the packed record
     constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
-    __shared__ float4 s_slab[WPB_B][32 * PIX];          // {A, T, E, -} per (row, pixel)
+    constexpr bool SEGD = segmented<CH>();
+    __shared__ float2 s_slab[WPB_B][32 * PIX];          // {alpha T, v_sigma} per (row, pixel)
     __shared__ Rec s_rec[WPB_B][32];                    // k.z / k.w carry the entry's tile-list position / Gaussian id
-    __shared__ float4 s_vo[WPB_B][UPW][PIX][NV4];
+    __shared__ float4 s_vo[WPB_B][PIX][UPW][NV4];        // the two units' v_out of a pixel side by side: distinct banks
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int slot = blockIdx.x * WPB_B + wib;
-    if (slot >= n_pairs) return;
-    const int tile = order[slot / PAIRS];
     const int half = lane >> 4, p = lane & (PIX - 1);
-    const Unit u = make_unit(slot % PAIRS, lane, tile, tile_w, W, H);
+    const int M = m_dev ? (int)*m_dev : M_host;
+    const int n_jobs = ctrl[CTRL_JOBS];                 // written by the forward
+
+    // Persistent warps draw jobs (pair of units, segment) from the queue the forward filled; the next ticket is in flight
+    // while a job is processed.
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ctrl + CTRL_CURSOR, 1);
+    for (;;) {
+    const int job = __shfl_sync(0xffffffffu, ticket, 0);
+    if (job >= n_jobs) break;
+    if (lane == 0) ticket = atomicAdd(ctrl + CTRL_CURSOR, 1);
+    const int2 jb = jobs[job];
+    const int tile = jb.x / PAIRS;
+    const Unit u = make_unit(jb.x % PAIRS, lane, tile, tile_w, W, H);
     const int unit = tile * SUBS + u.w;
     const size_t pix = u.inside ? (size_t)u.i * W + u.j : 0;
 
-    const int M = m_dev ? (int)*m_dev : M_host;
     const int start = offsets[tile];
     const int end = (tile == n_tiles - 1) ? M : offsets[tile + 1];
-    const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start);
-    int n = counts[unit];
+    // my unit's part of the job: sub-list entries [lo, hi) of the walk_n the forward found worth walking
+    const int walk_n = walk[unit];
+    const int lo = jb.y * SEG;
+    const int hi = SEGD ? min(walk_n, lo + SEG) : walk_n;
+    const int n = max(hi - lo, 0);
+    const int2 *list = entries + (size_t)SUBS * start + (size_t)u.w * (end - start) + lo;
 
     const float T_final = u.inside ? 1.0f - alphas[pix] : 1.0f;
     float v_out[CH];
@@ -517,60 +583,66 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
     }
     const float c0 = T_final * ((u.inside ? v_alphas[pix] : 0.f) - bg_dot);
     const int bin_final = u.inside ? last_ids[pix] : -1;
+    __syncwarp();   // the previous job's phase B has read s_vo
     {
         float vo4[NV4 * 4];
 #pragma unroll
         for (int k = 0; k < NV4 * 4; ++k) vo4[k] = (k < CH) ? v_out[k] : 0.f;
 #pragma unroll
         for (int k = 0; k < NV4; ++k)
-            s_vo[wib][half][p][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
-    }
-    int wmax = bin_final;     // per unit: maximum over its 16 pixels
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-
-    // Entries are sorted by tile-list position: drop the tail that lies behind every pixel's last contributor
-    // (binary search for the first position > wmax).
-    {
-        int lo = 0, hi_ = n;
-        while (lo < hi_) {
-            int mid = (lo + hi_) >> 1;
-            if (list[mid].x <= wmax) lo = mid + 1; else hi_ = mid;
-        }
-        n = lo;
+            s_vo[wib][p][half][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
     }
     const int n_max = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
-    if (n_max == 0) return;
 
-    float4 *const slab = s_slab[wib];
+    float2 *const slab = s_slab[wib];
     const float bx = (float)(u.j - (p & 3)) + 0.5f, by = (float)(u.i - (p >> 2)) + 0.5f;  // pixel (0,0) of my unit
     const float bx_other = __shfl_xor_sync(0xffffffffu, bx, 16);
     float T = T_final;
     float B = 0.f;    // suffix colour behind the current Gaussian, dotted with v_out
-
-    // walk back to front: per unit, step c covers sub-list indices [top - 16, top); lane (half, i) stages index
-    // top - 1 - i into shared-memory row 2 * i + half
-    const int li = lane & (CHUNK - 1);
-    const int my_row = 2 * li + half;
+    if (SEGD && hi < walk_n) {
+        // not my unit's last segment: T before entry `hi` and the colour accumulated from `hi` on, from the forward's
+        // checkpoints (slot 0 = final state, slot j = state before entry j * SEG)
+        const size_t cbk = (size_t)ckpt_base[unit];
+        const float4 ck = ckpt[(cbk + jb.y + 1) * PIX + p], fin = ckpt[cbk * PIX + p];
+        // The reference derives every T of the backward from T_final = 1 - alpha_out (rfstudio's gsplat: rasterize_to_
+        // pixels_bwd), i.e. from a value that carries the rounding of 1 - (1 - T): up to 6e-8 / T relative, 1e-4 for a
+        // nearly opaque pixel, in EVERY T of that pixel.  The checkpoint holds the forward's own T; scaling by
+        // (1 - alpha_out) / T_final reproduces the reference's chain.
+        const float ratio = T_final / fin.x;
+        T = ck.x * ratio;
+        B = (fin.y - ck.y) * v_out[0];
+        if (C3 > 1) B += (fin.z - ck.z) * v_out[C3 > 1 ? 1 : 0];
+        if (C3 > 2) B += (fin.w - ck.w) * v_out[C3 > 2 ? 2 : 0];
+        B *= ratio;
+    }
+    // walk back to front: per unit, a step covers sub-list indices [top - 16, top); index top - 1 - i goes to
+    // shared-memory row 2 * i + unit
+    // lane l stages shared-memory row l = entry l / 2 (from the top) of unit l % 2, as in the forward
+    const int li = lane >> 1;
+    const bool own = ((lane & 1) == half);
+    const int2 *const list_other = (const int2 *)__shfl_xor_sync(0xffffffffu, (unsigned long long)list, 16);
+    const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
+    const int2 *const slist = own ? list : list_other;
+    const int sn = own ? n : n_other;
     const Rec *const rows = &s_rec[wib][half];
     // same software pipeline as the forward: records one step ahead, list entries two steps ahead
     const int2 none = make_int2(0x7fffffff, 0);   // position beyond every last_id: a null row is never valid
     int2 e = none, e_next = none;
     Rec r = null_record();
-    if (n - 1 - li >= 0) { e = list[n - 1 - li]; r = rec[e.y]; }
-    if (n - CHUNK - 1 - li >= 0) e_next = list[n - CHUNK - 1 - li];
-    for (int top = n, walked = 0; walked < n_max; top -= CHUNK, walked += CHUNK) {
+    if (sn - 1 - li >= 0) { e = slist[sn - 1 - li]; r = rec[e.y]; }
+    if (sn - CHUNK - 1 - li >= 0) e_next = slist[sn - CHUNK - 1 - li];
+    for (int top = sn, walked = 0; walked < n_max; top -= CHUNK, walked += CHUNK) {
         __syncwarp();
         r.k.z = __int_as_float(e.x);
         r.k.w = __int_as_float(e.y);
-        s_rec[wib][my_row] = r;
+        s_rec[wib][lane] = r;
         __syncwarp();
         const int nt = top - CHUNK;
         e = e_next;
         e_next = none;
         r = null_record();
         if (nt - 1 - li >= 0) r = rec[e.y];
-        if (nt - CHUNK - 1 - li >= 0) e_next = list[nt - CHUNK - 1 - li];
+        if (nt - CHUNK - 1 - li >= 0) e_next = slist[nt - CHUNK - 1 - li];
 
         // ---- phase A: lane = (unit, pixel) --------------------------------------------------------------------
         unsigned mine_mask = 0u;   // bit t: shared-memory row t (one of my unit's) contributes to my pixel
@@ -600,12 +672,18 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
                 wg[s] = w;
                 mine_mask |= valid ? (1u << (t + half)) : 0u;
             }
-            // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch
+            // the recurrence: alpha == 0 (pair does not contribute) makes every update the identity, so no branch.
+            // v_alpha = T (c . v_out) - E with E = (B - c0) / (1 - alpha) is the reference's expression ((c T - buffer /
+            // (1 - alpha)) . v_out + T_final / (1 - alpha) (v_alpha_out - bg . v_out)) with the per-pixel constants folded
+            // into c0; a clamped alpha passes no gradient to sigma / opacity; d alpha / d sigma = -alpha.
 #pragma unroll
             for (int s = 0; s < BSZ; ++s) {
-                T *= rag[s];
-                slab[slab_at(2 * (t0 + s) + half, p)] = make_float4(Ag[s], T, rag[s] * (B - c0), 0.f);
-                B += wg[s] * (al[s] * T);
+                T *= rag[s];                                  // T before this Gaussian
+                const float fac = al[s] * T;
+                const float v_alpha = T * wg[s] - rag[s] * (B - c0);
+                const float v_sigma = (Ag[s] <= GSB_ALPHA_CLAMP) ? -Ag[s] * v_alpha : 0.f;
+                slab[slab_at(2 * (t0 + s) + half, p)] = make_float2(fac, v_sigma);
+                B += wg[s] * fac;
             }
         }
         const unsigned touched = __reduce_or_sync(0xffffffffu, mine_mask);   // also orders phase A's stores before phase B
@@ -620,40 +698,24 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
             const int g = __float_as_int(kk.w);
             const int hb = lane & 1;                                   // the unit this row belongs to
             const float ox = (hb == half) ? bx : bx_other;             // pixel (0,0) of that unit (same row of pixels)
-            float col[CH];
-            col[0] = c.x;
-            if (CH > 1) col[1] = c.y;
-            if (CH > 2) col[2] = c.z;
             const bool mine = (touched >> lane) & 1u;
-            if (CH > 3) {
-#pragma unroll
-                for (int k = 3; k < CH; ++k) col[k] = mine ? __ldg(colors + (size_t)g * CH + k) : 0.f;
-            }
             float g_col[CH];
 #pragma unroll
             for (int k = 0; k < CH; ++k) g_col[k] = 0.f;
             float s0 = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f;   // moments of v_sigma
-            const float4 *row = slab + lane * PIX;
+            const float2 *row = slab + lane * PIX;
 #pragma unroll 8
             for (int pp = 0; pp < PIX; ++pp) {
-                const float4 ate = row[(pp + lane) & (PIX - 1)];
-                const float A = ate.x, Tp = ate.y, Ep = ate.z;
-                float vo[NV4 * 4];
+                const float2 fv = row[(pp + lane) & (PIX - 1)];
+                const float fac = fv.x, v_sigma = fv.y;
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
-                    const float4 v4 = s_vo[wib][hb][pp][k];
-                    vo[4 * k] = v4.x; vo[4 * k + 1] = v4.y; vo[4 * k + 2] = v4.z; vo[4 * k + 3] = v4.w;
+                    const float4 v4 = s_vo[wib][pp][hb][k];
+                    g_col[4 * k] += fac * v4.x;
+                    if (4 * k + 1 < CH) g_col[4 * k + 1 < CH ? 4 * k + 1 : 0] += fac * v4.y;
+                    if (4 * k + 2 < CH) g_col[4 * k + 2 < CH ? 4 * k + 2 : 0] += fac * v4.z;
+                    if (4 * k + 3 < CH) g_col[4 * k + 3 < CH ? 4 * k + 3 : 0] += fac * v4.w;
                 }
-                const float fac = fminf(GSB_ALPHA_CLAMP, A) * Tp;
-                float w = 0.f;
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    w += col[k] * vo[k];
-                    g_col[k] += fac * vo[k];
-                }
-                float v_alpha = Tp * w - Ep;
-                v_alpha = (A <= GSB_ALPHA_CLAMP) ? v_alpha : 0.f;   // clamped alpha passes no gradient to sigma / opacity
-                const float v_sigma = -A * v_alpha;                 // d alpha / d sigma = -alpha
                 const float dx = kk.x - (ox + (float)(pp & 3)), dy = kk.y - (by + (float)(pp >> 2));   // exact pixel centre
                 const float t1 = v_sigma * dx, t2 = v_sigma * dy;
                 s0 += v_sigma;
@@ -678,21 +740,30 @@ composite_bwd_kernel(int W, int H, int tile_w, int n_pairs, const Rec *__restric
             }
         }
     }
+    }   // job loop
 }
 
 struct Workspace {
     Rec *rec;
-    int32_t *counts, *tile_len, *work, *order;   // sub-list lengths; per tile: listed / walked entries (LPT keys), tile order
+    int32_t *counts, *walk, *ckpt_base;   // per unit: sub-list length, entries the backward walks, first checkpoint block
+    int32_t *tile_len, *order;            // per tile: listed entries (the forward's LPT key), tile order
+    int32_t *ctrl;                        // CTRL_JOBS, CTRL_CKPTS, CTRL_CURSOR
+    int2 *jobs;                           // backward work items {tile * 8 + pair, segment}
+    float4 *ckpt;                         // checkpoint blocks of 16 float4 {T, r, g, b}
     int2 *entries;
 };
 
-
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// sum over units of ceil(n / SEG) <= sum n / SEG + #(units with n > SEG) <= 2 * SUBS * M / SEG
+size_t ckpt_blocks(int64_t M) { return 2 * (size_t)SUBS * (size_t)M / SEG + 1; }
+// sum over pairs of ceil(n_max / SEG) <= #pairs + SUBS * M / SEG
+size_t job_capacity(int64_t M, int n_tiles) { return (size_t)n_tiles * (SUBS / UPW) + (size_t)SUBS * (size_t)M / SEG + 1; }
+
 size_t workspace_bytes(int64_t N, int64_t M, int n_tiles) {
-    return align256(sizeof(Rec) * (size_t)N) + 4 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
-           align256(sizeof(int2) * (size_t)SUBS * (size_t)M) +
-           256;
+    return align256(sizeof(Rec) * (size_t)N) + 3 * align256(sizeof(int32_t) * (size_t)n_tiles * SUBS) +
+           2 * align256(sizeof(int32_t) * (size_t)n_tiles) + 256 + align256(sizeof(int2) * job_capacity(M, n_tiles)) +
+           align256(sizeof(float4) * PIX * ckpt_blocks(M)) + align256(sizeof(int2) * (size_t)SUBS * (size_t)M) + 256;
 }
 
 Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
@@ -700,13 +771,16 @@ Workspace carve(void *ws, int64_t N, int64_t M, int n_tiles) {
     Workspace w;
     w.rec = reinterpret_cast<Rec *>(p);
     p += align256(sizeof(Rec) * (size_t)N);
-    const size_t ub = align256(sizeof(int32_t) * (size_t)n_tiles * SUBS);
+    const size_t ub = align256(sizeof(int32_t) * (size_t)n_tiles * SUBS), tb = align256(sizeof(int32_t) * (size_t)n_tiles);
     w.counts = reinterpret_cast<int32_t *>(p); p += ub;
-    w.tile_len = reinterpret_cast<int32_t *>(p); p += ub;
-    w.work = reinterpret_cast<int32_t *>(p); p += ub;
-    w.order = reinterpret_cast<int32_t *>(p); p += ub;
+    w.walk = reinterpret_cast<int32_t *>(p); p += ub;
+    w.ckpt_base = reinterpret_cast<int32_t *>(p); p += ub;
+    w.tile_len = reinterpret_cast<int32_t *>(p); p += tb;
+    w.order = reinterpret_cast<int32_t *>(p); p += tb;
+    w.ctrl = reinterpret_cast<int32_t *>(p); p += 256;
+    w.jobs = reinterpret_cast<int2 *>(p); p += align256(sizeof(int2) * job_capacity(M, n_tiles));
+    w.ckpt = reinterpret_cast<float4 *>(p); p += align256(sizeof(float4) * PIX * ckpt_blocks(M));
     w.entries = reinterpret_cast<int2 *>(p);
-    (void)M;
     return w;
 }
 
@@ -723,13 +797,19 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
                                                                     conics, colors, opacities, opacity_is_logit,
                                                                     comps, w.rec);
     build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, m_dev, offsets, flatten_ids, w.rec,
-                                                             w.entries, w.counts, w.tile_len, w.work);
+                                                             w.entries, w.counts, w.tile_len, w.ctrl);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.tile_len, w.order);
     composite_fwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB), 32 * WPB, 0, st>>>(
         W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
-        w.work, render, alphas, last_ids);
+        w.walk, w.ckpt_base, w.ctrl, w.jobs, w.ckpt, render, alphas, last_ids);
     return 0;
 }
+
+// Resident CTAs per SM the persistent backward asks for (40 KB of shared memory each); surplus CTAs find the queue
+// empty and leave.
+#ifndef GSB_BWD_CTAS_PER_SM
+#define GSB_BWD_CTAS_PER_SM 5
+#endif
 
 template <int CH>
 int launch_bwd(int W, int H, int64_t N, const float *colors, const float *background, const int32_t *offsets,
@@ -737,12 +817,15 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
                const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, void *ws,
                cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
-    int n_tiles = tw * th, n_units = n_tiles * SUBS;
+    int n_tiles = tw * th;
     Workspace w = carve(ws, N, M, n_tiles);
-    lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.work, w.order);   // order by the forward's measured work
-    composite_bwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB_B), 32 * WPB_B, 0, st>>>(
-        W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
-        alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
+    static const int sms = gsb_sm_count();
+    const int64_t want = (int64_t)gsb_div_up((int64_t)job_capacity(M, n_tiles), WPB_B);
+    const int grid = (int)(want < (int64_t)sms * GSB_BWD_CTAS_PER_SM ? want : (int64_t)sms * GSB_BWD_CTAS_PER_SM);
+    if (cudaMemsetAsync(w.ctrl + CTRL_CURSOR, 0, sizeof(int32_t), st) != cudaSuccess) return 1;   // a forward may be walked twice
+    composite_bwd_kernel<CH><<<grid, 32 * WPB_B, 0, st>>>(
+        W, H, tw, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.walk, w.ckpt_base, w.ctrl,
+        w.jobs, w.ckpt, alphas, last_ids, v_render, v_alphas, v_means2d, v_conics, v_colors, v_opacities);
     return 0;
 }
 

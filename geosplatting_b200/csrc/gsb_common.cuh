@@ -37,6 +37,14 @@ void gsb_set_error(const char *fmt, ...);
 
 static inline int gsb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// SMs of the current device (148 on a B200): the grid unit of the persistent kernels.
+static inline int gsb_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        n = 148;
+    return n;
+}
+
 // floor(log2(n_tiles)) + 1, the number of key bits the tile id occupies.
 static inline __host__ __device__ int gsb_tile_bits(int n_tiles) {
     int b = 0;

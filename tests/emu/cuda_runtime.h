@@ -82,6 +82,10 @@ static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+// two 'SMs': persistent kernels get a grid smaller than their job count and have to loop
+static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 2; return cudaSuccess; }
 typedef void *cudaEvent_t;
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 // the host build is one stream in program order: events and cross-stream waits are no-ops
