@@ -124,20 +124,24 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
     rec[g] = r;
 }
 
-// One CTA (32 warps) per tile walks the tile's depth-sorted list ONCE, 1024 entries per step, and appends every entry
-// to the sub-lists of the sub-rectangles its extent overlaps, order preserved (per sub-rectangle: ballot + popc
-// inside a warp, a 32 x 16 table of warp counts across the CTA).  Loads are software-pipelined two steps deep
-// (list entry -> record is a dependent gather).  Sub-list w of tile t lives at entries[SUBS * start_t + w * len_t ...]
-// (worst-case capacity, no global prefix sum needed).  The kernel's duration is the longest tile list's number of steps
-// times the latency of a step (two block barriers + the gather): 1024 entries per step keeps that at ~12 steps for the
-// 11.6 k-entry silhouette tiles of the bench scene (256 per step: 46 steps, 70 us).
+// One CTA per tile walks the tile's depth-sorted list ONCE, 512 entries per step, and appends every entry to the
+// sub-lists of the sub-rectangles its extent overlaps, order preserved (per sub-rectangle: ballot + popc inside a
+// warp, a 16 x 16 table of warp counts across the CTA).  Loads are software-pipelined two steps deep (list entry ->
+// record is a dependent gather).  Sub-list w of tile t lives at entries[SUBS * start_t + w * len_t ...] (worst-case
+// capacity, no global prefix sum needed).  32 registers per thread (the per-lane prefix counts are packed 5 bits each)
+// keep four CTAs -- four tiles -- resident per SM: a tile's first step exposes the whole gather chain, and the tiles of
+// the bench scene are 2.6 steps long on average.  Measured (composite_fwd entry point, alone): 1024 threads x 1 CTA
+// 0.249 ms, 1024 x 2 0.243, 512 x 4 0.231, 256 x 8 0.242 (the 11.6 k-entry silhouette tiles become 46-step tails).
 #ifndef GSB_BUILD_THREADS
-#define GSB_BUILD_THREADS 1024
+#define GSB_BUILD_THREADS 512
+#endif
+#ifndef GSB_BUILD_MINB
+#define GSB_BUILD_MINB 4    // 32 registers: four 512-thread CTAs (four tiles) per SM hide each other's gather latency
 #endif
 constexpr int BUILD_THREADS = GSB_BUILD_THREADS;
 constexpr int BUILD_WARPS = BUILD_THREADS / 32;
 
-__global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_w, int n_tiles, int M_host,
+__global__ void __launch_bounds__(BUILD_THREADS, GSB_BUILD_MINB) build_sublists_kernel(int tile_w, int n_tiles, int M_host,
                                                                         const int64_t *__restrict__ m_dev,
                                                                         const int32_t *__restrict__ offsets,
                                                                         const int32_t *__restrict__ flatten_ids,
@@ -189,11 +193,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
         for (int r = 0; r < GSB_TILE / SUB_H; ++r)
             if (fabsf(k0.y - (y0 + (float)(r * SUB_H))) <= k0.w + rhy) rowm |= 0xFu << (4 * r);
         const unsigned hits = (colm * 0x1111u) & rowm;
-        int my_pre[SUBS];            // hits of lower lanes of my warp
+        unsigned my_pre[3] = {0u, 0u, 0u};   // hits of lower lanes of my warp, 5 bits per sub-rectangle (6 + 6 + 4)
 #pragma unroll
         for (int w = 0; w < SUBS; ++w) {
             const unsigned m = __ballot_sync(0xffffffffu, (hits >> w) & 1u);
-            my_pre[w] = __popc(m & ((1u << lane) - 1u));
+            my_pre[w / 6] |= (unsigned)__popc(m & ((1u << lane) - 1u)) << (5 * (w % 6));
             if (lane == w) s_cnt[par][warp][w] = __popc(m);
         }
         __syncthreads();
@@ -213,7 +217,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
 #pragma unroll
         for (int w = 0; w < SUBS; ++w) {
             if (hits & (1u << w))
-                out[(size_t)w * len + s_base[par][w] + s_pre[par][warp][w] + my_pre[w]] = make_int2(base + tid, gid0);
+                out[(size_t)w * len + s_base[par][w] + s_pre[par][warp][w] + (int)((my_pre[w / 6] >> (5 * (w % 6))) & 31u)] =
+                    make_int2(base + tid, gid0);
         }
         gid0 = gid1; gid1 = gid2; k0 = k1;
     }
@@ -221,19 +226,19 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_sublists_kernel(int tile_
     __syncthreads();
     if (tid < SUBS) counts[tile * SUBS + tid] = s_base[par][tid];
     if (tid == 0) {
-        int tot = 0;
+        // the forward's scheduling key: the tile's LONGEST sub-list (a warp is busy as long as its longer list; a
+        // silhouette tile with one 2 500-entry unit and fourteen empty ones must start early, which its mean hides)
+        int key = 0;
 #pragma unroll
-        for (int k = 0; k < SUBS; ++k) tot += s_base[par][k];
-        tile_len[tile] = tot;                        // the forward's scheduling key
+        for (int k = 0; k < SUBS; ++k) key = max(key, s_base[par][k]);
+        tile_len[tile] = key;
     }
 }
 
 // Longest-processing-time-first order of the TILES (their 16 units stay adjacent in launch order so that they
-// share the tile's records in L1/L2): single-CTA counting sort on the mean per-unit work (4096 buckets of width 4,
-// heaviest first; order inside a bucket is irrelevant).  `n_units` here is the number of tiles.
-__device__ __forceinline__ int tile_work(const int32_t *__restrict__ per_tile, int tile) {
-    return per_tile[tile] / SUBS;  // mean sub-list length of the tile's units
-}
+// share the tile's records in L1/L2): single-CTA counting sort on the key build_sublists left per tile (4096 buckets
+// of width 4, heaviest first; order inside a bucket is irrelevant).  `n_units` here is the number of tiles.
+__device__ __forceinline__ int tile_work(const int32_t *__restrict__ per_tile, int tile) { return per_tile[tile]; }
 
 __global__ void __launch_bounds__(1024) lpt_order_kernel(int n_units, const int32_t *__restrict__ counts,
                                                           int32_t *__restrict__ order) {
@@ -746,7 +751,7 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
 struct Workspace {
     Rec *rec;
     int32_t *counts, *walk, *ckpt_base;   // per unit: sub-list length, entries the backward walks, first checkpoint block
-    int32_t *tile_len, *order;            // per tile: listed entries (the forward's LPT key), tile order
+    int32_t *tile_len, *order;            // per tile: longest sub-list (the forward's LPT key), tile order
     int32_t *ctrl;                        // CTRL_JOBS, CTRL_CKPTS, CTRL_CURSOR
     int2 *jobs;                           // backward work items {tile * 8 + pair, segment}
     float4 *ckpt;                         // checkpoint blocks of 16 float4 {T, r, g, b}

@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(int N, const float *__re
     colors[3 * i + 2] = o.color.z;
 }
 
-__global__ void __launch_bounds__(256) shade_bwd_kernel(int N, const float *__restrict__ means,
+#ifndef GSB_SHADE_BWD_MINB
+#define GSB_SHADE_BWD_MINB 3   // 80 registers (172 B of spills): latency-bound kernel, +50 % resident warps wins 3 %
+#endif
+__global__ void __launch_bounds__(256, GSB_SHADE_BWD_MINB) shade_bwd_kernel(int N, const float *__restrict__ means,
                                                          const float *__restrict__ normals,
                                                          const float *__restrict__ kd, const float *__restrict__ ks,
                                                          ShadeParams p, const float2 *__restrict__ lut, EnvStack env,
