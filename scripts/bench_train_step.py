@@ -49,24 +49,26 @@ def step():
     stats.update(gaussians=int(metrics["#gaussians"]), loss=float(metrics["loss"]))
 
 
-for _ in range(3):
+for _ in range(5):          # the first steps size the speculative capacities and fill the allocator's cache
     step()
 torch.cuda.synchronize()
-n = 5
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(n):
+n = 8
+evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+for a, b in evs:
+    a.record()
     step()
-b.record()
+    b.record()
 torch.cuda.synchronize()
-ms = a.elapsed_time(b) / n
+per_step = sorted(a.elapsed_time(b) for a, b in evs)
+ms = per_step[n // 2]       # median; min / max reported beside it
 _lib.CallStats.reset(timing=True)
 step()
 per = {k: round(v, 3) for k, (c, v) in _lib.CallStats.durations_ms().items() if v > 0.05}
 launches = _lib.CallStats.launches()
 _lib.CallStats.reset()
 out = {"what": "whole stage-1 training step through model.GeoSplatter.training_loss + Adam, 8 views 800x800", "resolution": R,
-       **stats, "ms_per_step": round(ms, 3), "views_per_s": round(8 / (ms / 1e3), 2), "steps_timed": n,
+       **stats, "ms_per_step": round(ms, 3), "ms_per_step_min_max": [round(per_step[0], 3), round(per_step[-1], 3)],
+       "views_per_s": round(8 / (ms / 1e3), 2), "steps_timed": n,
        "entry_point_ms_one_step": per, "gpu_launches_one_step": launches,
        "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
 print(json.dumps(out))

@@ -82,6 +82,37 @@ def test_full_size_config_matches_oracle():
         assert float((a.cpu() - b).abs().max()) <= 2e-5 * float(b.abs().max())
 
 
+def test_clustered_points_table_gradient_matches_oracle():
+    """Points in MESH ORDER (32 consecutive points are neighbours on a surface, as MGAdaptor emits them): at the coarse levels
+    the 32 points of a warp fall into a handful of cells and the backward sums them inside the warp before it touches the
+    table (hashgrid.cu: warp_grouped_add); finer levels scatter per lane.  Ragged count (not a multiple of 32); table and
+    position gradients against the CPU oracle."""
+    torch.manual_seed(4)
+    enc = E.HashEncoding(E.MLP([32, 32, 2]), log2_hashmap_size=14, max_res=2048, grad_scaling=None).to("cpu")
+    with torch.no_grad():
+        enc.hash_table.mul_(1000.0)
+    gen = torch.Generator().manual_seed(8)
+    n = 32 * 40 + 13
+    centres = torch.nn.functional.normalize(torch.randn(n // 32 + 1, 3, generator=gen), dim=-1) * 0.6
+    x = centres.repeat_interleave(32, 0)[:n] + 4e-3 * torch.randn(n, 3, generator=gen)   # patches of 32 neighbours
+    cot = torch.randn(n, 32, generator=gen)
+    scal = OE.level_scalings(16, 16, 2048)
+    ox, ot = x.clone().requires_grad_(True), enc.hash_table.detach().clone().requires_grad_(True)
+    o_feats = OE.hash_encode(ox, ot, scal, 14)
+    og = torch.autograd.grad((o_feats * cot).sum(), [ox, ot])
+    enc = enc.to(DEV)
+    dx = x.to(DEV).requires_grad_(True)
+    feats = enc.encode(dx)
+    assert torch.equal(feats.cpu(), o_feats.detach())
+    dg = torch.autograd.grad((feats * cot.to(DEV)).sum(), [dx, enc.hash_table])
+    for a, b in zip(dg, og):
+        assert float((a.cpu() - b).abs().max()) <= 2e-5 * float(b.abs().max())
+    # the coarse levels really are shared inside a warp: 32 consecutive points, at most a few distinct cells at level 0,
+    # (nearly) all distinct at the finest level
+    cells = lambda lvl: [len(torch.unique(torch.floor((x[i:i + 32] * 0.5 + 0.5) * scal[lvl]), dim=0)) for i in range(0, n, 32)]
+    assert max(cells(0)) <= 6 and min(cells(15)[:-1]) >= 16, (cells(0), cells(15))
+
+
 def test_edge_cases():
     enc = E.HashEncoding(E.MLP([32, 16, 2]), log2_hashmap_size=8, max_res=512, grad_scaling=None).to(DEV)
     with torch.no_grad():

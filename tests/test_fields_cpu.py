@@ -32,6 +32,10 @@ def test_hash_grid_kernel_source_on_host_matches_reference_code(host_hashgrid, t
     GE.test_fields_match_reference_code(tag, layers, act)
 
 
+def test_warp_aggregated_table_gradient_on_host(host_hashgrid):
+    GE.test_clustered_points_table_gradient_matches_oracle()
+
+
 def test_mgadapter_kernel_source_on_host_reference_fixture(host_mgadapter):
     GM.test_against_reference_fixture()
 
