@@ -22,6 +22,7 @@
 // Replaces gsplat 1.4.0 rasterize_to_pixels_fwd/bwd (third-party), reached from
 // rfstudio/model/gsplat.py:334-355.  Bound: FP32 / MUFU issue, not HBM.
 #include "gsb_common.cuh"
+#include "composite_rec.cuh"
 
 #define LOG2E 1.4426950408889634f
 #define LOG2_ALPHA_MIN (-7.994353436858858f)   // log2(1/255)
@@ -55,11 +56,7 @@ constexpr int BSZ = GSB_BG;                               // entries evaluated t
 static_assert(GSB_FG >= 1 && 16 % GSB_FG == 0, "GSB_FG: divisor of 16");
 static_assert(GSB_BG >= 1 && 16 % GSB_BG == 0, "GSB_BG: divisor of 16");
 
-struct Rec {
-    float4 k;  // x, y, hx, hy
-    float4 q;  // -log2e * (a/2, b, c/2), log2(opacity)
-    float4 c;  // r, g, b, opacity
-};
+using Rec = GsbRec;   // composite_rec.cuh
 
 __device__ __forceinline__ float ex2_approx(float x) {
 #ifdef GSB_NO_INLINE_PTX   // host compilation of this file by tests/emu
@@ -81,19 +78,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
 #endif
 }
 
-// Half extents of {d : 0.5 d^T C d <= tau}, tau = ln(255 * opac): the only region where alpha >= 1/255.
-// Negative when the Gaussian can contribute nowhere.  Inflated so that rounding in the per-pixel evaluation can
-// never contradict a cull.
-__device__ __forceinline__ float2 alpha_extent(float ca, float cb, float cc, float opac) {
-    float t = 255.0f * opac;
-    if (!(t > 1.0f)) return make_float2(-1e30f, -1e30f);
-    float tau2 = 2.0f * logf(t);
-    float det = ca * cc - cb * cb;
-    if (!(det > 0.f)) return make_float2(1e30f, 1e30f);  // degenerate conic: never cull
-    float hx = sqrtf(tau2 * cc / det), hy = sqrtf(tau2 * ca / det);
-    return make_float2(hx * 1.0005f + 0.02f, hy * 1.0005f + 0.02f);
-}
-
 // log2 of alpha before the 0.999 clamp at offset (dx, dy) from the centre; 5 FMA-class instructions
 __device__ __forceinline__ float log2_alpha(const float4 q, float dx, float dy) {
     return fmaf(q.z * dy, dy, fmaf(fmaf(q.y, dy, q.x * dx), dx, q.w));
@@ -107,20 +91,11 @@ __global__ void __launch_bounds__(256) pack_records_kernel(int N, const float2 *
                                                             const float *__restrict__ comps, Rec *__restrict__ rec) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
-    float2 xy = means2d[g];
-    float ca = conics[3 * g], cb = conics[3 * g + 1], cc = conics[3 * g + 2];
-    float op = opacities[g];
-    if (opacity_is_logit) op = 1.0f / (1.0f + expf(-op));   // torch.sigmoid (rfstudio/model/gsplat.py:338)
-    if (comps) op *= comps[g];                               // antialiasing compensation (gsplat: opacities * compensations)
-    float2 ext = alpha_extent(ca, cb, cc, op);
-    Rec r;
-    r.k = make_float4(xy.x, xy.y, ext.x, ext.y);
-    // op <= 0 (or NaN): log2 -> -inf / NaN, every comparison in the kernels fails, the record contributes nowhere
-    r.q = make_float4(-0.5f * LOG2E * ca, -LOG2E * cb, -0.5f * LOG2E * cc, log2f(op));
     float c3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < (CH < 3 ? CH : 3); ++k) c3[k] = colors[(size_t)g * CH + k];
-    r.c = make_float4(c3[0], c3[1], c3[2], op);
+    const Rec r = gsb_pack_record(means2d[g], conics[3 * g], conics[3 * g + 1], conics[3 * g + 2], c3[0], c3[1], c3[2],
+                                  opacities[g], opacity_is_logit, comps ? comps[g] : 1.0f);
     rec[g] = r;
 }
 
@@ -793,11 +768,11 @@ template <int CH>
 int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conics, const float *colors,
                const float *opacities, int opacity_is_logit, const float *comps, const float *background,
                const int32_t *offsets, const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render,
-               float *alphas, int32_t *last_ids, void *ws, cudaStream_t st) {
+               float *alphas, int32_t *last_ids, void *ws, bool prepacked, cudaStream_t st) {
     int tw = (W + GSB_TILE - 1) / GSB_TILE, th = (H + GSB_TILE - 1) / GSB_TILE;
     int n_tiles = tw * th, n_units = n_tiles * SUBS;
     Workspace w = carve(ws, N, M, n_tiles);
-    if (N > 0)
+    if (N > 0 && !prepacked)   // the batch driver's shade forward has written the records already
         pack_records_kernel<CH><<<gsb_div_up(N, 256), 256, 0, st>>>((int)N, reinterpret_cast<const float2 *>(means2d),
                                                                     conics, colors, opacities, opacity_is_logit,
                                                                     comps, w.rec);
@@ -858,12 +833,19 @@ GSB_API int gsb_composite_workspace_bytes(int64_t N, int64_t M, int32_t width, i
     return GSB_OK;
 }
 
+// Where the records live inside a compositing workspace (its first block): for a producer that packs them itself.
+void *gsb_composite_records(void *workspace) {
+    return reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+}
+
 // `M` is the CAPACITY of the tile lists when `m_dev` (the device-resident intersection count) is given, else the count.
+// `prepacked`: the records of all N Gaussians are already at gsb_composite_records(workspace) (colours included), and
+// means2d / conics / opacities / comps are not read.
 int gsb_composite_fwd_impl(int32_t width, int32_t height, int32_t channels, int64_t N, const float *means2d,
                            const float *conics, const float *colors, const float *opacities, int32_t opacity_is_logit,
                            const float *comps, const float *background, const int32_t *offsets,
                            const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render, float *alphas,
-                           int32_t *last_ids, void *workspace, size_t workspace_bytes_, void *stream) {
+                           int32_t *last_ids, void *workspace, size_t workspace_bytes_, int32_t prepacked, void *stream) {
     GSB_CHECK_ARG(width > 0 && height > 0 && N >= 0 && M >= 0 && M < 134217727LL);
     GSB_CHECK_ARG(offsets && render && alphas && last_ids && workspace);
     GSB_CHECK_ARG(M == 0 || (means2d && conics && colors && opacities && flatten_ids));
@@ -875,7 +857,8 @@ int gsb_composite_fwd_impl(int32_t width, int32_t height, int32_t channels, int6
     int rc = 0;
     GSB_DISPATCH_CH(channels, (rc = launch_fwd<C_>(width, height, N, means2d, conics, colors, opacities,
                                                     opacity_is_logit, comps, background, offsets, flatten_ids, M, m_dev,
-                                                    render, alphas, last_ids, workspace, (cudaStream_t)stream)));
+                                                    render, alphas, last_ids, workspace, prepacked != 0,
+                                                    (cudaStream_t)stream)));
     if (rc != 0) {
         gsb_set_error("gsb_composite_fwd: internal sort scratch too small");
         return GSB_ENOMEM;
@@ -908,7 +891,7 @@ GSB_API int gsb_composite_fwd(int32_t width, int32_t height, int32_t channels, i
                               void *stream) {
     return gsb_composite_fwd_impl(width, height, channels, N, means2d, conics, colors, opacities, opacity_is_logit, comps,
                                   background, offsets, flatten_ids, M, nullptr, render, alphas, last_ids, workspace,
-                                  workspace_bytes_, stream);
+                                  workspace_bytes_, 0, stream);
 }
 
 GSB_API int gsb_composite_bwd(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,

@@ -6,6 +6,7 @@
 // HBM-bound streaming kernel; replaces ~25 elementwise torch kernels + 3 nvdiffrast texture kernels
 // per view of rfstudio/model/geosplat.py:83-121 and rfstudio/graphics/_mesh/_texture.py:571-613.
 #include "texture_math.cuh"
+#include "composite_rec.cuh"
 
 namespace {
 
@@ -194,11 +195,18 @@ __device__ __forceinline__ void shade_one(const float m[3], const float n[3], co
     v_ks[1] = v_met * p.max_metallic;
 }
 
+// What the compositing record needs besides the colour (composite_rec.cuh); `rec == nullptr`: colours only.
+struct PackArgs {
+    const float2 *means2d;
+    const float *conics, *opacity_logits, *comps;
+    GsbRec *rec;
+};
+
 __global__ void __launch_bounds__(256) shade_fwd_kernel(int N, const float *__restrict__ means,
                                                          const float *__restrict__ normals,
                                                          const float *__restrict__ kd, const float *__restrict__ ks,
                                                          ShadeParams p, const float2 *__restrict__ lut, EnvStack env,
-                                                         float *__restrict__ colors) {
+                                                         float *__restrict__ colors, PackArgs pk) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
@@ -211,6 +219,9 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(int N, const float *__re
     colors[3 * i] = o.color.x;
     colors[3 * i + 1] = o.color.y;
     colors[3 * i + 2] = o.color.z;
+    if (pk.rec)
+        pk.rec[i] = gsb_pack_record(pk.means2d[i], pk.conics[3 * i], pk.conics[3 * i + 1], pk.conics[3 * i + 2], o.color.x,
+                                    o.color.y, o.color.z, pk.opacity_logits[i], 1, pk.comps ? pk.comps[i] : 1.0f);
 }
 
 #ifndef GSB_SHADE_BWD_MINB
@@ -352,21 +363,34 @@ extern "C" __attribute__((visibility("default"))) int gsb_envstack_unpack_grad(i
     return GSB_OK;
 }
 
+// The shade forward, optionally also packing the compositing records (batch driver): `rec` = gsb_composite_records(ws).
+int gsb_shade_fwd_impl(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
+                       const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack, int32_t R0,
+                       int32_t L, int32_t Rb, float min_roughness, float max_metallic, float env_min_roughness,
+                       float env_max_roughness, int32_t mode, float *colors, const float *means2d, const float *conics,
+                       const float *opacity_logits, const float *comps, void *rec, void *stream) {
+    GSB_CHECK_ARG(N >= 0 && cam_pos_host && mode >= 0 && mode <= 2 && lut_res > 1 && L >= 2 && R0 > 0 && Rb > 0);
+    if (N == 0) return GSB_OK;
+    GSB_CHECK_ARG(means && normals && kd && ks && fg_lut && env_stack && colors);
+    GSB_CHECK_ARG(rec == nullptr || (means2d && conics && opacity_logits));
+    ShadeParams p;
+    fill_params(p, cam_pos_host, min_roughness, max_metallic, env_min_roughness, env_max_roughness, mode, lut_res);
+    EnvStack e{env_stack, R0, L, Rb};
+    PackArgs pk{reinterpret_cast<const float2 *>(means2d), conics, opacity_logits, comps, reinterpret_cast<GsbRec *>(rec)};
+    shade_fwd_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+        N, means, normals, kd, ks, p, reinterpret_cast<const float2 *>(fg_lut), e, colors, pk);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int gsb_shade_fwd(
     int32_t N, const float *means, const float *normals, const float *kd, const float *ks, const float *cam_pos_host,
     const float *fg_lut, int32_t lut_res, const float *env_stack, int32_t R0, int32_t L, int32_t Rb,
     float min_roughness, float max_metallic, float env_min_roughness, float env_max_roughness, int32_t mode,
     float *colors, void *stream) {
-    GSB_CHECK_ARG(N >= 0 && cam_pos_host && mode >= 0 && mode <= 2 && lut_res > 1 && L >= 2 && R0 > 0 && Rb > 0);
-    if (N == 0) return GSB_OK;
-    GSB_CHECK_ARG(means && normals && kd && ks && fg_lut && env_stack && colors);
-    ShadeParams p;
-    fill_params(p, cam_pos_host, min_roughness, max_metallic, env_min_roughness, env_max_roughness, mode, lut_res);
-    EnvStack e{env_stack, R0, L, Rb};
-    shade_fwd_kernel<<<gsb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        N, means, normals, kd, ks, p, reinterpret_cast<const float2 *>(fg_lut), e, colors);
-    GSB_CHECK_LAUNCH();
-    return GSB_OK;
+    return gsb_shade_fwd_impl(N, means, normals, kd, ks, cam_pos_host, fg_lut, lut_res, env_stack, R0, L, Rb, min_roughness,
+                              max_metallic, env_min_roughness, env_max_roughness, mode, colors, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int gsb_shade_bwd(

@@ -21,7 +21,13 @@ int gsb_composite_fwd_impl(int32_t width, int32_t height, int32_t channels, int6
                            const float *conics, const float *colors, const float *opacities, int32_t opacity_is_logit,
                            const float *comps, const float *background, const int32_t *offsets,
                            const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render, float *alphas,
-                           int32_t *last_ids, void *workspace, size_t workspace_bytes_, void *stream);
+                           int32_t *last_ids, void *workspace, size_t workspace_bytes_, int32_t prepacked, void *stream);
+void *gsb_composite_records(void *workspace);
+int gsb_shade_fwd_impl(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
+                       const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack, int32_t R0,
+                       int32_t L, int32_t Rb, float min_roughness, float max_metallic, float env_min_roughness,
+                       float env_max_roughness, int32_t mode, float *colors, const float *means2d, const float *conics,
+                       const float *opacity_logits, const float *comps, void *rec, void *stream);
 int gsb_composite_bwd_impl(int32_t width, int32_t height, int32_t channels, int64_t N, const float *colors,
                            const float *background, const int32_t *offsets, int64_t M, const int64_t *m_dev,
                            const float *alphas, const int32_t *last_ids, const float *v_render, const float *v_alphas,
@@ -338,16 +344,20 @@ GSB_API int gsb_batch_forward(const gsb_view_config *cfg, int32_t n_views, const
                                  t1.comps, t1.tpg, st));
         VIEW_TRY(gsb_bin2_count(cfg->N, t1.depths, t1.tpg, t1.order, t1.cum, k1.m_eff + 1, t1.scratch, b.v.bin_n, st));
         VIEW_TRY(gsb_bin2_publish(cfg->N, t1.cum, m_cap, k1.m_eff, totals_out ? totals_out + v : nullptr, st));
-        VIEW_TRY(gsb_shade_fwd(cfg->N, means, normals, kd, ks, cam_pos_host + 3 * v, fg_lut, cfg->lut_res, env_stack,
-                               cfg->R0, cfg->L, cfg->Rb, cfg->min_roughness, cfg->max_metallic,
-                               cfg->env_min_roughness, cfg->env_max_roughness, cfg->mode, k1.colors, st));
+        // the shade writes the compositing records (colour, folded conic, extents, opacity) straight into the
+        // compositing workspace: no pack pass, no colour round trip
+        VIEW_TRY(gsb_shade_fwd_impl(cfg->N, means, normals, kd, ks, cam_pos_host + 3 * v, fg_lut, cfg->lut_res, env_stack,
+                                    cfg->R0, cfg->L, cfg->Rb, cfg->min_roughness, cfg->max_metallic,
+                                    cfg->env_min_roughness, cfg->env_max_roughness, cfg->mode, k1.colors, t1.means2d,
+                                    t1.conics, opacity_logits, cam->antialiased ? t1.comps : nullptr,
+                                    gsb_composite_records(k2.comp_ws), st));
         // ---- finish: binning on the capacity, compositing, tone map
         VIEW_TRY(gsb_bin2_sort_cap(cfg->N, m_cap, k1.m_eff, t1.means2d, k1.radii, t1.order, t1.cum, cam, flatten_ids,
                                    k2.offsets, sort_scratch, b.v.bin_m, st));
         VIEW_TRY(gsb_composite_fwd_impl(cfg->width, cfg->height, 3, cfg->N, t1.means2d, t1.conics, k1.colors,
                                         opacity_logits, 1, cam->antialiased ? t1.comps : nullptr, nullptr, k2.offsets,
                                         flatten_ids, m_cap, k1.m_eff, k2.render, k2.alphas, k2.last_ids, k2.comp_ws,
-                                        b.v.comp_ws, st));
+                                        b.v.comp_ws, 1, st));
         VIEW_TRY(gsb_tonemap_planar_fwd((int64_t)P, k2.render, k2.alphas, exposures + (size_t)exposure_stride * v,
                                         cfg->naive_tonemap, out + 4 * P * (size_t)v, st));
     }

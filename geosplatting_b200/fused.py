@@ -20,6 +20,7 @@ At ~1.2 ms of device time per view the host would otherwise be the bottleneck (s
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import List, NamedTuple, Optional, Sequence
 
 import torch
@@ -256,10 +257,16 @@ def _view_backward(sh: _Shared, v: _View, v_out: Tensor, g: _Grads, v_exp: Tenso
 
 
 # ---- batch driver: ONE C-ABI call per batch each way, nothing waits for a view's intersection count (csrc/view.cu) -----
-_caps: dict = {}          # (device, N, W, H) -> capacity of the tile lists (intersections per view)
+_caps: dict = {}          # (device, size class of N, W, H) -> capacity of the tile lists (intersections per view)
 _pinned_pool: list = []   # recycled pinned int64 buffers the device publishes the raw counts to
 CAP_MARGIN = 1.25
 CAP_QUANTUM = 1 << 16
+
+
+def _size_class(N: int) -> int:
+    """Scenes within ~12 % of each other share a capacity: a trainer whose mesh (and with it the Gaussian count) changes a
+    little every step (FlexiCubes re-extraction, geosplat.py:735-760) must not re-probe -- and wait for -- every batch."""
+    return int(math.log(max(N, 1)) / math.log(1.125))
 
 
 def _round_cap(m: int) -> int:
@@ -314,7 +321,7 @@ def _batch_forward(sh: _Shared, cameras, exposures, side) -> tuple:
     W, H = b.cams[0].width, b.cams[0].height
     b.cfg = _view_config(sh, b.cams[0])
     b.ex_all, b.ex_stride = _exposure_array(exposures, dev)
-    b.key = (dev.index if dev.index is not None else torch.cuda.current_device(), N, W, H)
+    b.key = (dev.index if dev.index is not None else torch.cuda.current_device(), _size_class(N), W, H)
     ns = len(b.streams)
     out = torch.empty(n, H, W, 4, dtype=torch.float32, device=dev)
     probing = b.key not in _caps

