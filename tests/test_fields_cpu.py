@@ -60,14 +60,15 @@ def test_warp_reductions_under_simt(monkeypatch):
     GM.test_tonemap_against_reference_fixture()
 
 
+@pytest.mark.parametrize("defines", [(), ("GSB_MLP_PPL=4", "GSB_MLP_BWD_WARPS=3", "GSB_MLP_FWD_WARPS=5")])
 @pytest.mark.parametrize("layers,act,n", [([32, 32, 32, 3], "sigmoid", 133), ([32, 32, 2], "none", 64),
                                           ([32, 32, 1], "none", 7), ([32, 32, 32, 4], "none", 300)])
-def test_fused_mlp_kernel_source_on_host_against_torch(monkeypatch, layers, act, n):
-    """csrc/mlp.cu (all layers + activations in one kernel; backward = recompute + chain + the three weight gradients
-    through shared-memory transposes) under the SIMT emulation, against torch.nn.functional.linear / relu / sigmoid:
+def test_fused_mlp_kernel_source_on_host_against_torch(monkeypatch, layers, act, n, defines):
+    """csrc/mlp.cu (all layers + activations in one kernel as register-tiled products over transposed shared-memory
+    tiles; backward = recompute + chain + the three weight gradients; 8 or 4 points per lane) under the SIMT emulation, against torch.nn.functional.linear / relu / sigmoid:
     values 1e-6, gradients 1e-5 of their largest entry; with and without the reference's input rounding; ragged N."""
     import torch
-    route(monkeypatch, emu.build("mlp", simt=True), E)
+    route(monkeypatch, emu.build("mlp", simt=True, defines=defines), E)
     gen = torch.Generator().manual_seed(len(layers) * 100 + n)
     mlp = E.MLP(layers, activation=act)
     x = torch.randn(n, 32, generator=gen)
