@@ -501,9 +501,25 @@ __global__ void __launch_bounds__(128) specular_plan_fill_kernel(int R, const fl
     walk_cone_rows(R, bounds, cutoff, g, 0, 6, vis);
 }
 
+#ifndef GSB_PLAN_DEPTH
+#define GSB_PLAN_DEPTH 4
+#endif
+#ifndef GSB_PLAN_MINB
+#define GSB_PLAN_MINB 1
+#endif
+#ifndef GSB_PLAN_PARTS_TARGET
+#define GSB_PLAN_PARTS_TARGET 49152   // warps per level the split aims for (measured, as_envstack fwd+bwd: 6 k 5.36 ms, 12 k 5.01, 24 k 4.85, 48 k 4.60, 96 k 4.65)
+#endif
+int plan_parts(int R) {
+    const int patches = 6 * R * R / 32;
+    int parts = 1;
+    while (parts < 16 && patches * parts < GSB_PLAN_PARTS_TARGET) parts *= 2;
+    return parts;
+}
+
 // acc[t] += sum over the patch's taps of W[tap][lane] * pre[source texel]: same epilogues as the gather kernel
 template <bool BWD, bool SPLIT>
-__global__ void __launch_bounds__(128) specular_apply_kernel(int R, const float4 *__restrict__ dirs,
+__global__ void __launch_bounds__(128, GSB_PLAN_MINB) specular_apply_kernel(int R, const float4 *__restrict__ dirs,
                                                               const float4 *__restrict__ pre,
                                                               const int *__restrict__ seg_start,
                                                               const int4 *__restrict__ segs,
@@ -514,24 +530,58 @@ __global__ void __launch_bounds__(128) specular_apply_kernel(int R, const float4
     PatchGeom g;
     if (!patch_geom(R, dirs, patch, lane, g)) return;
     const size_t pf = (size_t)patch * 6;
-    const int s0 = seg_start[pf + (SPLIT ? blockIdx.y : 0)], s1 = seg_start[pf + (SPLIT ? blockIdx.y + 1 : 6)];
+    int s0 = seg_start[pf], s1 = seg_start[pf + 6];
+    if (SPLIT) {
+        // an EVEN share of the patch's row segments (a split by source face leaves most of a cone in one part: the
+        // coarse levels have few patches with long tap lists, and a level's duration was one warp's serial stream)
+        const long long n = s1 - s0;
+        const int a = s0 + (int)(n * blockIdx.y / gridDim.y), b = s0 + (int)(n * (blockIdx.y + 1) / gridDim.y);
+        s0 = a;
+        s1 = b;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int last = 6 * R * R - 1;
-    for (int i = s0; i < s1; ++i) {
-        const int4 sg = __ldg(segs + i);
-        const float4 *w4 = reinterpret_cast<const float4 *>(weights) + (size_t)(sg.z >> 2) * 32 + lane;
-        const int groups = (sg.y + 3) >> 2;
-        // 4 groups = 16 taps per iteration: four independent 16-byte weight loads per lane in flight (2 KB per warp)
-#pragma unroll 4
-        for (int gi = 0; gi < groups; ++gi) {
-            const float4 k = __ldcs(w4 + (size_t)gi * 32);     // streamed once per pass: do not keep it in L1 / L2
-            const int x = sg.x + 4 * gi;                        // the padded tail (zero weights) stays inside the buffer
-            const float4 P0 = __ldg(pre + x), P1 = __ldg(pre + min(x + 1, last));
-            const float4 P2 = __ldg(pre + min(x + 2, last)), P3 = __ldg(pre + min(x + 3, last));
-            acc.x += P0.x * k.x; acc.y += P0.y * k.x; acc.z += P0.z * k.x; acc.w += P0.w * k.x;
-            acc.x += P1.x * k.y; acc.y += P1.y * k.y; acc.z += P1.z * k.y; acc.w += P1.w * k.y;
-            acc.x += P2.x * k.z; acc.y += P2.y * k.z; acc.z += P2.z * k.z; acc.w += P2.w * k.z;
-            acc.x += P3.x * k.w; acc.y += P3.y * k.w; acc.z += P3.z * k.w; acc.w += P3.w * k.w;
+    if (s1 > s0) {
+        // The weights of consecutive segments are consecutive in memory ([group of 4 taps][lane] float4), so the stream
+        // is read through a register ring DEPTH groups deep that does not care where a segment ends: DEPTH 16-byte
+        // loads per lane stay in flight (a row segment is only ~6 groups long at 512^2, and a per-segment loop drained
+        // the pipeline at every segment: 4.2 TB/s).  The segment headers, one ahead, only say which source texels a
+        // group multiplies.
+        constexpr int DEPTH = GSB_PLAN_DEPTH;
+        int4 sg = __ldg(segs + s0);
+        int4 sg_next = (s0 + 1 < s1) ? __ldg(segs + s0 + 1) : sg;
+        const int4 sg_last = __ldg(segs + s1 - 1);
+        const int g0 = sg.z >> 2, G = ((sg_last.z >> 2) + ((sg_last.y + 3) >> 2)) - g0;   // groups of my share
+        const float4 *w4 = reinterpret_cast<const float4 *>(weights) + (size_t)g0 * 32 + lane;
+        int seg = s0, left = (sg.y + 3) >> 2, x = sg.x;        // current segment, groups left in it, next source texel
+        float4 ring[DEPTH];
+#pragma unroll
+        for (int j = 0; j < DEPTH; ++j) ring[j] = (j < G) ? __ldcs(w4 + (size_t)j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = 0; base < G; base += DEPTH) {
+#pragma unroll
+            for (int j = 0; j < DEPTH; ++j) {
+                const int gi = base + j;
+                const float4 k = ring[j];
+                if (gi + DEPTH < G) ring[j] = __ldcs(w4 + (size_t)(gi + DEPTH) * 32);   // streamed once per pass
+                if (gi < G) {
+                    while (left == 0) {                         // next segment (its header was fetched one ahead)
+                        ++seg;
+                        sg = sg_next;
+                        if (seg + 1 < s1) sg_next = __ldg(segs + seg + 1);
+                        left = (sg.y + 3) >> 2;
+                        x = sg.x;
+                    }
+                    // the padded tail of a segment (zero weights) stays inside the buffer
+                    const float4 P0 = __ldg(pre + x), P1 = __ldg(pre + min(x + 1, last));
+                    const float4 P2 = __ldg(pre + min(x + 2, last)), P3 = __ldg(pre + min(x + 3, last));
+                    acc.x += P0.x * k.x; acc.y += P0.y * k.x; acc.z += P0.z * k.x; acc.w += P0.w * k.x;
+                    acc.x += P1.x * k.y; acc.y += P1.y * k.y; acc.z += P1.z * k.y; acc.w += P1.w * k.y;
+                    acc.x += P2.x * k.z; acc.y += P2.y * k.z; acc.z += P2.z * k.z; acc.w += P2.w * k.z;
+                    acc.x += P3.x * k.w; acc.y += P3.y * k.w; acc.z += P3.z * k.w; acc.w += P3.w * k.w;
+                    x += 4;
+                    --left;
+                }
+            }
         }
     }
     const int t = g.t;
@@ -741,10 +791,12 @@ static int plan_apply(int32_t R, const float *src, int src_stride, const float *
     const int total = 6 * R * R;
     dir_table_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, dirs);
     prep_source_kernel<<<gsb_div_up(total, 256), 256, 0, st>>>(R, src, src_stride, fwd_out, dirs, mode, pre);
-    if (R <= 64) {
+    // parts per patch: enough warps to keep every SM streaming (a 64^2 level has 768 patches of ~2 500 taps)
+    const int parts = plan_parts(R);
+    if (parts > 1) {
         float4 *accum = pre + 6 * (size_t)R * R;
         GSB_CHECK_CUDA(cudaMemsetAsync(accum, 0, sizeof(float4) * total, st));
-        specular_apply_kernel<BWD, true><<<dim3(gsb_div_up(total / 32, 4), 6), 128, 0, st>>>(
+        specular_apply_kernel<BWD, true><<<dim3(gsb_div_up(total / 32, 4), parts), 128, 0, st>>>(
             R, dirs, pre, seg_start, reinterpret_cast<const int4 *>(segs), weights, normalize, dst, accum);
         specular_finalize_kernel<BWD><<<gsb_div_up(total, 256), 256, 0, st>>>(R, accum, dirs, normalize, dst);
     } else {

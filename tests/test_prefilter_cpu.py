@@ -110,10 +110,14 @@ def test_bounds_are_the_exact_box_of_the_fp32_cone_test(lib, R, rough):
 
 
 @pytest.mark.parametrize("R,rough", [(16, 1.0), (32, 0.5), (64, 0.185), (64, 0.08)])
-def test_cached_plan_reproduces_the_on_the_fly_prefilter_bit_for_bit(lib, R, rough):
+def test_cached_plan_reproduces_the_on_the_fly_prefilter(lib, R, rough):
     """gsb_specular_plan_count / _fill build the per-(tap, lane) weight table once; gsb_specular_plan_fwd / _bwd then
-    stream it.  Same traversal, same weight expression, same tap order as gsb_specular_cubemap_fwd / _bwd: the results
-    must be IDENTICAL (forward with and without normalisation, backward with and without the forward's weight sums)."""
+    stream it.  Same traversal, same weight expression, same tap order as gsb_specular_cubemap_fwd / _bwd; the two paths
+    cut a texel's sum into partial sums differently (the gather per source face, the plan into even shares of the row
+    segments, so that the few patches of a coarse level keep every SM busy), so the results agree to the rounding of
+    that association (sums of ~2 000 fp32 terms): 5e-6 of the largest entry (forward with and without normalisation, backward with and without the
+    forward's weight sums).  With one part per patch (GSB_PLAN_PARTS_TARGET=0) and a gather that is not split either
+    (R > 64 on the GPU) they are identical to the bit."""
     ct = P.ndf_cutoff_costheta(rough)
     c = _cubemap(R, 11 + R).numpy()
     i32, f32 = C.c_int32, C.c_float
@@ -140,7 +144,7 @@ def test_cached_plan_reproduces_the_on_the_fly_prefilter_bit_for_bit(lib, R, rou
                                             None) == 0
         assert lib.gsb_specular_plan_fwd(i32(R), _p(c), _p(seg_start), _p(segs), _p(weights), i32(normalize), _p(b),
                                          _p(ws), None) == 0, lib.gsb_last_error()
-        assert np.array_equal(a, b), normalize
+        assert np.abs(a - b).max() <= 5e-6 * np.abs(a).max(), (normalize, np.abs(a - b).max())
     g = torch.randn(6, R, R, 4, generator=torch.Generator().manual_seed(5)).numpy()
     for fwd_out in (None, b):
         ga, gb = np.zeros((6, R, R, 3), np.float32), np.zeros((6, R, R, 3), np.float32)
@@ -148,4 +152,4 @@ def test_cached_plan_reproduces_the_on_the_fly_prefilter_bit_for_bit(lib, R, rou
                                             None) == 0
         assert lib.gsb_specular_plan_bwd(i32(R), _p(seg_start), _p(segs), _p(weights), _p(g), _p(fwd_out), _p(gb), _p(ws),
                                          None) == 0, lib.gsb_last_error()
-        assert np.array_equal(ga, gb)
+        assert np.abs(ga - gb).max() <= 5e-6 * np.abs(ga).max(), np.abs(ga - gb).max()
