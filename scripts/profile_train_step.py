@@ -60,7 +60,7 @@ b.record()
 torch.cuda.synchronize()
 ms_step = a.elapsed_time(b) / 5
 
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
 
@@ -114,6 +114,16 @@ for g, d in groups.items():
     top = sorted(d.items(), key=lambda kv: -kv[1][1])[:14]
     out["groups"][g] = {"total_ms": round(tot / 1e3, 3), "launches": sum(c for c, _ in d.values()),
                         "top": [{"kernel": k, "launches": c, "ms": round(t / 1e3, 3)} for k, (c, t) in top]}
+# which torch operators own the elementwise time (self device time, grouped by input shapes)
+ops = []
+for ka in prof.key_averages(group_by_input_shape=True):
+    t = getattr(ka, "self_device_time_total", None)
+    if t is None:
+        t = ka.self_cuda_time_total
+    if t > 0 and (ka.key.startswith("aten::") or "Optimizer" in ka.key):
+        ops.append((t, ka.key, ka.count, str(ka.input_shapes)[:120]))
+ops.sort(reverse=True)
+out["torch_ops_by_self_device_time"] = [{"op": k, "calls": c, "ms": round(t / 1e3, 3), "shapes": sh} for t, k, c, sh in ops[:30]]
 os.makedirs(os.path.dirname(OUT) or ".", exist_ok=True)
 json.dump(out, open(OUT, "w"), indent=1)
 print(json.dumps({k: (v if not isinstance(v, dict) else {g: x["total_ms"] for g, x in v.items()}) for k, v in out.items()}))

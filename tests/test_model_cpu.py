@@ -86,3 +86,26 @@ def test_no_cpu_path_and_missing_lut():
     m2 = GeoSplatter(resolution=4, light_resolution=16)
     with pytest.raises(RuntimeError, match="DFG table"):
         m2.render_report([])
+
+
+def test_flexicubes_weight_node_equals_the_sliced_expressions():
+    """model._FlexiWeights (one autograd node for the three weight slices and the |w| regulariser of geosplat.py:756-766)
+    against the plain sliced expressions: same values, same gradient, also when a slice is unused."""
+    import torch
+
+    from geosplatting_b200.model import _FlexiWeights
+    gen = torch.Generator().manual_seed(3)
+    w0 = torch.randn(57, 21, generator=gen)
+    ca, cb, cg = torch.randn(57, 8, generator=gen), torch.randn(57, 12, generator=gen), torch.randn(57, 1, generator=gen)
+    for use_gamma in (True, False):
+        w = w0.clone().requires_grad_(True)
+        a, b, g, m = _FlexiWeights.apply(w)
+        loss = (a * ca).sum() + (b * cb).sum() + m * 0.1 + ((g * cg).sum() if use_gamma else 0.0)
+        (gw,) = torch.autograd.grad(loss, w)
+        r = w0.clone().requires_grad_(True)
+        ref = (r[:, :8] * ca).sum() + (r[:, 8:20] * cb).sum() + r[:, :20].abs().mean() * 0.1 + \
+            ((r[:, 20:] * cg).sum() if use_gamma else 0.0)
+        (gr,) = torch.autograd.grad(ref, r)
+        assert torch.equal(a, w0[:, :8]) and torch.equal(b, w0[:, 8:20]) and torch.equal(g, w0[:, 20:])
+        assert float((loss - ref).abs()) <= 1e-5 * float(ref.abs())
+        assert float((gw - gr).abs().max()) <= 1e-6 * float(gr.abs().max())
