@@ -507,6 +507,22 @@ constexpr int WPB_B = GSB_WPB_B;   // warps per CTA in the backward (6 KB of sha
 // cover all 32 banks both when the lanes are pixels of one row (phase A) and when they are rows at one pixel (phase B)
 __device__ __forceinline__ int slab_at(int row, int p) { return row * PIX + ((p + row) & (PIX - 1)); }
 
+// The backward's staged record, permuted so that what phase A needs per entry -- centre, folded conic, log2(opacity),
+// colour, list position: 10 floats -- is two 16-byte loads and one 8-byte load (a 16-byte shared-memory load costs four
+// wavefronts of the L1 data pipe however few distinct addresses it has, and that pipe is this kernel's bound).
+struct SRec {
+    float4 a;   // x, y, q.x, q.y
+    float4 b;   // q.z, q.w = log2(opacity), r, g
+    float4 c;   // b, tile-list position, Gaussian id (bit patterns), opacity
+};
+__device__ __forceinline__ SRec stage_record(const Rec &r, int2 e) {
+    SRec s;
+    s.a = make_float4(r.k.x, r.k.y, r.q.x, r.q.y);
+    s.b = make_float4(r.q.z, r.q.w, r.c.x, r.c.y);
+    s.c = make_float4(r.c.z, __int_as_float(e.x), __int_as_float(e.y), r.c.w);
+    return s;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(32 * WPB_B, GSB_MINB_B)
 composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
@@ -523,8 +539,14 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
     constexpr int NV4 = (CH + 3) / 4;                   // float4s of v_out per pixel
     constexpr bool SEGD = segmented<CH>();
     __shared__ float2 s_slab[WPB_B][32 * PIX];          // {alpha T, v_sigma} per (row, pixel)
-    __shared__ Rec s_rec[WPB_B][32];                    // k.z / k.w carry the entry's tile-list position / Gaussian id
-    __shared__ float4 s_vo[WPB_B][PIX][UPW][NV4];        // the two units' v_out of a pixel side by side: distinct banks
+    __shared__ SRec s_rec[WPB_B][32];
+    // v_out of the two units' pixels, side by side per pixel (distinct banks).  Up to three channels: 8 + 4 bytes in two
+    // arrays (three wavefronts per load pair; as one float4 the compiler fuses them back into a four-wavefront LDS.128)
+    constexpr bool NARROW = CH <= 3;
+    __shared__ float4 s_vo[NARROW ? 1 : WPB_B][NARROW ? 1 : PIX][UPW][NV4];
+    __shared__ float2 s_vo01[NARROW ? WPB_B : 1][NARROW ? PIX : 1][UPW];
+    __shared__ float s_vo2[NARROW ? WPB_B : 1][NARROW ? PIX : 1][UPW];
+    static_assert(sizeof(SRec) == 48, "staged record");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int half = lane >> 4, p = lane & (PIX - 1);
     const int M = m_dev ? (int)*m_dev : M_host;
@@ -568,9 +590,14 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
         float vo4[NV4 * 4];
 #pragma unroll
         for (int k = 0; k < NV4 * 4; ++k) vo4[k] = (k < CH) ? v_out[k] : 0.f;
+        if (NARROW) {
+            s_vo01[wib][p][half] = make_float2(vo4[0], vo4[1]);
+            s_vo2[wib][p][half] = vo4[2];
+        } else {
 #pragma unroll
-        for (int k = 0; k < NV4; ++k)
-            s_vo[wib][p][half][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
+            for (int k = 0; k < NV4; ++k)
+                s_vo[wib][p][half][k] = make_float4(vo4[4 * k], vo4[4 * k + 1], vo4[4 * k + 2], vo4[4 * k + 3]);
+        }
     }
     const int n_max = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
 
@@ -604,7 +631,7 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
     const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
     const int2 *const slist = own ? list : list_other;
     const int sn = own ? n : n_other;
-    const Rec *const rows = &s_rec[wib][half];
+    const SRec *const rows = &s_rec[wib][half];
     // same software pipeline as the forward: records one step ahead, list entries two steps ahead
     const int2 none = make_int2(0x7fffffff, 0);   // position beyond every last_id: a null row is never valid
     int2 e = none, e_next = none;
@@ -613,9 +640,7 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
     if (sn - CHUNK - 1 - li >= 0) e_next = slist[sn - CHUNK - 1 - li];
     for (int top = sn, walked = 0; walked < n_max; top -= CHUNK, walked += CHUNK) {
         __syncwarp();
-        r.k.z = __int_as_float(e.x);
-        r.k.w = __int_as_float(e.y);
-        s_rec[wib][lane] = r;
+        s_rec[wib][lane] = stage_record(r, e);
         __syncwarp();
         const int nt = top - CHUNK;
         e = e_next;
@@ -633,21 +658,22 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
 #pragma unroll
             for (int s = 0; s < BSZ; ++s) {
                 const int t = 2 * (t0 + s);
-                const float4 kk = rows[t].k;
-                const float4 q = rows[t].q;
-                const float4 c = rows[t].c;
-                const float l2a = log2_alpha(q, kk.x - u.px, kk.y - u.py);
+                const float4 ra = rows[t].a, rb = rows[t].b;
+                const float2 rc = *reinterpret_cast<const float2 *>(&rows[t].c);      // blue, list position
+                const float4 q = make_float4(ra.z, ra.w, rb.x, rb.y);
+                const float l2a = log2_alpha(q, ra.x - u.px, ra.y - u.py);
                 const float araw = ex2_approx(l2a);
-                const bool valid = (__float_as_int(kk.z) <= bin_final) && (l2a <= q.w) && (l2a >= LOG2_ALPHA_MIN);
+                const bool valid = (__float_as_int(rc.y) <= bin_final) && (l2a <= q.w) && (l2a >= LOG2_ALPHA_MIN);
                 Ag[s] = valid ? araw : 0.f;
                 al[s] = fminf(GSB_ALPHA_CLAMP, Ag[s]);
                 rag[s] = rcp_approx(1.0f - al[s]);
-                float w = c.x * v_out[0];
-                if (C3 > 1) w += c.y * v_out[1];
-                if (C3 > 2) w += c.z * v_out[2];
+                float w = rb.z * v_out[0];
+                if (C3 > 1) w += rb.w * v_out[1];
+                if (C3 > 2) w += rc.x * v_out[2];
                 if (CH > 3) {
+                    const int gid = __float_as_int(rows[t].c.z);
 #pragma unroll
-                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)__float_as_int(kk.w) * CH + k) * v_out[k];
+                    for (int k = 3; k < CH; ++k) w += __ldg(colors + (size_t)gid * CH + k) * v_out[k];
                 }
                 wg[s] = w;
                 mine_mask |= valid ? (1u << (t + half)) : 0u;
@@ -672,10 +698,11 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
 
         // ---- phase B: lane = Gaussian (shared-memory row `lane`: entry lane / 2 of unit lane % 2) -------------
         {
-            const float4 kk = s_rec[wib][lane].k;
-            const float4 q = s_rec[wib][lane].q;
-            const float4 c = s_rec[wib][lane].c;
-            const int g = __float_as_int(kk.w);
+            const float4 ra = s_rec[wib][lane].a, rb = s_rec[wib][lane].b, rc = s_rec[wib][lane].c;
+            const float2 kk = make_float2(ra.x, ra.y);                 // centre
+            const float3 q = make_float3(ra.z, ra.w, rb.x);            // folded conic
+            const int g = __float_as_int(rc.z);
+            const float opac = rc.w;
             const int hb = lane & 1;                                   // the unit this row belongs to
             const float ox = (hb == half) ? bx : bx_other;             // pixel (0,0) of that unit (same row of pixels)
             const bool mine = (touched >> lane) & 1u;
@@ -688,13 +715,20 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
             for (int pp = 0; pp < PIX; ++pp) {
                 const float2 fv = row[(pp + lane) & (PIX - 1)];
                 const float fac = fv.x, v_sigma = fv.y;
+                if (NARROW) {
+                    const float2 v01 = s_vo01[wib][pp][hb];
+                    g_col[0] += fac * v01.x;
+                    if (CH > 1) g_col[CH > 1 ? 1 : 0] += fac * v01.y;
+                    if (CH > 2) g_col[CH > 2 ? 2 : 0] += fac * s_vo2[wib][pp][hb];
+                } else {
 #pragma unroll
-                for (int k = 0; k < NV4; ++k) {
-                    const float4 v4 = s_vo[wib][pp][hb][k];
-                    g_col[4 * k] += fac * v4.x;
-                    if (4 * k + 1 < CH) g_col[4 * k + 1 < CH ? 4 * k + 1 : 0] += fac * v4.y;
-                    if (4 * k + 2 < CH) g_col[4 * k + 2 < CH ? 4 * k + 2 : 0] += fac * v4.z;
-                    if (4 * k + 3 < CH) g_col[4 * k + 3 < CH ? 4 * k + 3 : 0] += fac * v4.w;
+                    for (int k = 0; k < NV4; ++k) {
+                        const float4 v4 = s_vo[wib][pp][hb][k];
+                        g_col[4 * k] += fac * v4.x;
+                        if (4 * k + 1 < CH) g_col[4 * k + 1 < CH ? 4 * k + 1 : 0] += fac * v4.y;
+                        if (4 * k + 2 < CH) g_col[4 * k + 2 < CH ? 4 * k + 2 : 0] += fac * v4.z;
+                        if (4 * k + 3 < CH) g_col[4 * k + 3 < CH ? 4 * k + 3 : 0] += fac * v4.w;
+                    }
                 }
                 const float dx = kk.x - (ox + (float)(pp & 3)), dy = kk.y - (by + (float)(pp >> 2));   // exact pixel centre
                 const float t1 = v_sigma * dx, t2 = v_sigma * dy;
@@ -716,7 +750,7 @@ composite_bwd_kernel(int W, int H, int tile_w, const Rec *__restrict__ rec,
                 atomicAdd(v_means2d + 2 * (size_t)g, ca * sx + cb * sy);
                 atomicAdd(v_means2d + 2 * (size_t)g + 1, cb * sx + cc * sy);
                 // d alpha / d opacity = exp(-sigma) = A / opacity, and sum A v_alpha = -s0
-                atomicAdd(v_opacities + g, -s0 / c.w);
+                atomicAdd(v_opacities + g, -s0 / opac);
             }
         }
     }
