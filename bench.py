@@ -540,11 +540,12 @@ def run_b200(a):
                 "alg_bytes_per_launch": alg[dom], "avg_ms": round(dom_ms, 4),
                 "avg_ms_alone": per_kernel[dom]["avg_ms"], "frac_alone": per_kernel[dom]["frac"],
                 "launches_timed": len(live_ms) if live else per_kernel[dom]["calls"],
-                "note": "avg_ms / achieved / frac: CUDA events recorded by the per-view driver around the compositing "
-                        "backward of every view INSIDE the timed region (gsb_view_backward probe), where the kernels of "
-                        "up to three views share the SMs; avg_ms_alone / frac_alone: the same entry point in the "
-                        "instrumented pass (one view at a time).  The composite kernels are FP32/MUFU issue bound, not "
-                        "HBM bound (DESIGN.md section 4): every listed Gaussian is evaluated at 32 pixel centres",
+                "note": "avg_ms / achieved / frac: CUDA events recorded by the batch driver around the compositing "
+                        "backward of every view INSIDE the timed region (gsb_batch_backward probe events), where the "
+                        "kernels of up to four views share the SMs; avg_ms_alone / frac_alone: the same entry point in "
+                        "the instrumented pass (one view at a time).  The kernel is NOT HBM bound (DESIGN.md section 4): "
+                        "every sub-list entry is evaluated at the 16 pixel centres of a 4x4 unit out of shared memory; "
+                        "ncu: L1 / shared-memory data pipe 78-85 % busy, issue 50-56 %, DRAM < 3 %",
                 "pix_gauss_evals_upper_per_launch": 256.0 * M}
 
     out = None
