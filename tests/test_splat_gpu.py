@@ -257,3 +257,36 @@ def test_inplace_update_between_forward_and_backward_is_caught():
         p[0].add_(0.01)
     with pytest.raises(RuntimeError, match="modified by an inplace operation"):
         torch.autograd.grad(sum(i.sum() for i in imgs), p)
+
+
+def test_batch_capacity_survives_a_scene_that_changes_size_every_step():
+    """A trainer's Gaussian count changes a little every step (FlexiCubes re-extraction).  The batch driver keeps its
+    speculative tile-list capacity per SIZE CLASS of the scene (fused._size_class, +-12 %), so only the first batch of a
+    class is probed (waited for); later batches of slightly different N reuse the capacity, stay exact (same images as
+    the per-view path that sizes everything exactly) and never overflow."""
+    from geosplatting_b200 import fused
+    from geosplatting_b200.fused import splat_views
+    cams = scenes.orbit_cameras(3, 200, 160, seed=4)
+    gen = torch.Generator().manual_seed(2)
+    cube = torch.exp(0.5 * torch.randn(6, 64, 64, 3, generator=gen)).clamp_min(1e-2).to(DEV)
+    env = splitsum.as_envstack(cube)
+    lut = torch.from_numpy(synthetic_fg_lut()).to(DEV)
+    ex = torch.ones(1, device=DEV)
+    names = ("means", "scales", "quats", "opacities", "kd", "ks", "normals")
+    sg = scenes.surface_gaussians(21_000, seed=3)
+    full = {"means": sg["means"], "scales": sg["scales"].log(), "quats": sg["quats"],
+            "opacities": torch.logit(sg["opacities"])[:, None], "kd": sg["kd"], "ks": sg["ks"], "normals": sg["normals"]}
+    keys_before = set(fused._caps)
+    classes = set()
+    for n in (20_000, 20_350, 20_100, 21_000):
+        assert fused._size_class(n) == fused._size_class(20_000)
+        t = {k: v[:n].to(DEV).requires_grad_(True) for k, v in full.items()}
+        kw = dict(exposures=ex, envmap=env, fg_lut=lut, min_roughness=0.1, max_metallic=1.0)
+        imgs = splat_views(*[t[k] for k in names], cams, **kw)                       # batch driver (default)
+        ref = splat_views(*[t[k] for k in names], cams, native=True, **kw)           # per-view driver, exact sizes
+        g = torch.autograd.grad(sum(i.sum() for i in imgs), [t["means"]])[0]         # backward checks the counts
+        assert bool(torch.isfinite(g).all())
+        for a, b in zip(imgs, ref):
+            assert torch.equal(a, b)
+        classes |= set(fused._caps) - keys_before
+    assert len(classes) == 1, classes                      # one capacity entry for the four scene sizes
