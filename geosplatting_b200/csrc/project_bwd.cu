@@ -16,12 +16,33 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     if (i >= N) return;
     float vm3[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
     float v_logit = 0.f;
+    {
+        // The VJP is linear in the cotangents.  A Gaussian that was culled, or that no pixel's gradient reached (behind
+        // an opaque surface, off screen: about half of a closed mesh), has nothing to add: leave before touching its
+        // parameters -- in a batch (accumulate) not even its outputs.  (x != 0 is true for NaN: those still propagate.)
+        bool touched = false;
+        if (radii[i] > 0) {
+            const float2 m2 = v_means2d[i];
+            touched = m2.x != 0.f || m2.y != 0.f || v_conics[3 * i] != 0.f || v_conics[3 * i + 1] != 0.f ||
+                      v_conics[3 * i + 2] != 0.f || (v_depths && v_depths[i] != 0.f) || (v_comps && v_comps[i] != 0.f) ||
+                      (v_opacities_eff && v_opacities_eff[i] != 0.f);
+        }
+        if (!touched) {
+            if (!accumulate) {
+                v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
+                reinterpret_cast<float4 *>(v_quats)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
+                if (v_opacity_logits) v_opacity_logits[i] = 0.f;
+            }
+            return;
+        }
+    }
     ProjOut o;
     float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
     float4 q4 = reinterpret_cast<const float4 *>(quats)[i];
     float q[4] = {q4.x, q4.y, q4.z, q4.w};
     float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
-    if (radii[i] > 0 && gsb_project_one<false>(m, q, s, cam, o)) {   // the forward's cull verdict is final
+    if (gsb_project_one<false>(m, q, s, cam, o)) {   // radii > 0 (checked above): the forward's cull verdict is final
         const float fx = cam.fx, fy = cam.fy;
         float a = o.conic[0], b = o.conic[1], c = o.conic[2];
         float va = v_conics[3 * i], vb = 0.5f * v_conics[3 * i + 1], vc = v_conics[3 * i + 2];

@@ -238,13 +238,24 @@ __global__ void __launch_bounds__(256, GSB_SHADE_BWD_MINB) shade_bwd_kernel(int 
                                                          long long hot_begin, long long hot_texels, int accumulate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const float vc0 = v_colors[3 * i], vc1 = v_colors[3 * i + 1], vc2 = v_colors[3 * i + 2];
+    if (vc0 == 0.f && vc1 == 0.f && vc2 == 0.f) {
+        // linear in the colour cotangent: a Gaussian no pixel's gradient reached (culled, occluded -- about half of a
+        // closed mesh) adds nothing; in a batch (accumulate) not even its outputs are touched
+        if (!accumulate) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v_means[3 * i + k] = 0.f; v_normals[3 * i + k] = 0.f; v_kd[3 * i + k] = 0.f; }
+            reinterpret_cast<float2 *>(v_ks)[i] = make_float2(0.f, 0.f);
+        }
+        return;
+    }
     EnvGrad v_env{v_env_stack, replicas ? replicas + 4 * hot_texels * (blockIdx.x % SHADE_REPLICAS) : nullptr, hot_begin};
     float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
     float n[3] = {normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]};
     float k3[3] = {kd[3 * i], kd[3 * i + 1], kd[3 * i + 2]};
     float2 s2 = reinterpret_cast<const float2 *>(ks)[i];
     float k2[2] = {s2.x, s2.y};
-    float vc[3] = {v_colors[3 * i], v_colors[3 * i + 1], v_colors[3 * i + 2]};
+    float vc[3] = {vc0, vc1, vc2};
     float vm[3], vn[3], vkd[3], vks[2];
     ShadeFwd o;
     shade_one<true>(m, n, k3, k2, p, lut, env, o, vc, vm, vn, vkd, vks, v_env);
