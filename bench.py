@@ -343,6 +343,7 @@ def run_b200(a):
         # memory, and that drain (190 MB) is 30 % of a two-batch region but not of a trainer's steady state; the number
         # of views timed is reported as e2e.steps
         n_b = max(6, min(12, a.steps // B))
+        _E2E_DEBUG = os.environ.get("GSB_E2E_DEBUG", "")   # 'noup' / 'nodown': diagnosis only (an e2e without its copies is not an e2e)
         cot_host = [torch.randn(H, W, 4, generator=gen).pin_memory() for _ in range(B)]
         img_host = [[torch.empty(H, W, 4).pin_memory() for _ in range(B)] for _ in range(2)]
         grad_host = [{k: torch.empty_like(host[k]).pin_memory() for k in PARAM_NAMES} for _ in range(2)]
@@ -359,10 +360,11 @@ def run_b200(a):
             b_ = i % 2
             with torch.cuda.stream(s_in):
                 s_in.wait_event(ev_free[b_])            # the compute that last read this buffer set is done
-                for k in PARAM_NAMES:
-                    dev_in[b_][k].copy_(host[k], non_blocking=True)
-                for j in range(B):
-                    dev_cot[b_][j].copy_(cot_host[j], non_blocking=True)
+                if _E2E_DEBUG != "noup":
+                    for k in PARAM_NAMES:
+                        dev_in[b_][k].copy_(host[k], non_blocking=True)
+                    for j in range(B):
+                        dev_cot[b_][j].copy_(cot_host[j], non_blocking=True)
                 ev_in[b_].record(s_in)
 
         def e2e_batch(i):
@@ -384,10 +386,12 @@ def run_b200(a):
                 for j, im in enumerate(imgs):
                     im_d = im.detach()
                     im_d.record_stream(s_out)
-                    img_host[b_][j].copy_(im_d, non_blocking=True)
+                    if _E2E_DEBUG != "nodown":
+                        img_host[b_][j].copy_(im_d, non_blocking=True)
                 for k, gk in zip(PARAM_NAMES, grads):
                     gk.record_stream(s_out)
-                    grad_host[b_][k].copy_(gk, non_blocking=True)
+                    if _E2E_DEBUG != "nodown":
+                        grad_host[b_][k].copy_(gk, non_blocking=True)
                 grads[-1].record_stream(s_out)
                 ex_host.copy_(grads[-1], non_blocking=True)
                 ev_out[b_].record(s_out)
