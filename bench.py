@@ -407,11 +407,20 @@ def run_b200(a):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         gc.collect()
         gc.disable()
+        trace = os.environ.get("GSB_E2E_TRACE")            # diagnosis: chrome trace of the e2e region (slows it down)
+        if trace:
+            from torch.profiler import ProfilerActivity, profile
+            prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+            prof.__enter__()
         s.record()
         for i in range(2, 2 + n_b):
             e2e_batch(i)
         s_cmp.wait_stream(s_out)                          # the last batch's results have landed in host memory
         e.record()
+        if trace:
+            torch.cuda.synchronize()
+            prof.__exit__(None, None, None)
+            prof.export_chrome_trace(trace)
         barrier()
         gc.enable()
         te = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
