@@ -280,11 +280,19 @@ def run_b200(a):
     # CPython's cyclic collector walks every live object when its generation-2 threshold trips (~30 ms with torch
     # loaded): a stop-the-world pause longer than four views.  Nothing in a view creates reference cycles.
     gc.disable()
+    main_trace = os.environ.get("GSB_TRACE")   # diagnosis: chrome trace of the timed region (the profiler slows it down)
+    if main_trace:
+        from torch.profiler import ProfilerActivity, profile
+        main_prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+        main_prof.__enter__()
     t_begin.record()
     run_steps(a.steps, batch_marks)
     wait_collective()                          # the last collective completes inside the timed region
     t_end.record()
     barrier()
+    if main_trace:
+        main_prof.__exit__(None, None, None)
+        main_prof.export_chrome_trace(main_trace)
     gc.enable()
     wall = time.perf_counter() - wall0
     batches = {"views": [m[0] for m in batch_marks], "device_ms": [round(m[1].elapsed_time(m[2]), 3) for m in batch_marks],

@@ -21,6 +21,8 @@
 //
 // Replaces gsplat 1.4.0 rasterize_to_pixels_fwd/bwd (third-party), reached from
 // rfstudio/model/gsplat.py:334-355.  Bound: FP32 / MUFU issue, not HBM.
+#include <stdlib.h>
+
 #include "gsb_common.cuh"
 #include "composite_rec.cuh"
 
@@ -813,7 +815,11 @@ int launch_fwd(int W, int H, int64_t N, const float *means2d, const float *conic
     build_sublists_kernel<<<n_tiles, BUILD_THREADS, 0, st>>>(tw, n_tiles, (int)M, m_dev, offsets, flatten_ids, w.rec,
                                                              w.entries, w.counts, w.tile_len, w.ctrl);
     lpt_order_kernel<<<1, 1024, 0, st>>>(n_tiles, w.tile_len, w.order);
-    composite_fwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB), 32 * WPB, 0, st>>>(
+    // experiment knob: unused dynamic shared memory per CTA caps the forward's residency and leaves registers to the
+    // kernels of other views (GSB_FWD_PAD_KB, read once)
+    static const int pad_kb = getenv("GSB_FWD_PAD_KB") ? atoi(getenv("GSB_FWD_PAD_KB")) : 0;
+    if (pad_kb > 0) cudaFuncSetAttribute(composite_fwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+    composite_fwd_kernel<CH><<<gsb_div_up(n_units / UPW, WPB), 32 * WPB, (size_t)pad_kb * 1024, st>>>(
         W, H, tw, n_units / UPW, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.counts, w.order,
         w.walk, w.ckpt_base, w.ctrl, w.jobs, w.ckpt, render, alphas, last_ids);
     return 0;
@@ -835,7 +841,8 @@ int launch_bwd(int W, int H, int64_t N, const float *colors, const float *backgr
     Workspace w = carve(ws, N, M, n_tiles);
     static const int sms = gsb_sm_count();
     const int64_t want = (int64_t)gsb_div_up((int64_t)job_capacity(M, n_tiles), WPB_B);
-    const int grid = (int)(want < (int64_t)sms * GSB_BWD_CTAS_PER_SM ? want : (int64_t)sms * GSB_BWD_CTAS_PER_SM);
+    static const int per_sm = getenv("GSB_BWD_CTAS") ? atoi(getenv("GSB_BWD_CTAS")) : GSB_BWD_CTAS_PER_SM;   // experiment knob
+    const int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     if (cudaMemsetAsync(w.ctrl + CTRL_CURSOR, 0, sizeof(int32_t), st) != cudaSuccess) return 1;   // a forward may be walked twice
     composite_bwd_kernel<CH><<<grid, 32 * WPB_B, 0, st>>>(
         W, H, tw, w.rec, colors, background, offsets, n_tiles, (int)M, m_dev, w.entries, w.walk, w.ckpt_base, w.ctrl,

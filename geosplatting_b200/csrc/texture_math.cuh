@@ -102,7 +102,8 @@ __device__ __forceinline__ void gsb_cube_weights(const CubeTaps &t, float w[4]) 
     w[2] = (1.f - t.fu) * t.fv;
     w[3] = t.fu * t.fv;
     if (t.missing >= 0) {
-        float wm = w[t.missing] * 0.33333333f;
+        // (selects, not w[t.missing]: a register array indexed by a run-time value lives in local memory)
+        float wm = (t.missing == 0 ? w[0] : t.missing == 1 ? w[1] : t.missing == 2 ? w[2] : w[3]) * 0.33333333f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = (k == t.missing) ? 0.f : w[k] + wm;
     }
@@ -123,29 +124,34 @@ __device__ __forceinline__ float3 gsb_fetch3(const float *__restrict__ tex, int 
 template <int STRIDE, bool WITH_GRAD>
 __device__ __forceinline__ float3 gsb_cube_sample(const float *__restrict__ tex, const CubeTaps &t, float3 *d_fu,
                                                   float3 *d_fv) {
-    float3 a[4];
-    float3 sum = make_float3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (t.idx[k] >= 0) {
-            a[k] = gsb_fetch3<STRIDE>(tex, t.idx[k]);
-            sum.x += a[k].x; sum.y += a[k].y; sum.z += a[k].z;
-        } else {
-            a[k] = make_float3(0.f, 0.f, 0.f);
-        }
-    }
+    // four named texels, not an array: "if (k == t.missing) a[k] = ..." is turned into a run-time indexed store by
+    // the compiler, which puts the whole array into local memory (48 bytes of stack traffic per sample)
+    const float3 zero = make_float3(0.f, 0.f, 0.f);
+    float3 a0 = t.idx[0] >= 0 ? gsb_fetch3<STRIDE>(tex, t.idx[0]) : zero;
+    float3 a1 = t.idx[1] >= 0 ? gsb_fetch3<STRIDE>(tex, t.idx[1]) : zero;
+    float3 a2 = t.idx[2] >= 0 ? gsb_fetch3<STRIDE>(tex, t.idx[2]) : zero;
+    float3 a3 = t.idx[3] >= 0 ? gsb_fetch3<STRIDE>(tex, t.idx[3]) : zero;
     if (t.missing >= 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (k == t.missing) a[k] = make_float3(sum.x * 0.33333333f, sum.y * 0.33333333f, sum.z * 0.33333333f);
+        // same order of additions as a loop over k = 0..3 that skips the missing tap
+        float3 sum = zero;
+        if (t.idx[0] >= 0) { sum.x += a0.x; sum.y += a0.y; sum.z += a0.z; }
+        if (t.idx[1] >= 0) { sum.x += a1.x; sum.y += a1.y; sum.z += a1.z; }
+        if (t.idx[2] >= 0) { sum.x += a2.x; sum.y += a2.y; sum.z += a2.z; }
+        if (t.idx[3] >= 0) { sum.x += a3.x; sum.y += a3.y; sum.z += a3.z; }
+        const float3 third = make_float3(sum.x * 0.33333333f, sum.y * 0.33333333f, sum.z * 0.33333333f);
+        const int ms = t.missing;
+        a0 = ms == 0 ? third : a0;
+        a1 = ms == 1 ? third : a1;
+        a2 = ms == 2 ? third : a2;
+        a3 = ms == 3 ? third : a3;
     }
     float fu = t.fu, fv = t.fv;
-    float3 top = make_float3(a[0].x + (a[1].x - a[0].x) * fu, a[0].y + (a[1].y - a[0].y) * fu, a[0].z + (a[1].z - a[0].z) * fu);
-    float3 bot = make_float3(a[2].x + (a[3].x - a[2].x) * fu, a[2].y + (a[3].y - a[2].y) * fu, a[2].z + (a[3].z - a[2].z) * fu);
+    float3 top = make_float3(a0.x + (a1.x - a0.x) * fu, a0.y + (a1.y - a0.y) * fu, a0.z + (a1.z - a0.z) * fu);
+    float3 bot = make_float3(a2.x + (a3.x - a2.x) * fu, a2.y + (a3.y - a2.y) * fu, a2.z + (a3.z - a2.z) * fu);
     if (WITH_GRAD) {
-        *d_fu = make_float3((a[1].x - a[0].x) * (1.f - fv) + (a[3].x - a[2].x) * fv,
-                            (a[1].y - a[0].y) * (1.f - fv) + (a[3].y - a[2].y) * fv,
-                            (a[1].z - a[0].z) * (1.f - fv) + (a[3].z - a[2].z) * fv);
+        *d_fu = make_float3((a1.x - a0.x) * (1.f - fv) + (a3.x - a2.x) * fv,
+                            (a1.y - a0.y) * (1.f - fv) + (a3.y - a2.y) * fv,
+                            (a1.z - a0.z) * (1.f - fv) + (a3.z - a2.z) * fv);
         *d_fv = make_float3(bot.x - top.x, bot.y - top.y, bot.z - top.z);
     }
     return make_float3(top.x + (bot.x - top.x) * fv, top.y + (bot.y - top.y) * fv, top.z + (bot.z - top.z) * fv);
@@ -174,20 +180,23 @@ __device__ __forceinline__ void gsb_cube_scatter(float *__restrict__ v_tex, cons
 // Chain (v_fu, v_fv) (cotangents of the fractional texel coordinates) back to the direction.
 __device__ __forceinline__ void gsb_cube_dir_grad(const CubeUV &q, float x, float y, float z, int R, float v_fu,
                                                   float v_fv, float v_dir[3]) {
-    float d[3] = {x, y, z};
-    float c = d[q.ic], a = d[q.ia], b = d[q.ib];
+    // (ia, ib, ic) is one of (2,1,0), (0,2,1), (0,1,2): selects instead of run-time indexed arrays (local memory)
+    float c = q.ic == 0 ? x : (q.ic == 1 ? y : z);
+    float a = q.ia == 0 ? x : z;
+    float b = q.ib == 1 ? y : z;
     float ac = fabsf(c);
     float m = 0.5f / ac;
     float Rf = (float)R;
     // clamp(u,0,1): zero gradient when saturated (ties only)
     float gu = (q.u > 0.f && q.u < 1.f) ? v_fu * Rf : 0.f;
     float gv = (q.v > 0.f && q.v < 1.f) ? v_fv * Rf : 0.f;
-    v_dir[0] = v_dir[1] = v_dir[2] = 0.f;
-    v_dir[q.ia] += gu * q.su * m;
-    v_dir[q.ib] += gv * q.sv * m;
     // d(1/|c|)/dc = -sign(c)/c^2
     float dm = -0.5f * ((c < 0.f) ? -1.f : 1.f) / (c * c);
-    v_dir[q.ic] += (gu * q.su * a + gv * q.sv * b) * dm;
+    const float ga = gu * q.su * m, gb = gv * q.sv * m, gc = (gu * q.su * a + gv * q.sv * b) * dm;
+    // the three indices are distinct: every component receives exactly one of the three terms
+    v_dir[0] = q.ia == 0 ? ga : gc;                            // ia is 0 or 2; when it is 2, ic is 0
+    v_dir[1] = q.ib == 1 ? gb : gc;                            // ib is 1 or 2; when it is 2, ic is 1
+    v_dir[2] = q.ic == 2 ? gc : (q.ia == 2 ? ga : gb);
 }
 
 // ---- 2D bilinear, clamp-to-edge (FG LUT: [H,W,2], u -> column, v -> row) -------------------------------
