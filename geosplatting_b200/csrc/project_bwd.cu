@@ -16,10 +16,16 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
     if (i >= N) return;
     float vm3[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
     float v_logit = 0.f;
+    ProjOut o;
+    float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
+    float4 q4 = reinterpret_cast<const float4 *>(quats)[i];
+    float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
     {
         // The VJP is linear in the cotangents.  A Gaussian that was culled, or that no pixel's gradient reached (behind
-        // an opaque surface, off screen: about half of a closed mesh), has nothing to add: leave before touching its
-        // parameters -- in a batch (accumulate) not even its outputs.  (x != 0 is true for NaN: those still propagate.)
+        // an opaque surface, off screen: about half of a closed mesh), has nothing to add: leave before the arithmetic --
+        // in a batch (accumulate) also before its outputs are read and rewritten.  (Its parameters were requested above
+        // together with the cotangents: one round trip to memory, not two.)  (x != 0 is true for NaN: those still propagate.)
         bool touched = false;
         if (radii[i] > 0) {
             const float2 m2 = v_means2d[i];
@@ -37,11 +43,6 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(
             return;
         }
     }
-    ProjOut o;
-    float m[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
-    float4 q4 = reinterpret_cast<const float4 *>(quats)[i];
-    float q[4] = {q4.x, q4.y, q4.z, q4.w};
-    float s[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
     if (gsb_project_one<false>(m, q, s, cam, o)) {   // radii > 0 (checked above): the forward's cull verdict is final
         const float fx = cam.fx, fy = cam.fy;
         float a = o.conic[0], b = o.conic[1], c = o.conic[2];

@@ -231,6 +231,13 @@ struct EnvStack {
     const float *data;  // float4 texels
     int R0, L, Rb;
     __host__ __device__ __forceinline__ long long level_offset(int l) const {  // in texels
+        // sum over k < l of 6 (R0 >> k)^2.  A power-of-two R0 whose levels stay >= 1 texel has the closed form
+        // 8 (R0^2 - (R0 >> l)^2): the shade kernels ask for three offsets per Gaussian, and the loop was 64-bit
+        // arithmetic per level each time.
+        if ((R0 & (R0 - 1)) == 0 && (R0 >> l) >= 1) {
+            const long long r0 = R0, rl = R0 >> l;
+            return 8 * (r0 * r0 - rl * rl);
+        }
         long long o = 0;
         for (int k = 0; k < l; ++k) { long long r = R0 >> k; o += 6 * r * r; }
         return o;
