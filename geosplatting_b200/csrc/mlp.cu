@@ -233,8 +233,11 @@ __global__ void __launch_bounds__(32 * FWD_WARPS) mlp_fwd_kernel(int64_t N, cons
             const int p = lane + 32 * half;
             float z[4];
             output_layer(h, sw.woutT, p, z);
-            if (n0 + p < N)
-                for (int o = 0; o < dout; ++o) y[(n0 + p) * dout + o] = activate(z[o], act);
+            if (n0 + p < N) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o)       // static indices: z[] stays in registers
+                    if (o < dout) y[(n0 + p) * dout + o] = activate(z[o], act);
+            }
         }
     }
 }
@@ -312,13 +315,16 @@ __global__ void __launch_bounds__(32 * BWD_WARPS) mlp_bwd_kernel(int64_t N, cons
             const bool live = n0 + p < N;
             float z[4], dz[4] = {0.f, 0.f, 0.f, 0.f};
             output_layer(t_c, sw.woutT, p, z);
-            for (int o = 0; o < dout; ++o) {
-                const float g = live ? v_y[(n0 + p) * dout + o] : 0.f;
-                if (act == 1) {
-                    const float yv = 1.0f / (1.0f + expf(-z[o]));
-                    dz[o] = g * yv * (1.0f - yv);
-                } else {
-                    dz[o] = g;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {         // static indices: z[] / dz[] stay in registers
+                if (o < dout) {
+                    const float g = live ? v_y[(n0 + p) * dout + o] : 0.f;
+                    if (act == 1) {
+                        const float yv = 1.0f / (1.0f + expf(-z[o]));
+                        dz[o] = g * yv * (1.0f - yv);
+                    } else {
+                        dz[o] = g;
+                    }
                 }
             }
             *reinterpret_cast<float4 *>(t_dz + 4 * p) = make_float4(dz[0], dz[1], dz[2], dz[3]);
@@ -392,7 +398,9 @@ __global__ void __launch_bounds__(32 * BWD_WARPS) mlp_bwd_kernel(int64_t N, cons
 #pragma unroll
             for (int b = 0; b < 8; ++b) atomicAdd(v_w1 + (i0 + a) * D + jg + 4 * b, acc1[a][b]);
     }
-    for (int o = 0; o < dout; ++o) atomicAdd(v_wout + o * D + lane, accout[o]);
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (o < dout) atomicAdd(v_wout + o * D + lane, accout[o]);
 }
 
 int check(int64_t N, int32_t n_hidden, int32_t dout, int32_t act) {
