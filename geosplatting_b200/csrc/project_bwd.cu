@@ -5,7 +5,10 @@
 // through autograd from rfstudio/model/gsplat.py:334-355.
 #include "project_math.cuh"
 
-__global__ void __launch_bounds__(256) project_bwd_kernel(
+#ifndef GSB_PROJECT_BWD_MINB
+#define GSB_PROJECT_BWD_MINB 5   // 48 registers: the kernel waits for memory (long scoreboard), 0.056 -> 0.046 ms with 40 resident warps
+#endif
+__global__ void __launch_bounds__(256, GSB_PROJECT_BWD_MINB) project_bwd_kernel(
     int N, const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
     CamK cam, const int32_t *__restrict__ radii, const float2 *__restrict__ v_means2d,
     const float *__restrict__ v_depths, const float *__restrict__ v_conics, const float *__restrict__ v_comps,
