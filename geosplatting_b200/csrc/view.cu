@@ -14,6 +14,8 @@
 //   tmp2  : flatten_ids[M] i32 | sort scratch                                       finish only
 //   tmp3  : v_render[P,3] | v_alphas[P] | v_means2d[N,2] v_conics[N,3] v_colors[N,3] v_opacities[N] | shade replicas
 //                                                                                   backward only
+#include <stdlib.h>
+
 #include "gsb_common.cuh"
 
 // internal entry points with a device-resident intersection count (composite.cu, binsort.cu)
@@ -23,6 +25,10 @@ int gsb_composite_fwd_impl(int32_t width, int32_t height, int32_t channels, int6
                            const int32_t *flatten_ids, int64_t M, const int64_t *m_dev, float *render, float *alphas,
                            int32_t *last_ids, void *workspace, size_t workspace_bytes_, int32_t prepacked, void *stream);
 void *gsb_composite_records(void *workspace);
+extern "C" int gsb_tile_partition_supported(int n_tiles);
+extern "C" int gsb_tile_partition_cap(int32_t N, int64_t cap, const int64_t *m_eff, const float *means2d, const int32_t *radii,
+                           const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam, int32_t *flatten_ids,
+                           int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream);
 int gsb_shade_fwd_impl(int32_t N, const float *means, const float *normals, const float *kd, const float *ks,
                        const float *cam_pos_host, const float *fg_lut, int32_t lut_res, const float *env_stack, int32_t R0,
                        int32_t L, int32_t Rb, float min_roughness, float max_metallic, float env_min_roughness,
@@ -352,8 +358,13 @@ GSB_API int gsb_batch_forward(const gsb_view_config *cfg, int32_t n_views, const
                                     t1.conics, opacity_logits, cam->antialiased ? t1.comps : nullptr,
                                     gsb_composite_records(k2.comp_ws), st));
         // ---- finish: binning on the capacity, compositing, tone map
-        VIEW_TRY(gsb_bin2_sort_cap(cfg->N, m_cap, k1.m_eff, t1.means2d, k1.radii, t1.order, t1.cum, cam, flatten_ids,
-                                   k2.offsets, sort_scratch, b.v.bin_m, st));
+        // stable partition by tile in one pass where the image has at most 4096 tiles (tilepart.cu), else the radix sort
+        if (gsb_tile_partition_supported((int)T) && !getenv("GSB_BIN2_RADIX"))
+            VIEW_TRY(gsb_tile_partition_cap(cfg->N, m_cap, k1.m_eff, t1.means2d, k1.radii, t1.order, t1.cum, cam,
+                                            flatten_ids, k2.offsets, sort_scratch, b.v.bin_m, st));
+        else
+            VIEW_TRY(gsb_bin2_sort_cap(cfg->N, m_cap, k1.m_eff, t1.means2d, k1.radii, t1.order, t1.cum, cam, flatten_ids,
+                                       k2.offsets, sort_scratch, b.v.bin_m, st));
         VIEW_TRY(gsb_composite_fwd_impl(cfg->width, cfg->height, 3, cfg->N, t1.means2d, t1.conics, k1.colors,
                                         opacity_logits, 1, cam->antialiased ? t1.comps : nullptr, nullptr, k2.offsets,
                                         flatten_ids, m_cap, k1.m_eff, k2.render, k2.alphas, k2.last_ids, k2.comp_ws,

@@ -151,3 +151,43 @@ def test_bin_indices_are_bit_exact_on_the_host(libs, binlib, res, n, kw):
     assert np.array_equal(keys_s, o_keys) and np.array_equal(vals_s, o_vals) and np.array_equal(off1, o_off.reshape(-1))
     assert np.array_equal(flat2, o_vals) and np.array_equal(off2, o_off.reshape(-1))
     assert flat2.size == int(o_tpg.sum())
+
+
+@pytest.mark.parametrize("res,n,kw,slack", [((256, 256), 10_000, {}, 1.3), ((320, 200), 6000, dict(extent=3.5, scale_hi=1.2), 1.0),
+                                            ((16, 16), 50, {}, 2.0), ((64, 48), 1, {}, 1.0)])
+def test_stable_tile_partition_equals_the_sort_on_the_host(res, n, kw, slack):
+    """csrc/tilepart.cu (the batch driver's second binning stage: a stable partition of the depth-ordered pairs by tile
+    -- chunk histograms, a scan, a warp-ranked scatter -- instead of a radix sort) against the radix-sort path
+    gsb_bin2_sort on the same depth order: flatten_ids and per-tile offsets identical.  Several chunks of 16 384 pairs
+    (big splats), a capacity larger than the count (the tail is never touched), one tile, one Gaussian."""
+    lib = emu.build("project_fwd", "binsort", "tilepart", simt=True)
+    g, cam = _scene(n, res, seed=9, **kw)
+    gc, radii, means2d, depths, conics, comps, tpg = _project(lib, g, cam, True)
+    N = radii.shape[0]
+    tw, th = (gc.width + 15) // 16, (gc.height + 15) // 16
+    i32, i64, sz = C.c_int32, C.c_int64, C.c_size_t
+    nb = sz(0)
+    assert lib.gsb_bin2_workspace_bytes(i32(N), i64(0), C.byref(nb)) == 0
+    ws = np.full(nb.value, 0xFF, np.uint8)
+    order, cum, total = np.zeros(N, np.int32), np.zeros(N, np.int64), np.zeros(1, np.int64)
+    assert lib.gsb_bin2_count(i32(N), _p(depths), _p(tpg), _p(order), _p(cum), _p(total), _p(ws), sz(ws.size), None) == 0
+    M = int(total[0])
+    assert lib.gsb_bin2_workspace_bytes(i32(0), i64(max(M, 1)), C.byref(nb)) == 0
+    ws = np.full(nb.value, 0xFF, np.uint8)
+    flat_ref, off_ref = np.zeros(M, np.int32), np.zeros(tw * th, np.int32)
+    assert lib.gsb_bin2_sort(i32(N), i64(M), _p(means2d), _p(radii), _p(order), _p(cum), C.byref(gc), _p(flat_ref),
+                             _p(off_ref), _p(ws), sz(ws.size), None) == 0, lib.gsb_last_error()
+    cap = int(M * slack) + 7
+    lib.gsb_tile_partition_bytes.restype = C.c_size_t
+    need = lib.gsb_tile_partition_bytes(i64(cap), i32(tw * th))
+    ws2 = np.full(need + 256, 0xFF, np.uint8)
+    m_eff = np.asarray([min(M, cap)], np.int64)
+    flat, off = np.full(cap, -7, np.int32), np.full(tw * th, -7, np.int32)
+    assert lib.gsb_tile_partition_supported(i32(tw * th)) == 1
+    assert lib.gsb_tile_partition_cap(i32(N), i64(cap), _p(m_eff), _p(means2d), _p(radii), _p(order), _p(cum), C.byref(gc),
+                                      _p(flat), _p(off), _p(ws2), sz(ws2.size), None) == 0, lib.gsb_last_error()
+    assert np.array_equal(off, off_ref)
+    assert np.array_equal(flat[:M], flat_ref)
+    assert (flat[M:] == -7).all()                       # nothing behind the count was written
+    if n >= 6000:
+        assert M > 2 * 16384                            # the scatter really ran over several chunks
