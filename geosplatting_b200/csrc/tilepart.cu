@@ -26,13 +26,16 @@ int gsb_isect_tiles_ordered_cap(int32_t N, const float *means2d, const int32_t *
 
 namespace {
 
-constexpr int TP_CHUNK = 16384;                 // pairs per chunk
+#ifndef GSB_TP_CHUNK
+#define GSB_TP_CHUNK 16384
+#endif
+constexpr int TP_CHUNK = GSB_TP_CHUNK;          // pairs per chunk
 constexpr int TP_THREADS = 512, TP_WARPS = TP_THREADS / 32;
 constexpr int TP_SLICE = TP_CHUNK / TP_WARPS;   // consecutive pairs owned by one warp
 constexpr int TP_ROUNDS = TP_SLICE / 32;
 constexpr int TP_MAX_TILES = 4096;
 constexpr int TP_TILE_BITS = 12;
-static_assert(TP_ROUNDS == 32 && (1 << TP_TILE_BITS) == TP_MAX_TILES, "tilepart shape");
+static_assert((TP_ROUNDS == 32 || TP_ROUNDS == 16) && (1 << TP_TILE_BITS) == TP_MAX_TILES, "tilepart shape");
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -44,8 +47,18 @@ __global__ void __launch_bounds__(TP_THREADS) tile_count_kernel(const int64_t *_
     if (c0 >= M) return;
     for (int t = threadIdx.x; t < n_tiles; t += TP_THREADS) tp_smem[t] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < TP_CHUNK; i += TP_THREADS)
-        if (c0 + i < M) atomicAdd(&tp_smem[keys[c0 + i]], 1u);
+    // eight independent loads in flight per thread, then their eight shared-memory atomics
+    for (int i0 = threadIdx.x; i0 < TP_CHUNK; i0 += 8 * TP_THREADS) {
+        uint32_t k[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t idx = c0 + i0 + j * TP_THREADS;
+            k[j] = idx < M ? keys[idx] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (k[j] != 0xffffffffu) atomicAdd(&tp_smem[k[j]], 1u);
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles; t += TP_THREADS) H[(size_t)blockIdx.x * n_tiles + t] = tp_smem[t];
 }
@@ -133,7 +146,8 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
     const int64_t M = *m_eff, c0 = (int64_t)blockIdx.x * TP_CHUNK;
     if (c0 >= M) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < TP_WARPS * n_tiles; i += TP_THREADS) cnt[i] = 0;
+    for (int i = tid; i < TP_WARPS * n_tiles / 2 + 1; i += TP_THREADS)      // 32-bit stores (n_tiles * 16 warps is even)
+        if (2 * i < TP_WARPS * n_tiles) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
     for (int t = tid; t < n_tiles; t += TP_THREADS)
         base32[t] = (uint32_t)offsets[t] + Hx[(size_t)blockIdx.x * n_tiles + t];
     __syncthreads();
@@ -141,11 +155,19 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
     const int64_t s0 = c0 + (int64_t)warp * TP_SLICE;
     const unsigned lt = (1u << lane) - 1u;
     uint32_t rank[TP_ROUNDS];
+    uint32_t kbuf[16];                         // the keys of 16 rounds at a time: loads in flight instead of one per round
 #pragma unroll
     for (int r = 0; r < TP_ROUNDS; ++r) {
+        if ((r & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int64_t ix = s0 + (r + j) * 32 + lane;
+                kbuf[j] = ix < M ? keys[ix] : 0u;
+            }
+        }
         const int64_t idx = s0 + r * 32 + lane;
         const bool valid = idx < M;
-        const uint32_t key = valid ? keys[idx] : 0u;
+        const uint32_t key = kbuf[r & 15];
         // the lanes that hold my tile (match.any written with ballots: the host build of this file has no match)
         unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
