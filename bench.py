@@ -587,6 +587,11 @@ def run_b200(a):
                                        f"gradient buffer" if world > 1 else "")},
             "sequential_ms_per_view": round(seq_ms / a.steps, 4), "batches": batches,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
+            "kernels_note": "instrumented pass: one view at a time on one stream through the per-view operators, every "
+                            "C-ABI entry point bracketed by CUDA events.  Two differences from the timed batch path: its "
+                            "second binning stage is the radix sort (gsb_bin2_sort) where the batch driver runs the "
+                            "one-pass tile partition (csrc/tilepart.cu, ~0.08 ms instead of ~0.115), and it packs the "
+                            "compositing records in gsb_composite_fwd where the batch driver's shade forward writes them",
             "wall_s_timed_region": round(wall, 3), "impl": "b200",
         }
         if full:
