@@ -16,8 +16,9 @@
 //                     over the 16 warps' counters orders the slices -- and gid goes to
 //                     offsets[tile] + H[chunk][tile] + prefix[warp][tile] + rank.
 // Only the m_eff pairs that exist are touched (the count stays on the device): no sentinel fill, no capacity-sized
-// passes.  Needs n_tiles <= 4096 (16 warps x n_tiles 16-bit counters + n_tiles bases in shared memory: 147 KB);
-// larger images keep the radix sort.
+// passes.  The scatter kernel's shape follows the image: 16 / 8 / 4 warps per CTA for up to 4096 / 10 240 / 16 384
+// tiles (W warps x n_tiles 16-bit counters + n_tiles bases in shared memory, at most 205 KB); larger images keep the
+// radix sort.
 #include "gsb_common.cuh"
 
 int gsb_isect_tiles_ordered_cap(int32_t N, const float *means2d, const int32_t *radii, const int32_t *order,
@@ -26,29 +27,36 @@ int gsb_isect_tiles_ordered_cap(int32_t N, const float *means2d, const int32_t *
 
 namespace {
 
-#ifndef GSB_TP_CHUNK
-#define GSB_TP_CHUNK 16384
-#endif
-constexpr int TP_CHUNK = GSB_TP_CHUNK;          // pairs per chunk
-constexpr int TP_THREADS = 512, TP_WARPS = TP_THREADS / 32;
-constexpr int TP_SLICE = TP_CHUNK / TP_WARPS;   // consecutive pairs owned by one warp
+constexpr int TP_SLICE = 1024;                  // consecutive pairs owned by one warp of the scatter kernel
 constexpr int TP_ROUNDS = TP_SLICE / 32;
-constexpr int TP_MAX_TILES = 4096;
-constexpr int TP_TILE_BITS = 12;
-static_assert((TP_ROUNDS == 32 || TP_ROUNDS == 16) && (1 << TP_TILE_BITS) == TP_MAX_TILES, "tilepart shape");
+constexpr int TP_THREADS = 512;                 // histogram / offsets kernels
+constexpr int TP_MAX_TILES = 16384;
+// Shape of the scatter kernel by image size: W warps per CTA, a chunk = W slices, (4 + 2 W) bytes of shared memory per tile.
+//   n_tiles <= 4096 : 16 warps, 16 384-pair chunks, 12 key bits (147 KB at 4096 tiles)
+//   n_tiles <= 10240:  8 warps,  8 192-pair chunks, 14 key bits (205 KB at 10 240 tiles; 1600 x 1600 has 10 000)
+//   n_tiles <= 16384:  4 warps,  4 096-pair chunks, 14 key bits (197 KB)
+struct TpShape {
+    int warps, bits;
+    int chunk() const { return warps * TP_SLICE; }
+};
+TpShape tp_shape(int n_tiles) {
+    if (n_tiles <= 4096) return {16, 12};
+    if (n_tiles <= 10240) return {8, 14};
+    return {4, 14};
+}
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 __global__ void __launch_bounds__(TP_THREADS) tile_count_kernel(const int64_t *__restrict__ m_eff,
-                                                                 const uint32_t *__restrict__ keys, int n_tiles,
+                                                                 const uint32_t *__restrict__ keys, int n_tiles, int chunk,
                                                                  uint32_t *__restrict__ H) {
     extern __shared__ uint32_t tp_smem[];
-    const int64_t M = *m_eff, c0 = (int64_t)blockIdx.x * TP_CHUNK;
+    const int64_t M = *m_eff, c0 = (int64_t)blockIdx.x * chunk;
     if (c0 >= M) return;
     for (int t = threadIdx.x; t < n_tiles; t += TP_THREADS) tp_smem[t] = 0u;
     __syncthreads();
     // eight independent loads in flight per thread, then their eight shared-memory atomics
-    for (int i0 = threadIdx.x; i0 < TP_CHUNK; i0 += 8 * TP_THREADS) {
+    for (int i0 = threadIdx.x; i0 < chunk; i0 += 8 * TP_THREADS) {
         uint32_t k[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -68,14 +76,14 @@ __global__ void __launch_bounds__(TP_THREADS) tile_count_kernel(const int64_t *_
 // eighths before it (two coalesced sweeps over H, 8 x the threads of one thread per tile).  Separate input and output
 // arrays keep the loads of the unrolled loops independent of the stores.
 constexpr int TPX = 64, TPY = 8;
-__global__ void __launch_bounds__(TPX * TPY) tile_prefix_kernel(const int64_t *__restrict__ m_eff, int n_tiles,
+__global__ void __launch_bounds__(TPX * TPY) tile_prefix_kernel(const int64_t *__restrict__ m_eff, int n_tiles, int chunk,
                                                                  const uint32_t *__restrict__ H, uint32_t *__restrict__ Hx,
                                                                  uint32_t *__restrict__ totals) {
     __shared__ uint32_t part[TPY][TPX];
     const int x = threadIdx.x % TPX, y = threadIdx.x / TPX;
     const int t = blockIdx.x * TPX + x;
     const int64_t M = *m_eff;
-    const int n_chunks = (int)((M + TP_CHUNK - 1) / TP_CHUNK);
+    const int n_chunks = (int)((M + chunk - 1) / chunk);
     const int per = (n_chunks + TPY - 1) / TPY, c_lo = min(y * per, n_chunks), c_hi = min(c_lo + per, n_chunks);
     uint32_t sum = 0u;
     if (t < n_tiles) {
@@ -97,44 +105,52 @@ __global__ void __launch_bounds__(TPX * TPY) tile_prefix_kernel(const int64_t *_
     }
 }
 
-// isect_offsets = exclusive scan of the tiles' totals (n_tiles <= 4096 values): one CTA, thread tid scans tiles
-// 8 tid .. 8 tid + 7 from a coalesced copy in shared memory.
+// isect_offsets = exclusive scan of the tiles' totals: one CTA, 4096 tiles at a time (thread tid scans tiles
+// 8 tid .. 8 tid + 7 of the group from a coalesced copy in shared memory), a carry between the groups.
 __global__ void __launch_bounds__(TP_THREADS) tile_offsets_kernel(int n_tiles, const uint32_t *__restrict__ totals,
                                                                    int32_t *__restrict__ offsets) {
-    __shared__ uint32_t stage[TP_MAX_TILES];
-    __shared__ uint32_t warp_tot[TP_WARPS];
-    constexpr int PER = TP_MAX_TILES / TP_THREADS;
+    constexpr int GROUP = 4096, PER = GROUP / TP_THREADS, NW = TP_THREADS / 32;
+    __shared__ uint32_t stage[GROUP];
+    __shared__ uint32_t warp_tot[NW];
+    __shared__ uint32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int t = tid; t < n_tiles; t += TP_THREADS) stage[t] = totals[t];
-    __syncthreads();
-    uint32_t v[PER], sum = 0u;
+    if (tid == 0) carry = 0u;
+    for (int g0 = 0; g0 < n_tiles; g0 += GROUP) {
+        const int n = min(GROUP, n_tiles - g0);
+        __syncthreads();                      // carry written, stage free
+        for (int t = tid; t < n; t += TP_THREADS) stage[t] = totals[g0 + t];
+        __syncthreads();
+        uint32_t v[PER], sum = 0u;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int t = tid * PER + k;
-        v[k] = t < n_tiles ? stage[t] : 0u;
-        sum += v[k];
-    }
-    uint32_t incl = sum;
+        for (int k = 0; k < PER; ++k) {
+            const int t = tid * PER + k;
+            v[k] = t < n ? stage[t] : 0u;
+            sum += v[k];
+        }
+        uint32_t incl = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t before = incl - sum;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t before = carry + incl - sum;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int t = tid * PER + k;
-        if (t < n_tiles) stage[t] = before;
-        before += v[k];
+        for (int k = 0; k < PER; ++k) {
+            const int t = tid * PER + k;
+            if (t < n) stage[t] = before;
+            before += v[k];
+        }
+        __syncthreads();                      // every thread has read the carry
+        if (tid == TP_THREADS - 1) carry = before;
+        for (int t = tid; t < n; t += TP_THREADS) offsets[g0 + t] = (int32_t)stage[t];
     }
-    __syncthreads();
-    for (int t = tid; t < n_tiles; t += TP_THREADS) offsets[t] = (int32_t)stage[t];
 }
 
-__global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t *__restrict__ m_eff,
+template <int WARPS, int BITS>
+__global__ void __launch_bounds__(32 * WARPS) tile_scatter_kernel(const int64_t *__restrict__ m_eff,
                                                                    const uint32_t *__restrict__ keys,
                                                                    const int32_t *__restrict__ gids, int n_tiles,
                                                                    const uint32_t *__restrict__ Hx,
@@ -142,13 +158,14 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
                                                                    int32_t *__restrict__ flatten_ids) {
     extern __shared__ uint32_t tp_smem[];
     uint32_t *const base32 = tp_smem;                                                // [n_tiles]
-    uint16_t *const cnt = reinterpret_cast<uint16_t *>(tp_smem + n_tiles);          // [TP_WARPS][n_tiles]
-    const int64_t M = *m_eff, c0 = (int64_t)blockIdx.x * TP_CHUNK;
+    uint16_t *const cnt = reinterpret_cast<uint16_t *>(tp_smem + n_tiles);          // [WARPS][n_tiles]
+    constexpr int THREADS = 32 * WARPS;
+    const int64_t M = *m_eff, c0 = (int64_t)blockIdx.x * (WARPS * TP_SLICE);
     if (c0 >= M) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < TP_WARPS * n_tiles / 2 + 1; i += TP_THREADS)      // 32-bit stores (n_tiles * 16 warps is even)
-        if (2 * i < TP_WARPS * n_tiles) reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
-    for (int t = tid; t < n_tiles; t += TP_THREADS)
+    for (int i = tid; i < WARPS * n_tiles / 2; i += THREADS)                // 32-bit stores (WARPS is even)
+        reinterpret_cast<uint32_t *>(cnt)[i] = 0u;
+    for (int t = tid; t < n_tiles; t += THREADS)
         base32[t] = (uint32_t)offsets[t] + Hx[(size_t)blockIdx.x * n_tiles + t];
     __syncthreads();
     uint16_t *const mine = cnt + (size_t)warp * n_tiles;
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
         // the lanes that hold my tile (match.any written with ballots: the host build of this file has no match)
         unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-        for (int b = 0; b < TP_TILE_BITS; ++b) {
+        for (int b = 0; b < BITS; ++b) {
             const unsigned bal = __ballot_sync(0xffffffffu, (key >> b) & 1u);
             peers &= ((key >> b) & 1u) ? bal : ~bal;
         }
@@ -187,10 +204,10 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
     }
     __syncthreads();
     // exclusive prefix of the 16 warps' counts per tile (fits 16 bits: a chunk has 16 384 pairs)
-    for (int t = tid; t < n_tiles; t += TP_THREADS) {
+    for (int t = tid; t < n_tiles; t += THREADS) {
         uint32_t run = 0u;
 #pragma unroll
-        for (int w = 0; w < TP_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t v = cnt[(size_t)w * n_tiles + t];
             cnt[(size_t)w * n_tiles + t] = (uint16_t)run;
             run += v;
@@ -210,15 +227,30 @@ __global__ void __launch_bounds__(TP_THREADS) tile_scatter_kernel(const int64_t 
 }  // namespace
 
 // (C linkage so that the host-build tests can call them; hidden in the product library, which exports the header only)
-// Bytes of scratch gsb_tile_partition_cap needs for `cap` pairs: keys | gids | H.
+// Bytes of scratch gsb_tile_partition_cap needs for `cap` pairs: keys | gids | H | Hx | totals.
 extern "C" size_t gsb_tile_partition_bytes(int64_t cap, int n_tiles) {
-    const size_t n_chunks = (size_t)((cap + TP_CHUNK - 1) / TP_CHUNK);
+    const int chunk = tp_shape(n_tiles).chunk();
+    const size_t n_chunks = (size_t)((cap + chunk - 1) / chunk);
     return 2 * align256(sizeof(uint32_t) * (size_t)cap) + 2 * align256(sizeof(uint32_t) * n_chunks * (size_t)n_tiles) +
            align256(sizeof(uint32_t) * (size_t)n_tiles) + 256;
 }
 
-// 1 when the partition path can take an image of n_tiles tiles.
-extern "C" int gsb_tile_partition_supported(int n_tiles) { return n_tiles >= 1 && n_tiles <= TP_MAX_TILES; }
+// 1 when the batch driver should take the partition path for an image of n_tiles tiles.  The kernels work up to 16 384
+// tiles, but the chunk-by-tile histogram matrix grows with both: at 1600 x 1600 with 5 M Gaussians (10 000 tiles, 12 M
+// pairs in 1 500 chunks: 2 x 60 MB of H) the partition LOSES to the radix sort (281 against 299 views/s); at 800 x 800 it
+// wins (2 500 tiles: +3.5 % at 1 M Gaussians, +3 % at 2 M).
+extern "C" int gsb_tile_partition_supported(int n_tiles) { return n_tiles >= 1 && n_tiles <= 4096; }
+
+namespace {
+template <int WARPS, int BITS>
+int launch_scatter(int n_chunks, const int64_t *m_eff, const uint32_t *keys, const int32_t *gids, int n_tiles,
+                   const uint32_t *Hx, const int32_t *offsets, int32_t *flatten_ids, cudaStream_t st) {
+    const size_t smem = sizeof(uint32_t) * (size_t)n_tiles + sizeof(uint16_t) * (size_t)WARPS * n_tiles;
+    GSB_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel<WARPS, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tile_scatter_kernel<WARPS, BITS><<<n_chunks, 32 * WARPS, smem, st>>>(m_eff, keys, gids, n_tiles, Hx, offsets, flatten_ids);
+    return GSB_OK;
+}
+}  // namespace
 
 // Same contract as gsb_bin2_sort_cap (binsort.cu): emission in depth order (guarded by the capacity), then
 // flatten_ids = the pairs' Gaussian ids grouped by tile in emission order, offsets = first pair of every tile.
@@ -229,7 +261,7 @@ extern "C" int gsb_tile_partition_cap(int32_t N, int64_t cap, const int64_t *m_e
     cudaStream_t st = (cudaStream_t)stream;
     const int tile_w = (cam->width + GSB_TILE - 1) / GSB_TILE, tile_h = (cam->height + GSB_TILE - 1) / GSB_TILE;
     const int n_tiles = tile_w * tile_h;
-    GSB_CHECK_ARG(gsb_tile_partition_supported(n_tiles));
+    GSB_CHECK_ARG(n_tiles >= 1 && n_tiles <= TP_MAX_TILES);
     GSB_CHECK_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)n_tiles, st));   // stays when N == 0
     if (cap == 0 || N == 0) return GSB_OK;
     GSB_CHECK_ARG(means2d && radii && order && cum_ordered && flatten_ids && workspace);
@@ -238,23 +270,27 @@ extern "C" int gsb_tile_partition_cap(int32_t N, int64_t cap, const int64_t *m_e
                       gsb_tile_partition_bytes(cap, n_tiles));
         return GSB_ENOMEM;
     }
+    const TpShape shape = tp_shape(n_tiles);
+    const int chunk = shape.chunk(), n_chunks = (int)((cap + chunk - 1) / chunk);
     char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     uint32_t *keys = reinterpret_cast<uint32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)cap);
     int32_t *gids = reinterpret_cast<int32_t *>(p); p += align256(sizeof(uint32_t) * (size_t)cap);
-    const size_t hb = align256(sizeof(uint32_t) * (size_t)((cap + TP_CHUNK - 1) / TP_CHUNK) * (size_t)n_tiles);
+    const size_t hb = align256(sizeof(uint32_t) * (size_t)n_chunks * (size_t)n_tiles);
     uint32_t *H = reinterpret_cast<uint32_t *>(p); p += hb;
     uint32_t *Hx = reinterpret_cast<uint32_t *>(p); p += hb;
     uint32_t *totals = reinterpret_cast<uint32_t *>(p);
     int rc = gsb_isect_tiles_ordered_cap(N, means2d, radii, order, cum_ordered, cam, cap, keys, gids, stream);
     if (rc != GSB_OK) return rc;
-    const int n_chunks = (int)((cap + TP_CHUNK - 1) / TP_CHUNK);
     const size_t smem_count = sizeof(uint32_t) * (size_t)n_tiles;
-    const size_t smem_scatter = sizeof(uint32_t) * (size_t)n_tiles + sizeof(uint16_t) * (size_t)TP_WARPS * n_tiles;
-    GSB_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-    tile_count_kernel<<<n_chunks, TP_THREADS, smem_count, st>>>(m_eff, keys, n_tiles, H);
-    tile_prefix_kernel<<<gsb_div_up(n_tiles, TPX), TPX * TPY, 0, st>>>(m_eff, n_tiles, H, Hx, totals);
+    if (smem_count > 48 * 1024)
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+    tile_count_kernel<<<n_chunks, TP_THREADS, smem_count, st>>>(m_eff, keys, n_tiles, chunk, H);
+    tile_prefix_kernel<<<gsb_div_up(n_tiles, TPX), TPX * TPY, 0, st>>>(m_eff, n_tiles, chunk, H, Hx, totals);
     tile_offsets_kernel<<<1, TP_THREADS, 0, st>>>(n_tiles, totals, offsets);
-    tile_scatter_kernel<<<n_chunks, TP_THREADS, smem_scatter, st>>>(m_eff, keys, gids, n_tiles, Hx, offsets, flatten_ids);
+    if (shape.warps == 16) rc = launch_scatter<16, 12>(n_chunks, m_eff, keys, gids, n_tiles, Hx, offsets, flatten_ids, st);
+    else if (shape.warps == 8) rc = launch_scatter<8, 14>(n_chunks, m_eff, keys, gids, n_tiles, Hx, offsets, flatten_ids, st);
+    else rc = launch_scatter<4, 14>(n_chunks, m_eff, keys, gids, n_tiles, Hx, offsets, flatten_ids, st);
+    if (rc != GSB_OK) return rc;
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

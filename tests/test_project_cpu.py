@@ -154,12 +154,15 @@ def test_bin_indices_are_bit_exact_on_the_host(libs, binlib, res, n, kw):
 
 
 @pytest.mark.parametrize("res,n,kw,slack", [((256, 256), 10_000, {}, 1.3), ((320, 200), 6000, dict(extent=3.5, scale_hi=1.2), 1.0),
-                                            ((16, 16), 50, {}, 2.0), ((64, 48), 1, {}, 1.0)])
+                                            ((16, 16), 50, {}, 2.0), ((64, 48), 1, {}, 1.0),
+                                            ((1100, 1000), 4000, dict(extent=3.0, scale_hi=0.6), 1.1),     # 4 347 tiles: 8 warps
+                                            ((2000, 1900), 4000, dict(extent=3.0, scale_hi=0.5), 1.2)])    # 14 875 tiles: 4 warps
 def test_stable_tile_partition_equals_the_sort_on_the_host(res, n, kw, slack):
     """csrc/tilepart.cu (the batch driver's second binning stage: a stable partition of the depth-ordered pairs by tile
     -- chunk histograms, a scan, a warp-ranked scatter -- instead of a radix sort) against the radix-sort path
     gsb_bin2_sort on the same depth order: flatten_ids and per-tile offsets identical.  Several chunks of 16 384 pairs
-    (big splats), a capacity larger than the count (the tail is never touched), one tile, one Gaussian."""
+    (big splats), a capacity larger than the count (the tail is never touched), one tile, one Gaussian, and the two
+    smaller kernel shapes that images of more than 4 096 / 10 240 tiles select."""
     lib = emu.build("project_fwd", "binsort", "tilepart", simt=True)
     g, cam = _scene(n, res, seed=9, **kw)
     gc, radii, means2d, depths, conics, comps, tpg = _project(lib, g, cam, True)
@@ -183,11 +186,11 @@ def test_stable_tile_partition_equals_the_sort_on_the_host(res, n, kw, slack):
     ws2 = np.full(need + 256, 0xFF, np.uint8)
     m_eff = np.asarray([min(M, cap)], np.int64)
     flat, off = np.full(cap, -7, np.int32), np.full(tw * th, -7, np.int32)
-    assert lib.gsb_tile_partition_supported(i32(tw * th)) == 1
+    assert lib.gsb_tile_partition_supported(i32(tw * th)) == int(tw * th <= 4096)     # the batch driver's policy
     assert lib.gsb_tile_partition_cap(i32(N), i64(cap), _p(m_eff), _p(means2d), _p(radii), _p(order), _p(cum), C.byref(gc),
                                       _p(flat), _p(off), _p(ws2), sz(ws2.size), None) == 0, lib.gsb_last_error()
     assert np.array_equal(off, off_ref)
     assert np.array_equal(flat[:M], flat_ref)
     assert (flat[M:] == -7).all()                       # nothing behind the count was written
-    if n >= 6000:
+    if n == 6000:
         assert M > 2 * 16384                            # the scatter really ran over several chunks
