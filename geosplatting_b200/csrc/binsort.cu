@@ -167,13 +167,13 @@ extern "C" __attribute__((visibility("default"))) int gsb_bin2_workspace_bytes(i
 
 // Depth order of the Gaussians (stable: ties keep ascending index), the prefix sum of tiles-per-Gaussian in that
 // order, and M published to *total_out (device or pinned host memory, see gsb_isect_total).
-extern "C" __attribute__((visibility("default"))) int gsb_bin2_count(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order,
-                              int64_t *cum_ordered, int64_t *total_out, void *workspace, size_t workspace_bytes,
-                              void *stream) {
-    GSB_CHECK_ARG(N >= 0 && total_out != nullptr);
+// `total_out` may be null for the batch driver, whose gsb_bin2_publish reads M off cum_ordered itself (one launch less).
+int gsb_bin2_order(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order, int64_t *cum_ordered,
+                   int64_t *total_out, void *workspace, size_t workspace_bytes, void *stream) {
+    GSB_CHECK_ARG(N >= 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0) {
-        GSB_CHECK_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+        if (total_out) GSB_CHECK_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
         return GSB_OK;
     }
     GSB_CHECK_ARG(depths && tiles_per_gauss && order && cum_ordered && workspace);
@@ -197,9 +197,16 @@ extern "C" __attribute__((visibility("default"))) int gsb_bin2_count(int32_t N, 
         thrust::counting_iterator<int32_t>(0), OrderedTiles{tiles_per_gauss, order});
     tb = ordered_scan_temp_bytes(N);
     GSB_CHECK_CUDA(cub::DeviceScan::InclusiveSum(temp, tb, in, cum_ordered, (int)N, st));
-    isect_total_kernel<<<1, 1, 0, st>>>(N, cum_ordered, total_out);
+    if (total_out) isect_total_kernel<<<1, 1, 0, st>>>(N, cum_ordered, total_out);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gsb_bin2_count(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order,
+                              int64_t *cum_ordered, int64_t *total_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    GSB_CHECK_ARG(total_out != nullptr);
+    return gsb_bin2_order(N, depths, tiles_per_gauss, order, cum_ordered, total_out, workspace, workspace_bytes, stream);
 }
 
 __global__ void __launch_bounds__(256) tile_offsets_kernel(int64_t M, const uint32_t *__restrict__ tile_keys, int n_tiles,

@@ -39,6 +39,8 @@ int gsb_composite_bwd_impl(int32_t width, int32_t height, int32_t channels, int6
                            const float *alphas, const int32_t *last_ids, const float *v_render, const float *v_alphas,
                            float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                            const void *workspace, void *stream);
+int gsb_bin2_order(int32_t N, const float *depths, const int32_t *tiles_per_gauss, int32_t *order, int64_t *cum_ordered,
+                   int64_t *total_out, void *workspace, size_t workspace_bytes, void *stream);
 int gsb_bin2_publish(int32_t N, const int64_t *cum_ordered, int64_t cap, int64_t *m_eff, int64_t *total_out, void *stream);
 int gsb_bin2_sort_cap(int32_t N, int64_t cap, const int64_t *m_eff, const float *means2d, const int32_t *radii,
                       const int32_t *order, const int64_t *cum_ordered, const gsb_camera *cam, int32_t *flatten_ids,
@@ -348,7 +350,7 @@ GSB_API int gsb_batch_forward(const gsb_view_config *cfg, int32_t n_views, const
         // ---- prepare: projection, depth order + intersection count (published, not awaited), shade
         VIEW_TRY(gsb_project_fwd(cfg->N, means, quats, scales, cam, k1.radii, t1.means2d, t1.depths, t1.conics,
                                  t1.comps, t1.tpg, st));
-        VIEW_TRY(gsb_bin2_count(cfg->N, t1.depths, t1.tpg, t1.order, t1.cum, k1.m_eff + 1, t1.scratch, b.v.bin_n, st));
+        VIEW_TRY(gsb_bin2_order(cfg->N, t1.depths, t1.tpg, t1.order, t1.cum, nullptr, t1.scratch, b.v.bin_n, st));
         VIEW_TRY(gsb_bin2_publish(cfg->N, t1.cum, m_cap, k1.m_eff, totals_out ? totals_out + v : nullptr, st));
         // the shade writes the compositing records (colour, folded conic, extents, opacity) straight into the
         // compositing workspace: no pack pass, no colour round trip
